@@ -1,0 +1,740 @@
+// b200sep: host side of the C ABI declared in include/b200sep.h -- model creation (weight folding,
+// operand conversion, TMA descriptors), per-batch layout tables, and the launch sequence of one
+// Conv-TasNet forward over a ragged batch of segments; plus the batched PIT entry point.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/b200sep.h"
+#include "bandwidth_kernels.cuh"
+#include "common.cuh"
+#include "epilogues.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "pit.cuh"
+
+using namespace b200sep;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CK(expr)                                                                            \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                       __FILE__, __LINE__);                                 \
+  } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D fp16 tensor map: inner dimension `inner` elements (contiguous), `outer` rows of pitch
+// `pitch_bytes`; box = box_inner x box_outer; 128-byte swizzle (box_inner * 2 bytes must be 128).
+static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
+                        uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+// activations [n_tiles][C][128] fp16 as a 2-D tensor (128 x n_tiles*C), box 64 x 64
+static int make_tmap_act(CUtensorMap* tm, const void* base, int n_tiles, int C) {
+  return make_tmap_2d(tm, base, TILE_M, (uint64_t)n_tiles * C, TILE_M * 2, 64, 64);
+}
+// weights [N][K] fp16, box 64(k) x bn rows
+static int make_tmap_w(CUtensorMap* tm, const void* base, int N, int K, int bn) {
+  return make_tmap_2d(tm, base, K, N, (uint64_t)K * 2, 64, bn);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pinned staging ring for per-call tables (H2D without pageable-copy synchronisation)
+// ------------------------------------------------------------------------------------------------
+struct StagingSlot {
+  void* host = nullptr;
+  size_t cap = 0;
+  cudaEvent_t ev = nullptr;
+};
+struct Staging {
+  static constexpr int kSlots = 8;
+  StagingSlot slots[kSlots];
+  int next = 0;
+  std::mutex mu;
+  // Returns a pinned buffer of at least `bytes`, safe to overwrite (its previous use has completed).
+  int acquire(size_t bytes, StagingSlot** out) {
+    StagingSlot& s = slots[next];
+    next = (next + 1) % kSlots;
+    if (!s.ev) CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+    else CK(cudaEventSynchronize(s.ev));
+    if (s.cap < bytes) {
+      if (s.host) CK(cudaFreeHost(s.host));
+      s.host = nullptr;
+      s.cap = 0;
+      const size_t cap = align_up(bytes * 2, 4096);
+      CK(cudaHostAlloc(&s.host, cap, cudaHostAllocDefault));
+      s.cap = cap;
+    }
+    *out = &s;
+    return 0;
+  }
+  ~Staging() {
+    for (auto& s : slots) {
+      if (s.host) cudaFreeHost(s.host);
+      if (s.ev) cudaEventDestroy(s.ev);
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// model
+// ------------------------------------------------------------------------------------------------
+struct BlockW {
+  void* w_in = nullptr;   // [512][128] T
+  float* b_in = nullptr;  // [512]
+  float a1 = 0.25f;
+  float *g1 = nullptr, *be1 = nullptr, *wd = nullptr, *bd = nullptr;  // [512],[512],[512][3],[512]
+  float a2 = 0.25f;
+  void* w_rs = nullptr;  // [256][512] T ([128][512] for the last block): (W . gamma2)
+  float *rs = nullptr, *cb = nullptr;
+  int dilation = 1;
+  int n_out = 256;
+  CUtensorMap tm_in, tm_rs;
+};
+
+struct b200sep_model {
+  b200sep_config cfg;
+  int device = 0;
+  int n_sm = 148;
+  int n_layers = 0;
+  bool half = true, use_tc = true;
+  std::vector<void*> allocs;
+  float *enc_w = nullptr, *dec_w = nullptr;
+  void* bn_w = nullptr;
+  float *bn_rs = nullptr, *bn_cb = nullptr;
+  std::vector<BlockW> blocks;
+  void* mask_w = nullptr;
+  float* mask_b = nullptr;
+  float alpha_mask = 0.25f;
+  CUtensorMap tm_bn, tm_mask;
+  Staging staging;
+  std::mutex mu;
+  int debug_stop_after = 0;  // 0 = run everything; k = stop after k-th launch (tests)
+};
+
+static Staging g_pit_staging;
+static std::mutex g_pit_mu;
+
+template <typename T> static T host_cvt(float v);
+template <> float host_cvt<float>(float v) { return v; }
+template <> __half host_cvt<__half>(float v) { return __float2half_rn(v); }
+static inline float host_back(float v) { return v; }
+static inline float host_back(__half v) { return __half2float(v); }
+
+static int dev_upload(b200sep_model* m, const void* src, size_t bytes, void** out) {
+  void* d = nullptr;
+  CK(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
+  m->allocs.push_back(d);
+  CK(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+  *out = d;
+  return 0;
+}
+static int dev_upload_f(b200sep_model* m, const std::vector<float>& v, float** out) {
+  return dev_upload(m, v.data(), v.size() * sizeof(float), reinterpret_cast<void**>(out));
+}
+
+// Folds gamma into W (operand type T), returns rowsum of the rounded operand and W*beta + b.
+template <typename T>
+static int fold_and_upload(b200sep_model* m, const std::vector<const float*>& Ws, const std::vector<const float*>& bs,
+                           int rows_each, int K, const float* gamma, const float* beta, void** d_w, float** d_rs,
+                           float** d_cb) {
+  const int N = rows_each * (int)Ws.size();
+  std::vector<T> w((size_t)N * K);
+  std::vector<float> rs(N), cb(N);
+  for (size_t g = 0; g < Ws.size(); ++g)
+    for (int r = 0; r < rows_each; ++r) {
+      const int n = (int)g * rows_each + r;
+      double srs = 0.0, scb = 0.0;
+      for (int k = 0; k < K; ++k) {
+        const float wv = Ws[g][(size_t)r * K + k];
+        const T q = host_cvt<T>(wv * gamma[k]);
+        w[(size_t)n * K + k] = q;
+        srs += (double)host_back(q);
+        scb += (double)wv * (double)beta[k];
+      }
+      rs[n] = (float)srs;
+      cb[n] = (float)(scb + (double)bs[g][r]);
+    }
+  if (dev_upload(m, w.data(), w.size() * sizeof(T), d_w)) return 1;
+  if (dev_upload_f(m, rs, d_rs)) return 1;
+  if (dev_upload_f(m, cb, d_cb)) return 1;
+  return 0;
+}
+
+template <typename T>
+static int upload_cvt(b200sep_model* m, const float* src, size_t n, void** out) {
+  std::vector<T> w(n);
+  for (size_t i = 0; i < n; ++i) w[i] = host_cvt<T>(src[i]);
+  return dev_upload(m, w.data(), n * sizeof(T), out);
+}
+
+template <typename T>
+static int build_weights(b200sep_model* m, const b200sep_weights* w) {
+  const b200sep_config& c = m->cfg;
+  const int L = c.kernel_size, S = c.n_src;
+  if (dev_upload(m, w->enc_filters, (size_t)C_ENC * L * 4, reinterpret_cast<void**>(&m->enc_w))) return 1;
+  if (dev_upload(m, w->dec_filters, (size_t)C_ENC * L * 4, reinterpret_cast<void**>(&m->dec_w))) return 1;
+  if (fold_and_upload<T>(m, {w->bn_weight}, {w->bn_bias}, C_BN, C_ENC, w->bn_gamma, w->bn_beta, &m->bn_w,
+                         &m->bn_rs, &m->bn_cb))
+    return 1;
+  m->blocks.resize(m->n_layers);
+  for (int i = 0; i < m->n_layers; ++i) {
+    BlockW& b = m->blocks[i];
+    const bool last = (i == m->n_layers - 1);
+    b.dilation = 1 << (i % c.n_blocks);
+    if (upload_cvt<T>(m, w->in_weight[i], (size_t)C_HID * C_BN, &b.w_in)) return 1;
+    if (dev_upload(m, w->in_bias[i], C_HID * 4, reinterpret_cast<void**>(&b.b_in))) return 1;
+    b.a1 = w->prelu1[i][0];
+    if (dev_upload(m, w->norm1_gamma[i], C_HID * 4, reinterpret_cast<void**>(&b.g1))) return 1;
+    if (dev_upload(m, w->norm1_beta[i], C_HID * 4, reinterpret_cast<void**>(&b.be1))) return 1;
+    if (dev_upload(m, w->dw_weight[i], C_HID * 3 * 4, reinterpret_cast<void**>(&b.wd))) return 1;
+    if (dev_upload(m, w->dw_bias[i], C_HID * 4, reinterpret_cast<void**>(&b.bd))) return 1;
+    b.a2 = w->prelu2[i][0];
+    if (!last) {
+      b.n_out = 2 * C_BN;
+      if (fold_and_upload<T>(m, {w->res_weight[i], w->skip_weight[i]}, {w->res_bias[i], w->skip_bias[i]}, C_BN,
+                             C_HID, w->norm2_gamma[i], w->norm2_beta[i], &b.w_rs, &b.rs, &b.cb))
+        return 1;
+    } else {  // the last block's residual output is never read: skip half only
+      b.n_out = C_SKIP;
+      if (fold_and_upload<T>(m, {w->skip_weight[i]}, {w->skip_bias[i]}, C_SKIP, C_HID, w->norm2_gamma[i],
+                             w->norm2_beta[i], &b.w_rs, &b.rs, &b.cb))
+        return 1;
+    }
+  }
+  m->alpha_mask = w->mask_prelu[0];
+  if (upload_cvt<T>(m, w->mask_weight, (size_t)S * C_ENC * C_SKIP, &m->mask_w)) return 1;
+  if (dev_upload(m, w->mask_bias, (size_t)S * C_ENC * 4, reinterpret_cast<void**>(&m->mask_b))) return 1;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch layout
+// ------------------------------------------------------------------------------------------------
+struct Layout {
+  int n_seg = 0, n_tiles = 0;
+  size_t tables_bytes = 0;
+  // byte offsets inside the workspace
+  size_t o_tables, o_enc, o_x, o_xa, o_skip, o_skipa, o_h1, o_h2, o_masked, o_p0, o_p1, o_p2, total;
+  // offsets inside the table block
+  size_t t_in_off, t_out_off, t_len, t_frames, t_tile0, t_ntiles, t_tile_seg;
+};
+
+static int compute_layout(const b200sep_config& c, bool half, const int32_t* lens, int n_seg, Layout* lo) {
+  if (n_seg <= 0 || !lens) return fail("empty batch");
+  long long tiles = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    if (lens[i] < c.kernel_size)
+      return fail("segment %d has %d samples < kernel_size %d (conv1d would fail in the reference too)", i,
+                  lens[i], c.kernel_size);
+    const long long F = (lens[i] - c.kernel_size) / c.stride + 1;
+    tiles += (F + TILE_M - 1) / TILE_M;
+  }
+  if (tiles > (1ll << 22)) return fail("batch too large (%lld m-tiles)", tiles);
+  lo->n_seg = n_seg;
+  lo->n_tiles = (int)tiles;
+  size_t t = 0;
+  lo->t_in_off = t; t += align_up((size_t)n_seg * 8, 16);
+  lo->t_out_off = t; t += align_up((size_t)n_seg * 8, 16);
+  lo->t_len = t; t += align_up((size_t)n_seg * 4, 16);
+  lo->t_frames = t; t += align_up((size_t)n_seg * 4, 16);
+  lo->t_tile0 = t; t += align_up((size_t)n_seg * 4, 16);
+  lo->t_ntiles = t; t += align_up((size_t)n_seg * 4, 16);
+  lo->t_tile_seg = t; t += align_up((size_t)tiles * 4, 16);
+  lo->tables_bytes = t;
+  const size_t es = half ? 2 : 4;  // activation element size
+  const size_t rows = (size_t)tiles * TILE_M;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 1024); return r; };
+  lo->o_tables = take(lo->tables_bytes);
+  lo->o_enc = take(rows * C_ENC * es);
+  lo->o_x = take(rows * C_BN * 4);
+  lo->o_xa = half ? take(rows * C_BN * es) : lo->o_x;
+  lo->o_skip = take(rows * C_SKIP * 4);
+  lo->o_skipa = take(rows * C_SKIP * es);
+  lo->o_h1 = take(rows * C_HID * es);
+  lo->o_h2 = take(rows * C_HID * es);
+  lo->o_masked = take(rows * (size_t)c.n_src * C_ENC * es);
+  lo->o_p0 = take((size_t)tiles * 2 * 8);
+  lo->o_p1 = take((size_t)tiles * 8 * 8);
+  lo->o_p2 = take((size_t)tiles * 8 * 8);
+  lo->total = o;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+template <int BN, int K, class Epi>
+static int launch_tc(const b200sep_model* m, const CUtensorMap& ta, const CUtensorMap& tbm, int n_mtiles, int N,
+                     const Epi& epi, const Tables& tb, cudaStream_t st, uint32_t a_lbo = 8192, uint32_t a_sbo = 1024) {
+  using Cfg = tc::TcConfig<BN, K>;
+  auto kern = tc::gemm_tc_kernel<BN, K, Epi>;
+  static bool configured = false;  // per template instantiation
+  if (!configured) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int n_ntiles = N / BN;
+  const int total = n_mtiles * n_ntiles;
+  const int grid = std::min(total, m->n_sm);
+  kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(ta, tbm, n_mtiles, n_ntiles, a_lbo, a_sbo, epi, tb);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T, int K, class Epi>
+static int launch_simt(const T* A, const T* B, int n_mtiles, int N, const Epi& epi, const Tables& tb,
+                       cudaStream_t st) {
+  dim3 grid(N / 128, n_mtiles);
+  gemm_simt_kernel<T, K, Epi><<<grid, 256, 0, st>>>(A, B, epi, tb);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// One GEMM of the model in the configured engine.  BN is the tcgen05 N-tile.
+template <typename T, int BN, int K, class Epi>
+static int run_gemm(const b200sep_model* m, const T* A, const CUtensorMap* tmA, const T* B, const CUtensorMap* tmB,
+                    int n_mtiles, int N, const Epi& epi, const Tables& tb, cudaStream_t st) {
+  if constexpr (std::is_same<T, __half>::value) {
+    if (m->use_tc) return launch_tc<BN, K, Epi>(m, *tmA, *tmB, n_mtiles, N, epi, tb, st);
+  }
+  return launch_simt<T, K, Epi>(A, B, n_mtiles, N, epi, tb, st);
+}
+
+template <typename T, int L>
+static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const float* d_mix, float* d_out,
+                   uint8_t* ws, cudaStream_t st) {
+  const b200sep_config& c = m->cfg;
+  const int nt = lo.n_tiles;
+  T* enc = reinterpret_cast<T*>(ws + lo.o_enc);
+  float* x = reinterpret_cast<float*>(ws + lo.o_x);
+  T* xa = reinterpret_cast<T*>(ws + lo.o_xa);
+  float* skip = reinterpret_cast<float*>(ws + lo.o_skip);
+  T* skipa = reinterpret_cast<T*>(ws + lo.o_skipa);
+  T* h1 = reinterpret_cast<T*>(ws + lo.o_h1);
+  T* h2 = reinterpret_cast<T*>(ws + lo.o_h2);
+  T* masked = reinterpret_cast<T*>(ws + lo.o_masked);
+  float2* p0 = reinterpret_cast<float2*>(ws + lo.o_p0);
+  float2* p1 = reinterpret_cast<float2*>(ws + lo.o_p1);
+  float2* p2 = reinterpret_cast<float2*>(ws + lo.o_p2);
+  constexpr bool kHalf = std::is_same<T, __half>::value;
+  T* xa_or_null = kHalf ? xa : nullptr;
+  const T* a_x = kHalf ? xa : reinterpret_cast<const T*>(x);  // A operand of the in-conv
+
+  CUtensorMap tm_enc, tm_xa, tm_h2, tm_skipa;
+  if (kHalf && m->use_tc) {
+    if (make_tmap_act(&tm_enc, enc, nt, C_ENC)) return 1;
+    if (make_tmap_act(&tm_xa, xa, nt, C_BN)) return 1;
+    if (make_tmap_act(&tm_h2, h2, nt, C_HID)) return 1;
+    if (make_tmap_act(&tm_skipa, skipa, nt, C_SKIP)) return 1;
+  }
+  int launches = 0;
+  auto stop = [&]() { return m->debug_stop_after > 0 && ++launches >= m->debug_stop_after; };
+  const int slots1 = (kHalf && m->use_tc) ? 8 : C_HID / 128;  // partial slots the in-conv GEMM writes
+
+  // 1. encoder (+ bottleneck-gLN partials)
+  encoder_kernel<T, L><<<dim3(nt, 2), 256, 0, st>>>(d_mix, m->enc_w, enc, p0, tb);
+  CK(cudaGetLastError());
+  if (stop()) return 0;
+
+  // 2. bottleneck: x = Wb . gLN(tf_rep) + bb
+  {
+    EpiBottleneck<T> e{p0, 2, m->bn_rs, m->bn_cb, x, xa_or_null};
+    if (run_gemm<T, 128, C_ENC>(m, enc, &tm_enc, reinterpret_cast<const T*>(m->bn_w), &m->tm_bn, nt, C_BN, e, tb, st))
+      return 1;
+  }
+  if (stop()) return 0;
+
+  // 3. TCN blocks
+  for (int i = 0; i < m->n_layers; ++i) {
+    BlockW& b = m->blocks[i];
+    const bool first = (i == 0), last = (i == m->n_layers - 1);
+    {
+      EpiIn<T> e{b.b_in, b.a1, h1, p1};
+      if (run_gemm<T, 256, C_BN>(m, a_x, &tm_xa, reinterpret_cast<const T*>(b.w_in), &b.tm_in, nt, C_HID, e, tb, st))
+        return 1;
+    }
+    if (stop()) return 0;
+    {
+      DwParams p{b.g1, b.be1, b.wd, b.bd, b.a2, b.dilation};
+      dwconv_kernel<T><<<dim3(8, nt), 256, 0, st>>>(h1, h2, p1, slots1, p2, p, tb);
+      CK(cudaGetLastError());
+    }
+    if (stop()) return 0;
+    {
+      EpiResSkip<T> e{p2, 8, b.rs, b.cb, x, xa_or_null, skip, skipa, m->alpha_mask, last ? 0 : 1, first ? 1 : 0,
+                      last ? 1 : 0};
+      int rc;
+      if (!last)
+        rc = run_gemm<T, 256, C_HID>(m, h2, &tm_h2, reinterpret_cast<const T*>(b.w_rs), &b.tm_rs, nt, 2 * C_BN, e, tb, st);
+      else
+        rc = run_gemm<T, 128, C_HID>(m, h2, &tm_h2, reinterpret_cast<const T*>(b.w_rs), &b.tm_rs, nt, C_SKIP, e, tb, st);
+      if (rc) return 1;
+    }
+    if (stop()) return 0;
+  }
+
+  // 4. mask net + mask application
+  {
+    const int n_total = c.n_src * C_ENC;
+    if (kHalf) {
+      EpiMask<T, true> e{m->mask_b, enc, masked, n_total, c.mask_act};
+      if (run_gemm<T, 256, C_SKIP>(m, skipa, &tm_skipa, reinterpret_cast<const T*>(m->mask_w), &m->tm_mask, nt, n_total,
+                                   e, tb, st))
+        return 1;
+    } else {
+      EpiMask<T, false> e{m->mask_b, enc, masked, n_total, c.mask_act};
+      if (run_gemm<T, 256, C_SKIP>(m, skipa, &tm_skipa, reinterpret_cast<const T*>(m->mask_w), &m->tm_mask, nt, n_total,
+                                   e, tb, st))
+        return 1;
+    }
+  }
+  if (stop()) return 0;
+
+  // 5. decoder + overlap-add (d_out was zero-filled by the caller of forward())
+  decoder_kernel<T, L><<<dim3(nt, c.n_src), 256, 0, st>>>(masked, m->dec_w, d_out, c.n_src, tb);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int b200sep_version(void) { return B200SEP_VERSION; }
+const char* b200sep_last_error(void) { return g_err.c_str(); }
+
+int b200sep_model_create(const b200sep_config* cfg, const b200sep_weights* w, int device, b200sep_model** out) {
+  if (!cfg || !w || !out) return fail("null argument");
+  *out = nullptr;
+  const b200sep_config& c = *cfg;
+  if (c.n_src != 2 && c.n_src != 3) return fail("n_src must be 2 or 3 (got %d)", c.n_src);
+  if (c.n_filters != C_ENC || c.bn_chan != C_BN || c.hid_chan != C_HID || c.skip_chan != C_SKIP ||
+      c.conv_kernel_size != 3)
+    return fail("unsupported channel configuration N=%d B=%d H=%d Sc=%d P=%d (supported: 512/128/512/128/3)",
+                c.n_filters, c.bn_chan, c.hid_chan, c.skip_chan, c.conv_kernel_size);
+  if (!((c.kernel_size == 16 && c.stride == 8) || (c.kernel_size == 32 && c.stride == 16)))
+    return fail("unsupported filterbank (kernel_size=%d, stride=%d); supported (16,8) and (32,16)", c.kernel_size,
+                c.stride);
+  if (c.n_blocks < 1 || c.n_blocks > 10 || c.n_repeats < 1) return fail("bad n_blocks/n_repeats");
+  if (c.mask_act != B200SEP_MASK_SIGMOID && c.mask_act != B200SEP_MASK_RELU) return fail("bad mask_act");
+  if (c.precision < 0 || c.precision > 2) return fail("bad precision");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device: the b200 separation backend has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail("device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail("device %d is sm_%d%d; this backend is built for sm_100a (B200) only", device, prop.major,
+                prop.minor);
+  CK(cudaSetDevice(device));
+
+  b200sep_model* m = new b200sep_model();
+  m->cfg = c;
+  m->device = device;
+  m->n_sm = prop.multiProcessorCount;
+  m->n_layers = c.n_blocks * c.n_repeats;
+  m->half = (c.precision != B200SEP_PREC_FP32);
+  m->use_tc = (c.precision == B200SEP_PREC_FP16_TC);
+  const char* dbg = getenv("B200SEP_DEBUG_STOP_AFTER");
+  if (dbg) m->debug_stop_after = atoi(dbg);
+  int rc = m->half ? build_weights<__half>(m, w) : build_weights<float>(m, w);
+  if (!rc && m->use_tc) {
+    rc = make_tmap_w(&m->tm_bn, m->bn_w, C_BN, C_ENC, 128);
+    for (int i = 0; i < m->n_layers && !rc; ++i) {
+      BlockW& b = m->blocks[i];
+      rc = make_tmap_w(&b.tm_in, b.w_in, C_HID, C_BN, 256);
+      if (!rc) rc = make_tmap_w(&b.tm_rs, b.w_rs, b.n_out, C_HID, b.n_out == 256 ? 256 : 128);
+    }
+    if (!rc) rc = make_tmap_w(&m->tm_mask, m->mask_w, c.n_src * C_ENC, C_SKIP, 256);
+  }
+  if (rc) {
+    std::string keep = g_err;
+    b200sep_model_destroy(m);
+    g_err = keep;
+    return 1;
+  }
+  *out = m;
+  return 0;
+}
+
+void b200sep_model_destroy(b200sep_model* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+}
+
+int b200sep_debug_set_stop(b200sep_model* m, int stop_after) {
+  if (!m) return fail("null model");
+  m->debug_stop_after = stop_after;
+  return 0;
+}
+
+// Byte offsets of the intermediate buffers inside the workspace (tests read them back):
+// out[0..9] = enc, x, xa, skip, skipa, h1, h2, masked, n_tiles, total
+int b200sep_debug_layout(const b200sep_model* m, const int32_t* lens, int32_t n_seg, uint64_t* out) {
+  if (!m || !out) return fail("null argument");
+  Layout lo;
+  if (compute_layout(m->cfg, m->half, lens, n_seg, &lo)) return 1;
+  out[0] = lo.o_enc; out[1] = lo.o_x; out[2] = lo.o_xa; out[3] = lo.o_skip; out[4] = lo.o_skipa;
+  out[5] = lo.o_h1; out[6] = lo.o_h2; out[7] = lo.o_masked; out[8] = (uint64_t)lo.n_tiles; out[9] = lo.total;
+  return 0;
+}
+
+size_t b200sep_workspace_bytes(const b200sep_model* m, const int32_t* lens, int32_t n_seg) {
+  if (!m) { fail("null model"); return 0; }
+  Layout lo;
+  if (compute_layout(m->cfg, m->half, lens, n_seg, &lo)) return 0;
+  return lo.total;
+}
+
+int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* offsets, const int32_t* lens,
+                           int32_t n_seg, float* d_out, void* d_ws, size_t ws_bytes, void* stream) {
+  if (!m || !d_mix || !lens || !d_out || !d_ws) return fail("null argument");
+  if ((reinterpret_cast<uintptr_t>(d_ws) & 255u) != 0) return fail("d_ws must be 256-byte aligned");
+  Layout lo;
+  if (compute_layout(m->cfg, m->half, lens, n_seg, &lo)) return 1;
+  if (ws_bytes < lo.total) return fail("workspace too small: %zu < %zu bytes", ws_bytes, lo.total);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lock(m->mu);
+  CK(cudaSetDevice(m->device));
+
+  // ---- tables -> pinned staging -> workspace head
+  StagingSlot* slot = nullptr;
+  {
+    std::lock_guard<std::mutex> l2(m->staging.mu);
+    if (m->staging.acquire(lo.tables_bytes, &slot)) return 1;
+  }
+  uint8_t* h = static_cast<uint8_t*>(slot->host);
+  memset(h, 0, lo.tables_bytes);
+  int64_t* h_in = reinterpret_cast<int64_t*>(h + lo.t_in_off);
+  int64_t* h_out = reinterpret_cast<int64_t*>(h + lo.t_out_off);
+  int32_t* h_len = reinterpret_cast<int32_t*>(h + lo.t_len);
+  int32_t* h_fr = reinterpret_cast<int32_t*>(h + lo.t_frames);
+  int32_t* h_t0 = reinterpret_cast<int32_t*>(h + lo.t_tile0);
+  int32_t* h_nt = reinterpret_cast<int32_t*>(h + lo.t_ntiles);
+  int32_t* h_ts = reinterpret_cast<int32_t*>(h + lo.t_tile_seg);
+  int64_t run = 0, out_lo = INT64_MAX, out_hi = 0;
+  int tile = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    const int64_t off = offsets ? offsets[i] : run;
+    if (off < 0) return fail("negative offset for segment %d", i);
+    run += lens[i];
+    h_in[i] = off;
+    h_out[i] = off * m->cfg.n_src;
+    h_len[i] = lens[i];
+    const int F = (lens[i] - m->cfg.kernel_size) / m->cfg.stride + 1;
+    h_fr[i] = F;
+    h_t0[i] = tile;
+    const int ntile = (F + TILE_M - 1) / TILE_M;
+    h_nt[i] = ntile;
+    for (int t = 0; t < ntile; ++t) h_ts[tile + t] = i;
+    tile += ntile;
+    out_lo = std::min(out_lo, h_out[i]);
+    out_hi = std::max(out_hi, h_out[i] + (int64_t)lens[i] * m->cfg.n_src);
+  }
+  uint8_t* ws = static_cast<uint8_t*>(d_ws);
+  CK(cudaMemcpyAsync(ws + lo.o_tables, h, lo.tables_bytes, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(slot->ev, st));
+  // zero-fill the output span (overlap-add boundary hops accumulate atomically; pad_x_to_y tail)
+  CK(cudaMemsetAsync(d_out + out_lo, 0, (size_t)(out_hi - out_lo) * sizeof(float), st));
+
+  Tables tb;
+  uint8_t* t = ws + lo.o_tables;
+  tb.seg_in_off = reinterpret_cast<const int64_t*>(t + lo.t_in_off);
+  tb.seg_out_off = reinterpret_cast<const int64_t*>(t + lo.t_out_off);
+  tb.seg_len = reinterpret_cast<const int32_t*>(t + lo.t_len);
+  tb.seg_frames = reinterpret_cast<const int32_t*>(t + lo.t_frames);
+  tb.seg_tile0 = reinterpret_cast<const int32_t*>(t + lo.t_tile0);
+  tb.seg_ntiles = reinterpret_cast<const int32_t*>(t + lo.t_ntiles);
+  tb.tile_seg = reinterpret_cast<const int32_t*>(t + lo.t_tile_seg);
+  tb.n_seg = n_seg;
+  tb.n_tiles = lo.n_tiles;
+
+  const bool l16 = (m->cfg.kernel_size == 16);
+  if (m->half)
+    return l16 ? forward<__half, 16>(m, lo, tb, d_mix, d_out, ws, st) : forward<__half, 32>(m, lo, tb, d_mix, d_out, ws, st);
+  return l16 ? forward<float, 16>(m, lo, tb, d_mix, d_out, ws, st) : forward<float, 32>(m, lo, tb, d_mix, d_out, ws, st);
+}
+
+// ---------------------------------------------------------------------------------------------- PIT
+static int pit_geometry(const int32_t* lens, int n_seg, int* chunk, int* max_chunks) {
+  if (n_seg <= 0 || !lens) return fail("empty batch");
+  int max_len = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    if (lens[i] < 0) return fail("negative length");
+    max_len = std::max(max_len, lens[i]);
+  }
+  int ch = 8192;
+  while ((max_len + ch - 1) / ch > 64) ch *= 2;
+  *chunk = ch;
+  *max_chunks = std::max(1, (max_len + ch - 1) / ch);
+  return 0;
+}
+
+size_t b200sep_pit_workspace_bytes(const int32_t* lens, int32_t n_seg) {
+  int chunk, max_chunks;
+  if (pit_geometry(lens, n_seg, &chunk, &max_chunks)) return 0;
+  const size_t tables = align_up((size_t)n_seg * 8, 256) + align_up((size_t)n_seg * 4, 256);
+  return tables + (size_t)n_seg * max_chunks * PIT_NACC * sizeof(double);
+}
+
+int b200sep_pit_sisdr_batch(const float* d_refs, const float* d_ests, const float* d_mix, const int64_t* offsets,
+                            const int32_t* lens, int32_t n_seg, int32_t K, int32_t N, int32_t variant, double* d_pair,
+                            double* d_sisdr, double* d_sisdri, int32_t* d_perm, void* d_ws, size_t ws_bytes,
+                            void* stream) {
+  if (!d_refs || !d_ests || !d_mix || !lens || !d_pair || !d_sisdr || !d_sisdri || !d_perm || !d_ws)
+    return fail("null argument");
+  if (!(K == 2 || K == 3) || N < K || N > 3) return fail("PIT supports K in {2,3}, K <= N <= 3 (got K=%d N=%d)", K, N);
+  if (variant != B200SEP_PIT_OVERLAP3 && variant != B200SEP_PIT_EVALSRC) return fail("bad PIT variant");
+  if ((reinterpret_cast<uintptr_t>(d_ws) & 255u) != 0) return fail("d_ws must be 256-byte aligned");
+  int chunk, max_chunks;
+  if (pit_geometry(lens, n_seg, &chunk, &max_chunks)) return 1;
+  const size_t need = b200sep_pit_workspace_bytes(lens, n_seg);
+  if (ws_bytes < need) return fail("PIT workspace too small: %zu < %zu", ws_bytes, need);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lock(g_pit_mu);
+
+  const size_t off_bytes = align_up((size_t)n_seg * 8, 256), len_bytes = align_up((size_t)n_seg * 4, 256);
+  StagingSlot* slot = nullptr;
+  if (g_pit_staging.acquire(off_bytes + len_bytes, &slot)) return 1;
+  uint8_t* h = static_cast<uint8_t*>(slot->host);
+  int64_t* h_off = reinterpret_cast<int64_t*>(h);
+  int32_t* h_len = reinterpret_cast<int32_t*>(h + off_bytes);
+  int64_t run = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    h_off[i] = offsets ? offsets[i] : run;
+    run += lens[i];
+    h_len[i] = lens[i];
+  }
+  uint8_t* ws = static_cast<uint8_t*>(d_ws);
+  CK(cudaMemcpyAsync(ws, h, off_bytes + len_bytes, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(slot->ev, st));
+  double* partial = reinterpret_cast<double*>(ws + off_bytes + len_bytes);
+
+  PitArgs a{d_refs, d_ests, d_mix, reinterpret_cast<const int64_t*>(ws), reinterpret_cast<const int32_t*>(ws + off_bytes),
+            K, N, chunk, max_chunks};
+  dim3 grid(max_chunks, n_seg);
+  if (K == 2 && N == 2) pit_moments_kernel<2, 2><<<grid, 256, 0, st>>>(a, partial);
+  else if (K == 2 && N == 3) pit_moments_kernel<2, 3><<<grid, 256, 0, st>>>(a, partial);
+  else pit_moments_kernel<3, 3><<<grid, 256, 0, st>>>(a, partial);
+  CK(cudaGetLastError());
+  pit_finalize_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(partial, a.len, n_seg, max_chunks, K, N, variant, d_pair,
+                                                         d_sisdr, d_sisdri, d_perm);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- debug GEMM
+int b200sep_debug_gemm(const float* d_a, const float* d_b, float* d_c, int32_t M, int32_t N, int32_t K, int32_t bn,
+                       int32_t use_tc, void* stream) {
+  if (!d_a || !d_b || !d_c) return fail("null argument");
+  if (M % 128 || !(K == 128 || K == 512) || !(bn == 128 || bn == 256) || N % bn)
+    return fail("debug gemm: M%%128==0, K in {128,512}, bn in {128,256}, N%%bn==0 required");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail("sm_100 device required");
+  b200sep_model fake;
+  fake.n_sm = prop.multiProcessorCount;
+  const int nt = M / 128;
+  __half *a16 = nullptr, *b16 = nullptr;
+  CK(cudaMalloc(&a16, (size_t)M * K * 2));
+  CK(cudaMalloc(&b16, (size_t)N * K * 2));
+  to_tile_transposed_kernel<__half><<<1024, 256, 0, st>>>(d_a, a16, M, K);
+  convert_kernel<__half><<<1024, 256, 0, st>>>(d_b, b16, (size_t)N * K);
+  CK(cudaGetLastError());
+  Tables tb{};
+  tb.n_tiles = nt;
+  EpiPlain e{d_c, N};
+  int rc = 0;
+  if (use_tc) {
+    CUtensorMap ta, tbm;
+    rc = make_tmap_act(&ta, a16, nt, K);
+    if (!rc) rc = make_tmap_w(&tbm, b16, N, K, bn);
+    uint32_t lbo = 8192, sbo = 1024;
+    if (const char* s = getenv("B200SEP_DBG_A_LBO")) lbo = (uint32_t)atoi(s);
+    if (const char* s = getenv("B200SEP_DBG_A_SBO")) sbo = (uint32_t)atoi(s);
+    if (!rc) {
+      if (bn == 256 && K == 128) rc = launch_tc<256, 128, EpiPlain>(&fake, ta, tbm, nt, N, e, tb, st, lbo, sbo);
+      else if (bn == 256 && K == 512) rc = launch_tc<256, 512, EpiPlain>(&fake, ta, tbm, nt, N, e, tb, st, lbo, sbo);
+      else if (bn == 128 && K == 128) rc = launch_tc<128, 128, EpiPlain>(&fake, ta, tbm, nt, N, e, tb, st, lbo, sbo);
+      else rc = launch_tc<128, 512, EpiPlain>(&fake, ta, tbm, nt, N, e, tb, st, lbo, sbo);
+    }
+  } else {
+    if (N % 128) rc = fail("simt debug gemm needs N%%128==0");
+    else if (K == 128) rc = launch_simt<__half, 128, EpiPlain>(a16, b16, nt, N, e, tb, st);
+    else rc = launch_simt<__half, 512, EpiPlain>(a16, b16, nt, N, e, tb, st);
+  }
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(a16);
+  cudaFree(b16);
+  if (rc) return rc;
+  if (se != cudaSuccess) return fail("debug gemm execution failed: %s", cudaGetErrorString(se));
+  return 0;
+}
+
+}  // extern "C"

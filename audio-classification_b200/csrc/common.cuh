@@ -1,0 +1,89 @@
+// Shared definitions for the b200sep kernels (sm_100a only).
+//
+// Activation layout ("tile-transposed"): every per-frame activation tensor with C channels is
+// stored as buf[m_tile][c][128] -- frames are grouped in m-tiles of 128, and inside an m-tile the
+// frame index is the fastest dimension.  Each segment is padded to a whole number of m-tiles, so
+// an m-tile never straddles two segments.  Consequences:
+//   * a GEMM-epilogue thread owns one frame (= one TMEM lane); consecutive lanes touch consecutive
+//     addresses for every channel -> all epilogue loads/stores are coalesced without staging;
+//   * the tensor-core A operand (frames x channels) is "MN-major" and is fetched by TMA as
+//     64(k) x 64(m) boxes with the 128-byte swizzle;
+//   * the depthwise conv is a 1-D stencil along the contiguous dimension.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200sep {
+
+constexpr int TILE_M = 128;  // frames per m-tile
+constexpr int C_ENC = 512;   // n_filters (N)
+constexpr int C_BN = 128;    // bn_chan (B)
+constexpr int C_HID = 512;   // hid_chan (H)
+constexpr int C_SKIP = 128;  // skip_chan (Sc)
+constexpr float GLN_EPS = 1e-8f;
+
+// Per-batch tables (device pointers), built on the host for every call.
+struct Tables {
+  const int64_t* seg_in_off;   // [n_seg] sample offset of segment in d_mix
+  const int64_t* seg_out_off;  // [n_seg] float offset of segment in d_out (= n_src * in_off)
+  const int32_t* seg_len;      // [n_seg] T_i samples
+  const int32_t* seg_frames;   // [n_seg] F_i = (T_i - L) / stride + 1
+  const int32_t* seg_tile0;    // [n_seg] first m-tile of the segment
+  const int32_t* seg_ntiles;   // [n_seg] ceil(F_i / 128)
+  const int32_t* tile_seg;     // [n_tiles] m-tile -> segment
+  int32_t n_seg;
+  int32_t n_tiles;
+};
+
+__host__ __device__ __forceinline__ size_t tt_index(int m_tile, int C, int c, int r) {
+  return ((size_t)m_tile * C + c) * TILE_M + r;
+}
+
+// ---- element conversion helpers -------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+
+// ---- reductions ------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// gLN statistics of one segment from the per-tile partial sums a producer kernel left behind.
+// part[(tile0 + i) * slots + s] = (sum, sum of squares) over the valid frames of that slot.
+// Must be called by all 32 lanes of a warp; every lane (and every warp that repeats the call)
+// gets bit-identical results: fixed traversal order, fp64 accumulation, xor-butterfly.
+// count = C * F_i elements.  var = E[x^2] - mean^2 in fp64 (biased, like asteroid GlobLN).
+__device__ __forceinline__ void warp_seg_stats(const float2* __restrict__ part, int tile0,
+                                               int ntiles, int slots, double count, float& mean,
+                                               float& rstd) {
+  const int lane = threadIdx.x & 31;
+  const int n = ntiles * slots;
+  const float2* p = part + (size_t)tile0 * slots;
+  double s = 0.0, q = 0.0;
+  for (int i = lane; i < n; i += 32) {
+    const float2 v = p[i];
+    s += (double)v.x;
+    q += (double)v.y;
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  const double m = s / count;
+  double var = q / count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)GLN_EPS));
+}
+
+}  // namespace b200sep

@@ -1,0 +1,157 @@
+"""Batched PIT SI-SDR / SI-SDRi on the GPU, behind the reference's own function signatures.
+
+Replaces (``/root/reference``):
+  * ``scripts/osd/overlap3_core.py`` ``_si_sdr`` :48-63, ``_pit_best_si_sdr_k`` :66-100,
+    ``_compute_sdr_improvement_pit_k`` :103-117        (variant ``"overlap3"``)
+  * ``scripts/osd/evaluate_with_sources.py`` ``compute_sdr_improvement_pit`` :377-393,
+    ``compute_sdr_improvement_pit_k`` :431-441          (variant ``"evalsrc"``)
+
+``pit_sisdr_batch`` scores a whole list of segments in two kernel launches
+(``b200sep_pit_sisdr_batch``); the single-segment wrappers keep the reference call shape so the
+evaluation call site (``overlap3_core.py:726-728``) can switch with a one-line import change.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as nat
+
+
+@dataclass
+class PitResult:
+    sisdr: np.ndarray    # [n_seg] float64 best mean SI-SDR (NaN when undefined)
+    sisdri: np.ndarray   # [n_seg] float64 best - mean_i SI-SDR(ref_i, mix)
+    perm: np.ndarray     # [n_seg, K] int32: estimate index assigned to reference i (-1 when undefined)
+    swapped: np.ndarray  # [n_seg] bool, K=2 "evalsrc" variant only
+    pair: np.ndarray     # [n_seg, 3, 4] float64: pair[i][j] = SI-SDR(ref_i, est_j); [:, :, 3] = vs mixture
+
+
+def pit_sisdr_device(d_refs, d_ests, d_mix, lens: Sequence[int], K: int, N: int,
+                     variant: str = "overlap3"):
+    """Device-resident entry: all tensors 1-D float32 CUDA, ragged layout of include/b200sep.h
+    (segment i, source k at ``K*off_i + k*len_i``).  Returns CUDA tensors
+    ``(pair [n,3,4] f64, sisdr [n] f64, sisdri [n] f64, perm [n,4] i32)``; asynchronous."""
+    import torch
+    if variant not in nat.PIT_VARIANTS:
+        raise ValueError(f"unknown PIT variant {variant!r}")
+    n = len(lens)
+    dev = d_mix.device
+    for t in (d_refs, d_ests, d_mix):
+        if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+            raise RuntimeError("PIT inputs must be contiguous float32 CUDA tensors")
+    total = int(sum(int(v) for v in lens))
+    if d_refs.numel() < K * total or d_ests.numel() < N * total or d_mix.numel() < total:
+        raise RuntimeError("PIT input tensors are shorter than the ragged layout requires")
+    arr = nat.i32_array(lens)
+    need = int(nat.lib().b200sep_pit_workspace_bytes(arr, n))
+    if need == 0:
+        raise RuntimeError(f"b200sep_pit_workspace_bytes: {nat.last_error()}")
+    ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+    ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+    pair = torch.empty((n, 3, 4), dtype=torch.float64, device=dev)
+    sisdr = torch.empty(n, dtype=torch.float64, device=dev)
+    sisdri = torch.empty(n, dtype=torch.float64, device=dev)
+    perm = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        nat.check(nat.lib().b200sep_pit_sisdr_batch(
+            C.c_void_p(d_refs.data_ptr()), C.c_void_p(d_ests.data_ptr()), C.c_void_p(d_mix.data_ptr()),
+            None, arr, n, int(K), int(N), nat.PIT_VARIANTS[variant], C.c_void_p(pair.data_ptr()),
+            C.c_void_p(sisdr.data_ptr()), C.c_void_p(sisdri.data_ptr()), C.c_void_p(perm.data_ptr()),
+            C.c_void_p(ws_ptr), C.c_size_t(need), C.c_void_p(stream)), "b200sep_pit_sisdr_batch")
+    ws.record_stream(torch.cuda.current_stream(dev))
+    return pair, sisdr, sisdri, perm
+
+
+def _pack(list_of_lists: Sequence[Sequence[np.ndarray]], lens: Sequence[int], width: int) -> np.ndarray:
+    """[[src arrays] per segment] -> ragged 1-D float32 (segment-major, then source, then time)."""
+    out = np.empty(int(sum(lens)) * width, dtype=np.float32)
+    o = 0
+    for arrs, n in zip(list_of_lists, lens):
+        for a in arrs:
+            out[o:o + n] = np.asarray(a, dtype=np.float32).reshape(-1)[:n]
+            o += n
+    return out
+
+
+def pit_sisdr_batch(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.ndarray]],
+                    preds: Sequence[Sequence[np.ndarray]], variant: str = "overlap3",
+                    device: int = 0) -> PitResult:
+    """Host entry.  ``refs[i]`` has K (2 or 3) arrays, ``preds[i]`` N >= K arrays (same K, N for the
+    whole batch).  Arrays of one segment are truncated to their common length, as every reference
+    ``si_sdr`` does pairwise (``overlap3_core.py:49-52``) -- identical when, as at the call site,
+    all arrays of a segment were cut with the same sample indices."""
+    import torch
+    n = len(mixes)
+    if n == 0:
+        z = np.zeros(0)
+        return PitResult(z, z, np.zeros((0, 0), np.int32), np.zeros(0, bool), np.zeros((0, 3, 4)))
+    K, N = len(refs[0]), len(preds[0])
+    if any(len(r) != K for r in refs) or any(len(p) != N for p in preds):
+        raise ValueError("all segments of a batch must have the same K and N")
+    lens = [int(min([np.asarray(m).shape[-1]] + [np.asarray(a).shape[-1] for a in r] +
+                    [np.asarray(a).shape[-1] for a in p])) for m, r, p in zip(mixes, refs, preds)]
+    dev = torch.device("cuda", device)
+    h_mix = _pack([[m] for m in mixes], lens, 1)
+    h_ref = _pack(refs, lens, K)
+    h_est = _pack(preds, lens, N)
+    with torch.cuda.device(dev):
+        d_mix = torch.from_numpy(h_mix).to(dev)
+        d_ref = torch.from_numpy(h_ref).to(dev)
+        d_est = torch.from_numpy(h_est).to(dev)
+        pair, sisdr, sisdri, perm = pit_sisdr_device(d_ref, d_est, d_mix, lens, K, N, variant)
+        pair, sisdr, sisdri, perm = pair.cpu().numpy(), sisdr.cpu().numpy(), sisdri.cpu().numpy(), perm.cpu().numpy()
+    return PitResult(sisdr, sisdri, perm[:, :K].copy(), perm[:, 3].astype(bool), pair)
+
+
+# ---- reference-shaped single-segment wrappers ---------------------------------------------------
+def _compute_sdr_improvement_pit_k(mix_chunk: np.ndarray, refs: List[np.ndarray],
+                                   preds: List[np.ndarray]) -> Tuple[float, float, List[int]]:
+    """Same contract as ``overlap3_core._compute_sdr_improvement_pit_k`` (:103-117)."""
+    if len(refs) not in (2, 3) or len(preds) < len(refs):
+        return float("nan"), float("nan"), []
+    r = pit_sisdr_batch([mix_chunk], [refs], [preds], "overlap3")
+    if np.isnan(r.sisdr[0]) or np.isnan(r.sisdri[0]):
+        return float("nan"), float("nan"), []
+    return float(r.sisdr[0]), float(r.sisdri[0]), [int(v) for v in r.perm[0]]
+
+
+def _pit_best_si_sdr_k(refs: List[np.ndarray], preds: List[np.ndarray]) -> Tuple[float, List[int]]:
+    """Same contract as ``overlap3_core._pit_best_si_sdr_k`` (:66-100)."""
+    K = len(refs)
+    if K not in (2, 3):
+        raise ValueError("_pit_best_si_sdr_k supports K=2 or 3")
+    if len(preds) < K:
+        return float("nan"), []
+    r = pit_sisdr_batch([refs[0]], [refs], [preds], "overlap3")
+    if np.isnan(r.sisdr[0]):
+        return float("nan"), []
+    return float(r.sisdr[0]), [int(v) for v in r.perm[0]]
+
+
+def _si_sdr(reference: np.ndarray, estimation: np.ndarray) -> float:
+    """Same contract as ``overlap3_core._si_sdr`` (:48-63), evaluated on the device."""
+    r = pit_sisdr_batch([reference], [[reference, reference]], [[estimation, estimation]], "overlap3")
+    return float(r.pair[0, 0, 0])
+
+
+def compute_sdr_improvement_pit(mix_chunk, s1_ref, s2_ref, preds):
+    """Same contract as ``evaluate_with_sources.compute_sdr_improvement_pit`` (:377-393)."""
+    if len(preds) < 2:
+        return float("nan"), float("nan"), [], False
+    r = pit_sisdr_batch([mix_chunk], [[s1_ref, s2_ref]], [preds], "evalsrc")
+    return float(r.sisdr[0]), float(r.sisdri[0]), [int(v) for v in r.perm[0]], bool(r.swapped[0])
+
+
+def compute_sdr_improvement_pit_k(mix_chunk, refs, preds):
+    """Same contract as ``evaluate_with_sources.compute_sdr_improvement_pit_k`` (:431-441)."""
+    if len(refs) not in (2, 3):
+        raise NotImplementedError("Only K=2 or 3 refs are supported")
+    if len(preds) < len(refs):
+        return float("nan"), float("nan"), []
+    r = pit_sisdr_batch([mix_chunk], [refs], [preds], "evalsrc")
+    return float(r.sisdr[0]), float(r.sisdri[0]), [int(v) for v in r.perm[0]]

@@ -1,0 +1,92 @@
+"""Multi-GPU sharding of independent overlap segments.
+
+A segment's forward and its PIT score depend on nothing else (the reference calls the path at
+batch 1: ``/root/reference/src/osd/separation.py:77-83``), so N GPUs = N replicas of the model, each
+fed a disjoint shard.  No waveform ever crosses NVLink; the only collective is one ``all_gather`` of
+fixed-size per-segment metric records at the end of an evaluation sweep.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Sequence, Tuple
+
+import numpy as np
+
+__all__ = ["lpt_partition", "bucket_by_length", "gather_records", "frames_of"]
+
+
+def frames_of(n_samples: int, kernel_size: int = 16, stride: int = 8) -> int:
+    return (int(n_samples) - kernel_size) // stride + 1
+
+
+def lpt_partition(costs: Sequence[int], world_size: int) -> List[List[int]]:
+    """Deterministic longest-processing-time-first partition.  ``costs[i]`` ~ frames of segment i.
+    Returns, per rank, the (ascending) list of segment indices it owns."""
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    order = sorted(range(len(costs)), key=lambda i: (-int(costs[i]), i))
+    load = [0] * world_size
+    shards: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        shards[r].append(i)
+        load[r] += int(costs[i])
+    return [sorted(s) for s in shards]
+
+
+def bucket_by_length(indices: Sequence[int], lens: Sequence[int], max_samples: int) -> List[List[int]]:
+    """Length-bucketed batches of a rank's shard: segments sorted by length, cut into batches of at
+    most ``max_samples`` samples (bounds the workspace, keeps similar lengths together so the
+    per-kernel tile waves are even).  Deterministic."""
+    order = sorted(indices, key=lambda i: (int(lens[i]), i))
+    out: List[List[int]] = []
+    cur: List[int] = []
+    tot = 0
+    for i in order:
+        n = int(lens[i])
+        if cur and tot + n > max_samples:
+            out.append(cur)
+            cur, tot = [], 0
+        cur.append(i)
+        tot += n
+    if cur:
+        out.append(cur)
+    return out
+
+
+def gather_records(local_ids: Sequence[int], local_records: np.ndarray, n_total: int,
+                   device=None) -> np.ndarray:
+    """all_gather of per-segment metric records.  ``local_records`` is ``[len(local_ids), R]``
+    float64 (e.g. sisdr, sisdri, perm...).  Returns ``[n_total, R]`` with every segment's record in
+    global order on every rank (NaN where no rank reported).  Uses the initialised
+    ``torch.distributed`` backend (NCCL over NVLink on GPUs, gloo in CPU tests); with no process
+    group it is the identity scatter."""
+    import torch
+    import torch.distributed as dist
+    local_records = np.asarray(local_records, dtype=np.float64).reshape(len(local_ids), -1)
+    R = local_records.shape[1] if local_records.size else 0
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        out = np.full((n_total, R), np.nan)
+        if len(local_ids):
+            out[np.asarray(local_ids, dtype=np.int64)] = local_records
+        return out
+    world = dist.get_world_size()
+    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    # fixed-size payload per rank: count, R, then (id, record) rows padded to the max shard size
+    n_loc = torch.tensor([len(local_ids), R], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, n_loc)
+    max_n = int(max(int(c[0]) for c in counts))
+    R = int(max(int(c[1]) for c in counts))
+    payload = torch.full((max_n, R + 1), float("nan"), dtype=torch.float64, device=dev)
+    if len(local_ids):
+        payload[:len(local_ids), 0] = torch.as_tensor(np.asarray(local_ids, dtype=np.float64), device=dev)
+        payload[:len(local_ids), 1:] = torch.as_tensor(local_records, device=dev)
+    gathered = [torch.empty_like(payload) for _ in range(world)]
+    dist.all_gather(gathered, payload)
+    out = np.full((n_total, R), np.nan)
+    for r, g in enumerate(gathered):
+        k = int(counts[r][0])
+        if k:
+            g = g[:k].cpu().numpy()
+            out[g[:, 0].astype(np.int64)] = g[:, 1:]
+    return out

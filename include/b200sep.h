@@ -1,0 +1,180 @@
+/*
+ * b200sep -- C ABI of the B200-native Conv-TasNet separation + PIT SI-SDR backend.
+ *
+ * This is the drop-in boundary for the reference's separation stage.  Plain pointers and
+ * sizes only (no torch types).  Every entry point names the reference interface it replaces
+ * (paths relative to the reference repo NatsuiroGinga/audio-classification).
+ *
+ * Conventions
+ *   - All `d_*` pointers are DEVICE pointers on the model's device; everything else is host.
+ *   - Every function returning int returns 0 on success, non-zero on failure; the message is
+ *     available from b200sep_last_error() (thread-local).  There is no CPU fallback: a missing
+ *     sm_100 device is an error.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
+ *     enqueued asynchronously on it; no call synchronises the device.
+ *   - Segments ("overlap segments" / "chunks") are independent units.  A batch is a ragged
+ *     concatenation: segment i is `lens[i]` fp32 samples starting at `d_mix + offsets[i]`
+ *     (offsets == NULL means tightly packed: offsets[i] = sum(lens[0..i-1])).
+ *     Separated output for segment i, source s is `lens[i]` fp32 samples at
+ *     `d_out + n_src * offsets[i] + s * lens[i]`  -- i.e. exactly the (n_src, T) array the
+ *     reference returns per call, concatenated.
+ */
+#ifndef B200SEP_H_
+#define B200SEP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SEP_VERSION 100 /* 0.1.0 */
+
+/* mask activation of TDConvNet (asteroid mask_act) */
+#define B200SEP_MASK_SIGMOID 0
+#define B200SEP_MASK_RELU 1
+
+/* arithmetic of the 1x1-conv GEMMs and activation storage */
+#define B200SEP_PREC_FP32 0      /* fp32 storage, CUDA-core fp32 GEMMs ("exact" mode, >= 100 dB vs oracle) */
+#define B200SEP_PREC_FP16_TC 1   /* fp16 operands, fp32 accumulate, tcgen05/TMEM/TMA GEMMs (default)       */
+#define B200SEP_PREC_FP16_SIMT 2 /* fp16 storage, CUDA-core GEMMs (validation of the tensor-core path)     */
+
+/*
+ * Hyper-parameters of asteroid.models.ConvTasNet (constructor kwargs; replaces the model
+ * built at src/osd/separation.py:44-50).  Supported: n_src in {2,3}; n_filters=512,
+ * bn_chan=128, hid_chan=512, skip_chan=128, conv_kernel_size=3; (kernel_size, stride) in
+ * {(16,8),(32,16)}; any n_blocks<=10, n_repeats>=1; gLN; sigmoid or relu mask.
+ */
+typedef struct b200sep_config {
+  int32_t n_src;
+  int32_t n_filters;        /* N */
+  int32_t kernel_size;      /* L */
+  int32_t stride;
+  int32_t bn_chan;          /* B */
+  int32_t hid_chan;         /* H */
+  int32_t skip_chan;        /* Sc */
+  int32_t conv_kernel_size; /* P */
+  int32_t n_blocks;         /* X */
+  int32_t n_repeats;        /* R */
+  int32_t mask_act;         /* B200SEP_MASK_* */
+  int32_t precision;        /* B200SEP_PREC_* */
+} b200sep_config;
+
+/*
+ * Raw fp32 HOST tensors of an Asteroid ConvTasNet state_dict (key names in comments; this is
+ * what torch.load(checkpoint)["state_dict"] holds, src/osd/separation.py:53-56).  Per-block
+ * arrays have n_blocks*n_repeats entries, block i = masker.TCN.{i}.  The library copies,
+ * folds the gLN affine parameters into the following convolution and converts to the GEMM
+ * operand type at create time; the caller's buffers are not referenced afterwards.
+ */
+typedef struct b200sep_weights {
+  const float* enc_filters;     /* encoder.filterbank._filters        (N,1,L) */
+  const float* dec_filters;     /* decoder.filterbank._filters        (N,1,L) */
+  const float* bn_gamma;        /* masker.bottleneck.0.gamma          (N)     */
+  const float* bn_beta;         /* masker.bottleneck.0.beta           (N)     */
+  const float* bn_weight;       /* masker.bottleneck.1.weight         (B,N,1) */
+  const float* bn_bias;         /* masker.bottleneck.1.bias           (B)     */
+  const float* const* in_weight;   /* TCN.i.shared_block.0.weight     (H,B,1) */
+  const float* const* in_bias;     /* TCN.i.shared_block.0.bias       (H)     */
+  const float* const* prelu1;      /* TCN.i.shared_block.1.weight     (1)     */
+  const float* const* norm1_gamma; /* TCN.i.shared_block.2.gamma      (H)     */
+  const float* const* norm1_beta;  /* TCN.i.shared_block.2.beta       (H)     */
+  const float* const* dw_weight;   /* TCN.i.shared_block.3.weight     (H,1,P) */
+  const float* const* dw_bias;     /* TCN.i.shared_block.3.bias       (H)     */
+  const float* const* prelu2;      /* TCN.i.shared_block.4.weight     (1)     */
+  const float* const* norm2_gamma; /* TCN.i.shared_block.5.gamma      (H)     */
+  const float* const* norm2_beta;  /* TCN.i.shared_block.5.beta       (H)     */
+  const float* const* res_weight;  /* TCN.i.res_conv.weight           (B,H,1) */
+  const float* const* res_bias;    /* TCN.i.res_conv.bias             (B)     */
+  const float* const* skip_weight; /* TCN.i.skip_conv.weight          (Sc,H,1)*/
+  const float* const* skip_bias;   /* TCN.i.skip_conv.bias            (Sc)    */
+  const float* mask_prelu;      /* masker.mask_net.0.weight           (1)     */
+  const float* mask_weight;     /* masker.mask_net.1.weight           (S*N,Sc,1) */
+  const float* mask_bias;       /* masker.mask_net.1.bias             (S*N)   */
+} b200sep_weights;
+
+typedef struct b200sep_model b200sep_model; /* opaque: device weights, TMA descriptors */
+
+/* Library / ABI version (B200SEP_VERSION). */
+int b200sep_version(void);
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char* b200sep_last_error(void);
+
+/*
+ * Replaces Separator._init_asteroid (src/osd/separation.py:36-64): build the model on CUDA
+ * device `device` from host weights.  Fails (no fallback) if the device is not sm_100.
+ */
+int b200sep_model_create(const b200sep_config* cfg, const b200sep_weights* w, int device,
+                         b200sep_model** out);
+
+void b200sep_model_destroy(b200sep_model* m);
+
+/*
+ * Bytes of device scratch b200sep_separate_batch needs for this batch (activations of every
+ * layer for all segments + tables).  The caller owns the scratch; nothing is allocated inside
+ * the timed call.  Returns 0 and sets the error on invalid input (e.g. a segment shorter than
+ * kernel_size, which the reference's conv1d would also reject).
+ */
+size_t b200sep_workspace_bytes(const b200sep_model* m, const int32_t* lens, int32_t n_seg);
+
+/*
+ * Replaces the forward at src/osd/separation.py:82-83 (`est = self._model(x)`, x = (1,T)),
+ * batched over independent segments: ConvTasNet forward of every segment, each normalised
+ * (gLN) over its own frames exactly as a batch-1 call would be.  Bytes of d_out between
+ * segments (when offsets leave gaps) are zero-filled.  `d_ws` must be 256-byte aligned.
+ */
+int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* offsets,
+                           const int32_t* lens, int32_t n_seg, float* d_out, void* d_ws,
+                           size_t ws_bytes, void* stream);
+
+/* PIT enumeration / tie-break order to reproduce */
+#define B200SEP_PIT_OVERLAP3 0 /* scripts/osd/overlap3_core.py:66-117                         */
+#define B200SEP_PIT_EVALSRC 1  /* scripts/osd/evaluate_with_sources.py:334-441                */
+
+/* doubles of device scratch needed by b200sep_pit_sisdr_batch */
+size_t b200sep_pit_workspace_bytes(const int32_t* lens, int32_t n_seg);
+
+/*
+ * Replaces _compute_sdr_improvement_pit_k / _pit_best_si_sdr_k / _si_sdr
+ * (scripts/osd/overlap3_core.py:48-117) and compute_sdr_improvement_pit[_k]
+ * (scripts/osd/evaluate_with_sources.py:377-441), batched: one pass over the samples
+ * accumulates all first/second moments in fp64, then every pair SI-SDR and every permutation
+ * is scored on the device.
+ *   d_refs : K  reference sources per segment, segment i source k at d_refs + K*offsets[i] + k*lens[i]
+ *   d_ests : N  estimates per segment (same layout with N; the layout b200sep_separate_batch writes)
+ *   d_mix  : mixture, segment i at d_mix + offsets[i]
+ *   K in {2,3}, K <= N <= 3.
+ * Outputs (device):
+ *   d_pair  [n_seg][3][4] fp64 : pair[i][j] = SI-SDR(ref_i, est_j) dB for j<N, pair[i][3] = SI-SDR(ref_i, mix)
+ *   d_sisdr [n_seg] fp64       : best mean SI-SDR over permutations
+ *   d_sisdri[n_seg] fp64       : best - mean_i SI-SDR(ref_i, mix)
+ *   d_perm  [n_seg][4] int32   : perm[i] = estimate index assigned to reference i (i<K);
+ *                                perm[3] = "swapped" flag of the K=2 EVALSRC variant, else 0
+ */
+int b200sep_pit_sisdr_batch(const float* d_refs, const float* d_ests, const float* d_mix,
+                            const int64_t* offsets, const int32_t* lens, int32_t n_seg,
+                            int32_t K, int32_t N, int32_t variant, double* d_pair,
+                            double* d_sisdr, double* d_sisdri, int32_t* d_perm, void* d_ws,
+                            size_t ws_bytes, void* stream);
+
+/*
+ * Development/validation hook: raw GEMM  C[M,N] = A * B^T  through the same tcgen05/TMA
+ * kernel the model uses (A given row-major [M,K] fp32 on device, B [N,K] fp32 on device,
+ * both rounded to fp16; C fp32 row-major).  M multiple of 128, K multiple of 64,
+ * N multiple of `bn` (128 or 256).  Used by tests to check the tensor-core path in isolation.
+ */
+int b200sep_debug_gemm(const float* d_a, const float* d_b, float* d_c, int32_t M, int32_t N,
+                       int32_t K, int32_t bn, int32_t use_tc, void* stream);
+
+/* Test hooks: stop the forward after the k-th kernel launch (0 = run everything), and report the
+ * byte offsets of the intermediate activations inside the workspace:
+ * out[0..9] = enc, x, xa, skip, skipa, h1, h2, masked, n_tiles, total. */
+int b200sep_debug_set_stop(b200sep_model* m, int stop_after);
+int b200sep_debug_layout(const b200sep_model* m, const int32_t* lens, int32_t n_seg, uint64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SEP_H_ */
