@@ -25,7 +25,7 @@ EXPORTS = [
     "b200sep_version", "b200sep_last_error", "b200sep_model_create", "b200sep_model_destroy",
     "b200sep_workspace_bytes", "b200sep_separate_batch", "b200sep_pit_workspace_bytes",
     "b200sep_pit_sisdr_batch", "b200sep_debug_gemm", "b200sep_debug_set_stop",
-    "b200sep_debug_layout",
+    "b200sep_debug_layout", "b200sep_profile_enable", "b200sep_profile_read",
 ]
 
 
@@ -94,6 +94,10 @@ def lib() -> C.CDLL:
         L.b200sep_debug_set_stop.argtypes = [vp, C.c_int]
         L.b200sep_debug_layout.restype = C.c_int
         L.b200sep_debug_layout.argtypes = [vp, i32p, i32, C.POINTER(C.c_uint64)]
+        L.b200sep_profile_enable.restype = C.c_int
+        L.b200sep_profile_enable.argtypes = [vp, C.c_int]
+        L.b200sep_profile_read.restype = C.c_int
+        L.b200sep_profile_read.argtypes = [vp, C.POINTER(C.c_float), i32, i32p]
         _lib = L
     return _lib
 

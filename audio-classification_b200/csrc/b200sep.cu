@@ -166,6 +166,10 @@ struct b200sep_model {
   Staging staging;
   std::mutex mu;
   int debug_stop_after = 0;  // 0 = run everything; k = stop after k-th launch (tests)
+  // optional per-launch CUDA-event timing (bench.py roofline pass)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  int prof_n = 0;
 };
 
 static Staging g_pit_staging;
@@ -386,7 +390,21 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
     if (make_tmap_act(&tm_skipa, skipa, nt, C_SKIP)) return 1;
   }
   int launches = 0;
-  auto stop = [&]() { return m->debug_stop_after > 0 && ++launches >= m->debug_stop_after; };
+  m->prof_n = 0;
+  auto prof_mark = [&]() {
+    if (!m->prof_on) return;
+    if ((int)m->prof_ev.size() <= m->prof_n) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      m->prof_ev.push_back(e);
+    }
+    cudaEventRecord(m->prof_ev[m->prof_n++], st);
+  };
+  prof_mark();
+  auto stop = [&]() {
+    prof_mark();
+    return m->debug_stop_after > 0 && ++launches >= m->debug_stop_after;
+  };
   const int slots1 = (kHalf && m->use_tc) ? 8 : C_HID / 128;  // partial slots the in-conv GEMM writes
 
   // 1. encoder (+ bottleneck-gLN partials)
@@ -451,6 +469,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
   // 5. decoder + overlap-add (d_out was zero-filled by the caller of forward())
   decoder_kernel<T, L><<<dim3(nt, c.n_src), 256, 0, st>>>(masked, m->dec_w, d_out, c.n_src, tb);
   CK(cudaGetLastError());
+  prof_mark();
   return 0;
 }
 
@@ -522,12 +541,33 @@ void b200sep_model_destroy(b200sep_model* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   for (void* p : m->allocs) cudaFree(p);
+  for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
   delete m;
 }
 
 int b200sep_debug_set_stop(b200sep_model* m, int stop_after) {
   if (!m) return fail("null model");
   m->debug_stop_after = stop_after;
+  return 0;
+}
+
+int b200sep_profile_enable(b200sep_model* m, int on) {
+  if (!m) return fail("null model");
+  m->prof_on = on != 0;
+  return 0;
+}
+
+// Durations (ms) of the launches of the most recent b200sep_separate_batch call made while
+// profiling was enabled, in launch order: encoder, bottleneck, then per block (in-conv GEMM,
+// depthwise, res/skip GEMM), mask GEMM, decoder.  Synchronises on the last launch.
+int b200sep_profile_read(b200sep_model* m, float* ms_out, int32_t cap, int32_t* n_out) {
+  if (!m || !ms_out || !n_out) return fail("null argument");
+  std::lock_guard<std::mutex> lock(m->mu);
+  const int n = m->prof_n - 1;
+  *n_out = n > 0 ? n : 0;
+  if (n <= 0) return 0;
+  CK(cudaEventSynchronize(m->prof_ev[m->prof_n - 1]));
+  for (int i = 0; i < n && i < cap; ++i) CK(cudaEventElapsedTime(&ms_out[i], m->prof_ev[i], m->prof_ev[i + 1]));
   return 0;
 }
 

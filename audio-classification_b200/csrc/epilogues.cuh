@@ -62,7 +62,7 @@ struct EpiBottleneck {
       const int n = n0 + j;
       float v = fmaf(st.rstd, fmaf(-mr, __ldg(rs + n), acc[j]), __ldg(cb + n));
       if (!valid) v = 0.f;
-      const size_t idx = tt_index(m_tile, C_BN, n, r);
+      const size_t idx = tt_index(m_tile, C_BN, n0, r) + (size_t)j * TILE_M;
       x[idx] = v;
       if (xa != nullptr) xa[idx] = from_f32<T>(v);
     }
@@ -93,7 +93,7 @@ struct EpiIn {
       float v = acc[j] + __ldg(bias + n);
       v = (v > 0.f) ? v : alpha * v;
       if (!valid) v = 0.f;
-      h1[tt_index(m_tile, C_HID, n, r)] = from_f32<T>(v);
+      h1[tt_index(m_tile, C_HID, n0, r) + (size_t)j * TILE_M] = from_f32<T>(v);
       st.s += v;
       st.q = fmaf(v, v, st.q);
     }
@@ -128,24 +128,41 @@ struct EpiResSkip {
     const bool valid = (st.t0 + r) < st.F;
     const bool is_res = has_res && (n0 < C_BN);
     const int c0 = (has_res && !is_res) ? (n0 - C_BN) : n0;
+    const size_t idx0 = tt_index(m_tile, C_BN, c0, r);
+    // issue all loads of the chunk first: they are independent, and consecutive lanes (frames) hit
+    // consecutive addresses, so W x 128 B per warp are in flight instead of one dependent load
+    float old[W];
+    const bool need_old = is_res || !first;
+    const float* __restrict__ src = is_res ? x : skip;
+    if (need_old) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) old[j] = __ldcs(src + idx0 + (size_t)j * TILE_M);
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j) old[j] = 0.f;
+    }
+    float out[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) {
       const int n = n0 + j;
       float v = fmaf(st.rstd, fmaf(-st.mean, __ldg(rs + n), acc[j]), __ldg(cb + n));
       if (!valid) v = 0.f;
-      const size_t idx = tt_index(m_tile, C_BN, c0 + j, r);
-      if (is_res) {
-        const float xn = x[idx] + v;
-        x[idx] = xn;
-        if (xa != nullptr) xa[idx] = from_f32<T>(xn);
-      } else {
-        const float sn = first ? v : (skip[idx] + v);
-        if (!last) {
-          skip[idx] = sn;
-        } else {
-          skipa[idx] = from_f32<T>((sn > 0.f) ? sn : alpha_mask * sn);
-        }
+      out[j] = old[j] + v;
+    }
+    if (is_res) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) x[idx0 + (size_t)j * TILE_M] = out[j];
+      if (xa != nullptr) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) xa[idx0 + (size_t)j * TILE_M] = from_f32<T>(out[j]);
       }
+    } else if (!last) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) skip[idx0 + (size_t)j * TILE_M] = out[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        skipa[idx0 + (size_t)j * TILE_M] = from_f32<T>((out[j] > 0.f) ? out[j] : alpha_mask * out[j]);
     }
   }
   __device__ __forceinline__ void tile_end(EpiState&, int, int, int) const {}
@@ -169,10 +186,15 @@ struct EpiMask {
   }
   template <int W>
   __device__ __forceinline__ void apply(EpiState& st, int m_tile, int r, int n0, const float* acc) const {
+    // a chunk never straddles a source boundary (W divides 512)
+    const T* __restrict__ ep = enc + tt_index(m_tile, C_ENC, n0 & (C_ENC - 1), r);
+    T* __restrict__ mp = masked + tt_index(m_tile, n_total, n0, r);
+    float e[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) e[j] = to_f32(ep[(size_t)j * TILE_M]);
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-      const int n = n0 + j;
-      const float v = acc[j] + __ldg(bias + n);
+      const float v = acc[j] + __ldg(bias + n0 + j);
       float m;
       if (act == 0) {
         if (kFast) m = __fdividef(1.f, 1.f + __expf(-v));
@@ -180,8 +202,7 @@ struct EpiMask {
       } else {
         m = fmaxf(v, 0.f);
       }
-      const float e = to_f32(enc[tt_index(m_tile, C_ENC, n & (C_ENC - 1), r)]);
-      masked[tt_index(m_tile, n_total, n, r)] = from_f32<T>(m * e);
+      mp[(size_t)j * TILE_M] = from_f32<T>(m * e[j]);
     }
   }
   __device__ __forceinline__ void tile_end(EpiState&, int, int, int) const {}

@@ -78,13 +78,56 @@ def _pack(list_of_lists: Sequence[Sequence[np.ndarray]], lens: Sequence[int], wi
     return out
 
 
+def _select_host(M: np.ndarray, base_vals: np.ndarray, K: int, N: int, variant: str):
+    """Host replay of the device finalize step (same enumeration / tie-break order as the reference:
+    ``overlap3_core.py:78-97`` or ``evaluate_with_sources.py:352-373, 418-427``) for the rare segment
+    whose arrays have different lengths and therefore needed several device passes."""
+    import itertools
+    best, idx, swapped = -1e9, [], False
+    if variant == "overlap3":
+        for cols in itertools.combinations(range(N), K):
+            for perm in itertools.permutations(range(K), K):
+                vals = [M[perm[r], cols[r]] for r in range(K)]
+                if any(np.isnan(v) for v in vals):
+                    continue
+                s = 0.0
+                for v in vals:
+                    s += float(v)
+                mean = s / float(K)
+                if mean > best:
+                    best, idx = mean, [cols[perm.index(i)] for i in range(K)]
+        base = float(np.mean([float(v) for v in base_vals[:K]]))
+    elif K == 2:
+        for j in range(N):
+            for k in range(N):
+                if j == k:
+                    continue
+                s12, s21 = 0.5 * (M[0, j] + M[1, k]), 0.5 * (M[0, k] + M[1, j])
+                cur, sw = (s12, False) if s12 >= s21 else (s21, True)
+                if cur > best:
+                    best, idx, swapped = float(cur), [j, k], sw
+        base = 0.5 * (float(base_vals[0]) + float(base_vals[1]))
+    else:
+        for cols in itertools.combinations(range(N), 3):
+            for perm in itertools.permutations(cols, 3):
+                cur = (M[0, perm[0]] + M[1, perm[1]] + M[2, perm[2]]) / 3.0
+                if cur > best:
+                    best, idx = float(cur), list(perm)
+        base = float(np.mean([float(v) for v in base_vals[:3]]))
+    if not idx or np.isnan(base):
+        return float("nan"), float("nan"), [-1] * K, False
+    return best, best - base, idx, swapped
+
+
 def pit_sisdr_batch(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.ndarray]],
                     preds: Sequence[Sequence[np.ndarray]], variant: str = "overlap3",
                     device: int = 0) -> PitResult:
     """Host entry.  ``refs[i]`` has K (2 or 3) arrays, ``preds[i]`` N >= K arrays (same K, N for the
-    whole batch).  Arrays of one segment are truncated to their common length, as every reference
-    ``si_sdr`` does pairwise (``overlap3_core.py:49-52``) -- identical when, as at the call site,
-    all arrays of a segment were cut with the same sample indices."""
+    whole batch).  Every reference ``si_sdr`` truncates ITS two arguments to their common length
+    (``overlap3_core.py:49-52``).  At the reference call site all arrays of a segment are cut with
+    the same sample indices, so one device pass per segment suffices; a segment whose arrays differ
+    in length is scored with one device pass per distinct truncation length and assembled on the
+    host, which reproduces the pairwise truncation exactly."""
     import torch
     n = len(mixes)
     if n == 0:
@@ -93,19 +136,52 @@ def pit_sisdr_batch(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.ndar
     K, N = len(refs[0]), len(preds[0])
     if any(len(r) != K for r in refs) or any(len(p) != N for p in preds):
         raise ValueError("all segments of a batch must have the same K and N")
-    lens = [int(min([np.asarray(m).shape[-1]] + [np.asarray(a).shape[-1] for a in r] +
-                    [np.asarray(a).shape[-1] for a in p])) for m, r, p in zip(mixes, refs, preds)]
+    # pseudo-segments: (segment index, truncation length)
+    jobs, ragged = [], {}
+    for i, (m, r, p) in enumerate(zip(mixes, refs, preds)):
+        lr = [int(np.asarray(a).shape[-1]) for a in r]
+        lp = [int(np.asarray(a).shape[-1]) for a in p]
+        lm = int(np.asarray(m).shape[-1])
+        if len(set(lr + lp + [lm])) == 1:
+            jobs.append((i, lm))
+        else:
+            need = sorted({min(a, b) for a in lr for b in lp} | {min(a, lm) for a in lr})
+            ragged[i] = {"lr": lr, "lp": lp, "lm": lm, "jobs": {}}
+            for ln in need:
+                ragged[i]["jobs"][ln] = len(jobs)
+                jobs.append((i, ln))
+    lens = [ln for _, ln in jobs]
+
+    def cut(a, ln):
+        a = np.asarray(a, dtype=np.float32).reshape(-1)
+        return a[:ln] if a.shape[0] >= ln else np.concatenate([a, np.zeros(ln - a.shape[0], np.float32)])
+
+    h_mix = _pack([[cut(mixes[i], ln)] for i, ln in jobs], lens, 1)
+    h_ref = _pack([[cut(a, ln) for a in refs[i]] for i, ln in jobs], lens, K)
+    h_est = _pack([[cut(a, ln) for a in preds[i]] for i, ln in jobs], lens, N)
     dev = torch.device("cuda", device)
-    h_mix = _pack([[m] for m in mixes], lens, 1)
-    h_ref = _pack(refs, lens, K)
-    h_est = _pack(preds, lens, N)
     with torch.cuda.device(dev):
         d_mix = torch.from_numpy(h_mix).to(dev)
         d_ref = torch.from_numpy(h_ref).to(dev)
         d_est = torch.from_numpy(h_est).to(dev)
         pair, sisdr, sisdri, perm = pit_sisdr_device(d_ref, d_est, d_mix, lens, K, N, variant)
         pair, sisdr, sisdri, perm = pair.cpu().numpy(), sisdr.cpu().numpy(), sisdri.cpu().numpy(), perm.cpu().numpy()
-    return PitResult(sisdr, sisdri, perm[:, :K].copy(), perm[:, 3].astype(bool), pair)
+    o_pair = np.full((n, 3, 4), np.nan)
+    o_sisdr, o_sisdri = np.full(n, np.nan), np.full(n, np.nan)
+    o_perm, o_sw = np.full((n, K), -1, np.int32), np.zeros(n, bool)
+    for j, (i, _ln) in enumerate(jobs):
+        if i not in ragged:
+            o_pair[i], o_sisdr[i], o_sisdri[i] = pair[j], sisdr[j], sisdri[j]
+            o_perm[i], o_sw[i] = perm[j, :K], bool(perm[j, 3])
+    for i, info in ragged.items():
+        M = np.full((3, 4), np.nan)
+        for a in range(K):
+            for b in range(N):
+                M[a, b] = pair[info["jobs"][min(info["lr"][a], info["lp"][b])], a, b]
+            M[a, 3] = pair[info["jobs"][min(info["lr"][a], info["lm"])], a, 3]
+        best, sdri, idx, sw = _select_host(M[:, :3], M[:, 3], K, N, variant)
+        o_pair[i], o_sisdr[i], o_sisdri[i], o_perm[i], o_sw[i] = M, best, sdri, idx, sw
+    return PitResult(o_sisdr, o_sisdri, o_perm, o_sw, o_pair)
 
 
 # ---- reference-shaped single-segment wrappers ---------------------------------------------------

@@ -107,6 +107,16 @@ class SeparationEngine:
         workspace.record_stream(torch.cuda.current_stream(dev))
         return out
 
+    def profile_last_call(self, enable: bool = True):
+        """Per-launch durations (ms) of the most recent forward issued while profiling was on."""
+        nat.check(nat.lib().b200sep_profile_enable(self._handle, 1 if enable else 0), "profile_enable")
+
+    def profile_read(self) -> List[float]:
+        buf = (C.c_float * 256)()
+        n = C.c_int32(0)
+        nat.check(nat.lib().b200sep_profile_read(self._handle, buf, 256, C.byref(n)), "profile_read")
+        return [float(buf[i]) for i in range(min(n.value, 256))]
+
     # ------------------------------------------------------------------ host boundary
     def separate_batch(self, chunks: Sequence[np.ndarray]) -> List[List[np.ndarray]]:
         """numpy in -> numpy out through pinned staging: one H2D copy, one forward, one D2H copy."""

@@ -168,6 +168,15 @@ int b200sep_pit_sisdr_batch(const float* d_refs, const float* d_ests, const floa
 int b200sep_debug_gemm(const float* d_a, const float* d_b, float* d_c, int32_t M, int32_t N,
                        int32_t K, int32_t bn, int32_t use_tc, void* stream);
 
+/*
+ * Per-launch timing for the roofline report (bench.py): when enabled, b200sep_separate_batch
+ * brackets every kernel launch with CUDA events on the caller's stream; b200sep_profile_read
+ * returns the durations (ms) of the last call in launch order: encoder, bottleneck GEMM, then per
+ * TCN block (in-conv GEMM, depthwise conv, res/skip GEMM), mask GEMM, decoder.
+ */
+int b200sep_profile_enable(b200sep_model* m, int on);
+int b200sep_profile_read(b200sep_model* m, float* ms_out, int32_t cap, int32_t* n_out);
+
 /* Test hooks: stop the forward after the k-th kernel launch (0 = run everything), and report the
  * byte offsets of the intermediate activations inside the workspace:
  * out[0..9] = enc, x, xa, skip, skipa, h1, h2, masked, n_tiles, total. */
