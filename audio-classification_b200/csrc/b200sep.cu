@@ -338,7 +338,7 @@ static int launch_tc(const b200sep_model* m, const CUtensorMap& ta, const CUtens
   const int n_ntiles = N / BN;
   const int total = n_mtiles * n_ntiles;
   const int grid = std::min(total, m->n_sm);
-  kern<<<grid, 256, Cfg::SMEM_BYTES, st>>>(ta, tbm, n_mtiles, n_ntiles, a_lbo, a_sbo, epi, tb);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tbm, n_mtiles, n_ntiles, a_lbo, a_sbo, epi, tb);
   CK(cudaGetLastError());
   return 0;
 }
@@ -405,7 +405,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
     prof_mark();
     return m->debug_stop_after > 0 && ++launches >= m->debug_stop_after;
   };
-  const int slots1 = (kHalf && m->use_tc) ? 8 : C_HID / 128;  // partial slots the in-conv GEMM writes
+  const int slots1 = (kHalf && m->use_tc) ? C_HID / 256 : C_HID / 128;  // partial slots the in-conv GEMM writes
 
   // 1. encoder (+ bottleneck-gLN partials)
   encoder_kernel<T, L><<<dim3(nt, 2), 256, 0, st>>>(d_mix, m->enc_w, enc, p0, tb);
@@ -432,12 +432,16 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
     if (stop()) return 0;
     {
       DwParams p{b.g1, b.be1, b.wd, b.bd, b.a2, b.dilation};
-      dwconv_kernel<T><<<dim3(8, nt), 256, 0, st>>>(h1, h2, p1, slots1, p2, p, tb);
+      const dim3 g(DW_SLOTS, nt);
+      if (b.dilation == 1) dwconv_kernel<T, 1><<<g, 256, 0, st>>>(h1, h2, p1, slots1, p2, p, tb);
+      else if (b.dilation == 2) dwconv_kernel<T, 2><<<g, 256, 0, st>>>(h1, h2, p1, slots1, p2, p, tb);
+      else if (b.dilation == 4) dwconv_kernel<T, 4><<<g, 256, 0, st>>>(h1, h2, p1, slots1, p2, p, tb);
+      else dwconv_kernel<T, 0><<<g, 256, 0, st>>>(h1, h2, p1, slots1, p2, p, tb);
       CK(cudaGetLastError());
     }
     if (stop()) return 0;
     {
-      EpiResSkip<T> e{p2, 8, b.rs, b.cb, x, xa_or_null, skip, skipa, m->alpha_mask, last ? 0 : 1, first ? 1 : 0,
+      EpiResSkip<T> e{p2, DW_SLOTS, b.rs, b.cb, x, xa_or_null, skip, skipa, m->alpha_mask, last ? 0 : 1, first ? 1 : 0,
                       last ? 1 : 0};
       int rc;
       if (!last)

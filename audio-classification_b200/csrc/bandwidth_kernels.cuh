@@ -91,12 +91,19 @@ __global__ void __launch_bounds__(256) encoder_kernel(const float* __restrict__ 
 // Depthwise dilated conv stage of a Conv1DBlock (ops 5-7 of section 2.2):
 //   y   = gLN1(h1)            (gamma1/beta1, statistics from the producing GEMM's partials)
 //   u   = dwconv_k3(y; dilation d, zero padding d) + bias
-//   h2  = PReLU(u)            and (sum, sumsq) partials of h2 for gLN2 (slots = 8 per m-tile)
+//   h2  = PReLU(u)            and (sum, sumsq) partials of h2 for gLN2 (slots = DW_SLOTS per m-tile)
 // The zero padding applies to y (the normalised signal) at the TRUE segment ends, so taps that
 // fall outside [0, F_i) contribute nothing -- not even beta.
-// grid = (8 channel groups of 64, n_tiles), 256 threads: warp -> 8 channels, lane -> 4 consecutive
-// frames (one 8/16-byte vector).  Taps at +-d are vector loads from the shifted position when
-// d % 4 == 0, and lane shuffles (+ one edge vector) when d is 1 or 2.
+//
+// gLN1 is folded into the taps: with a = gamma*rstd, b = beta - a*mean,
+//   u = bias + sum_k valid_k * (w_k*a * h_k + w_k*b)
+// and for interior frames (all three taps inside the segment) u = c + wa0*h[t-d] + wa1*h[t] + wa2*h[t+d]
+// -- 3 FMAs per output.  The per-channel constants are computed once per CTA into shared memory.
+//
+// grid = (512 / DW_CH channel groups, n_tiles), 256 threads.  A thread owns 8 consecutive frames
+// (one 16-byte vector of fp16) of one channel per step; a warp covers 2 channels x 128 frames per
+// step.  Taps at +-d are aligned vector loads from the shifted position when d % 8 == 0, and
+// lane shuffles (+ one edge vector from the neighbouring m-tile) when d is 1, 2 or 4.
 // =================================================================================================
 struct DwParams {
   const float* gamma1;  // [512]
@@ -107,62 +114,110 @@ struct DwParams {
   int dilation;
 };
 
-template <typename T> struct Vec4;
-template <> struct Vec4<float> {
-  float4 v;
-  __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
-  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = v; }
-  __device__ __forceinline__ void get(float (&o)[4]) const { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
-  __device__ __forceinline__ void set(const float (&o)[4]) { v = make_float4(o[0], o[1], o[2], o[3]); }
-};
-template <> struct Vec4<__half> {
-  uint2 v;
-  __device__ __forceinline__ void load(const __half* p) { v = *reinterpret_cast<const uint2*>(p); }
-  __device__ __forceinline__ void store(__half* p) const { *reinterpret_cast<uint2*>(p) = v; }
-  __device__ __forceinline__ void get(float (&o)[4]) const {
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+constexpr int DW_CH = 128;              // channels per CTA
+constexpr int DW_SLOTS = C_HID / DW_CH; // stat partial slots per m-tile
+
+// 8 consecutive frames of one channel
+template <typename T> struct Vec8;
+template <> struct Vec8<__half> {
+  uint4 v;
+  __device__ __forceinline__ void load(const __half* p) { v = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(__half* p) const { *reinterpret_cast<uint4*>(p) = v; }
+  __device__ __forceinline__ void zero() { v = make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ void get(float (&o)[8]) const {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      o[2 * i] = f.x; o[2 * i + 1] = f.y;
+    }
   }
-  __device__ __forceinline__ void set(const float (&o)[4]) {
-    const __half2 a = __floats2half2_rn(o[0], o[1]);
-    const __half2 b = __floats2half2_rn(o[2], o[3]);
-    v.x = *reinterpret_cast<const uint32_t*>(&a);
-    v.y = *reinterpret_cast<const uint32_t*>(&b);
+  __device__ __forceinline__ void set(const float (&o)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __half2 h = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    v = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __device__ __forceinline__ Vec8 shfl_up16() const {
+    Vec8 r;
+    r.v.x = __shfl_up_sync(0xffffffffu, v.x, 1, 16); r.v.y = __shfl_up_sync(0xffffffffu, v.y, 1, 16);
+    r.v.z = __shfl_up_sync(0xffffffffu, v.z, 1, 16); r.v.w = __shfl_up_sync(0xffffffffu, v.w, 1, 16);
+    return r;
+  }
+  __device__ __forceinline__ Vec8 shfl_down16() const {
+    Vec8 r;
+    r.v.x = __shfl_down_sync(0xffffffffu, v.x, 1, 16); r.v.y = __shfl_down_sync(0xffffffffu, v.y, 1, 16);
+    r.v.z = __shfl_down_sync(0xffffffffu, v.z, 1, 16); r.v.w = __shfl_down_sync(0xffffffffu, v.w, 1, 16);
+    return r;
+  }
+};
+template <> struct Vec8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p); b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void store(float* p) const {
+    *reinterpret_cast<float4*>(p) = a; *reinterpret_cast<float4*>(p + 4) = b;
+  }
+  __device__ __forceinline__ void zero() { a = make_float4(0, 0, 0, 0); b = a; }
+  __device__ __forceinline__ void get(float (&o)[8]) const {
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  }
+  __device__ __forceinline__ void set(const float (&o)[8]) {
+    a = make_float4(o[0], o[1], o[2], o[3]); b = make_float4(o[4], o[5], o[6], o[7]);
+  }
+  __device__ __forceinline__ Vec8 shfl_up16() const {
+    Vec8 r;
+    r.a.x = __shfl_up_sync(0xffffffffu, a.x, 1, 16); r.a.y = __shfl_up_sync(0xffffffffu, a.y, 1, 16);
+    r.a.z = __shfl_up_sync(0xffffffffu, a.z, 1, 16); r.a.w = __shfl_up_sync(0xffffffffu, a.w, 1, 16);
+    r.b.x = __shfl_up_sync(0xffffffffu, b.x, 1, 16); r.b.y = __shfl_up_sync(0xffffffffu, b.y, 1, 16);
+    r.b.z = __shfl_up_sync(0xffffffffu, b.z, 1, 16); r.b.w = __shfl_up_sync(0xffffffffu, b.w, 1, 16);
+    return r;
+  }
+  __device__ __forceinline__ Vec8 shfl_down16() const {
+    Vec8 r;
+    r.a.x = __shfl_down_sync(0xffffffffu, a.x, 1, 16); r.a.y = __shfl_down_sync(0xffffffffu, a.y, 1, 16);
+    r.a.z = __shfl_down_sync(0xffffffffu, a.z, 1, 16); r.a.w = __shfl_down_sync(0xffffffffu, a.w, 1, 16);
+    r.b.x = __shfl_down_sync(0xffffffffu, b.x, 1, 16); r.b.y = __shfl_down_sync(0xffffffffu, b.y, 1, 16);
+    r.b.z = __shfl_down_sync(0xffffffffu, b.z, 1, 16); r.b.w = __shfl_down_sync(0xffffffffu, b.w, 1, 16);
+    return r;
   }
 };
 
-// Loads the 4 frames [t, t+4) of channel c of segment-relative frame t (t % 4 == 0) as floats,
-// or zeros when the group lies outside the segment's m-tiles.
+// The 8 frames [t, t+8) (t % 8 == 0, segment-relative) of channel c, or zeros outside the segment's
+// m-tiles.
 template <typename T>
-__device__ __forceinline__ void load_group(const T* __restrict__ buf, int tile0, int ntiles, int c,
-                                           int t, float (&o)[4]) {
-  if (t < 0 || t >= ntiles * TILE_M) {
-    o[0] = o[1] = o[2] = o[3] = 0.f;
-    return;
-  }
-  Vec4<T> v;
-  v.load(buf + tt_index(tile0 + (t >> 7), C_HID, c, t & (TILE_M - 1)));
-  v.get(o);
+__device__ __forceinline__ Vec8<T> load_group8(const T* __restrict__ buf, int tile0, int ntiles, int c, int t) {
+  Vec8<T> v;
+  if (t < 0 || t >= ntiles * TILE_M) v.zero();
+  else v.load(buf + tt_index(tile0 + (t >> 7), C_HID, c, t & (TILE_M - 1)));
+  return v;
 }
 
-template <typename T>
+// D = compile-time dilation for the shuffle path (1, 2, 4); D = 0 selects the aligned-load path
+// (runtime dilation d, d % 8 == 0).
+template <typename T, int D>
 __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ h1,  // [nt][512][128]
                                                      T* __restrict__ h2,        // [nt][512][128]
                                                      const float2* __restrict__ part1, int slots1,
-                                                     float2* __restrict__ part2,  // [nt][8]
+                                                     float2* __restrict__ part2,  // [nt][DW_SLOTS]
                                                      DwParams p, Tables tb) {
   __shared__ float s_stat[2];
   __shared__ float s_red[16];
-  const int cg = blockIdx.x;  // 64-channel group
+  __shared__ float4 s_par[DW_CH][2];  // {wa0, wa1, wa2, c_interior}, {wb0, wb1, wb2, bias}
+  const int cg = blockIdx.x;
   const int m_tile = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int seg = tb.tile_seg[m_tile];
   const int tile0 = tb.seg_tile0[seg];
   const int ntiles = tb.seg_ntiles[seg];
   const int F = tb.seg_frames[seg];
-  const int t_base = (m_tile - tile0) * TILE_M + lane * 4;  // first of this lane's 4 frames
-  const int d = p.dilation;
+  const int sub = lane >> 4;                                      // which of the warp's 2 channels
+  const int t_base = (m_tile - tile0) * TILE_M + (lane & 15) * 8;  // first of this thread's 8 frames
+  const int d = (D > 0) ? D : p.dilation;
 
   if (warp == 0) {
     float mean, rstd;
@@ -170,57 +225,73 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ h1,  
     if (lane == 0) { s_stat[0] = mean; s_stat[1] = rstd; }
   }
   __syncthreads();
-  const float mean = s_stat[0], rstd = s_stat[1];
-
-  float s_acc = 0.f, q_acc = 0.f;
-#pragma unroll 2
-  for (int j = 0; j < 8; ++j) {
-    const int c = cg * 64 + warp * 8 + j;
-    const float g = p.gamma1[c] * rstd;
-    const float b = p.beta1[c] - g * mean;  // y = g*h + b
+  if (tid < DW_CH) {
+    const int c = cg * DW_CH + tid;
+    const float a = p.gamma1[c] * s_stat[1];
+    const float b = p.beta1[c] - a * s_stat[0];  // y = a*h + b
     const float w0 = p.w[c * 3 + 0], w1 = p.w[c * 3 + 1], w2 = p.w[c * 3 + 2];
     const float bias = p.bias[c];
+    s_par[tid][0] = make_float4(w0 * a, w1 * a, w2 * a, bias + (w0 + w1 + w2) * b);
+    s_par[tid][1] = make_float4(w0 * b, w1 * b, w2 * b, bias);
+  }
+  __syncthreads();
 
-    float ctr[4], lft[4], rgt[4];
-    load_group(h1, tile0, ntiles, c, t_base, ctr);
-    if ((d & 3) == 0) {
-      load_group(h1, tile0, ntiles, c, t_base - d, lft);
-      load_group(h1, tile0, ntiles, c, t_base + d, rgt);
+  const bool interior = (t_base - d >= 0) && (t_base + 7 + d < F);
+  const float alpha = p.alpha2;
+  float s_acc = 0.f, q_acc = 0.f;
+  constexpr int STEPS = DW_CH / 16;  // 16 channels per CTA step (8 warps x 2)
+#pragma unroll 4
+  for (int it = 0; it < STEPS; ++it) {
+    const int cl = it * 16 + warp * 2 + sub;
+    const int c = cg * DW_CH + cl;
+    const Vec8<T> vc = load_group8(h1, tile0, ntiles, c, t_base);
+    float ctr[8], lft[8], rgt[8];
+    vc.get(ctr);
+    if (D == 0) {
+      load_group8(h1, tile0, ntiles, c, t_base - d).get(lft);
+      load_group8(h1, tile0, ntiles, c, t_base + d).get(rgt);
     } else {
-      // d in {1,2}: neighbours come from the adjacent lanes' vectors (edge lanes load one more)
-      float pv[4], nv[4];
+      Vec8<T> vp = vc.shfl_up16(), vn = vc.shfl_down16();
+      if ((lane & 15) == 0) vp = load_group8(h1, tile0, ntiles, c, t_base - 8);
+      if ((lane & 15) == 15) vn = load_group8(h1, tile0, ntiles, c, t_base + 8);
+      float pv[8], nv[8];
+      vp.get(pv);
+      vn.get(nv);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        pv[i] = __shfl_up_sync(0xffffffffu, ctr[i], 1);
-        nv[i] = __shfl_down_sync(0xffffffffu, ctr[i], 1);
-      }
-      if (lane == 0) load_group(h1, tile0, ntiles, c, t_base - 4, pv);
-      if (lane == 31) load_group(h1, tile0, ntiles, c, t_base + 4, nv);
-      if (d == 1) {
-        lft[0] = pv[3]; lft[1] = ctr[0]; lft[2] = ctr[1]; lft[3] = ctr[2];
-        rgt[0] = ctr[1]; rgt[1] = ctr[2]; rgt[2] = ctr[3]; rgt[3] = nv[0];
-      } else {  // d == 2
-        lft[0] = pv[2]; lft[1] = pv[3]; lft[2] = ctr[0]; lft[3] = ctr[1];
-        rgt[0] = ctr[2]; rgt[1] = ctr[3]; rgt[2] = nv[0]; rgt[3] = nv[1];
+      for (int i = 0; i < 8; ++i) {
+        lft[i] = (i - D >= 0) ? ctr[(i - D) & 7] : pv[(8 + i - D) & 7];
+        rgt[i] = (i + D < 8) ? ctr[(i + D) & 7] : nv[(i + D - 8) & 7];
       }
     }
-    float o[4];
+    const float4 pa = s_par[cl][0];
+    float o[8];
+    if (interior) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int t = t_base + i;
-      float u = bias;
-      if (t - d >= 0 && t - d < F) u = fmaf(w0, fmaf(g, lft[i], b), u);
-      if (t < F) u = fmaf(w1, fmaf(g, ctr[i], b), u);
-      if (t + d < F) u = fmaf(w2, fmaf(g, rgt[i], b), u);
-      u = (u > 0.f) ? u : p.alpha2 * u;
-      if (t >= F) u = 0.f;
-      o[i] = u;
-      s_acc += u;
-      q_acc = fmaf(u, u, q_acc);
+      for (int i = 0; i < 8; ++i) {
+        const float u = fmaf(pa.x, lft[i], fmaf(pa.y, ctr[i], fmaf(pa.z, rgt[i], pa.w)));
+        o[i] = fmaxf(u, 0.f) + alpha * fminf(u, 0.f);
+      }
+    } else {
+      const float4 pb = s_par[cl][1];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int t = t_base + i;
+        float u = pb.w;
+        if (t - d >= 0 && t - d < F) u += fmaf(pa.x, lft[i], pb.x);
+        if (t < F) u += fmaf(pa.y, ctr[i], pb.y);
+        if (t + d < F) u += fmaf(pa.z, rgt[i], pb.z);
+        u = fmaxf(u, 0.f) + alpha * fminf(u, 0.f);
+        o[i] = (t < F) ? u : 0.f;
+      }
     }
-    Vec4<T> ov;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s_acc += o[i];
+      q_acc = fmaf(o[i], o[i], q_acc);
+    }
+    Vec8<T> ov;
     ov.set(o);
-    ov.store(h2 + tt_index(m_tile, C_HID, c, lane * 4));
+    ov.store(h2 + tt_index(m_tile, C_HID, c, (lane & 15) * 8));
   }
   s_acc = warp_sum(s_acc);
   q_acc = warp_sum(q_acc);
@@ -230,7 +301,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ h1,  
     float s = 0.f, q = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) { s += s_red[w]; q += s_red[8 + w]; }
-    part2[(size_t)m_tile * 8 + cg] = make_float2(s, q);
+    part2[(size_t)m_tile * DW_SLOTS + cg] = make_float2(s, q);
   }
 }
 

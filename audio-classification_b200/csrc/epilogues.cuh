@@ -30,12 +30,22 @@ __device__ __forceinline__ void epi_tile_ctx(EpiState& st, int m_tile, const Tab
   st.q = 0.f;
 }
 
-// Writes this warp's (sum, sumsq) partial: part[m_tile * slots + slot].
+// Writes an already block-reduced (sum, sumsq) partial (single calling thread):
+// part[m_tile * slots + slot].
 __device__ __forceinline__ void epi_write_partial(EpiState& st, float2* part, int m_tile, int slots,
                                                   int slot) {
-  const float s = warp_sum(st.s), q = warp_sum(st.q);
-  if ((threadIdx.x & 31) == 0) part[(size_t)m_tile * slots + slot] = make_float2(s, q);
+  part[(size_t)m_tile * slots + slot] = make_float2(st.s, st.q);
 }
+
+// 4 consecutive fp32 parameters with one 16-byte read-only load (n % 4 == 0).
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// Every epilogue provides
+//   tile_begin(st, m_tile, tb)                 warp-collective: tile context (+ folded gLN statistics)
+//   prefetch<W>(m_tile, r, n0, pre)            issue the global loads apply() will need (may be a no-op)
+//   apply<W>(st, m_tile, r, n0, acc, pre)      consume W consecutive output channels of frame r
+//   tile_end(st, m_tile, slots, slot)          single thread: write the block-reduced stat partial
+// W is 32 (tcgen05 kernel) or 4 (CUDA-core kernel); n0 % W == 0.
 
 // -------------------------------------------------------------------------------------------------
 // Bottleneck: x = conv1x1(gLN_N(tf_rep))  (masker.bottleneck).  Writes the fp32
@@ -54,17 +64,30 @@ struct EpiBottleneck {
     warp_seg_stats(part_in, tile0, ntiles, slots_in, (double)C_ENC * (double)st.F, st.mean, st.rstd);
   }
   template <int W>
-  __device__ __forceinline__ void apply(EpiState& st, int m_tile, int r, int n0, const float* acc) const {
+  __device__ __forceinline__ void prefetch(int, int, int, float (&)[W]) const {}
+  template <int W>
+  __device__ __forceinline__ void apply(EpiState& st, int m_tile, int r, int n0, const float* acc,
+                                        const float (&)[W]) const {
     const bool valid = (st.t0 + r) < st.F;
-    const float mr = st.mean;
+    const float nm = -st.mean, rstd = st.rstd;
+    const size_t idx0 = tt_index(m_tile, C_BN, n0, r);
+    float out[W];
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+      const float4 r4 = ldg4(rs + n0 + 4 * q), c4 = ldg4(cb + n0 + 4 * q);
+      out[4 * q + 0] = fmaf(rstd, fmaf(nm, r4.x, acc[4 * q + 0]), c4.x);
+      out[4 * q + 1] = fmaf(rstd, fmaf(nm, r4.y, acc[4 * q + 1]), c4.y);
+      out[4 * q + 2] = fmaf(rstd, fmaf(nm, r4.z, acc[4 * q + 2]), c4.z);
+      out[4 * q + 3] = fmaf(rstd, fmaf(nm, r4.w, acc[4 * q + 3]), c4.w);
+    }
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-      const int n = n0 + j;
-      float v = fmaf(st.rstd, fmaf(-mr, __ldg(rs + n), acc[j]), __ldg(cb + n));
-      if (!valid) v = 0.f;
-      const size_t idx = tt_index(m_tile, C_BN, n0, r) + (size_t)j * TILE_M;
-      x[idx] = v;
-      if (xa != nullptr) xa[idx] = from_f32<T>(v);
+      if (!valid) out[j] = 0.f;
+      x[idx0 + (size_t)j * TILE_M] = out[j];
+    }
+    if (xa != nullptr) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) xa[idx0 + (size_t)j * TILE_M] = from_f32<T>(out[j]);
     }
   }
   __device__ __forceinline__ void tile_end(EpiState&, int, int, int) const {}
@@ -85,18 +108,32 @@ struct EpiIn {
     epi_tile_ctx(st, m_tile, tb, seg, tile0, ntiles);
   }
   template <int W>
-  __device__ __forceinline__ void apply(EpiState& st, int m_tile, int r, int n0, const float* acc) const {
+  __device__ __forceinline__ void prefetch(int, int, int, float (&)[W]) const {}
+  template <int W>
+  __device__ __forceinline__ void apply(EpiState& st, int m_tile, int r, int n0, const float* acc,
+                                        const float (&)[W]) const {
     const bool valid = (st.t0 + r) < st.F;
+    T* __restrict__ dst = h1 + tt_index(m_tile, C_HID, n0, r);
+    float out[W];
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+      const float4 b4 = ldg4(bias + n0 + 4 * q);
+      out[4 * q + 0] = acc[4 * q + 0] + b4.x;
+      out[4 * q + 1] = acc[4 * q + 1] + b4.y;
+      out[4 * q + 2] = acc[4 * q + 2] + b4.z;
+      out[4 * q + 3] = acc[4 * q + 3] + b4.w;
+    }
+    float s = 0.f, q2 = 0.f;
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-      const int n = n0 + j;
-      float v = acc[j] + __ldg(bias + n);
-      v = (v > 0.f) ? v : alpha * v;
+      float v = fmaxf(out[j], 0.f) + alpha * fminf(out[j], 0.f);
       if (!valid) v = 0.f;
-      h1[tt_index(m_tile, C_HID, n0, r) + (size_t)j * TILE_M] = from_f32<T>(v);
-      st.s += v;
-      st.q = fmaf(v, v, st.q);
+      dst[(size_t)j * TILE_M] = from_f32<T>(v);
+      s += v;
+      q2 = fmaf(v, v, q2);
     }
+    st.s += s;
+    st.q += q2;
   }
   __device__ __forceinline__ void tile_end(EpiState& st, int m_tile, int slots, int slot) const {
     epi_write_partial(st, part_out, m_tile, slots, slot);
@@ -123,32 +160,39 @@ struct EpiResSkip {
     epi_tile_ctx(st, m_tile, tb, seg, tile0, ntiles);
     warp_seg_stats(part_in, tile0, ntiles, slots_in, (double)C_HID * (double)st.F, st.mean, st.rstd);
   }
+  // old x / skip values: independent loads, consecutive lanes (frames) hit consecutive addresses
   template <int W>
-  __device__ __forceinline__ void apply(EpiState& st, int m_tile, int r, int n0, const float* acc) const {
+  __device__ __forceinline__ void prefetch(int m_tile, int r, int n0, float (&pre)[W]) const {
+    const bool is_res = has_res && (n0 < C_BN);
+    const int c0 = (has_res && !is_res) ? (n0 - C_BN) : n0;
+    if (is_res || !first) {
+      const float* __restrict__ src = (is_res ? x : skip) + tt_index(m_tile, C_BN, c0, r);
+#pragma unroll
+      for (int j = 0; j < W; ++j) pre[j] = __ldcs(src + (size_t)j * TILE_M);
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j) pre[j] = 0.f;
+    }
+  }
+  template <int W>
+  __device__ __forceinline__ void apply(EpiState& st, int m_tile, int r, int n0, const float* acc,
+                                        const float (&pre)[W]) const {
     const bool valid = (st.t0 + r) < st.F;
     const bool is_res = has_res && (n0 < C_BN);
     const int c0 = (has_res && !is_res) ? (n0 - C_BN) : n0;
     const size_t idx0 = tt_index(m_tile, C_BN, c0, r);
-    // issue all loads of the chunk first: they are independent, and consecutive lanes (frames) hit
-    // consecutive addresses, so W x 128 B per warp are in flight instead of one dependent load
-    float old[W];
-    const bool need_old = is_res || !first;
-    const float* __restrict__ src = is_res ? x : skip;
-    if (need_old) {
-#pragma unroll
-      for (int j = 0; j < W; ++j) old[j] = __ldcs(src + idx0 + (size_t)j * TILE_M);
-    } else {
-#pragma unroll
-      for (int j = 0; j < W; ++j) old[j] = 0.f;
-    }
+    const float nm = -st.mean, rstd = st.rstd;
     float out[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) {
-      const int n = n0 + j;
-      float v = fmaf(st.rstd, fmaf(-st.mean, __ldg(rs + n), acc[j]), __ldg(cb + n));
-      if (!valid) v = 0.f;
-      out[j] = old[j] + v;
+    for (int q = 0; q < W / 4; ++q) {
+      const float4 r4 = ldg4(rs + n0 + 4 * q), c4 = ldg4(cb + n0 + 4 * q);
+      out[4 * q + 0] = fmaf(rstd, fmaf(nm, r4.x, acc[4 * q + 0]), c4.x);
+      out[4 * q + 1] = fmaf(rstd, fmaf(nm, r4.y, acc[4 * q + 1]), c4.y);
+      out[4 * q + 2] = fmaf(rstd, fmaf(nm, r4.z, acc[4 * q + 2]), c4.z);
+      out[4 * q + 3] = fmaf(rstd, fmaf(nm, r4.w, acc[4 * q + 3]), c4.w);
     }
+#pragma unroll
+    for (int j = 0; j < W; ++j) out[j] = pre[j] + (valid ? out[j] : 0.f);
     if (is_res) {
 #pragma unroll
       for (int j = 0; j < W; ++j) x[idx0 + (size_t)j * TILE_M] = out[j];
@@ -162,7 +206,7 @@ struct EpiResSkip {
     } else {
 #pragma unroll
       for (int j = 0; j < W; ++j)
-        skipa[idx0 + (size_t)j * TILE_M] = from_f32<T>((out[j] > 0.f) ? out[j] : alpha_mask * out[j]);
+        skipa[idx0 + (size_t)j * TILE_M] = from_f32<T>(fmaxf(out[j], 0.f) + alpha_mask * fminf(out[j], 0.f));
     }
   }
   __device__ __forceinline__ void tile_end(EpiState&, int, int, int) const {}
@@ -184,25 +228,36 @@ struct EpiMask {
     int seg, tile0, ntiles;
     epi_tile_ctx(st, m_tile, tb, seg, tile0, ntiles);
   }
+  // encoder output of the same (frame, filter); a chunk never straddles a source boundary
   template <int W>
-  __device__ __forceinline__ void apply(EpiState& st, int m_tile, int r, int n0, const float* acc) const {
-    // a chunk never straddles a source boundary (W divides 512)
+  __device__ __forceinline__ void prefetch(int m_tile, int r, int n0, float (&pre)[W]) const {
     const T* __restrict__ ep = enc + tt_index(m_tile, C_ENC, n0 & (C_ENC - 1), r);
-    T* __restrict__ mp = masked + tt_index(m_tile, n_total, n0, r);
-    float e[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) e[j] = to_f32(ep[(size_t)j * TILE_M]);
+    for (int j = 0; j < W; ++j) pre[j] = to_f32(ep[(size_t)j * TILE_M]);
+  }
+  template <int W>
+  __device__ __forceinline__ void apply(EpiState&, int m_tile, int r, int n0, const float* acc,
+                                        const float (&pre)[W]) const {
+    T* __restrict__ mp = masked + tt_index(m_tile, n_total, n0, r);
+    float v[W];
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+      const float4 b4 = ldg4(bias + n0 + 4 * q);
+      v[4 * q + 0] = acc[4 * q + 0] + b4.x;
+      v[4 * q + 1] = acc[4 * q + 1] + b4.y;
+      v[4 * q + 2] = acc[4 * q + 2] + b4.z;
+      v[4 * q + 3] = acc[4 * q + 3] + b4.w;
+    }
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-      const float v = acc[j] + __ldg(bias + n0 + j);
       float m;
       if (act == 0) {
-        if (kFast) m = __fdividef(1.f, 1.f + __expf(-v));
-        else m = 1.f / (1.f + expf(-v));
+        if (kFast) m = __fdividef(1.f, 1.f + __expf(-v[j]));
+        else m = 1.f / (1.f + expf(-v[j]));
       } else {
-        m = fmaxf(v, 0.f);
+        m = fmaxf(v[j], 0.f);
       }
-      mp[(size_t)j * TILE_M] = from_f32<T>(m * e[j]);
+      mp[(size_t)j * TILE_M] = from_f32<T>(m * pre[j]);
     }
   }
   __device__ __forceinline__ void tile_end(EpiState&, int, int, int) const {}
@@ -214,7 +269,10 @@ struct EpiPlain {
   static constexpr bool kStats = false;
   __device__ __forceinline__ void tile_begin(EpiState& st, int, const Tables&) const { st.s = st.q = 0.f; }
   template <int W>
-  __device__ __forceinline__ void apply(EpiState&, int m_tile, int r, int n0, const float* acc) const {
+  __device__ __forceinline__ void prefetch(int, int, int, float (&)[W]) const {}
+  template <int W>
+  __device__ __forceinline__ void apply(EpiState&, int m_tile, int r, int n0, const float* acc,
+                                        const float (&)[W]) const {
 #pragma unroll
     for (int j = 0; j < W; ++j) c[((size_t)m_tile * TILE_M + r) * N + n0 + j] = acc[j];
   }

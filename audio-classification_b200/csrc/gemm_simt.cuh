@@ -90,8 +90,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = tx + 16 * i;
-    epi.template apply<4>(st, m_tile, r, n_tile * BN + ty * 4, &acc[i][0]);
-    epi.template apply<4>(st, m_tile, r, n_tile * BN + 64 + ty * 4, &acc[i][4]);
+    float pre0[4], pre1[4];
+    epi.template prefetch<4>(m_tile, r, n_tile * BN + ty * 4, pre0);
+    epi.template prefetch<4>(m_tile, r, n_tile * BN + 64 + ty * 4, pre1);
+    epi.template apply<4>(st, m_tile, r, n_tile * BN + ty * 4, &acc[i][0], pre0);
+    epi.template apply<4>(st, m_tile, r, n_tile * BN + 64 + ty * 4, &acc[i][4], pre1);
   }
   if (Epi::kStats) {
     // block-level reduction -> one partial per (m_tile, n_tile): slots = N / 128
@@ -100,9 +103,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
     const int warp = tid >> 5, lane = tid & 31;
     if (lane == 0) { s_red[warp] = s; s_red[8 + warp] = q; }
     __syncthreads();
-    if (warp == 0) {
-      st.s = (lane < 8) ? s_red[lane] : 0.f;
-      st.q = (lane < 8) ? s_red[8 + lane] : 0.f;
+    if (tid == 0) {
+      float ts = 0.f, tq = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { ts += s_red[w]; tq += s_red[8 + w]; }
+      st.s = ts;
+      st.q = tq;
       epi.tile_end(st, m_tile, gridDim.x, n_tile);
     }
   }

@@ -10,9 +10,12 @@
 //   D : 128 lanes x BN fp32 columns in TMEM, double-buffered (2*BN columns) so the epilogue of
 //       work item i overlaps the MMAs of work item i+1.
 //
-// Warp roles (256 threads, 1 CTA / SM, persistent over (m_tile, n_tile) work items):
+// Warp roles (384 threads, 1 CTA / SM, persistent over (m_tile, n_tile) work items):
 //   warp 0 : TMA producer (one elected lane)      warp 2 : TMEM allocator
-//   warp 1 : tcgen05.mma issuer (one lane)        warps 4-7 : epilogue (lane = frame, tcgen05.ld)
+//   warp 1 : tcgen05.mma issuer (one lane)        warps 4-11 : epilogue (lane = frame, tcgen05.ld);
+//   two epilogue warps share each 32-lane TMEM quadrant and split the BN columns, so every SM
+//   sub-partition has two warps to interleave; global operands of the epilogue (old x / skip, the
+//   encoder output) are prefetched one 32-column chunk ahead, across work items.
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
 #pragma once
 #include "common.cuh"
@@ -130,11 +133,14 @@ struct TcConfig {
   static constexpr int B_STAGE = BN * 64 * 2;       // 16 / 32 KiB
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BN;          // double-buffered accumulator
-  static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) + 1024 /*align slack*/ + 512 /*barriers, stats*/;
+  static constexpr int THREADS = 384;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int NCH = BN / 64;               // 32-column chunks per epilogue warp
 };
 
 template <int BN, int K, class Epi>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                int n_mtiles, int n_ntiles, uint32_t a_lbo, uint32_t a_sbo, Epi epi, Tables tb) {
   using Cfg = TcConfig<BN, K>;
@@ -149,6 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * Cfg::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * Cfg::STAGES + 2 + s); };
   const uint32_t tmem_ptr_smem = bar0 + 8u * (2 * Cfg::STAGES + 4);
+  const uint32_t red_smem = bar0 + 256u;  // [2][8] float2 block-level stat reduction
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = n_mtiles * n_ntiles;
@@ -164,7 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 128);
+      mbar_init(tempty_bar(s), 32 * Cfg::EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -229,10 +236,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     __syncwarp();
   } else if (warp >= 4) {
     // ================================ epilogue ====================================
-    const int ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew + 32)
-    const int r = ew * 32 + lane;
+    const int ew = warp - 4;       // 0..7
+    const int quad = ew & 3;       // == warp % 4 -> TMEM lanes [32*quad, 32*quad + 32)
+    const int half = ew >> 2;      // which half of the BN columns
+    const int r = quad * 32 + lane;
+    constexpr int NCH = Cfg::NCH;
+    float pre[2][32];
     int it = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+    int w = blockIdx.x;
+    if (w < total) {
+      const int m_tile = w / n_ntiles, n_tile = w % n_ntiles;
+      epi.template prefetch<32>(m_tile, r, n_tile * BN + half * (BN / 2), pre[0]);
+    }
+    for (; w < total; w += gridDim.x, ++it) {
       const int m_tile = w / n_ntiles, n_tile = w % n_ntiles;
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
@@ -240,17 +256,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       epi.tile_begin(st, m_tile, tb);  // overlaps the MMAs of this work item
       mbar_wait(tfull_bar(as), aphase);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
+      const int n_base = n_tile * BN + half * (BN / 2);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        if (c + 1 < NCH) {
+          epi.template prefetch<32>(m_tile, r, n_base + (c + 1) * 32, pre[(c + 1) & 1]);
+        } else {
+          const int wn = w + gridDim.x;  // first chunk of the next work item
+          if (wn < total) epi.template prefetch<32>(wn / n_ntiles, r, (wn % n_ntiles) * BN + half * (BN / 2), pre[0]);
+        }
         float v[32];
         tmem_ld32(taddr + (uint32_t)(c * 32), v);
         tmem_ld_wait();
-        epi.template apply<32>(st, m_tile, r, n_tile * BN + c * 32, v);
+        epi.template apply<32>(st, m_tile, r, n_base + c * 32, v, pre[c & 1]);
       }
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(as));
-      if (Epi::kStats) epi.tile_end(st, m_tile, n_ntiles * 4, n_tile * 4 + ew);
+      if (Epi::kStats) {
+        // block-level reduction of the 8 epilogue warps -> one partial per (m_tile, n_tile)
+        const float s = warp_sum(st.s), q = warp_sum(st.q);
+        const uint32_t slot = red_smem + (uint32_t)(((it & 1) * 8 + ew) * 8);
+        if (lane == 0) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(slot), "f"(s), "f"(q) : "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (ew == 0 && lane == 0) {
+          float ts = 0.f, tq = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float a, b;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(red_smem + (uint32_t)(((it & 1) * 8 + k) * 8)));
+            ts += a; tq += b;
+          }
+          st.s = ts; st.q = tq;
+          epi.tile_end(st, m_tile, n_ntiles, n_tile);
+        }
+      }
     }
   }
 
