@@ -425,18 +425,31 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
     BlockW& b = m->blocks[i];
     const bool first = (i == 0), last = (i == m->n_layers - 1);
     {
-      EpiIn<T> e{b.b_in, b.a1, h1, p1};
-      if (run_gemm<T, 256, C_BN>(m, a_x, &tm_xa, reinterpret_cast<const T*>(b.w_in), &b.tm_in, nt, C_HID, e, tb, st))
-        return 1;
+      int rc;
+      if (b.a1 >= 0.f && b.a1 <= 1.f) {
+        EpiIn<T, true> e{b.b_in, b.a1, h1, p1};
+        rc = run_gemm<T, 256, C_BN>(m, a_x, &tm_xa, reinterpret_cast<const T*>(b.w_in), &b.tm_in, nt, C_HID, e, tb, st);
+      } else {
+        EpiIn<T, false> e{b.b_in, b.a1, h1, p1};
+        rc = run_gemm<T, 256, C_BN>(m, a_x, &tm_xa, reinterpret_cast<const T*>(b.w_in), &b.tm_in, nt, C_HID, e, tb, st);
+      }
+      if (rc) return 1;
     }
     if (stop()) return 0;
     {
       DwParams p{b.g1, b.be1, b.wd, b.bd, b.a2, b.dilation};
       const dim3 g(DW_SLOTS, nt);
-      if (b.dilation == 1) dwconv_kernel<T, 1><<<g, 256, 0, st>>>(h1, h2, p1, slots1, p2, p, tb);
-      else if (b.dilation == 2) dwconv_kernel<T, 2><<<g, 256, 0, st>>>(h1, h2, p1, slots1, p2, p, tb);
-      else if (b.dilation == 4) dwconv_kernel<T, 4><<<g, 256, 0, st>>>(h1, h2, p1, slots1, p2, p, tb);
-      else dwconv_kernel<T, 0><<<g, 256, 0, st>>>(h1, h2, p1, slots1, p2, p, tb);
+      const bool a01 = b.a2 >= 0.f && b.a2 <= 1.f;
+#define DW_LAUNCH(D_)                                                                         \
+  do {                                                                                        \
+    if (a01) dwconv_kernel<T, D_, true><<<g, 256, 0, st>>>(h1, h2, p1, slots1, p2, p, tb);      \
+    else dwconv_kernel<T, D_, false><<<g, 256, 0, st>>>(h1, h2, p1, slots1, p2, p, tb);         \
+  } while (0)
+      if (b.dilation == 1) DW_LAUNCH(1);
+      else if (b.dilation == 2) DW_LAUNCH(2);
+      else if (b.dilation == 4) DW_LAUNCH(4);
+      else DW_LAUNCH(0);
+#undef DW_LAUNCH
       CK(cudaGetLastError());
     }
     if (stop()) return 0;
@@ -471,8 +484,17 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
   if (stop()) return 0;
 
   // 5. decoder + overlap-add (d_out was zero-filled by the caller of forward())
-  decoder_kernel<T, L><<<dim3(nt, c.n_src), 256, 0, st>>>(masked, m->dec_w, d_out, c.n_src, tb);
-  CK(cudaGetLastError());
+  {
+    constexpr int kSmem = decoder_smem_bytes<L>();
+    auto kern = decoder_kernel<T, L>;
+    static bool configured = false;  // per template instantiation
+    if (!configured) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+      configured = true;
+    }
+    kern<<<dim3(nt, c.n_src), 256, kSmem, st>>>(masked, m->dec_w, d_out, c.n_src, tb);
+    CK(cudaGetLastError());
+  }
   prof_mark();
   return 0;
 }

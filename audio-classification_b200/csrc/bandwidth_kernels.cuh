@@ -197,15 +197,72 @@ __device__ __forceinline__ Vec8<T> load_group8(const T* __restrict__ buf, int ti
   return v;
 }
 
+// One step = one channel per half-warp (8 consecutive frames per thread).  INTERIOR: every tap of
+// every frame of this thread lies inside the segment -> branch-free packed-FMA path.
+template <typename T, int D, bool INTERIOR, bool A01>
+__device__ __forceinline__ void dw_step(const T* __restrict__ h1, T* __restrict__ h2, const float4 (*s_par)[2],
+                                        int tile0, int ntiles, int m_tile, int c, int cl, int t_base, int d, int F,
+                                        int lane16, float alpha, float2& s2, float2& q2) {
+  const Vec8<T> vc = load_group8(h1, tile0, ntiles, c, t_base);
+  float ctr[8], lft[8], rgt[8];
+  if (D == 0) {
+    const Vec8<T> vl = load_group8(h1, tile0, ntiles, c, t_base - d);
+    const Vec8<T> vr = load_group8(h1, tile0, ntiles, c, t_base + d);
+    vc.get(ctr); vl.get(lft); vr.get(rgt);
+  } else {
+    Vec8<T> vp = vc.shfl_up16(), vn = vc.shfl_down16();
+    if (lane16 == 0) vp = load_group8(h1, tile0, ntiles, c, t_base - 8);
+    if (lane16 == 15) vn = load_group8(h1, tile0, ntiles, c, t_base + 8);
+    float pv[8], nv[8];
+    vc.get(ctr); vp.get(pv); vn.get(nv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      lft[i] = (i - D >= 0) ? ctr[(i - D) & 7] : pv[(8 + i - D) & 7];
+      rgt[i] = (i + D < 8) ? ctr[(i + D) & 7] : nv[(i + D - 8) & 7];
+    }
+  }
+  const float4 pa = s_par[cl][0];
+  float o[8];
+  if (INTERIOR) {
+    const float2 w0 = make_float2(pa.x, pa.x), w1 = make_float2(pa.y, pa.y), w2 = make_float2(pa.z, pa.z);
+    const float2 cw = make_float2(pa.w, pa.w);
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      float2 u = fma2(make_float2(lft[i], lft[i + 1]), w0,
+                      fma2(make_float2(ctr[i], ctr[i + 1]), w1, fma2(make_float2(rgt[i], rgt[i + 1]), w2, cw)));
+      u = prelu2<A01>(u, alpha);
+      o[i] = u.x; o[i + 1] = u.y;
+      s2 = add2(s2, u);
+      q2 = fma2(u, u, q2);
+    }
+  } else {
+    const float4 pb = s_par[cl][1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = t_base + i;
+      float u = pb.w;
+      if (t - d >= 0 && t - d < F) u += fmaf(pa.x, lft[i], pb.x);
+      if (t < F) u += fmaf(pa.y, ctr[i], pb.y);
+      if (t + d < F) u += fmaf(pa.z, rgt[i], pb.z);
+      u = fmaxf(u, 0.f) + alpha * fminf(u, 0.f);
+      o[i] = (t < F) ? u : 0.f;
+      s2.x += o[i];
+      q2.x = fmaf(o[i], o[i], q2.x);
+    }
+  }
+  Vec8<T> ov;
+  ov.set(o);
+  ov.store(h2 + tt_index(m_tile, C_HID, c, lane16 * 8));
+}
+
 // D = compile-time dilation for the shuffle path (1, 2, 4); D = 0 selects the aligned-load path
 // (runtime dilation d, d % 8 == 0).
-template <typename T, int D>
-__global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ h1,  // [nt][512][128]
+template <typename T, int D, bool A01>
+__global__ void __launch_bounds__(256, 4) dwconv_kernel(const T* __restrict__ h1,  // [nt][512][128]
                                                      T* __restrict__ h2,        // [nt][512][128]
                                                      const float2* __restrict__ part1, int slots1,
                                                      float2* __restrict__ part2,  // [nt][DW_SLOTS]
                                                      DwParams p, Tables tb) {
-  __shared__ float s_stat[2];
   __shared__ float s_red[16];
   __shared__ float4 s_par[DW_CH][2];  // {wa0, wa1, wa2, c_interior}, {wb0, wb1, wb2, bias}
   const int cg = blockIdx.x;
@@ -215,20 +272,18 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ h1,  
   const int tile0 = tb.seg_tile0[seg];
   const int ntiles = tb.seg_ntiles[seg];
   const int F = tb.seg_frames[seg];
-  const int sub = lane >> 4;                                      // which of the warp's 2 channels
-  const int t_base = (m_tile - tile0) * TILE_M + (lane & 15) * 8;  // first of this thread's 8 frames
+  const int sub = lane >> 4;                              // which of the warp's 2 channels
+  const int lane16 = lane & 15;
+  const int t_base = (m_tile - tile0) * TILE_M + lane16 * 8;  // first of this thread's 8 frames
   const int d = (D > 0) ? D : p.dilation;
 
-  if (warp == 0) {
-    float mean, rstd;
-    warp_seg_stats(part1, tile0, ntiles, slots1, (double)C_HID * (double)F, mean, rstd);
-    if (lane == 0) { s_stat[0] = mean; s_stat[1] = rstd; }
-  }
-  __syncthreads();
+  // every warp reduces the (tiny) partial list itself: identical results, no extra barrier
+  float mean, rstd;
+  warp_seg_stats(part1, tile0, ntiles, slots1, (double)C_HID * (double)F, mean, rstd);
   if (tid < DW_CH) {
     const int c = cg * DW_CH + tid;
-    const float a = p.gamma1[c] * s_stat[1];
-    const float b = p.beta1[c] - a * s_stat[0];  // y = a*h + b
+    const float a = p.gamma1[c] * rstd;
+    const float b = p.beta1[c] - a * mean;  // y = a*h + b
     const float w0 = p.w[c * 3 + 0], w1 = p.w[c * 3 + 1], w2 = p.w[c * 3 + 2];
     const float bias = p.bias[c];
     s_par[tid][0] = make_float4(w0 * a, w1 * a, w2 * a, bias + (w0 + w1 + w2) * b);
@@ -236,65 +291,27 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ h1,  
   }
   __syncthreads();
 
-  const bool interior = (t_base - d >= 0) && (t_base + 7 + d < F);
+  // CTA-uniform: every tap of every frame of this m-tile lies inside the segment (the shuffle path
+  // needs all lanes of a warp in the same branch)
+  const int tile_t0 = (m_tile - tile0) * TILE_M;
+  const bool interior = (tile_t0 - d >= 0) && (tile_t0 + TILE_M - 1 + d < F);
   const float alpha = p.alpha2;
-  float s_acc = 0.f, q_acc = 0.f;
+  float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
   constexpr int STEPS = DW_CH / 16;  // 16 channels per CTA step (8 warps x 2)
-#pragma unroll 4
-  for (int it = 0; it < STEPS; ++it) {
-    const int cl = it * 16 + warp * 2 + sub;
-    const int c = cg * DW_CH + cl;
-    const Vec8<T> vc = load_group8(h1, tile0, ntiles, c, t_base);
-    float ctr[8], lft[8], rgt[8];
-    vc.get(ctr);
-    if (D == 0) {
-      load_group8(h1, tile0, ntiles, c, t_base - d).get(lft);
-      load_group8(h1, tile0, ntiles, c, t_base + d).get(rgt);
-    } else {
-      Vec8<T> vp = vc.shfl_up16(), vn = vc.shfl_down16();
-      if ((lane & 15) == 0) vp = load_group8(h1, tile0, ntiles, c, t_base - 8);
-      if ((lane & 15) == 15) vn = load_group8(h1, tile0, ntiles, c, t_base + 8);
-      float pv[8], nv[8];
-      vp.get(pv);
-      vn.get(nv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        lft[i] = (i - D >= 0) ? ctr[(i - D) & 7] : pv[(8 + i - D) & 7];
-        rgt[i] = (i + D < 8) ? ctr[(i + D) & 7] : nv[(i + D - 8) & 7];
-      }
-    }
-    const float4 pa = s_par[cl][0];
-    float o[8];
-    if (interior) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float u = fmaf(pa.x, lft[i], fmaf(pa.y, ctr[i], fmaf(pa.z, rgt[i], pa.w)));
-        o[i] = fmaxf(u, 0.f) + alpha * fminf(u, 0.f);
-      }
-    } else {
-      const float4 pb = s_par[cl][1];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int t = t_base + i;
-        float u = pb.w;
-        if (t - d >= 0 && t - d < F) u += fmaf(pa.x, lft[i], pb.x);
-        if (t < F) u += fmaf(pa.y, ctr[i], pb.y);
-        if (t + d < F) u += fmaf(pa.z, rgt[i], pb.z);
-        u = fmaxf(u, 0.f) + alpha * fminf(u, 0.f);
-        o[i] = (t < F) ? u : 0.f;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      s_acc += o[i];
-      q_acc = fmaf(o[i], o[i], q_acc);
-    }
-    Vec8<T> ov;
-    ov.set(o);
-    ov.store(h2 + tt_index(m_tile, C_HID, c, (lane & 15) * 8));
+  const int cl0 = warp * 2 + sub;
+  if (interior) {
+#pragma unroll 2
+    for (int it = 0; it < STEPS; ++it)
+      dw_step<T, D, true, A01>(h1, h2, s_par, tile0, ntiles, m_tile, cg * DW_CH + it * 16 + cl0, it * 16 + cl0, t_base,
+                               d, F, lane16, alpha, s2, q2);
+  } else {
+#pragma unroll 1
+    for (int it = 0; it < STEPS; ++it)
+      dw_step<T, D, false, A01>(h1, h2, s_par, tile0, ntiles, m_tile, cg * DW_CH + it * 16 + cl0, it * 16 + cl0, t_base,
+                                d, F, lane16, alpha, s2, q2);
   }
-  s_acc = warp_sum(s_acc);
-  q_acc = warp_sum(q_acc);
+  float s_acc = warp_sum(s2.x + s2.y);
+  float q_acc = warp_sum(q2.x + q2.y);
   if (lane == 0) { s_red[warp] = s_acc; s_red[8 + warp] = q_acc; }
   __syncthreads();
   if (tid == 0) {
@@ -308,19 +325,36 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ h1,  
 // =================================================================================================
 // Decoder: dec[s][f*stride + l] += sum_n masked[s][n][f] * Wd[n][l]   (asteroid Decoder(FreeFB) =
 // conv_transpose1d with stride L/2, no bias) followed by pad_x_to_y (zero tail).  d_out is zero-
-// filled before this kernel.  grid = (n_tiles, n_src), 256 threads = (frame r, half of the 512
-// channels); each thread accumulates the L taps of its frame, halves are combined in shared memory,
-// then the overlap-add of the two half-frames per hop is done in shared memory and written with
-// coalesced stores.  Only the two hops shared with the neighbouring m-tiles use atomicAdd; with a
+// filled before this kernel.  grid = (n_tiles, n_src), 256 threads = (64 frame pairs) x (4 quarters of
+// the 512 filters).  The filterbank sits in shared memory (broadcast reads); a thread accumulates the
+// L taps of its two frames as packed fp32 pairs (taps l, l+1).  The four partial sums per frame are
+// combined in shared memory, where the overlap-add of the two half-frames per hop also happens;
+// stores are coalesced.  Only the two hops shared with the neighbouring m-tiles use atomicAdd; with a
 // zeroed destination the sum of exactly two addends is order-independent, so the result is
 // deterministic.
 // =================================================================================================
+template <int L>
+constexpr int decoder_smem_bytes() {
+  return (C_ENC * L * 4 > 4 * TILE_M * (L + 1) * 4) ? C_ENC * L * 4 : 4 * TILE_M * (L + 1) * 4;
+}
+
+template <typename T> struct Ld2;
+template <> struct Ld2<__half> {
+  __device__ __forceinline__ static float2 ld(const __half* p) {
+    return __half22float2(*reinterpret_cast<const __half2*>(p));
+  }
+};
+template <> struct Ld2<float> {
+  __device__ __forceinline__ static float2 ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
+};
+
 template <typename T, int L>
 __global__ void __launch_bounds__(256) decoder_kernel(const T* __restrict__ masked,  // [nt][S*512][128]
                                                       const float* __restrict__ w_dec,  // [512][L]
                                                       float* __restrict__ out, int n_src, Tables tb) {
   constexpr int S = L / 2;
-  __shared__ float s_d[TILE_M][L + 1];
+  extern __shared__ __align__(16) float s_dec[];
+  float4* s_w4 = reinterpret_cast<float4*>(s_dec);  // [512][L/4] while accumulating
   const int m_tile = blockIdx.x;
   const int src = blockIdx.y;
   const int tid = threadIdx.x;
@@ -328,35 +362,41 @@ __global__ void __launch_bounds__(256) decoder_kernel(const T* __restrict__ mask
   const int t0 = (m_tile - tb.seg_tile0[seg]) * TILE_M;
   const int F = tb.seg_frames[seg];
   const int T_len = tb.seg_len[seg];
-  const int r = tid & (TILE_M - 1);
-  const int nh = tid >> 7;
+  const int fp = tid & 63;  // frames 2fp, 2fp+1
+  const int nq = tid >> 6;  // filters [128 nq, 128 nq + 128)
 
-  float acc[L];
+  const float4* wg = reinterpret_cast<const float4*>(w_dec);
+  for (int i = tid; i < C_ENC * L / 4; i += 256) s_w4[i] = __ldg(wg + i);
+  __syncthreads();
+
+  float2 acc[2][L / 2];
 #pragma unroll
-  for (int l = 0; l < L; ++l) acc[l] = 0.f;
-  const T* mp = masked + tt_index(m_tile, n_src * C_ENC, src * C_ENC + nh * 256, r);
-  const float4* wp = reinterpret_cast<const float4*>(w_dec + (size_t)nh * 256 * L);
-#pragma unroll 2
-  for (int n = 0; n < 256; ++n) {
-    const float m = to_f32(mp[(size_t)n * TILE_M]);
+  for (int l = 0; l < L / 2; ++l) acc[0][l] = acc[1][l] = make_float2(0.f, 0.f);
+  const T* mp = masked + tt_index(m_tile, n_src * C_ENC, src * C_ENC + nq * 128, 2 * fp);
+  const float4* wp = s_w4 + (size_t)nq * 128 * (L / 4);
+#pragma unroll 4
+  for (int n = 0; n < 128; ++n) {
+    const float2 m = Ld2<T>::ld(mp + (size_t)n * TILE_M);
+    const float2 m0 = make_float2(m.x, m.x), m1 = make_float2(m.y, m.y);
 #pragma unroll
     for (int q = 0; q < L / 4; ++q) {
-      const float4 w = __ldg(wp + n * (L / 4) + q);
-      acc[4 * q + 0] = fmaf(m, w.x, acc[4 * q + 0]);
-      acc[4 * q + 1] = fmaf(m, w.y, acc[4 * q + 1]);
-      acc[4 * q + 2] = fmaf(m, w.z, acc[4 * q + 2]);
-      acc[4 * q + 3] = fmaf(m, w.w, acc[4 * q + 3]);
+      const float4 w = wp[n * (L / 4) + q];
+      acc[0][2 * q + 0] = fma2(make_float2(w.x, w.y), m0, acc[0][2 * q + 0]);
+      acc[0][2 * q + 1] = fma2(make_float2(w.z, w.w), m0, acc[0][2 * q + 1]);
+      acc[1][2 * q + 0] = fma2(make_float2(w.x, w.y), m1, acc[1][2 * q + 0]);
+      acc[1][2 * q + 1] = fma2(make_float2(w.z, w.w), m1, acc[1][2 * q + 1]);
     }
   }
-  if (nh == 1) {
+  __syncthreads();  // filterbank no longer needed: reuse the buffer for the partial frames
+  float (*s_d)[TILE_M][L + 1] = reinterpret_cast<float (*)[TILE_M][L + 1]>(s_dec);
 #pragma unroll
-    for (int l = 0; l < L; ++l) s_d[r][l] = acc[l];
-  }
-  __syncthreads();
-  if (nh == 0) {
-    const bool valid = (t0 + r) < F;
+  for (int f = 0; f < 2; ++f) {
+    const bool valid = (t0 + 2 * fp + f) < F;
 #pragma unroll
-    for (int l = 0; l < L; ++l) s_d[r][l] = valid ? (acc[l] + s_d[r][l]) : 0.f;
+    for (int l = 0; l < L / 2; ++l) {
+      s_d[nq][2 * fp + f][2 * l + 0] = valid ? acc[f][l].x : 0.f;
+      s_d[nq][2 * fp + f][2 * l + 1] = valid ? acc[f][l].y : 0.f;
+    }
   }
   __syncthreads();
 
@@ -369,8 +409,14 @@ __global__ void __launch_bounds__(256) decoder_kernel(const T* __restrict__ mask
     const int f_lo = t0 + hh - 1;  // frame contributing taps [S, L)
     float v = 0.f;
     bool any = false;
-    if (hh < TILE_M && f_hi < F) { v += s_d[hh][l]; any = true; }
-    if (hh >= 1 && f_lo < F) { v += s_d[hh - 1][S + l]; any = true; }
+    if (hh < TILE_M && f_hi < F) {
+      v += (s_d[0][hh][l] + s_d[1][hh][l]) + (s_d[2][hh][l] + s_d[3][hh][l]);
+      any = true;
+    }
+    if (hh >= 1 && f_lo < F) {
+      v += (s_d[0][hh - 1][S + l] + s_d[1][hh - 1][S + l]) + (s_d[2][hh - 1][S + l] + s_d[3][hh - 1][S + l]);
+      any = true;
+    }
     if (!any) continue;
     const size_t idx = (size_t)(t0 + hh) * S + l;  // < (F-1)*S + L <= T_len
     if (hh == 0 || hh == TILE_M) atomicAdd(o + idx, v);

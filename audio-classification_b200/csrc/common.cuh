@@ -48,6 +48,22 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 
+// ---- packed fp32x2 math (sm_100 FADD2 / FMUL2 / FFMA2: two fp32 lanes per issue slot) ----------
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+// PReLU.  A01 (0 <= alpha <= 1, the practical case): max(v, alpha*v) is exact and costs 1.5 issue
+// slots per element with the packed multiply; otherwise the general max(v,0) + alpha*min(v,0).
+template <bool A01>
+__device__ __forceinline__ float2 prelu2(float2 v, float alpha) {
+  if (A01) {
+    const float2 t = mul2(v, make_float2(alpha, alpha));
+    return make_float2(fmaxf(v.x, t.x), fmaxf(v.y, t.y));
+  }
+  return make_float2(fmaxf(v.x, 0.f) + alpha * fminf(v.x, 0.f), fmaxf(v.y, 0.f) + alpha * fminf(v.y, 0.f));
+}
+
 // ---- reductions ------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

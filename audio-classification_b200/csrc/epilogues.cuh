@@ -68,23 +68,24 @@ struct EpiBottleneck {
   template <int W>
   __device__ __forceinline__ void apply(EpiState& st, int m_tile, int r, int n0, const float* acc,
                                         const float (&)[W]) const {
-    const bool valid = (st.t0 + r) < st.F;
-    const float nm = -st.mean, rstd = st.rstd;
+    const float vm = ((st.t0 + r) < st.F) ? 1.f : 0.f;
+    const float2 rstd2 = make_float2(st.rstd * vm, st.rstd * vm);
+    const float2 nmr2 = make_float2(-st.mean * st.rstd * vm, -st.mean * st.rstd * vm);
+    const float2 vm2 = make_float2(vm, vm);
     const size_t idx0 = tt_index(m_tile, C_BN, n0, r);
     float out[W];
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) {
       const float4 r4 = ldg4(rs + n0 + 4 * q), c4 = ldg4(cb + n0 + 4 * q);
-      out[4 * q + 0] = fmaf(rstd, fmaf(nm, r4.x, acc[4 * q + 0]), c4.x);
-      out[4 * q + 1] = fmaf(rstd, fmaf(nm, r4.y, acc[4 * q + 1]), c4.y);
-      out[4 * q + 2] = fmaf(rstd, fmaf(nm, r4.z, acc[4 * q + 2]), c4.z);
-      out[4 * q + 3] = fmaf(rstd, fmaf(nm, r4.w, acc[4 * q + 3]), c4.w);
+      // out = vm * (rstd * (acc - mean * rs) + cb)
+      const float2 t0 = fma2(make_float2(r4.x, r4.y), nmr2, mul2(make_float2(c4.x, c4.y), vm2));
+      const float2 t1 = fma2(make_float2(r4.z, r4.w), nmr2, mul2(make_float2(c4.z, c4.w), vm2));
+      const float2 o0 = fma2(make_float2(acc[4 * q + 0], acc[4 * q + 1]), rstd2, t0);
+      const float2 o1 = fma2(make_float2(acc[4 * q + 2], acc[4 * q + 3]), rstd2, t1);
+      out[4 * q + 0] = o0.x; out[4 * q + 1] = o0.y; out[4 * q + 2] = o1.x; out[4 * q + 3] = o1.y;
     }
 #pragma unroll
-    for (int j = 0; j < W; ++j) {
-      if (!valid) out[j] = 0.f;
-      x[idx0 + (size_t)j * TILE_M] = out[j];
-    }
+    for (int j = 0; j < W; ++j) x[idx0 + (size_t)j * TILE_M] = out[j];
     if (xa != nullptr) {
 #pragma unroll
       for (int j = 0; j < W; ++j) xa[idx0 + (size_t)j * TILE_M] = from_f32<T>(out[j]);
@@ -95,7 +96,7 @@ struct EpiBottleneck {
 
 // -------------------------------------------------------------------------------------------------
 // Block in-conv: h1 = PReLU(conv1x1(x) + b)   (shared_block.0/.1) + gLN1 partial statistics.
-template <typename T>
+template <typename T, bool A01>  // A01: 0 <= alpha <= 1, PReLU(v) == max(v, alpha*v)
 struct EpiIn {
   const float* bias;  // [512]
   float alpha;
@@ -109,31 +110,33 @@ struct EpiIn {
   }
   template <int W>
   __device__ __forceinline__ void prefetch(int, int, int, float (&)[W]) const {}
+  // Frames beyond the segment end keep whatever finite value falls out (their x is 0, so h1 =
+  // PReLU(bias)); nothing downstream reads them: the depthwise conv masks its taps by frame index.
+  // Only the statistics must exclude them (multiply by the 0/1 frame mask).
   template <int W>
   __device__ __forceinline__ void apply(EpiState& st, int m_tile, int r, int n0, const float* acc,
                                         const float (&)[W]) const {
-    const bool valid = (st.t0 + r) < st.F;
+    const float vm = ((st.t0 + r) < st.F) ? 1.f : 0.f;
+    const float2 vm2 = make_float2(vm, vm);
     T* __restrict__ dst = h1 + tt_index(m_tile, C_HID, n0, r);
-    float out[W];
+    float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) {
       const float4 b4 = ldg4(bias + n0 + 4 * q);
-      out[4 * q + 0] = acc[4 * q + 0] + b4.x;
-      out[4 * q + 1] = acc[4 * q + 1] + b4.y;
-      out[4 * q + 2] = acc[4 * q + 2] + b4.z;
-      out[4 * q + 3] = acc[4 * q + 3] + b4.w;
+      float2 v0 = add2(make_float2(acc[4 * q + 0], acc[4 * q + 1]), make_float2(b4.x, b4.y));
+      float2 v1 = add2(make_float2(acc[4 * q + 2], acc[4 * q + 3]), make_float2(b4.z, b4.w));
+      v0 = prelu2<A01>(v0, alpha);
+      v1 = prelu2<A01>(v1, alpha);
+      dst[(size_t)(4 * q + 0) * TILE_M] = from_f32<T>(v0.x);
+      dst[(size_t)(4 * q + 1) * TILE_M] = from_f32<T>(v0.y);
+      dst[(size_t)(4 * q + 2) * TILE_M] = from_f32<T>(v1.x);
+      dst[(size_t)(4 * q + 3) * TILE_M] = from_f32<T>(v1.y);
+      const float2 m0 = mul2(v0, vm2), m1 = mul2(v1, vm2);
+      s2 = add2(s2, add2(m0, m1));
+      q2 = fma2(m0, v0, fma2(m1, v1, q2));
     }
-    float s = 0.f, q2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < W; ++j) {
-      float v = fmaxf(out[j], 0.f) + alpha * fminf(out[j], 0.f);
-      if (!valid) v = 0.f;
-      dst[(size_t)j * TILE_M] = from_f32<T>(v);
-      s += v;
-      q2 = fmaf(v, v, q2);
-    }
-    st.s += s;
-    st.q += q2;
+    st.s += s2.x + s2.y;
+    st.q += q2.x + q2.y;
   }
   __device__ __forceinline__ void tile_end(EpiState& st, int m_tile, int slots, int slot) const {
     epi_write_partial(st, part_out, m_tile, slots, slot);
@@ -177,22 +180,24 @@ struct EpiResSkip {
   template <int W>
   __device__ __forceinline__ void apply(EpiState& st, int m_tile, int r, int n0, const float* acc,
                                         const float (&pre)[W]) const {
-    const bool valid = (st.t0 + r) < st.F;
+    const float vm = ((st.t0 + r) < st.F) ? 1.f : 0.f;
     const bool is_res = has_res && (n0 < C_BN);
     const int c0 = (has_res && !is_res) ? (n0 - C_BN) : n0;
     const size_t idx0 = tt_index(m_tile, C_BN, c0, r);
-    const float nm = -st.mean, rstd = st.rstd;
+    const float2 rstd2 = make_float2(st.rstd * vm, st.rstd * vm);
+    const float2 nmr2 = make_float2(-st.mean * st.rstd * vm, -st.mean * st.rstd * vm);
+    const float2 vm2 = make_float2(vm, vm);
     float out[W];
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) {
       const float4 r4 = ldg4(rs + n0 + 4 * q), c4 = ldg4(cb + n0 + 4 * q);
-      out[4 * q + 0] = fmaf(rstd, fmaf(nm, r4.x, acc[4 * q + 0]), c4.x);
-      out[4 * q + 1] = fmaf(rstd, fmaf(nm, r4.y, acc[4 * q + 1]), c4.y);
-      out[4 * q + 2] = fmaf(rstd, fmaf(nm, r4.z, acc[4 * q + 2]), c4.z);
-      out[4 * q + 3] = fmaf(rstd, fmaf(nm, r4.w, acc[4 * q + 3]), c4.w);
+      // out = old + vm * (rstd * (acc - mean * rs) + cb)
+      const float2 t0 = fma2(make_float2(r4.x, r4.y), nmr2, fma2(make_float2(c4.x, c4.y), vm2, make_float2(pre[4 * q + 0], pre[4 * q + 1])));
+      const float2 t1 = fma2(make_float2(r4.z, r4.w), nmr2, fma2(make_float2(c4.z, c4.w), vm2, make_float2(pre[4 * q + 2], pre[4 * q + 3])));
+      const float2 o0 = fma2(make_float2(acc[4 * q + 0], acc[4 * q + 1]), rstd2, t0);
+      const float2 o1 = fma2(make_float2(acc[4 * q + 2], acc[4 * q + 3]), rstd2, t1);
+      out[4 * q + 0] = o0.x; out[4 * q + 1] = o0.y; out[4 * q + 2] = o1.x; out[4 * q + 3] = o1.y;
     }
-#pragma unroll
-    for (int j = 0; j < W; ++j) out[j] = pre[j] + (valid ? out[j] : 0.f);
     if (is_res) {
 #pragma unroll
       for (int j = 0; j < W; ++j) x[idx0 + (size_t)j * TILE_M] = out[j];
@@ -243,21 +248,32 @@ struct EpiMask {
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) {
       const float4 b4 = ldg4(bias + n0 + 4 * q);
-      v[4 * q + 0] = acc[4 * q + 0] + b4.x;
-      v[4 * q + 1] = acc[4 * q + 1] + b4.y;
-      v[4 * q + 2] = acc[4 * q + 2] + b4.z;
-      v[4 * q + 3] = acc[4 * q + 3] + b4.w;
+      const float2 v0 = add2(make_float2(acc[4 * q + 0], acc[4 * q + 1]), make_float2(b4.x, b4.y));
+      const float2 v1 = add2(make_float2(acc[4 * q + 2], acc[4 * q + 3]), make_float2(b4.z, b4.w));
+      v[4 * q + 0] = v0.x; v[4 * q + 1] = v0.y; v[4 * q + 2] = v1.x; v[4 * q + 3] = v1.y;
     }
+    if (act == 0) {
+      if (kFast) {
+        // sigmoid(v) = 0.5 * tanh(0.5 v) + 0.5: one MUFU op per element (the exp + reciprocal form
+        // needs two and makes this epilogue MUFU-bound); tanh.approx abs. error ~5e-4 (~ fp16 ulp)
+        const float2 h2 = make_float2(0.5f, 0.5f);
 #pragma unroll
-    for (int j = 0; j < W; ++j) {
-      float m;
-      if (act == 0) {
-        if (kFast) m = __fdividef(1.f, 1.f + __expf(-v[j]));
-        else m = 1.f / (1.f + expf(-v[j]));
+        for (int j = 0; j < W; j += 2) {
+          const float2 a = mul2(make_float2(v[j], v[j + 1]), h2);
+          float t0, t1;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a.x));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a.y));
+          const float2 m = mul2(fma2(make_float2(t0, t1), h2, h2), make_float2(pre[j], pre[j + 1]));
+          mp[(size_t)j * TILE_M] = from_f32<T>(m.x);
+          mp[(size_t)(j + 1) * TILE_M] = from_f32<T>(m.y);
+        }
       } else {
-        m = fmaxf(v[j], 0.f);
+#pragma unroll
+        for (int j = 0; j < W; ++j) mp[(size_t)j * TILE_M] = from_f32<T>(pre[j] / (1.f + expf(-v[j])));
       }
-      mp[(size_t)j * TILE_M] = from_f32<T>(m * pre[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j) mp[(size_t)j * TILE_M] = from_f32<T>(fmaxf(v[j], 0.f) * pre[j]);
     }
   }
   __device__ __forceinline__ void tile_end(EpiState&, int, int, int) const {}

@@ -157,7 +157,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const uint32_t tmem_ptr_smem = bar0 + 8u * (2 * Cfg::STAGES + 4);
   const uint32_t red_smem = bar0 + 256u;  // [2][8] float2 block-level stat reduction
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index broadcast through a shuffle so the compiler can prove it warp-uniform (keeps the
+  // role branches and the memory descriptors on the uniform datapath)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
   const int total = n_mtiles * n_ntiles;
 
   if (warp == 0 && lane == 0) {
