@@ -325,6 +325,36 @@ static int compute_layout(const b200sep_config& c, bool half, const int32_t* len
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
+// EXPERIMENTAL, off by default (B200SEP_PDL=1 enables): with overlapping launches the per-SM L1 can
+// keep lines of a buffer that a later kernel rewrites (activations are re-used at fixed workspace
+// addresses every TCN block), and L1-cached / non-coherent loads then read stale data -- observed on
+// B200 in the fp32 mode.  Measured gain when it happens to be correct: ~3 %.
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200SEP_PDL");
+    v = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  return v == 1;
+}
+
+// Launch with programmatic stream serialisation (PDL): the kernel may start while its predecessor
+// drains; every kernel orders itself with griddepcontrol.wait (pdl_enter) before touching global data.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 template <int BN, int K, class Epi>
 static int launch_tc(const b200sep_model* m, const CUtensorMap& ta, const CUtensorMap& tbm, int n_mtiles, int N,
                      const Epi& epi, const Tables& tb, cudaStream_t st, uint32_t a_lbo = 8192, uint32_t a_sbo = 1024) {
@@ -338,8 +368,7 @@ static int launch_tc(const b200sep_model* m, const CUtensorMap& ta, const CUtens
   const int n_ntiles = N / BN;
   const int total = n_mtiles * n_ntiles;
   const int grid = std::min(total, m->n_sm);
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tbm, n_mtiles, n_ntiles, a_lbo, a_sbo, epi, tb);
-  CK(cudaGetLastError());
+  CK(launch_k(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, ta, tbm, n_mtiles, n_ntiles, a_lbo, a_sbo, epi, tb));
   return 0;
 }
 
@@ -347,8 +376,7 @@ template <typename T, int K, class Epi>
 static int launch_simt(const T* A, const T* B, int n_mtiles, int N, const Epi& epi, const Tables& tb,
                        cudaStream_t st) {
   dim3 grid(N / 128, n_mtiles);
-  gemm_simt_kernel<T, K, Epi><<<grid, 256, 0, st>>>(A, B, epi, tb);
-  CK(cudaGetLastError());
+  CK(launch_k(gemm_simt_kernel<T, K, Epi>, grid, dim3(256), 0, st, A, B, epi, tb));
   return 0;
 }
 
@@ -408,8 +436,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
   const int slots1 = (kHalf && m->use_tc) ? C_HID / 256 : C_HID / 128;  // partial slots the in-conv GEMM writes
 
   // 1. encoder (+ bottleneck-gLN partials)
-  encoder_kernel<T, L><<<dim3(nt, 2), 256, 0, st>>>(d_mix, m->enc_w, enc, p0, tb);
-  CK(cudaGetLastError());
+  CK(launch_k(encoder_kernel<T, L>, dim3(nt, 2), dim3(256), 0, st, d_mix, (const float*)m->enc_w, enc, p0, tb));
   if (stop()) return 0;
 
   // 2. bottleneck: x = Wb . gLN(tf_rep) + bb
@@ -442,15 +469,14 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
       const bool a01 = b.a2 >= 0.f && b.a2 <= 1.f;
 #define DW_LAUNCH(D_)                                                                         \
   do {                                                                                        \
-    if (a01) dwconv_kernel<T, D_, true><<<g, 256, 0, st>>>(h1, h2, p1, slots1, p2, p, tb);      \
-    else dwconv_kernel<T, D_, false><<<g, 256, 0, st>>>(h1, h2, p1, slots1, p2, p, tb);         \
+    if (a01) CK(launch_k(dwconv_kernel<T, D_, true>, g, dim3(256), 0, st, (const T*)h1, h2, (const float2*)p1, slots1, p2, p, tb)); \
+    else CK(launch_k(dwconv_kernel<T, D_, false>, g, dim3(256), 0, st, (const T*)h1, h2, (const float2*)p1, slots1, p2, p, tb));     \
   } while (0)
       if (b.dilation == 1) DW_LAUNCH(1);
       else if (b.dilation == 2) DW_LAUNCH(2);
       else if (b.dilation == 4) DW_LAUNCH(4);
       else DW_LAUNCH(0);
 #undef DW_LAUNCH
-      CK(cudaGetLastError());
     }
     if (stop()) return 0;
     {
@@ -492,8 +518,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
       CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
       configured = true;
     }
-    kern<<<dim3(nt, c.n_src), 256, kSmem, st>>>(masked, m->dec_w, d_out, c.n_src, tb);
-    CK(cudaGetLastError());
+    CK(launch_k(kern, dim3(nt, c.n_src), dim3(256), kSmem, st, (const T*)masked, (const float*)m->dec_w, d_out, c.n_src, tb));
   }
   prof_mark();
   return 0;

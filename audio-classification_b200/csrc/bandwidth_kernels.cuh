@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256) encoder_kernel(const float* __restrict__ 
                                                       Tables tb) {
   constexpr int S = L / 2;
   constexpr int CH_PER_CTA = 256;
+  pdl_enter();
   __shared__ float4 s_w[CH_PER_CTA * L / 4];
   __shared__ float4 s_x4[(TILE_M * S + S) / 4 + 1];
   __shared__ float s_red[16];
@@ -114,7 +115,7 @@ struct DwParams {
   int dilation;
 };
 
-constexpr int DW_CH = 128;              // channels per CTA
+constexpr int DW_CH = 256;              // channels per CTA
 constexpr int DW_SLOTS = C_HID / DW_CH; // stat partial slots per m-tile
 
 // 8 consecutive frames of one channel
@@ -197,12 +198,56 @@ __device__ __forceinline__ Vec8<T> load_group8(const T* __restrict__ buf, int ti
   return v;
 }
 
-// One step = one channel per half-warp (8 consecutive frames per thread).  INTERIOR: every tap of
-// every frame of this thread lies inside the segment -> branch-free packed-FMA path.
-template <typename T, int D, bool INTERIOR, bool A01>
-__device__ __forceinline__ void dw_step(const T* __restrict__ h1, T* __restrict__ h2, const float4 (*s_par)[2],
-                                        int tile0, int ntiles, int m_tile, int c, int cl, int t_base, int d, int F,
-                                        int lane16, float alpha, float2& s2, float2& q2) {
+// One step = one channel per half-warp (8 consecutive frames per thread).
+// Interior tiles (every tap of every frame inside the segment): branch-free packed-FMA path with
+// precomputed tap pointers; the channel step only adds a constant stride.
+template <typename T, int D, bool A01>
+__device__ __forceinline__ void dw_step_interior(const T* __restrict__ pc, const T* __restrict__ pl,
+                                                 const T* __restrict__ pr, const T* __restrict__ pp,
+                                                 const T* __restrict__ pn, T* __restrict__ po, const float4 pa,
+                                                 int lane16, float alpha, float2& s2, float2& q2) {
+  Vec8<T> vc;
+  vc.load(pc);
+  float ctr[8], lft[8], rgt[8];
+  if (D == 0) {
+    Vec8<T> vl, vr;
+    vl.load(pl);
+    vr.load(pr);
+    vc.get(ctr); vl.get(lft); vr.get(rgt);
+  } else {
+    Vec8<T> vp = vc.shfl_up16(), vn = vc.shfl_down16();
+    if (lane16 == 0) vp.load(pp);
+    if (lane16 == 15) vn.load(pn);
+    float pv[8], nv[8];
+    vc.get(ctr); vp.get(pv); vn.get(nv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      lft[i] = (i - D >= 0) ? ctr[(i - D) & 7] : pv[(8 + i - D) & 7];
+      rgt[i] = (i + D < 8) ? ctr[(i + D) & 7] : nv[(i + D - 8) & 7];
+    }
+  }
+  const float2 w0 = make_float2(pa.x, pa.x), w1 = make_float2(pa.y, pa.y), w2 = make_float2(pa.z, pa.z);
+  const float2 cw = make_float2(pa.w, pa.w);
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    float2 u = fma2(make_float2(lft[i], lft[i + 1]), w0,
+                    fma2(make_float2(ctr[i], ctr[i + 1]), w1, fma2(make_float2(rgt[i], rgt[i + 1]), w2, cw)));
+    u = prelu2<A01>(u, alpha);
+    o[i] = u.x; o[i + 1] = u.y;
+    s2 = add2(s2, u);
+    q2 = fma2(u, u, q2);
+  }
+  Vec8<T> ov;
+  ov.set(o);
+  ov.store(po);
+}
+
+// Edge tiles: taps and frames are masked by segment-relative frame index.
+template <typename T, int D>
+__device__ __forceinline__ void dw_step_edge(const T* __restrict__ h1, T* __restrict__ h2, const float4 pa,
+                                             const float4 pb, int tile0, int ntiles, int m_tile, int c, int t_base,
+                                             int d, int F, int lane16, float alpha, float2& s2, float2& q2) {
   const Vec8<T> vc = load_group8(h1, tile0, ntiles, c, t_base);
   float ctr[8], lft[8], rgt[8];
   if (D == 0) {
@@ -221,34 +266,18 @@ __device__ __forceinline__ void dw_step(const T* __restrict__ h1, T* __restrict_
       rgt[i] = (i + D < 8) ? ctr[(i + D) & 7] : nv[(i + D - 8) & 7];
     }
   }
-  const float4 pa = s_par[cl][0];
   float o[8];
-  if (INTERIOR) {
-    const float2 w0 = make_float2(pa.x, pa.x), w1 = make_float2(pa.y, pa.y), w2 = make_float2(pa.z, pa.z);
-    const float2 cw = make_float2(pa.w, pa.w);
 #pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-      float2 u = fma2(make_float2(lft[i], lft[i + 1]), w0,
-                      fma2(make_float2(ctr[i], ctr[i + 1]), w1, fma2(make_float2(rgt[i], rgt[i + 1]), w2, cw)));
-      u = prelu2<A01>(u, alpha);
-      o[i] = u.x; o[i + 1] = u.y;
-      s2 = add2(s2, u);
-      q2 = fma2(u, u, q2);
-    }
-  } else {
-    const float4 pb = s_par[cl][1];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int t = t_base + i;
-      float u = pb.w;
-      if (t - d >= 0 && t - d < F) u += fmaf(pa.x, lft[i], pb.x);
-      if (t < F) u += fmaf(pa.y, ctr[i], pb.y);
-      if (t + d < F) u += fmaf(pa.z, rgt[i], pb.z);
-      u = fmaxf(u, 0.f) + alpha * fminf(u, 0.f);
-      o[i] = (t < F) ? u : 0.f;
-      s2.x += o[i];
-      q2.x = fmaf(o[i], o[i], q2.x);
-    }
+  for (int i = 0; i < 8; ++i) {
+    const int t = t_base + i;
+    float u = pb.w;
+    if (t - d >= 0 && t - d < F) u += fmaf(pa.x, lft[i], pb.x);
+    if (t < F) u += fmaf(pa.y, ctr[i], pb.y);
+    if (t + d < F) u += fmaf(pa.z, rgt[i], pb.z);
+    u = fmaxf(u, 0.f) + alpha * fminf(u, 0.f);
+    o[i] = (t < F) ? u : 0.f;
+    s2.x += o[i];
+    q2.x = fmaf(o[i], o[i], q2.x);
   }
   Vec8<T> ov;
   ov.set(o);
@@ -259,12 +288,13 @@ __device__ __forceinline__ void dw_step(const T* __restrict__ h1, T* __restrict_
 // (runtime dilation d, d % 8 == 0).
 template <typename T, int D, bool A01>
 __global__ void __launch_bounds__(256, 4) dwconv_kernel(const T* __restrict__ h1,  // [nt][512][128]
-                                                     T* __restrict__ h2,        // [nt][512][128]
-                                                     const float2* __restrict__ part1, int slots1,
-                                                     float2* __restrict__ part2,  // [nt][DW_SLOTS]
-                                                     DwParams p, Tables tb) {
+                                                        T* __restrict__ h2,        // [nt][512][128]
+                                                        const float2* __restrict__ part1, int slots1,
+                                                        float2* __restrict__ part2,  // [nt][DW_SLOTS]
+                                                        DwParams p, Tables tb) {
   __shared__ float s_red[16];
   __shared__ float4 s_par[DW_CH][2];  // {wa0, wa1, wa2, c_interior}, {wb0, wb1, wb2, bias}
+  pdl_enter();
   const int cg = blockIdx.x;
   const int m_tile = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -274,41 +304,51 @@ __global__ void __launch_bounds__(256, 4) dwconv_kernel(const T* __restrict__ h1
   const int F = tb.seg_frames[seg];
   const int sub = lane >> 4;                              // which of the warp's 2 channels
   const int lane16 = lane & 15;
-  const int t_base = (m_tile - tile0) * TILE_M + lane16 * 8;  // first of this thread's 8 frames
+  const int tile_t0 = (m_tile - tile0) * TILE_M;
+  const int t_base = tile_t0 + lane16 * 8;               // first of this thread's 8 frames
   const int d = (D > 0) ? D : p.dilation;
 
   // every warp reduces the (tiny) partial list itself: identical results, no extra barrier
   float mean, rstd;
   warp_seg_stats(part1, tile0, ntiles, slots1, (double)C_HID * (double)F, mean, rstd);
-  if (tid < DW_CH) {
-    const int c = cg * DW_CH + tid;
+  for (int i = tid; i < DW_CH; i += 256) {
+    const int c = cg * DW_CH + i;
     const float a = p.gamma1[c] * rstd;
     const float b = p.beta1[c] - a * mean;  // y = a*h + b
     const float w0 = p.w[c * 3 + 0], w1 = p.w[c * 3 + 1], w2 = p.w[c * 3 + 2];
     const float bias = p.bias[c];
-    s_par[tid][0] = make_float4(w0 * a, w1 * a, w2 * a, bias + (w0 + w1 + w2) * b);
-    s_par[tid][1] = make_float4(w0 * b, w1 * b, w2 * b, bias);
+    s_par[i][0] = make_float4(w0 * a, w1 * a, w2 * a, bias + (w0 + w1 + w2) * b);
+    s_par[i][1] = make_float4(w0 * b, w1 * b, w2 * b, bias);
   }
   __syncthreads();
 
   // CTA-uniform: every tap of every frame of this m-tile lies inside the segment (the shuffle path
   // needs all lanes of a warp in the same branch)
-  const int tile_t0 = (m_tile - tile0) * TILE_M;
   const bool interior = (tile_t0 - d >= 0) && (tile_t0 + TILE_M - 1 + d < F);
   const float alpha = p.alpha2;
   float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
   constexpr int STEPS = DW_CH / 16;  // 16 channels per CTA step (8 warps x 2)
   const int cl0 = warp * 2 + sub;
+  const int c0 = cg * DW_CH + cl0;
   if (interior) {
+    // tap pointers of channel c0; one channel step = +16 channels = 16 * 128 elements
+    auto ptr_at = [&](int t) { return h1 + tt_index(tile0 + (t >> 7), C_HID, c0, t & (TILE_M - 1)); };
+    const T* pc = ptr_at(t_base);
+    const T* pl = ptr_at(t_base - d);
+    const T* pr = ptr_at(t_base + d);
+    const T* pp = (D > 0 && lane16 == 0) ? ptr_at(t_base - 8) : pc;
+    const T* pn = (D > 0 && lane16 == 15) ? ptr_at(t_base + 8) : pc;
+    T* po = h2 + tt_index(m_tile, C_HID, c0, lane16 * 8);
+    constexpr size_t STRIDE = (size_t)16 * TILE_M;
 #pragma unroll 2
     for (int it = 0; it < STEPS; ++it)
-      dw_step<T, D, true, A01>(h1, h2, s_par, tile0, ntiles, m_tile, cg * DW_CH + it * 16 + cl0, it * 16 + cl0, t_base,
-                               d, F, lane16, alpha, s2, q2);
+      dw_step_interior<T, D, A01>(pc + it * STRIDE, pl + it * STRIDE, pr + it * STRIDE, pp + it * STRIDE,
+                                  pn + it * STRIDE, po + it * STRIDE, s_par[it * 16 + cl0][0], lane16, alpha, s2, q2);
   } else {
 #pragma unroll 1
     for (int it = 0; it < STEPS; ++it)
-      dw_step<T, D, false, A01>(h1, h2, s_par, tile0, ntiles, m_tile, cg * DW_CH + it * 16 + cl0, it * 16 + cl0, t_base,
-                                d, F, lane16, alpha, s2, q2);
+      dw_step_edge<T, D>(h1, h2, s_par[it * 16 + cl0][0], s_par[it * 16 + cl0][1], tile0, ntiles, m_tile, c0 + it * 16,
+                         t_base, d, F, lane16, alpha, s2, q2);
   }
   float s_acc = warp_sum(s2.x + s2.y);
   float q_acc = warp_sum(q2.x + q2.y);
@@ -353,6 +393,7 @@ __global__ void __launch_bounds__(256) decoder_kernel(const T* __restrict__ mask
                                                       const float* __restrict__ w_dec,  // [512][L]
                                                       float* __restrict__ out, int n_src, Tables tb) {
   constexpr int S = L / 2;
+  pdl_enter();
   extern __shared__ __align__(16) float s_dec[];
   float4* s_w4 = reinterpret_cast<float4*>(s_dec);  // [512][L/4] while accumulating
   const int m_tile = blockIdx.x;

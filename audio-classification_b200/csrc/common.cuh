@@ -41,6 +41,15 @@ __host__ __device__ __forceinline__ size_t tt_index(int m_tile, int C, int c, in
   return ((size_t)m_tile * C + c) * TILE_M + r;
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// Every forward kernel starts with pdl_enter(): it lets the NEXT kernel of the stream begin its launch
+// processing / prologue right away, then blocks until the PREVIOUS kernel has fully completed and
+// flushed its memory -- same ordering as plain stream serialisation, without the launch bubble.
+// (No-ops when the kernel was launched without the programmatic-serialisation attribute.)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
+
 // ---- element conversion helpers -------------------------------------------------------------
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }

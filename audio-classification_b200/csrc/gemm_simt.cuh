@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const T* __restrict__ A,
   constexpr int BK = 16, BN = 128, PAD = 4;
   __shared__ __align__(16) float As[2][BK][TILE_M];
   __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+  pdl_enter();
   const int n_tile = blockIdx.x, m_tile = blockIdx.y;
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;

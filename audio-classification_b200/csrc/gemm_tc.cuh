@@ -182,6 +182,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  // the set-up above touched no global data; from here on we read what the previous kernel wrote
+  pdl_enter();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
@@ -261,6 +263,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2));
       const int n_base = n_tile * BN + half * (BN / 2);
+      float v[2][32];
+      tmem_ld32(taddr, v[0]);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         if (c + 1 < NCH) {
@@ -269,10 +273,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           const int wn = w + gridDim.x;  // first chunk of the next work item
           if (wn < total) epi.template prefetch<32>(wn / n_ntiles, r, (wn % n_ntiles) * BN + half * (BN / 2), pre[0]);
         }
-        float v[32];
-        tmem_ld32(taddr + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
-        epi.template apply<32>(st, m_tile, r, n_base + c * 32, v, pre[c & 1]);
+        tmem_ld_wait();  // chunk c has landed in v[c & 1]
+        if (c + 1 < NCH) tmem_ld32(taddr + (uint32_t)((c + 1) * 32), v[(c + 1) & 1]);  // overlaps apply(c)
+        epi.template apply<32>(st, m_tile, r, n_base + c * 32, v[c & 1], pre[c & 1]);
       }
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(as));

@@ -51,6 +51,8 @@ class SeparationEngine:
             nat.check(nat.lib().b200sep_model_create(C.byref(cfg), C.byref(packed.struct), self.device,
                                                      C.byref(handle)), "b200sep_model_create")
         self._handle = handle
+        # default wave size: env override, else whole batch in one wave
+        self.wave_frames = int(os.environ.get("B200SEP_WAVE_FRAMES", "0")) or None
         self._lock = threading.Lock()
         self._pinned_in = None
         self._pinned_out = None
@@ -74,20 +76,43 @@ class SeparationEngine:
             raise RuntimeError(f"b200sep_workspace_bytes: {nat.last_error()}")
         return int(n)
 
-    def separate_device(self, d_mix, lens: Sequence[int], out=None, workspace=None):
+    def plan_waves(self, lens: Sequence[int], wave_frames: Optional[int]) -> List[range]:
+        """Splits a batch into consecutive "waves" of at most ``wave_frames`` encoder frames.  All
+        layers of one wave run before the next wave starts, re-using the same workspace addresses,
+        so the per-layer activations of a wave (~3.3 KB / frame in fp16 mode) can stay resident in
+        the 126 MB L2 instead of round-tripping through HBM between the kernels of a TCN block."""
+        n = len(lens)
+        if not wave_frames or wave_frames <= 0:
+            return [range(0, n)]
+        waves, start, acc = [], 0, 0
+        for i, t in enumerate(lens):
+            f = (int(t) - self.kernel_size) // self.stride + 1
+            if i > start and acc + f > wave_frames:
+                waves.append(range(start, i))
+                start, acc = i, 0
+            acc += f
+        waves.append(range(start, n))
+        return waves
+
+    def separate_device(self, d_mix, lens: Sequence[int], out=None, workspace=None,
+                        wave_frames: Optional[int] = None):
         """``d_mix``: 1-D float32 CUDA tensor holding the segments back to back; returns a 1-D
         float32 CUDA tensor with, for segment i, ``n_src`` waveforms of ``lens[i]`` samples at
         offset ``n_src * sum(lens[:i])``.  Asynchronous on the current stream."""
         torch = self._torch
         if self._handle is None:
             raise RuntimeError("Separator model is not initialized.")
-        total = int(sum(int(v) for v in lens))
+        lens = [int(v) for v in lens]
+        total = int(sum(lens))
         if d_mix.dtype != torch.float32 or d_mix.dim() != 1 or not d_mix.is_cuda or not d_mix.is_contiguous():
             raise RuntimeError("d_mix must be a contiguous 1-D float32 CUDA tensor")
         if d_mix.numel() < total:
             raise RuntimeError("d_mix is shorter than sum(lens)")
         dev = d_mix.device
-        need = self.workspace_bytes(lens)
+        if wave_frames is None:
+            wave_frames = self.wave_frames
+        waves = self.plan_waves(lens, wave_frames)
+        need = max(self.workspace_bytes(lens[w.start:w.stop]) for w in waves)
         if workspace is None:
             workspace = torch.empty(need + 256, dtype=torch.uint8, device=dev)
         ws_ptr = (workspace.data_ptr() + 255) // 256 * 256
@@ -96,13 +121,17 @@ class SeparationEngine:
             out = torch.empty(total * self.n_src, dtype=torch.float32, device=dev)
         elif out.numel() < total * self.n_src or out.dtype != torch.float32:
             raise RuntimeError("out buffer too small")
-        arr = nat.i32_array(lens)
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
-            nat.check(nat.lib().b200sep_separate_batch(
-                self._handle, C.c_void_p(d_mix.data_ptr()), None, arr, len(lens),
-                C.c_void_p(out.data_ptr()), C.c_void_p(ws_ptr), C.c_size_t(ws_bytes),
-                C.c_void_p(stream)), "b200sep_separate_batch")
+            off = 0
+            for w in waves:
+                wl = lens[w.start:w.stop]
+                arr = nat.i32_array(wl)
+                nat.check(nat.lib().b200sep_separate_batch(
+                    self._handle, C.c_void_p(d_mix.data_ptr() + 4 * off), None, arr, len(wl),
+                    C.c_void_p(out.data_ptr() + 4 * off * self.n_src), C.c_void_p(ws_ptr), C.c_size_t(ws_bytes),
+                    C.c_void_p(stream)), "b200sep_separate_batch")
+                off += sum(wl)
         # keep the workspace alive until the stream has consumed it
         workspace.record_stream(torch.cuda.current_stream(dev))
         return out
