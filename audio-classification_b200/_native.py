@@ -12,7 +12,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200sep.so")
+LIB_PATH = os.environ.get("B200SEP_LIB") or os.path.join(_HERE, "libb200sep.so")  # env override: kernel-variant A/B runs
 
 PREC_FP32, PREC_FP16_TC, PREC_FP16_SIMT = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "fp16": PREC_FP16_TC, "fp16_tc": PREC_FP16_TC,

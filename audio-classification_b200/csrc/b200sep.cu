@@ -277,7 +277,7 @@ struct Layout {
   // byte offsets inside the workspace
   size_t o_tables, o_enc, o_x, o_xa, o_skip, o_skipa, o_h1, o_h2, o_masked, o_p0, o_p1, o_p2, total;
   // offsets inside the table block
-  size_t t_in_off, t_out_off, t_len, t_frames, t_tile0, t_ntiles, t_tile_seg;
+  size_t t_info, t_in_off, t_out_off, t_inv, t_len, t_frames, t_tile0, t_ntiles, t_tile_seg;
 };
 
 static int compute_layout(const b200sep_config& c, bool half, const int32_t* lens, int n_seg, Layout* lo) {
@@ -294,8 +294,10 @@ static int compute_layout(const b200sep_config& c, bool half, const int32_t* len
   lo->n_seg = n_seg;
   lo->n_tiles = (int)tiles;
   size_t t = 0;
+  lo->t_info = t; t += align_up((size_t)tiles * sizeof(TileInfo), 16);
   lo->t_in_off = t; t += align_up((size_t)n_seg * 8, 16);
   lo->t_out_off = t; t += align_up((size_t)n_seg * 8, 16);
+  lo->t_inv = t; t += align_up((size_t)n_seg * 8, 16);
   lo->t_len = t; t += align_up((size_t)n_seg * 4, 16);
   lo->t_frames = t; t += align_up((size_t)n_seg * 4, 16);
   lo->t_tile0 = t; t += align_up((size_t)n_seg * 4, 16);
@@ -661,11 +663,13 @@ int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* 
   memset(h, 0, lo.tables_bytes);
   int64_t* h_in = reinterpret_cast<int64_t*>(h + lo.t_in_off);
   int64_t* h_out = reinterpret_cast<int64_t*>(h + lo.t_out_off);
+  double* h_inv = reinterpret_cast<double*>(h + lo.t_inv);
   int32_t* h_len = reinterpret_cast<int32_t*>(h + lo.t_len);
   int32_t* h_fr = reinterpret_cast<int32_t*>(h + lo.t_frames);
   int32_t* h_t0 = reinterpret_cast<int32_t*>(h + lo.t_tile0);
   int32_t* h_nt = reinterpret_cast<int32_t*>(h + lo.t_ntiles);
   int32_t* h_ts = reinterpret_cast<int32_t*>(h + lo.t_tile_seg);
+  TileInfo* h_ti = reinterpret_cast<TileInfo*>(h + lo.t_info);
   int64_t run = 0, out_lo = INT64_MAX, out_hi = 0;
   int tile = 0;
   for (int i = 0; i < n_seg; ++i) {
@@ -677,10 +681,16 @@ int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* 
     h_len[i] = lens[i];
     const int F = (lens[i] - m->cfg.kernel_size) / m->cfg.stride + 1;
     h_fr[i] = F;
+    h_inv[i] = 1.0 / ((double)C_HID * (double)F);
     h_t0[i] = tile;
     const int ntile = (F + TILE_M - 1) / TILE_M;
     h_nt[i] = ntile;
-    for (int t = 0; t < ntile; ++t) h_ts[tile + t] = i;
+    for (int t = 0; t < ntile; ++t) {
+      h_ts[tile + t] = i;
+      TileInfo& ti = h_ti[tile + t];
+      ti.seg = i; ti.t0 = t * TILE_M; ti.F = F; ti.tile0 = tile; ti.ntiles = ntile; ti.pad = 0;
+      ti.inv_count = h_inv[i];
+    }
     tile += ntile;
     out_lo = std::min(out_lo, h_out[i]);
     out_hi = std::max(out_hi, h_out[i] + (int64_t)lens[i] * m->cfg.n_src);
@@ -693,8 +703,10 @@ int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* 
 
   Tables tb;
   uint8_t* t = ws + lo.o_tables;
+  tb.tile_info = reinterpret_cast<const TileInfo*>(t + lo.t_info);
   tb.seg_in_off = reinterpret_cast<const int64_t*>(t + lo.t_in_off);
   tb.seg_out_off = reinterpret_cast<const int64_t*>(t + lo.t_out_off);
+  tb.seg_inv_count = reinterpret_cast<const double*>(t + lo.t_inv);
   tb.seg_len = reinterpret_cast<const int32_t*>(t + lo.t_len);
   tb.seg_frames = reinterpret_cast<const int32_t*>(t + lo.t_frames);
   tb.seg_tile0 = reinterpret_cast<const int32_t*>(t + lo.t_tile0);

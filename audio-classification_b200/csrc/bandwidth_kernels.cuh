@@ -30,9 +30,8 @@ __global__ void __launch_bounds__(256) encoder_kernel(const float* __restrict__ 
   const int m_tile = blockIdx.x;
   const int chalf = blockIdx.y;
   const int tid = threadIdx.x;
-  const int seg = tb.tile_seg[m_tile];
-  const int t0 = (m_tile - tb.seg_tile0[seg]) * TILE_M;
-  const int F = tb.seg_frames[seg];
+  const TileInfo ti = load_tile_info(tb.tile_info + m_tile);
+  const int seg = ti.seg, t0 = ti.t0, F = ti.F;
   const int T_len = tb.seg_len[seg];
   const float* x = mix + tb.seg_in_off[seg];
 
@@ -115,7 +114,16 @@ struct DwParams {
   int dilation;
 };
 
-constexpr int DW_CH = 256;              // channels per CTA
+#ifndef B200SEP_DW_CH
+#define B200SEP_DW_CH 256
+#endif
+#ifndef B200SEP_DW_UNROLL
+#define B200SEP_DW_UNROLL 2
+#endif
+#ifndef B200SEP_DW_MINB
+#define B200SEP_DW_MINB 4
+#endif
+constexpr int DW_CH = B200SEP_DW_CH;    // channels per CTA
 constexpr int DW_SLOTS = C_HID / DW_CH; // stat partial slots per m-tile
 
 // 8 consecutive frames of one channel
@@ -243,11 +251,17 @@ __device__ __forceinline__ void dw_step_interior(const T* __restrict__ pc, const
   ov.store(po);
 }
 
-// Edge tiles: taps and frames are masked by segment-relative frame index.
-template <typename T, int D>
+// Edge tiles: taps and frames are masked by segment-relative frame index.  The 0/1 masks depend only
+// on the thread's frames (not on the channel) and are computed once per thread; the arithmetic is
+// branch-free and packed:  u = bias + sum_k m_k * (wa_k * h_k + wb_k),  out = m_centre * PReLU(u).
+// Masked-out taps read zeros or finite dead-frame values, so 0 * h is exactly 0.
+struct DwEdgeMasks { float2 ml[4], mc[4], mr[4]; };
+
+template <typename T, int D, bool A01>
 __device__ __forceinline__ void dw_step_edge(const T* __restrict__ h1, T* __restrict__ h2, const float4 pa,
-                                             const float4 pb, int tile0, int ntiles, int m_tile, int c, int t_base,
-                                             int d, int F, int lane16, float alpha, float2& s2, float2& q2) {
+                                             const float4 pb, const DwEdgeMasks& mk, int tile0, int ntiles,
+                                             int m_tile, int c, int t_base, int d, int lane16, float alpha,
+                                             float2& s2, float2& q2) {
   const Vec8<T> vc = load_group8(h1, tile0, ntiles, c, t_base);
   float ctr[8], lft[8], rgt[8];
   if (D == 0) {
@@ -266,18 +280,20 @@ __device__ __forceinline__ void dw_step_edge(const T* __restrict__ h1, T* __rest
       rgt[i] = (i + D < 8) ? ctr[(i + D) & 7] : nv[(i + D - 8) & 7];
     }
   }
+  const float2 wa0 = make_float2(pa.x, pa.x), wa1 = make_float2(pa.y, pa.y), wa2 = make_float2(pa.z, pa.z);
+  const float2 wb0 = make_float2(pb.x, pb.x), wb1 = make_float2(pb.y, pb.y), wb2 = make_float2(pb.z, pb.z);
+  const float2 bias = make_float2(pb.w, pb.w);
   float o[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int t = t_base + i;
-    float u = pb.w;
-    if (t - d >= 0 && t - d < F) u += fmaf(pa.x, lft[i], pb.x);
-    if (t < F) u += fmaf(pa.y, ctr[i], pb.y);
-    if (t + d < F) u += fmaf(pa.z, rgt[i], pb.z);
-    u = fmaxf(u, 0.f) + alpha * fminf(u, 0.f);
-    o[i] = (t < F) ? u : 0.f;
-    s2.x += o[i];
-    q2.x = fmaf(o[i], o[i], q2.x);
+  for (int i = 0; i < 8; i += 2) {
+    const int k = i >> 1;
+    float2 u = fma2(fma2(make_float2(lft[i], lft[i + 1]), wa0, wb0), mk.ml[k], bias);
+    u = fma2(fma2(make_float2(ctr[i], ctr[i + 1]), wa1, wb1), mk.mc[k], u);
+    u = fma2(fma2(make_float2(rgt[i], rgt[i + 1]), wa2, wb2), mk.mr[k], u);
+    u = mul2(prelu2<A01>(u, alpha), mk.mc[k]);
+    o[i] = u.x; o[i + 1] = u.y;
+    s2 = add2(s2, u);
+    q2 = fma2(u, u, q2);
   }
   Vec8<T> ov;
   ov.set(o);
@@ -287,7 +303,7 @@ __device__ __forceinline__ void dw_step_edge(const T* __restrict__ h1, T* __rest
 // D = compile-time dilation for the shuffle path (1, 2, 4); D = 0 selects the aligned-load path
 // (runtime dilation d, d % 8 == 0).
 template <typename T, int D, bool A01>
-__global__ void __launch_bounds__(256, 4) dwconv_kernel(const T* __restrict__ h1,  // [nt][512][128]
+__global__ void __launch_bounds__(256, B200SEP_DW_MINB) dwconv_kernel(const T* __restrict__ h1,  // [nt][512][128]
                                                         T* __restrict__ h2,        // [nt][512][128]
                                                         const float2* __restrict__ part1, int slots1,
                                                         float2* __restrict__ part2,  // [nt][DW_SLOTS]
@@ -298,19 +314,17 @@ __global__ void __launch_bounds__(256, 4) dwconv_kernel(const T* __restrict__ h1
   const int cg = blockIdx.x;
   const int m_tile = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int seg = tb.tile_seg[m_tile];
-  const int tile0 = tb.seg_tile0[seg];
-  const int ntiles = tb.seg_ntiles[seg];
-  const int F = tb.seg_frames[seg];
+  const TileInfo ti = load_tile_info(tb.tile_info + m_tile);
+  const int tile0 = ti.tile0, ntiles = ti.ntiles, F = ti.F;
   const int sub = lane >> 4;                              // which of the warp's 2 channels
   const int lane16 = lane & 15;
-  const int tile_t0 = (m_tile - tile0) * TILE_M;
+  const int tile_t0 = ti.t0;
   const int t_base = tile_t0 + lane16 * 8;               // first of this thread's 8 frames
   const int d = (D > 0) ? D : p.dilation;
 
   // every warp reduces the (tiny) partial list itself: identical results, no extra barrier
   float mean, rstd;
-  warp_seg_stats(part1, tile0, ntiles, slots1, (double)C_HID * (double)F, mean, rstd);
+  warp_seg_stats(part1, tile0, ntiles, slots1, ti.inv_count, mean, rstd);
   for (int i = tid; i < DW_CH; i += 256) {
     const int c = cg * DW_CH + i;
     const float a = p.gamma1[c] * rstd;
@@ -340,15 +354,24 @@ __global__ void __launch_bounds__(256, 4) dwconv_kernel(const T* __restrict__ h1
     const T* pn = (D > 0 && lane16 == 15) ? ptr_at(t_base + 8) : pc;
     T* po = h2 + tt_index(m_tile, C_HID, c0, lane16 * 8);
     constexpr size_t STRIDE = (size_t)16 * TILE_M;
-#pragma unroll 2
+    constexpr int kUnroll = B200SEP_DW_UNROLL;
+#pragma unroll kUnroll
     for (int it = 0; it < STEPS; ++it)
       dw_step_interior<T, D, A01>(pc + it * STRIDE, pl + it * STRIDE, pr + it * STRIDE, pp + it * STRIDE,
                                   pn + it * STRIDE, po + it * STRIDE, s_par[it * 16 + cl0][0], lane16, alpha, s2, q2);
   } else {
+    DwEdgeMasks mk;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int ta = t_base + 2 * k, tb2 = ta + 1;
+      mk.ml[k] = make_float2((ta - d >= 0 && ta - d < F) ? 1.f : 0.f, (tb2 - d >= 0 && tb2 - d < F) ? 1.f : 0.f);
+      mk.mc[k] = make_float2(ta < F ? 1.f : 0.f, tb2 < F ? 1.f : 0.f);
+      mk.mr[k] = make_float2(ta + d < F ? 1.f : 0.f, tb2 + d < F ? 1.f : 0.f);
+    }
 #pragma unroll 1
     for (int it = 0; it < STEPS; ++it)
-      dw_step_edge<T, D>(h1, h2, s_par[it * 16 + cl0][0], s_par[it * 16 + cl0][1], tile0, ntiles, m_tile, c0 + it * 16,
-                         t_base, d, F, lane16, alpha, s2, q2);
+      dw_step_edge<T, D, A01>(h1, h2, s_par[it * 16 + cl0][0], s_par[it * 16 + cl0][1], mk, tile0, ntiles, m_tile,
+                              c0 + it * 16, t_base, d, lane16, alpha, s2, q2);
   }
   float s_acc = warp_sum(s2.x + s2.y);
   float q_acc = warp_sum(q2.x + q2.y);
@@ -399,9 +422,8 @@ __global__ void __launch_bounds__(256) decoder_kernel(const T* __restrict__ mask
   const int m_tile = blockIdx.x;
   const int src = blockIdx.y;
   const int tid = threadIdx.x;
-  const int seg = tb.tile_seg[m_tile];
-  const int t0 = (m_tile - tb.seg_tile0[seg]) * TILE_M;
-  const int F = tb.seg_frames[seg];
+  const TileInfo ti = load_tile_info(tb.tile_info + m_tile);
+  const int seg = ti.seg, t0 = ti.t0, F = ti.F;
   const int T_len = tb.seg_len[seg];
   const int fp = tid & 63;  // frames 2fp, 2fp+1
   const int nq = tid >> 6;  // filters [128 nq, 128 nq + 128)

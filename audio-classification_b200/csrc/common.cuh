@@ -23,9 +23,34 @@ constexpr int C_BN = 128;    // bn_chan (B)
 constexpr int C_HID = 512;   // hid_chan (H)
 constexpr int C_SKIP = 128;  // skip_chan (Sc)
 constexpr float GLN_EPS = 1e-8f;
+static_assert(C_ENC == C_HID, "one inverse element count per segment serves every gLN (all normalise 512 channels)");
+
+// Everything a kernel needs to know about an m-tile, in one 32-byte record (one load, no dependent
+// tile -> segment -> fields chain).
+struct __align__(16) TileInfo {
+  int32_t seg;      // segment index
+  int32_t t0;       // first segment-relative frame of the tile
+  int32_t F;        // valid frames of the segment
+  int32_t tile0;    // first m-tile of the segment
+  int32_t ntiles;   // m-tiles of the segment
+  int32_t pad;
+  double inv_count; // 1 / (512 * F)
+};
+static_assert(sizeof(TileInfo) == 32, "TileInfo must be 32 bytes");
+
+__device__ __forceinline__ TileInfo load_tile_info(const TileInfo* p) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  TileInfo ti;
+  ti.seg = (int)a.x; ti.t0 = (int)a.y; ti.F = (int)a.z; ti.tile0 = (int)a.w;
+  ti.ntiles = (int)b.x; ti.pad = 0;
+  ti.inv_count = __hiloint2double((int)b.w, (int)b.z);
+  return ti;
+}
 
 // Per-batch tables (device pointers), built on the host for every call.
 struct Tables {
+  const TileInfo* tile_info;   // [n_tiles]
   const int64_t* seg_in_off;   // [n_seg] sample offset of segment in d_mix
   const int64_t* seg_out_off;  // [n_seg] float offset of segment in d_out (= n_src * in_off)
   const int32_t* seg_len;      // [n_seg] T_i samples
@@ -33,6 +58,7 @@ struct Tables {
   const int32_t* seg_tile0;    // [n_seg] first m-tile of the segment
   const int32_t* seg_ntiles;   // [n_seg] ceil(F_i / 128)
   const int32_t* tile_seg;     // [n_tiles] m-tile -> segment
+  const double* seg_inv_count; // [n_seg] 1 / (512 * F_i): every gLN here normalises 512 channels
   int32_t n_seg;
   int32_t n_tiles;
 };
@@ -89,9 +115,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 // part[(tile0 + i) * slots + s] = (sum, sum of squares) over the valid frames of that slot.
 // Must be called by all 32 lanes of a warp; every lane (and every warp that repeats the call)
 // gets bit-identical results: fixed traversal order, fp64 accumulation, xor-butterfly.
-// count = C * F_i elements.  var = E[x^2] - mean^2 in fp64 (biased, like asteroid GlobLN).
+// inv_count = 1 / (C * F_i) (host-computed).  var = E[x^2] - mean^2 in fp64 (biased, like asteroid
+// GlobLN); the final reciprocal square root is taken in fp32 (rsqrtf + one Newton step).
 __device__ __forceinline__ void warp_seg_stats(const float2* __restrict__ part, int tile0,
-                                               int ntiles, int slots, double count, float& mean,
+                                               int ntiles, int slots, double inv_count, float& mean,
                                                float& rstd) {
   const int lane = threadIdx.x & 31;
   const int n = ntiles * slots;
@@ -104,11 +131,14 @@ __device__ __forceinline__ void warp_seg_stats(const float2* __restrict__ part, 
   }
   s = warp_sum(s);
   q = warp_sum(q);
-  const double m = s / count;
-  double var = q / count - m * m;
+  const double m = s * inv_count;
+  double var = fma(-m, m, q * inv_count);
   if (var < 0.0) var = 0.0;
   mean = (float)m;
-  rstd = (float)(1.0 / sqrt(var + (double)GLN_EPS));
+  const float ve = (float)var + GLN_EPS;
+  float y = rsqrtf(ve);
+  y = y * (1.5f - 0.5f * ve * y * y);  // Newton step: ~0.5 ulp
+  rstd = y;
 }
 
 }  // namespace b200sep

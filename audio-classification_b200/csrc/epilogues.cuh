@@ -15,17 +15,20 @@ namespace b200sep {
 
 struct EpiState {
   float mean, rstd;  // gLN statistics of the INPUT activation of this GEMM (if folded)
+  double inv_count;  // 1 / (512 * F) of the tile's segment
   float s, q;        // running (sum, sumsq) of this thread's outputs (if the epilogue emits stats)
   int F, t0;         // segment frame count, first segment-relative frame of the tile
 };
 
 __device__ __forceinline__ void epi_tile_ctx(EpiState& st, int m_tile, const Tables& tb, int& seg,
                                              int& tile0, int& ntiles) {
-  seg = tb.tile_seg[m_tile];
-  tile0 = tb.seg_tile0[seg];
-  ntiles = tb.seg_ntiles[seg];
-  st.F = tb.seg_frames[seg];
-  st.t0 = (m_tile - tile0) * TILE_M;
+  const TileInfo ti = load_tile_info(tb.tile_info + m_tile);
+  seg = ti.seg;
+  tile0 = ti.tile0;
+  ntiles = ti.ntiles;
+  st.F = ti.F;
+  st.inv_count = ti.inv_count;
+  st.t0 = ti.t0;
   st.s = 0.f;
   st.q = 0.f;
 }
@@ -61,7 +64,7 @@ struct EpiBottleneck {
   __device__ __forceinline__ void tile_begin(EpiState& st, int m_tile, const Tables& tb) const {
     int seg, tile0, ntiles;
     epi_tile_ctx(st, m_tile, tb, seg, tile0, ntiles);
-    warp_seg_stats(part_in, tile0, ntiles, slots_in, (double)C_ENC * (double)st.F, st.mean, st.rstd);
+    warp_seg_stats(part_in, tile0, ntiles, slots_in, st.inv_count, st.mean, st.rstd);
   }
   template <int W>
   __device__ __forceinline__ void prefetch(int, int, int, float (&)[W]) const {}
@@ -161,7 +164,7 @@ struct EpiResSkip {
   __device__ __forceinline__ void tile_begin(EpiState& st, int m_tile, const Tables& tb) const {
     int seg, tile0, ntiles;
     epi_tile_ctx(st, m_tile, tb, seg, tile0, ntiles);
-    warp_seg_stats(part_in, tile0, ntiles, slots_in, (double)C_HID * (double)st.F, st.mean, st.rstd);
+    warp_seg_stats(part_in, tile0, ntiles, slots_in, st.inv_count, st.mean, st.rstd);
   }
   // old x / skip values: independent loads, consecutive lanes (frames) hit consecutive addresses
   template <int W>

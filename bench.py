@@ -152,8 +152,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: 64 synthetic 3-speaker overlap segments U[0.2,4.0] s, 8 kHz, ConvTasNet n_src=3 random-init",
-                   "segments": len(lens), "sample_rate": SR, "n_src": N_SRC},
+        "config": {"workload": "configs[1]: 64 synthetic 3-speaker overlap segments U[0.2,4.0] s per GPU, 8 kHz, ConvTasNet n_src=3 random-init",
+                   "segments_per_gpu": len(lens), "sample_rate": SR, "n_src": N_SRC, "precision": "fp32 (torch CPU)",
+                   "parallelism": "rank 0 only: the reference is a single-process CPU loop"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthr, "kind": "port", "sample": sample,
                          "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
