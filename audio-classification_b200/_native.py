@@ -26,6 +26,7 @@ EXPORTS = [
     "b200sep_workspace_bytes", "b200sep_separate_batch", "b200sep_pit_workspace_bytes",
     "b200sep_pit_sisdr_batch", "b200sep_debug_gemm", "b200sep_debug_set_stop",
     "b200sep_debug_layout", "b200sep_profile_enable", "b200sep_profile_read",
+    "b200sep_debug_abort_flag", "b200sep_pipeline",
 ]
 
 
@@ -98,6 +99,10 @@ def lib() -> C.CDLL:
         L.b200sep_profile_enable.argtypes = [vp, C.c_int]
         L.b200sep_profile_read.restype = C.c_int
         L.b200sep_profile_read.argtypes = [vp, C.POINTER(C.c_float), i32, i32p]
+        L.b200sep_debug_abort_flag.restype = C.c_int
+        L.b200sep_debug_abort_flag.argtypes = [i32p, i32]
+        L.b200sep_pipeline.restype = C.c_int
+        L.b200sep_pipeline.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -109,6 +114,13 @@ def last_error() -> str:
 def check(rc: int, what: str) -> None:
     if rc != 0:
         raise RuntimeError(f"{what}: {last_error()}")
+
+
+def abort_flag(reset: bool = True) -> int:
+    """1 when a bounded device-side wait of the fused kernels ran out (synchronises the device)."""
+    v = C.c_int32(0)
+    check(lib().b200sep_debug_abort_flag(C.byref(v), 1 if reset else 0), "abort flag")
+    return int(v.value)
 
 
 def i32_array(vals):

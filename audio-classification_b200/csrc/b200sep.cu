@@ -22,6 +22,7 @@
 #include "epilogues.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "fused_block.cuh"
 #include "pit.cuh"
 
 using namespace b200sep;
@@ -154,6 +155,7 @@ struct b200sep_model {
   int n_sm = 148;
   int n_layers = 0;
   bool half = true, use_tc = true;
+  bool fused = true;  // fp16 tensor-core mode: two fused kernels per TCN block (fused_block.cuh)
   std::vector<void*> allocs;
   float *enc_w = nullptr, *dec_w = nullptr;
   void* bn_w = nullptr;
@@ -275,7 +277,7 @@ struct Layout {
   int n_seg = 0, n_tiles = 0;
   size_t tables_bytes = 0;
   // byte offsets inside the workspace
-  size_t o_tables, o_enc, o_x, o_xa, o_skip, o_skipa, o_h1, o_h2, o_masked, o_p0, o_p1, o_p2, total;
+  size_t o_tables, o_enc, o_x, o_xa, o_skip, o_skipa, o_h1, o_h2, o_g, o_masked, o_p0, o_p1, o_p2, total;
   // offsets inside the table block
   size_t t_info, t_in_off, t_out_off, t_inv, t_len, t_frames, t_tile0, t_ntiles, t_tile_seg;
 };
@@ -316,10 +318,11 @@ static int compute_layout(const b200sep_config& c, bool half, const int32_t* len
   lo->o_skipa = take(rows * C_SKIP * es);
   lo->o_h1 = take(rows * C_HID * es);
   lo->o_h2 = take(rows * C_HID * es);
+  lo->o_g = take(rows * 2 * C_BN * 2);  // raw [res | skip] GEMM output of the fused path (fp16)
   lo->o_masked = take(rows * (size_t)c.n_src * C_ENC * es);
   lo->o_p0 = take((size_t)tiles * 2 * 8);
   lo->o_p1 = take((size_t)tiles * 8 * 8);
-  lo->o_p2 = take((size_t)tiles * 8 * 8);
+  lo->o_p2 = take((size_t)tiles * 16 * 8);
   lo->total = o;
   return 0;
 }
@@ -392,6 +395,50 @@ static int run_gemm(const b200sep_model* m, const T* A, const CUtensorMap* tmA, 
   return launch_simt<T, K, Epi>(A, B, n_mtiles, N, epi, tb, st);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fused TCN block (fp16 tensor-core mode): launches of fused_block.cuh
+// ------------------------------------------------------------------------------------------------
+template <int BN, int D, bool A01>
+static int launch_dw_rs(const b200sep_model* m, const CUtensorMap& tmb, const __half* h1, __half* g, const float2* p1,
+                        int slots1, float2* p2, const DwParams& p, const Tables& tb, cudaStream_t st) {
+  using Cfg = fb::KaCfg<BN>;
+  auto kern = fb::dw_rs_kernel<BN, D, A01>;
+  static bool configured = false;  // per template instantiation
+  if (!configured) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int grid = std::min(tb.n_tiles, m->n_sm);
+  CK(launch_k(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmb, h1, g, p1, slots1, p2, p, tb));
+  return 0;
+}
+template <int BN, bool A01>
+static int launch_dw_rs_d(const b200sep_model* m, const CUtensorMap& tmb, const __half* h1, __half* g,
+                          const float2* p1, int slots1, float2* p2, const DwParams& p, const Tables& tb,
+                          cudaStream_t st) {
+  switch (p.dilation) {
+    case 1: return launch_dw_rs<BN, 1, A01>(m, tmb, h1, g, p1, slots1, p2, p, tb, st);
+    case 2: return launch_dw_rs<BN, 2, A01>(m, tmb, h1, g, p1, slots1, p2, p, tb, st);
+    case 4: return launch_dw_rs<BN, 4, A01>(m, tmb, h1, g, p1, slots1, p2, p, tb, st);
+    default: return launch_dw_rs<BN, 0, A01>(m, tmb, h1, g, p1, slots1, p2, p, tb, st);
+  }
+}
+template <bool A01>
+static int launch_apply_in(const b200sep_model* m, const CUtensorMap& tmw, const fb::ApplyParams& ap,
+                           const EpiIn<__half, A01>& epi, const Tables& tb, cudaStream_t st) {
+  using Cfg = fb::KbCfg;
+  auto kern = fb::apply_in_kernel<A01>;
+  static bool configured = false;  // per template instantiation
+  if (!configured) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int grid = std::min(tb.n_tiles, m->n_sm);
+  CK(launch_k(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmw, ap, epi, tb));
+  return 0;
+}
+
 template <typename T, int L>
 static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const float* d_mix, float* d_out,
                    uint8_t* ws, cudaStream_t st) {
@@ -404,6 +451,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
   T* skipa = reinterpret_cast<T*>(ws + lo.o_skipa);
   T* h1 = reinterpret_cast<T*>(ws + lo.o_h1);
   T* h2 = reinterpret_cast<T*>(ws + lo.o_h2);
+  __half* gbuf = reinterpret_cast<__half*>(ws + lo.o_g);
   T* masked = reinterpret_cast<T*>(ws + lo.o_masked);
   float2* p0 = reinterpret_cast<float2*>(ws + lo.o_p0);
   float2* p1 = reinterpret_cast<float2*>(ws + lo.o_p1);
@@ -450,7 +498,57 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
   if (stop()) return 0;
 
   // 3. TCN blocks
-  for (int i = 0; i < m->n_layers; ++i) {
+  bool fused_done = false;
+  if constexpr (kHalf) {
+    if (m->use_tc && m->fused) {
+      // two launches per block: K_B (apply previous G + in-conv GEMM -> h1), K_A (depthwise + [res|skip]
+      // GEMM -> raw G); after the last block the skip sum is completed and PReLU'd for the mask GEMM
+      constexpr int kSlots1 = fb::KbCfg::SLOTS, kSlots2 = fb::KaCfg<256>::SLOTS;
+      for (int i = 0; i < m->n_layers; ++i) {
+        BlockW& b = m->blocks[i];
+        const bool last = (i == m->n_layers - 1);
+        fb::ApplyParams ap{};
+        ap.x = x;
+        ap.skip = skip;
+        if (i > 0) {
+          ap.g = gbuf;
+          ap.part2 = p2;
+          ap.slots2 = kSlots2;
+          ap.rs = m->blocks[i - 1].rs;
+          ap.cb = m->blocks[i - 1].cb;
+          ap.first = (i == 1) ? 1 : 0;
+        }
+        int rc;
+        if (b.a1 >= 0.f && b.a1 <= 1.f) {
+          EpiIn<__half, true> e{b.b_in, b.a1, h1, p1};
+          rc = launch_apply_in<true>(m, b.tm_in, ap, e, tb, st);
+        } else {
+          EpiIn<__half, false> e{b.b_in, b.a1, h1, p1};
+          rc = launch_apply_in<false>(m, b.tm_in, ap, e, tb, st);
+        }
+        if (rc) return 1;
+        if (stop()) return 0;
+        DwParams p{b.g1, b.be1, b.wd, b.bd, b.a2, b.dilation};
+        const bool a01 = b.a2 >= 0.f && b.a2 <= 1.f;
+        if (!last) {
+          rc = a01 ? launch_dw_rs_d<256, true>(m, b.tm_rs, h1, gbuf, p1, kSlots1, p2, p, tb, st)
+                   : launch_dw_rs_d<256, false>(m, b.tm_rs, h1, gbuf, p1, kSlots1, p2, p, tb, st);
+        } else {
+          rc = a01 ? launch_dw_rs_d<128, true>(m, b.tm_rs, h1, gbuf, p1, kSlots1, p2, p, tb, st)
+                   : launch_dw_rs_d<128, false>(m, b.tm_rs, h1, gbuf, p1, kSlots1, p2, p, tb, st);
+        }
+        if (rc) return 1;
+        if (stop()) return 0;
+      }
+      const BlockW& lb = m->blocks[m->n_layers - 1];
+      CK(launch_k(fb::final_skip_kernel, dim3(nt), dim3(256), 0, st, (const __half*)gbuf, (const float2*)p2, kSlots2,
+                  (const float*)lb.rs, (const float*)lb.cb, (const float*)skip, skipa, m->alpha_mask,
+                  m->n_layers == 1 ? 1 : 0, tb));
+      if (stop()) return 0;
+      fused_done = true;
+    }
+  }
+  for (int i = 0; i < m->n_layers && !fused_done; ++i) {
     BlockW& b = m->blocks[i];
     const bool first = (i == 0), last = (i == m->n_layers - 1);
     {
@@ -568,6 +666,7 @@ int b200sep_model_create(const b200sep_config* cfg, const b200sep_weights* w, in
   m->n_layers = c.n_blocks * c.n_repeats;
   m->half = (c.precision != B200SEP_PREC_FP32);
   m->use_tc = (c.precision == B200SEP_PREC_FP16_TC);
+  if (const char* f = getenv("B200SEP_FUSED")) m->fused = atoi(f) != 0;
   const char* dbg = getenv("B200SEP_DEBUG_STOP_AFTER");
   if (dbg) m->debug_stop_after = atoi(dbg);
   int rc = m->half ? build_weights<__half>(m, w) : build_weights<float>(m, w);
@@ -604,6 +703,24 @@ int b200sep_debug_set_stop(b200sep_model* m, int stop_after) {
   return 0;
 }
 
+// 1 when a bounded device-side wait of the fused kernels ran out (a protocol bug; results are invalid).
+// Synchronises the device.  `reset` != 0 clears the flag afterwards.
+int b200sep_debug_abort_flag(int32_t* out, int32_t reset) {
+  if (!out) return fail("null argument");
+  int v = 0;
+  CK(cudaMemcpyFromSymbol(&v, b200sep::g_abort, sizeof(int)));
+  *out = v;
+  if (reset && v) {
+    const int z = 0;
+    CK(cudaMemcpyToSymbol(b200sep::g_abort, &z, sizeof(int)));
+  }
+  return 0;
+}
+
+// Launch sequence the model runs: 0 = unfused (encoder, bottleneck, 3 kernels per block, mask, decoder),
+// 1 = fused (encoder, bottleneck, 2 kernels per block, final skip, mask, decoder).
+int b200sep_pipeline(const b200sep_model* m) { return (m && m->half && m->use_tc && m->fused) ? 1 : 0; }
+
 int b200sep_profile_enable(b200sep_model* m, int on) {
   if (!m) return fail("null model");
   m->prof_on = on != 0;
@@ -632,6 +749,7 @@ int b200sep_debug_layout(const b200sep_model* m, const int32_t* lens, int32_t n_
   if (compute_layout(m->cfg, m->half, lens, n_seg, &lo)) return 1;
   out[0] = lo.o_enc; out[1] = lo.o_x; out[2] = lo.o_xa; out[3] = lo.o_skip; out[4] = lo.o_skipa;
   out[5] = lo.o_h1; out[6] = lo.o_h2; out[7] = lo.o_masked; out[8] = (uint64_t)lo.n_tiles; out[9] = lo.total;
+  out[10] = lo.o_g;
   return 0;
 }
 

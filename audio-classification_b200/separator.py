@@ -174,6 +174,8 @@ class SeparationEngine:
                 d_out = self.separate_device(d_mix, lens)
                 self._pinned_out[:total * S].copy_(d_out, non_blocking=True)
                 torch.cuda.current_stream(dev).synchronize()
+                if nat.abort_flag():
+                    raise RuntimeError("b200sep: a device-side pipeline wait timed out; results are invalid")
             hout = self._pinned_out.numpy()
             res: List[List[np.ndarray]] = []
             o = 0

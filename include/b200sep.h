@@ -179,9 +179,18 @@ int b200sep_profile_read(b200sep_model* m, float* ms_out, int32_t cap, int32_t* 
 
 /* Test hooks: stop the forward after the k-th kernel launch (0 = run everything), and report the
  * byte offsets of the intermediate activations inside the workspace:
- * out[0..9] = enc, x, xa, skip, skipa, h1, h2, masked, n_tiles, total. */
+ * out[0..10] = enc, x, xa, skip, skipa, h1, h2, masked, n_tiles, total, g. */
 int b200sep_debug_set_stop(b200sep_model* m, int stop_after);
 int b200sep_debug_layout(const b200sep_model* m, const int32_t* lens, int32_t n_seg, uint64_t* out);
+
+/* 1 when a bounded device-side wait of the fused kernels ran out (protocol bug: results invalid);
+ * synchronises the device; `reset` != 0 clears the flag. */
+int b200sep_debug_abort_flag(int32_t* out, int32_t reset);
+
+/* Launch sequence of the model: 0 = encoder, bottleneck GEMM, per TCN block (in-conv GEMM, depthwise
+ * conv, res/skip GEMM), mask GEMM, decoder; 1 = encoder, bottleneck GEMM, per TCN block (apply + in-conv
+ * GEMM, depthwise + res/skip GEMM), final skip, mask GEMM, decoder (fused fp16 tensor-core mode). */
+int b200sep_pipeline(const b200sep_model* m);
 
 #ifdef __cplusplus
 }

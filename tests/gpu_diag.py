@@ -92,9 +92,9 @@ def stage_check(precision: str):
     lens = [3000, 1700]
     mixes = [synth.make_mixture(7 + i, n, 3)[0] for i, n in enumerate(lens)]
     eng = b200sep.SeparationEngine(sd, args, 0, precision)
-    lay = (C.c_uint64 * 10)()
+    lay = (C.c_uint64 * 16)()
     nat.check(nat.lib().b200sep_debug_layout(eng._handle, nat.i32_array(lens), len(lens), lay), "layout")
-    o_enc, o_x, o_xa, o_skip, o_skipa, o_h1, o_h2, o_masked, n_tiles, total = [int(v) for v in lay]
+    o_enc, o_x, o_xa, o_skip, o_skipa, o_h1, o_h2, o_masked, n_tiles, total = [int(v) for v in lay][:10]
     half = precision != "fp32"
     es = 2 if half else 4
     tdt = torch.float16 if half else torch.float32
@@ -123,6 +123,16 @@ def stage_check(precision: str):
 
     run(1); report("enc", o_enc, 512, tdt, es, "enc")
     run(2); report("x(bottlenk)", o_x, 128, torch.float32, 4, "x_bn")
+    if nat.lib().b200sep_pipeline(eng._handle) == 1:
+        # fused pipeline: launch 3+2i = K_B(i) (applies block i-1, writes h1[i]), 4+2i = K_A(i) (raw G)
+        run(3); report("h1[0]", o_h1, 512, tdt, es, "h1_0"); print("   abort flag:", nat.abort_flag())
+        run(5); report("h1[1]", o_h1, 512, tdt, es, "h1_1"); report("x[0]", o_x, 128, torch.float32, 4, "x_0")
+        report("skip[0]", o_skip, 128, torch.float32, 4, "skip_0"); print("   abort flag:", nat.abort_flag())
+        run(7); report("x[1]", o_x, 128, torch.float32, 4, "x_1"); report("skip[1]", o_skip, 128, torch.float32, 4, "skip_1")
+        print("   abort flag:", nat.abort_flag())
+        nat.lib().b200sep_debug_set_stop(eng._handle, 0)
+        eng.close()
+        return
     for i in range(2):
         run(3 + 3 * i); report(f"h1[{i}]", o_h1, 512, tdt, es, f"h1_{i}")
         run(4 + 3 * i); report(f"h2[{i}]", o_h2, 512, tdt, es, f"h2_{i}")
