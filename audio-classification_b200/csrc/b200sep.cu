@@ -73,7 +73,8 @@ static EncodeTiledFn get_encode_fn() {
 // 2-D fp16 tensor map: inner dimension `inner` elements (contiguous), `outer` rows of pitch
 // `pitch_bytes`; box = box_inner x box_outer; 128-byte swizzle (box_inner * 2 bytes must be 128).
 static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
-                        uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer) {
+                        uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
+                        CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[2] = {inner, outer};
@@ -81,7 +82,7 @@ static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint6
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
@@ -89,6 +90,11 @@ static int make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint6
 // activations [n_tiles][C][128] fp16 as a 2-D tensor (128 x n_tiles*C), box 64 x 64
 static int make_tmap_act(CUtensorMap* tm, const void* base, int n_tiles, int C) {
   return make_tmap_2d(tm, base, TILE_M, (uint64_t)n_tiles * C, TILE_M * 2, 64, 64);
+}
+// raw (unswizzled) view of an activation buffer for the depthwise producers: box = `frames` x 64 channels
+static int make_tmap_act_raw(CUtensorMap* tm, const void* base, int n_tiles, int C, int frames) {
+  return make_tmap_2d(tm, base, TILE_M, (uint64_t)n_tiles * C, TILE_M * 2, (uint32_t)frames, 64,
+                      CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 // weights [N][K] fp16, box 64(k) x bn rows
 static int make_tmap_w(CUtensorMap* tm, const void* base, int N, int K, int bn) {
@@ -147,6 +153,8 @@ struct BlockW {
   int dilation = 1;
   int n_out = 256;
   CUtensorMap tm_in, tm_rs;
+  float4 *dw_t0 = nullptr, *dw_t1 = nullptr;  // folded depthwise tap tables (fused_block.cuh DwTab)
+  float* dw_cb = nullptr;
 };
 
 struct b200sep_model {
@@ -165,6 +173,7 @@ struct b200sep_model {
   float* mask_b = nullptr;
   float alpha_mask = 0.25f;
   CUtensorMap tm_bn, tm_mask;
+  float *skip_rs = nullptr, *skip_cb = nullptr;  // [n_layers][128] skip halves of rs / cb (skip_merge_kernel)
   Staging staging;
   std::mutex mu;
   int debug_stop_after = 0;  // 0 = run everything; k = stop after k-th launch (tests)
@@ -199,7 +208,7 @@ static int dev_upload_f(b200sep_model* m, const std::vector<float>& v, float** o
 template <typename T>
 static int fold_and_upload(b200sep_model* m, const std::vector<const float*>& Ws, const std::vector<const float*>& bs,
                            int rows_each, int K, const float* gamma, const float* beta, void** d_w, float** d_rs,
-                           float** d_cb) {
+                           float** d_cb, std::vector<float>* h_rs = nullptr, std::vector<float>* h_cb = nullptr) {
   const int N = rows_each * (int)Ws.size();
   std::vector<T> w((size_t)N * K);
   std::vector<float> rs(N), cb(N);
@@ -220,6 +229,8 @@ static int fold_and_upload(b200sep_model* m, const std::vector<const float*>& Ws
   if (dev_upload(m, w.data(), w.size() * sizeof(T), d_w)) return 1;
   if (dev_upload_f(m, rs, d_rs)) return 1;
   if (dev_upload_f(m, cb, d_cb)) return 1;
+  if (h_rs) *h_rs = rs;
+  if (h_cb) *h_cb = cb;
   return 0;
 }
 
@@ -240,6 +251,7 @@ static int build_weights(b200sep_model* m, const b200sep_weights* w) {
                          &m->bn_rs, &m->bn_cb))
     return 1;
   m->blocks.resize(m->n_layers);
+  std::vector<float> skip_rs, skip_cb;
   for (int i = 0; i < m->n_layers; ++i) {
     BlockW& b = m->blocks[i];
     const bool last = (i == m->n_layers - 1);
@@ -252,18 +264,40 @@ static int build_weights(b200sep_model* m, const b200sep_weights* w) {
     if (dev_upload(m, w->dw_weight[i], C_HID * 3 * 4, reinterpret_cast<void**>(&b.wd))) return 1;
     if (dev_upload(m, w->dw_bias[i], C_HID * 4, reinterpret_cast<void**>(&b.bd))) return 1;
     b.a2 = w->prelu2[i][0];
+    {  // folded depthwise tap tables (fp64 products, rounded once)
+      std::vector<float> t0(C_HID * 4), t1(C_HID * 4), tcb(C_HID);
+      for (int ch = 0; ch < C_HID; ++ch) {
+        const double g = w->norm1_gamma[i][ch], be = w->norm1_beta[i][ch], bias = w->dw_bias[i][ch];
+        const double w0 = w->dw_weight[i][ch * 3 + 0], w1 = w->dw_weight[i][ch * 3 + 1], w2 = w->dw_weight[i][ch * 3 + 2];
+        t0[ch * 4 + 0] = (float)(w0 * g); t0[ch * 4 + 1] = (float)(w1 * g); t0[ch * 4 + 2] = (float)(w2 * g);
+        t0[ch * 4 + 3] = (float)((w0 + w1 + w2) * g);
+        t1[ch * 4 + 0] = (float)(w0 * be); t1[ch * 4 + 1] = (float)(w1 * be); t1[ch * 4 + 2] = (float)(w2 * be);
+        t1[ch * 4 + 3] = (float)bias;
+        tcb[ch] = (float)((w0 + w1 + w2) * be + bias);
+      }
+      if (dev_upload_f(m, t0, reinterpret_cast<float**>(&b.dw_t0))) return 1;
+      if (dev_upload_f(m, t1, reinterpret_cast<float**>(&b.dw_t1))) return 1;
+      if (dev_upload_f(m, tcb, &b.dw_cb)) return 1;
+    }
+    std::vector<float> h_rs, h_cb;
     if (!last) {
       b.n_out = 2 * C_BN;
       if (fold_and_upload<T>(m, {w->res_weight[i], w->skip_weight[i]}, {w->res_bias[i], w->skip_bias[i]}, C_BN,
-                             C_HID, w->norm2_gamma[i], w->norm2_beta[i], &b.w_rs, &b.rs, &b.cb))
+                             C_HID, w->norm2_gamma[i], w->norm2_beta[i], &b.w_rs, &b.rs, &b.cb, &h_rs, &h_cb))
         return 1;
+      skip_rs.insert(skip_rs.end(), h_rs.begin() + C_BN, h_rs.end());
+      skip_cb.insert(skip_cb.end(), h_cb.begin() + C_BN, h_cb.end());
     } else {  // the last block's residual output is never read: skip half only
       b.n_out = C_SKIP;
       if (fold_and_upload<T>(m, {w->skip_weight[i]}, {w->skip_bias[i]}, C_SKIP, C_HID, w->norm2_gamma[i],
-                             w->norm2_beta[i], &b.w_rs, &b.rs, &b.cb))
+                             w->norm2_beta[i], &b.w_rs, &b.rs, &b.cb, &h_rs, &h_cb))
         return 1;
+      skip_rs.insert(skip_rs.end(), h_rs.begin(), h_rs.end());
+      skip_cb.insert(skip_cb.end(), h_cb.begin(), h_cb.end());
     }
   }
+  if (dev_upload_f(m, skip_rs, &m->skip_rs)) return 1;
+  if (dev_upload_f(m, skip_cb, &m->skip_cb)) return 1;
   m->alpha_mask = w->mask_prelu[0];
   if (upload_cvt<T>(m, w->mask_weight, (size_t)S * C_ENC * C_SKIP, &m->mask_w)) return 1;
   if (dev_upload(m, w->mask_bias, (size_t)S * C_ENC * 4, reinterpret_cast<void**>(&m->mask_b))) return 1;
@@ -277,12 +311,13 @@ struct Layout {
   int n_seg = 0, n_tiles = 0;
   size_t tables_bytes = 0;
   // byte offsets inside the workspace
-  size_t o_tables, o_enc, o_x, o_xa, o_skip, o_skipa, o_h1, o_h2, o_g, o_masked, o_p0, o_p1, o_p2, total;
+  size_t o_tables, o_enc, o_x, o_xa, o_skip, o_skipa, o_h1, o_h2, o_g, o_stash, o_masked, o_p0, o_p1, o_p2, total;
+  size_t stash_stride = 0, part2_stride = 0;  // elements per block slot
   // offsets inside the table block
   size_t t_info, t_in_off, t_out_off, t_inv, t_len, t_frames, t_tile0, t_ntiles, t_tile_seg;
 };
 
-static int compute_layout(const b200sep_config& c, bool half, const int32_t* lens, int n_seg, Layout* lo) {
+static int compute_layout(const b200sep_config& c, bool half, bool fused, const int32_t* lens, int n_seg, Layout* lo) {
   if (n_seg <= 0 || !lens) return fail("empty batch");
   long long tiles = 0;
   for (int i = 0; i < n_seg; ++i) {
@@ -313,16 +348,22 @@ static int compute_layout(const b200sep_config& c, bool half, const int32_t* len
   lo->o_tables = take(lo->tables_bytes);
   lo->o_enc = take(rows * C_ENC * es);
   lo->o_x = take(rows * C_BN * 4);
-  lo->o_xa = half ? take(rows * C_BN * es) : lo->o_x;
-  lo->o_skip = take(rows * C_SKIP * 4);
+  lo->o_xa = (half && !fused) ? take(rows * C_BN * es) : lo->o_x;
+  lo->o_skip = take(fused ? 0 : rows * C_SKIP * 4);
   lo->o_skipa = take(rows * C_SKIP * es);
   lo->o_h1 = take(rows * C_HID * es);
-  lo->o_h2 = take(rows * C_HID * es);
-  lo->o_g = take(rows * 2 * C_BN * 2);  // raw [res | skip] GEMM output of the fused path (fp16)
+  lo->o_h2 = take(fused ? 0 : rows * C_HID * es);
+  // fused path: raw residual-conv output (fp16) and one raw skip-conv stash slot per block; the unfused
+  // path's h2 and skip accumulators are not needed then
+  const int n_layers = c.n_blocks * c.n_repeats;
+  lo->o_g = take(fused ? rows * C_BN * 2 : 0);
+  lo->stash_stride = rows * C_SKIP;
+  lo->o_stash = take(fused ? (size_t)n_layers * lo->stash_stride * 2 : 0);
   lo->o_masked = take(rows * (size_t)c.n_src * C_ENC * es);
   lo->o_p0 = take((size_t)tiles * 2 * 8);
   lo->o_p1 = take((size_t)tiles * 8 * 8);
-  lo->o_p2 = take((size_t)tiles * 16 * 8);
+  lo->part2_stride = (size_t)tiles;
+  lo->o_p2 = take(fused ? (size_t)tiles * n_layers * 8 : (size_t)tiles * 8 * 8);
   lo->total = o;
   return 0;
 }
@@ -399,9 +440,18 @@ static int run_gemm(const b200sep_model* m, const T* A, const CUtensorMap* tmA, 
 // ------------------------------------------------------------------------------------------------
 // fused TCN block (fp16 tensor-core mode): launches of fused_block.cuh
 // ------------------------------------------------------------------------------------------------
+struct KaArgs {
+  const CUtensorMap* tm_b;
+  const CUtensorMap* tm_hc;
+  const CUtensorMap* tm_hh;
+  __half* g_res;
+  __half* g_skip;
+  const float2* p1;
+  float2* p2;
+  fb::DwTab tab;
+};
 template <int BN, int D, bool A01>
-static int launch_dw_rs(const b200sep_model* m, const CUtensorMap& tmb, const __half* h1, __half* g, const float2* p1,
-                        int slots1, float2* p2, const DwParams& p, const Tables& tb, cudaStream_t st) {
+static int launch_dw_rs(const b200sep_model* m, const KaArgs& a, const Tables& tb, cudaStream_t st) {
   using Cfg = fb::KaCfg<BN>;
   auto kern = fb::dw_rs_kernel<BN, D, A01>;
   static bool configured = false;  // per template instantiation
@@ -410,18 +460,17 @@ static int launch_dw_rs(const b200sep_model* m, const CUtensorMap& tmb, const __
     configured = true;
   }
   const int grid = std::min(tb.n_tiles, m->n_sm);
-  CK(launch_k(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmb, h1, g, p1, slots1, p2, p, tb));
+  CK(launch_k(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, *a.tm_b, *a.tm_hc, *a.tm_hh, a.g_res, a.g_skip,
+              a.p1, a.p2, a.tab, tb));
   return 0;
 }
 template <int BN, bool A01>
-static int launch_dw_rs_d(const b200sep_model* m, const CUtensorMap& tmb, const __half* h1, __half* g,
-                          const float2* p1, int slots1, float2* p2, const DwParams& p, const Tables& tb,
-                          cudaStream_t st) {
-  switch (p.dilation) {
-    case 1: return launch_dw_rs<BN, 1, A01>(m, tmb, h1, g, p1, slots1, p2, p, tb, st);
-    case 2: return launch_dw_rs<BN, 2, A01>(m, tmb, h1, g, p1, slots1, p2, p, tb, st);
-    case 4: return launch_dw_rs<BN, 4, A01>(m, tmb, h1, g, p1, slots1, p2, p, tb, st);
-    default: return launch_dw_rs<BN, 0, A01>(m, tmb, h1, g, p1, slots1, p2, p, tb, st);
+static int launch_dw_rs_d(const b200sep_model* m, const KaArgs& a, const Tables& tb, cudaStream_t st) {
+  switch (a.tab.dilation) {
+    case 1: return launch_dw_rs<BN, 1, A01>(m, a, tb, st);
+    case 2: return launch_dw_rs<BN, 2, A01>(m, a, tb, st);
+    case 4: return launch_dw_rs<BN, 4, A01>(m, a, tb, st);
+    default: return launch_dw_rs<BN, 0, A01>(m, a, tb, st);
   }
 }
 template <bool A01>
@@ -457,7 +506,8 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
   float2* p1 = reinterpret_cast<float2*>(ws + lo.o_p1);
   float2* p2 = reinterpret_cast<float2*>(ws + lo.o_p2);
   constexpr bool kHalf = std::is_same<T, __half>::value;
-  T* xa_or_null = kHalf ? xa : nullptr;
+  const bool fused_mode = kHalf && m->use_tc && m->fused;
+  T* xa_or_null = (kHalf && !fused_mode) ? xa : nullptr;
   const T* a_x = kHalf ? xa : reinterpret_cast<const T*>(x);  // A operand of the in-conv
 
   CUtensorMap tm_enc, tm_xa, tm_h2, tm_skipa;
@@ -500,23 +550,25 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
   // 3. TCN blocks
   bool fused_done = false;
   if constexpr (kHalf) {
-    if (m->use_tc && m->fused) {
-      // two launches per block: K_B (apply previous G + in-conv GEMM -> h1), K_A (depthwise + [res|skip]
-      // GEMM -> raw G); after the last block the skip sum is completed and PReLU'd for the mask GEMM
-      constexpr int kSlots1 = fb::KbCfg::SLOTS, kSlots2 = fb::KaCfg<256>::SLOTS;
+    if (fused_mode) {
+      // two launches per block: K_B (apply previous G_res + in-conv GEMM -> h1), K_A (depthwise + [res|skip]
+      // GEMM -> raw G_res + skip stash slot); after the last block the stash is merged into the mask operand
+      __half* stash = reinterpret_cast<__half*>(ws + lo.o_stash);
+      CUtensorMap tm_hc, tm_hh[5];  // raw h1 views: centre box and halo boxes of 8..128 frames
+      if (make_tmap_act_raw(&tm_hc, h1, nt, C_HID, TILE_M)) return 1;
+      for (int k = 0; k < 5; ++k)
+        if (make_tmap_act_raw(&tm_hh[k], h1, nt, C_HID, 8 << k)) return 1;
       for (int i = 0; i < m->n_layers; ++i) {
         BlockW& b = m->blocks[i];
         const bool last = (i == m->n_layers - 1);
+        if (b.dilation > 128) return fail("fused path supports dilations up to 128 (got %d)", b.dilation);
         fb::ApplyParams ap{};
         ap.x = x;
-        ap.skip = skip;
         if (i > 0) {
           ap.g = gbuf;
-          ap.part2 = p2;
-          ap.slots2 = kSlots2;
+          ap.part2 = p2 + (size_t)(i - 1) * lo.part2_stride;
           ap.rs = m->blocks[i - 1].rs;
           ap.cb = m->blocks[i - 1].cb;
-          ap.first = (i == 1) ? 1 : 0;
         }
         int rc;
         if (b.a1 >= 0.f && b.a1 <= 1.f) {
@@ -528,22 +580,20 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
         }
         if (rc) return 1;
         if (stop()) return 0;
-        DwParams p{b.g1, b.be1, b.wd, b.bd, b.a2, b.dilation};
+        int hk = 0;  // halo box: 8 frames for d < 8, else d frames
+        while ((8 << hk) < b.dilation) ++hk;
+        KaArgs ka{&b.tm_rs, &tm_hc, &tm_hh[hk], gbuf, stash + (size_t)i * lo.stash_stride, p1,
+                  p2 + (size_t)i * lo.part2_stride, fb::DwTab{b.dw_t0, b.dw_t1, b.dw_cb, b.a2, b.dilation}};
         const bool a01 = b.a2 >= 0.f && b.a2 <= 1.f;
-        if (!last) {
-          rc = a01 ? launch_dw_rs_d<256, true>(m, b.tm_rs, h1, gbuf, p1, kSlots1, p2, p, tb, st)
-                   : launch_dw_rs_d<256, false>(m, b.tm_rs, h1, gbuf, p1, kSlots1, p2, p, tb, st);
-        } else {
-          rc = a01 ? launch_dw_rs_d<128, true>(m, b.tm_rs, h1, gbuf, p1, kSlots1, p2, p, tb, st)
-                   : launch_dw_rs_d<128, false>(m, b.tm_rs, h1, gbuf, p1, kSlots1, p2, p, tb, st);
-        }
+        if (!last) rc = a01 ? launch_dw_rs_d<256, true>(m, ka, tb, st) : launch_dw_rs_d<256, false>(m, ka, tb, st);
+        else rc = a01 ? launch_dw_rs_d<128, true>(m, ka, tb, st) : launch_dw_rs_d<128, false>(m, ka, tb, st);
         if (rc) return 1;
         if (stop()) return 0;
       }
-      const BlockW& lb = m->blocks[m->n_layers - 1];
-      CK(launch_k(fb::final_skip_kernel, dim3(nt), dim3(256), 0, st, (const __half*)gbuf, (const float2*)p2, kSlots2,
-                  (const float*)lb.rs, (const float*)lb.cb, (const float*)skip, skipa, m->alpha_mask,
-                  m->n_layers == 1 ? 1 : 0, tb));
+      if (m->n_layers > fb::MAX_LAYERS) return fail("fused path supports up to %d TCN blocks", fb::MAX_LAYERS);
+      CK(launch_k(fb::skip_merge_kernel, dim3(nt), dim3(256), 0, st, (const __half*)stash, lo.stash_stride,
+                  (const float2*)p2, lo.part2_stride, (const float*)m->skip_rs, (const float*)m->skip_cb, skipa,
+                  m->alpha_mask, m->n_layers, tb));
       if (stop()) return 0;
       fused_done = true;
     }
@@ -746,7 +796,7 @@ int b200sep_profile_read(b200sep_model* m, float* ms_out, int32_t cap, int32_t* 
 int b200sep_debug_layout(const b200sep_model* m, const int32_t* lens, int32_t n_seg, uint64_t* out) {
   if (!m || !out) return fail("null argument");
   Layout lo;
-  if (compute_layout(m->cfg, m->half, lens, n_seg, &lo)) return 1;
+  if (compute_layout(m->cfg, m->half, m->half && m->use_tc && m->fused, lens, n_seg, &lo)) return 1;
   out[0] = lo.o_enc; out[1] = lo.o_x; out[2] = lo.o_xa; out[3] = lo.o_skip; out[4] = lo.o_skipa;
   out[5] = lo.o_h1; out[6] = lo.o_h2; out[7] = lo.o_masked; out[8] = (uint64_t)lo.n_tiles; out[9] = lo.total;
   out[10] = lo.o_g;
@@ -756,7 +806,7 @@ int b200sep_debug_layout(const b200sep_model* m, const int32_t* lens, int32_t n_
 size_t b200sep_workspace_bytes(const b200sep_model* m, const int32_t* lens, int32_t n_seg) {
   if (!m) { fail("null model"); return 0; }
   Layout lo;
-  if (compute_layout(m->cfg, m->half, lens, n_seg, &lo)) return 0;
+  if (compute_layout(m->cfg, m->half, m->half && m->use_tc && m->fused, lens, n_seg, &lo)) return 0;
   return lo.total;
 }
 
@@ -765,7 +815,7 @@ int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* 
   if (!m || !d_mix || !lens || !d_out || !d_ws) return fail("null argument");
   if ((reinterpret_cast<uintptr_t>(d_ws) & 255u) != 0) return fail("d_ws must be 256-byte aligned");
   Layout lo;
-  if (compute_layout(m->cfg, m->half, lens, n_seg, &lo)) return 1;
+  if (compute_layout(m->cfg, m->half, m->half && m->use_tc && m->fused, lens, n_seg, &lo)) return 1;
   if (ws_bytes < lo.total) return fail("workspace too small: %zu < %zu bytes", ws_bytes, lo.total);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   std::lock_guard<std::mutex> lock(m->mu);

@@ -1,20 +1,23 @@
 // Fused TCN-block kernels (sm_100a, fp16 tensor-core mode).  One Conv1DBlock is two
 // launches; the kernel boundaries are exactly the two segment-wide gLN reductions of the block:
 //
-//   K_B  apply_in_kernel :  x += gLN2-scaled res of the previous block, skip += ... (elementwise
-//                           prologue on G), x -> fp16 operand in shared memory -> tcgen05 in-conv
-//                           GEMM (128 -> 512, W_in resident in shared memory) -> bias + PReLU ->
-//                           h1 (fp16) + gLN1 partial sums.
-//   K_A  dw_rs_kernel    :  gLN1 folded into the dilated depthwise taps + PReLU computed by 16
-//                           producer warps straight into the swizzled shared-memory A-operand ring
+//   K_B  apply_in_kernel :  x += gLN2-scaled residual output of the previous block (elementwise
+//                           prologue on the raw G_res), x -> fp16 operand in shared memory -> tcgen05
+//                           in-conv GEMM (128 -> 512, W_in resident in shared memory) -> bias + PReLU
+//                           -> h1 (fp16) + gLN1 partial sums.
+//   K_A  dw_rs_kernel    :  raw h1 k-blocks (+ dilation halos) staged into shared memory by TMA; 16
+//                           producer warps fold gLN1 into the dilated depthwise taps, apply PReLU and
+//                           write the result straight into the swizzled shared-memory A-operand ring
 //                           (h2 never leaves the SM) -> tcgen05 [res | skip] GEMM (512 -> 256) on the
-//                           RAW h2 with gamma-folded weights -> G (fp16, raw) + gLN2 partial sums.
+//                           RAW h2 with gamma-folded weights -> raw G_res (fp16) + raw G_skip (fp16,
+//                           one stash slot per block) + gLN2 partial sums.
 //
 // G is "raw": the two per-segment gLN2 scalars are only known once every tile of the segment has been
-// through K_A, so they are applied by the next K_B's prologue:
-//     x_new = x + vm * (rstd2 * (G_res - mean2 * rs) + cb)        (rs, cb: see epilogues.cuh)
-// HBM bytes per frame and block: K_A 1024 (h1) + 512 (G); K_B 512 (G) + 2048 (x, skip r/w) + 1024 (h1)
-// = 5.1 KB vs 6.6 KB for the three unfused kernels, and one launch less.
+// through K_A, so they are applied by the consumer:
+//     x_new    = x + vm * (rstd2 * (G_res - mean2 * rs) + cb)              (next K_B prologue)
+//     skip_sum = sum_b vm * (rstd2_b * (G_skip_b - mean2_b * rs_b) + cb_b) (skip_merge_kernel, once)
+// HBM bytes per frame and block: K_A 1024 (h1) + 512 (G); K_B 256 (G_res) + 1024 (x r/w) + 1024 (h1);
+// + 256 per block read once by the skip merge = 4.1 KB vs 6.6 KB for the three unfused kernels.
 //
 // Every mbarrier wait is bounded (g_abort): a protocol bug degrades into wrong numbers plus an error
 // flag the host reads, never into a hung GPU.
@@ -40,16 +43,17 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n\t"
       "}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(2000)
+      : "r"(bar), "r"(parity), "r"(20000)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: ~seconds in the worst case, then flags the abort and lets the caller run on (all
 // addresses stay in bounds; the host reports the failure).
 __device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity) {
-  for (uint32_t i = 0; i < (1u << 21); ++i) {
+#pragma unroll 1
+  for (uint32_t i = 0; i < (1u << 18); ++i) {
     if (mbar_try(bar, parity)) return;
-    if ((i & 255u) == 255u && *reinterpret_cast<volatile int*>(&g_abort) != 0) return;
+    if ((i & 31u) == 31u && *reinterpret_cast<volatile int*>(&g_abort) != 0) return;
   }
   *reinterpret_cast<volatile int*>(&g_abort) = 1;
 }
@@ -59,6 +63,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 // byte offset of the 16-byte chunk (8 consecutive frames starting at frame f0, f0 % 8 == 0) of
 // k-row `row` (0..63) inside one 64(k) x 128(m) MN-major SWIZZLE_128B operand stage: two 64x64 boxes
 // 8 KiB apart (frames 0-63 / 64-127), 128-byte rows, chunk index xor (row & 7) -- the image a TMA
@@ -67,40 +76,7 @@ __device__ __forceinline__ uint32_t a_chunk_off(int row, int f0) {
   const int chunk = (f0 >> 3) & 7;
   return (uint32_t)((f0 >> 6) * 8192 + row * 128 + ((chunk ^ (row & 7)) << 4));
 }
-
-// =================================================================================================
-// K_A: depthwise stage (producer warps) + [res | skip] GEMM -> raw G
-// =================================================================================================
-template <int BN>
-struct KaCfg {
-  static constexpr int STAGES = 4;
-  static constexpr int A_STAGE = TILE_M * 64 * 2;  // 16 KiB
-  static constexpr int B_STAGE = BN * 64 * 2;      // 32 / 16 KiB
-  static constexpr int STAGE = A_STAGE + 32768;
-  static constexpr int PAR_BYTES = C_HID * 32;     // per-channel folded taps (2 x float4)
-  static constexpr int EPI_WARPS = 4, PROD_WARPS = 16;
-  static constexpr int THREADS = (EPI_WARPS + 2 + PROD_WARPS) * 32;  // 704
-  static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE + PAR_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int SLOTS = PROD_WARPS;         // gLN2 partial slots per m-tile
-};
-
-// register image of one producer step: the centre vector and the two shifted / neighbouring vectors
-struct DwLd { uint4 c, a, b; };
-
 __device__ __forceinline__ uint4 ldg_v4(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
-__device__ __forceinline__ uint4 shfl_up16_v4(uint4 v) {
-  uint4 r;
-  r.x = __shfl_up_sync(0xffffffffu, v.x, 1, 16); r.y = __shfl_up_sync(0xffffffffu, v.y, 1, 16);
-  r.z = __shfl_up_sync(0xffffffffu, v.z, 1, 16); r.w = __shfl_up_sync(0xffffffffu, v.w, 1, 16);
-  return r;
-}
-__device__ __forceinline__ uint4 shfl_down16_v4(uint4 v) {
-  uint4 r;
-  r.x = __shfl_down_sync(0xffffffffu, v.x, 1, 16); r.y = __shfl_down_sync(0xffffffffu, v.y, 1, 16);
-  r.z = __shfl_down_sync(0xffffffffu, v.z, 1, 16); r.w = __shfl_down_sync(0xffffffffu, v.w, 1, 16);
-  return r;
-}
 __device__ __forceinline__ void unpack8(const uint4 v, float (&o)[8]) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -118,20 +94,100 @@ __device__ __forceinline__ uint4 pack8(const float (&o)[8]) {
   }
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
-// left / right tap values of the thread's 8 frames
+
+// Per-CTA copy of the TileInfo records of the m-tiles this CTA will visit (tile it = blockIdx.x +
+// it * gridDim.x), so no tile starts with a dependent global load chain.
+constexpr int TI_CACHE = 32;
+__device__ __forceinline__ void ti_cache_fill(TileInfo* s_ti, const Tables& tb, int tid) {
+  if (tid < TI_CACHE) {
+    const int w = blockIdx.x + tid * gridDim.x;
+    if (w < tb.n_tiles) s_ti[tid] = load_tile_info(tb.tile_info + w);
+  }
+}
+__device__ __forceinline__ TileInfo ti_get(const TileInfo* s_ti, const Tables& tb, int it, int w) {
+  if (it < TI_CACHE) return s_ti[it];
+  return load_tile_info(tb.tile_info + w);
+}
+// Segment gLN statistics from single-slot per-tile partials; `pre` is this lane's (pre-fetched) first
+// element part[tile0 + lane] (zeros when lane >= ntiles).  Same arithmetic as warp_seg_stats.
+__device__ __forceinline__ void seg_stats_pre(const float2* __restrict__ part, const TileInfo& ti, float2 pre,
+                                              float& mean, float& rstd) {
+  const int lane = threadIdx.x & 31;
+  double s = (double)pre.x, q = (double)pre.y;
+  for (int i = lane + 32; i < ti.ntiles; i += 32) {
+    const float2 v = part[ti.tile0 + i];
+    s += (double)v.x;
+    q += (double)v.y;
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  const double m = s * ti.inv_count;
+  double var = fma(-m, m, q * ti.inv_count);
+  if (var < 0.0) var = 0.0;
+  mean = (float)m;
+  const float ve = (float)var + GLN_EPS;
+  float y = rsqrtf(ve);
+  y = y * (1.5f - 0.5f * ve * y * y);
+  rstd = y;
+}
+__device__ __forceinline__ float2 part_prefetch(const float2* __restrict__ part, const TileInfo& ti) {
+  const int lane = threadIdx.x & 31;
+  return (lane < ti.ntiles) ? part[ti.tile0 + lane] : make_float2(0.f, 0.f);
+}
+
+// =================================================================================================
+// K_A: depthwise stage (producer warps) + [res | skip] GEMM -> raw G
+// =================================================================================================
+// Static per-block tap table (built on the host, fp64): for channel c with depthwise taps w0..w2,
+// gLN1 gamma/beta and depthwise bias,
+//   t0[c] = { w0*gamma, w1*gamma, w2*gamma, (w0+w1+w2)*gamma }
+//   t1[c] = { w0*beta,  w1*beta,  w2*beta,  bias }
+//   cb[c] = (w0+w1+w2)*beta + bias
+// so that with the segment's (mean, rstd):  wa_k = t0_k * rstd,  wb_k = t1_k - t0_k * rstd*mean, and for
+// interior frames  u = cb - t0.w * rstd*mean + sum_k wa_k * h[t + (k-1) d].
+struct DwTab {
+  const float4* t0;  // [512]
+  const float4* t1;  // [512]
+  const float* cb;   // [512]
+  float alpha2;      // PReLU slope after the depthwise conv
+  int dilation;
+};
+
+template <int BN>
+struct KaCfg {
+  static constexpr int RAW_STAGES = 2, AB_STAGES = 2;
+  static constexpr int RAW_STAGE = 3 * 16384;        // centre 64 x 128, left halo, right halo (<= 64 x 128 each)
+  static constexpr int A_STAGE = TILE_M * 64 * 2;    // 16 KiB
+  static constexpr int B_STAGE = BN * 64 * 2;        // 32 / 16 KiB
+  static constexpr int AB_STAGE = A_STAGE + 32768;
+  static constexpr int TAB_BYTES = C_HID * (16 + 16 + 4);  // 18 KiB
+  static constexpr int EPI_WARPS = 4, PROD_WARPS = 16;
+  static constexpr int THREADS = (EPI_WARPS + 3 + PROD_WARPS) * 32;  // 736
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int OFF_AB = RAW_STAGES * RAW_STAGE;
+  static constexpr int OFF_TAB = OFF_AB + AB_STAGES * AB_STAGE;
+  static constexpr int OFF_TI = OFF_TAB + TAB_BYTES;
+  static constexpr int OFF_RED = OFF_TI + TI_CACHE * 32;
+  static constexpr int OFF_BAR = OFF_RED + 2 * PROD_WARPS * 8;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024 /*align*/;
+};
+
+struct DwEdge { float2 ml[4], mc[4], mr[4]; };
+
+// left / right tap values of the thread's 8 frames from the three 8-frame vectors (centre, the vector
+// `shift` frames to the left, the one to the right): D == 0 -> the vectors ARE the taps (d % 8 == 0);
+// D in {1,2,4} -> vectors are the neighbouring 8 frames and the taps are picked across the seam.
 template <int D>
-__device__ __forceinline__ void dw_taps(const DwLd& in, int lane16, float (&ctr)[8], float (&lft)[8], float (&rgt)[8]) {
-  unpack8(in.c, ctr);
+__device__ __forceinline__ void dw_taps(const uint4 vc, const uint4 va, const uint4 vb, float (&ctr)[8],
+                                        float (&lft)[8], float (&rgt)[8]) {
+  unpack8(vc, ctr);
   if (D == 0) {
-    unpack8(in.a, lft);
-    unpack8(in.b, rgt);
+    unpack8(va, lft);
+    unpack8(vb, rgt);
   } else {
-    uint4 vp = shfl_up16_v4(in.c), vn = shfl_down16_v4(in.c);
-    if (lane16 == 0) vp = in.a;
-    if (lane16 == 15) vn = in.b;
     float pv[8], nv[8];
-    unpack8(vp, pv);
-    unpack8(vn, nv);
+    unpack8(va, pv);
+    unpack8(vb, nv);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       lft[i] = (i - D >= 0) ? ctr[(i - D) & 7] : pv[(8 + i - D) & 7];
@@ -139,84 +195,55 @@ __device__ __forceinline__ void dw_taps(const DwLd& in, int lane16, float (&ctr)
     }
   }
 }
-template <int D, bool A01>
-__device__ __forceinline__ uint4 dw_compute_interior(const DwLd& in, const float4 pa, int lane16, float alpha,
-                                                     float2& s2, float2& q2) {
-  float ctr[8], lft[8], rgt[8];
-  dw_taps<D>(in, lane16, ctr, lft, rgt);
-  const float2 w0 = make_float2(pa.x, pa.x), w1 = make_float2(pa.y, pa.y), w2 = make_float2(pa.z, pa.z);
-  const float2 cw = make_float2(pa.w, pa.w);
-  float o[8];
-#pragma unroll
-  for (int i = 0; i < 8; i += 2) {
-    float2 u = fma2(make_float2(lft[i], lft[i + 1]), w0,
-                    fma2(make_float2(ctr[i], ctr[i + 1]), w1, fma2(make_float2(rgt[i], rgt[i + 1]), w2, cw)));
-    u = prelu2<A01>(u, alpha);
-    o[i] = u.x; o[i + 1] = u.y;
-    s2 = add2(s2, u);
-    q2 = fma2(u, u, q2);
-  }
-  return pack8(o);
-}
-template <int D, bool A01>
-__device__ __forceinline__ uint4 dw_compute_edge(const DwLd& in, const float4 pa, const float4 pb,
-                                                 const DwEdgeMasks& mk, int lane16, float alpha, float2& s2,
-                                                 float2& q2) {
-  float ctr[8], lft[8], rgt[8];
-  dw_taps<D>(in, lane16, ctr, lft, rgt);
-  const float2 wa0 = make_float2(pa.x, pa.x), wa1 = make_float2(pa.y, pa.y), wa2 = make_float2(pa.z, pa.z);
-  const float2 wb0 = make_float2(pb.x, pb.x), wb1 = make_float2(pb.y, pb.y), wb2 = make_float2(pb.z, pb.z);
-  const float2 bias = make_float2(pb.w, pb.w);
-  float o[8];
-#pragma unroll
-  for (int i = 0; i < 8; i += 2) {
-    const int k = i >> 1;
-    float2 u = fma2(fma2(make_float2(lft[i], lft[i + 1]), wa0, wb0), mk.ml[k], bias);
-    u = fma2(fma2(make_float2(ctr[i], ctr[i + 1]), wa1, wb1), mk.mc[k], u);
-    u = fma2(fma2(make_float2(rgt[i], rgt[i + 1]), wa2, wb2), mk.mr[k], u);
-    u = mul2(prelu2<A01>(u, alpha), mk.mc[k]);
-    o[i] = u.x; o[i + 1] = u.y;
-    s2 = add2(s2, u);
-    q2 = fma2(u, u, q2);
-  }
-  return pack8(o);
-}
-// 8 frames [t, t+8) of channel c of the segment, zeros outside the segment's m-tiles
-__device__ __forceinline__ uint4 ld_group8(const __half* __restrict__ h1, int tile0, int ntiles, int c, int t) {
-  if (t < 0 || t >= ntiles * TILE_M) return make_uint4(0, 0, 0, 0);
-  return ldg_v4(h1 + tt_index(tile0 + (t >> 7), C_HID, c, t & (TILE_M - 1)));
-}
 
 template <int BN, int D, bool A01>
-__global__ void __launch_bounds__(704, 1)
-dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __half* __restrict__ h1, __half* __restrict__ g,
-             const float2* __restrict__ part1, int slots1, float2* __restrict__ part2, DwParams p, Tables tb) {
+__global__ void __launch_bounds__(736, 1)
+dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_hc,
+             const __grid_constant__ CUtensorMap tm_hh, __half* __restrict__ g_res, __half* __restrict__ g_skip,
+             const float2* __restrict__ part1, float2* __restrict__ part2, DwTab p, Tables tb) {
   using Cfg = KaCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  auto stage_a = [&](int s) { return smem_base + (uint32_t)(s * Cfg::STAGE); };
-  auto stage_b = [&](int s) { return smem_base + (uint32_t)(s * Cfg::STAGE + Cfg::A_STAGE); };
-  const uint32_t par0 = smem_base + Cfg::STAGES * Cfg::STAGE;
-  const uint32_t bar0 = par0 + Cfg::PAR_BYTES;
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (Cfg::STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * Cfg::STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * Cfg::STAGES + 2 + s); };
-  const uint32_t tmem_ptr_smem = bar0 + 8u * (2 * Cfg::STAGES + 4);
-  float4* s_par = reinterpret_cast<float4*>(smem_raw + (par0 - smem_u32(smem_raw)));  // [512][2]
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  auto raw_st = [&](int s) { return smem_base + (uint32_t)(s * Cfg::RAW_STAGE); };
+  auto stage_a = [&](int s) { return smem_base + (uint32_t)(Cfg::OFF_AB + s * Cfg::AB_STAGE); };
+  auto stage_b = [&](int s) { return smem_base + (uint32_t)(Cfg::OFF_AB + s * Cfg::AB_STAGE + Cfg::A_STAGE); };
+  float4* s_t0 = reinterpret_cast<float4*>(smem_gen + Cfg::OFF_TAB);
+  float4* s_t1 = s_t0 + C_HID;
+  float* s_cb = reinterpret_cast<float*>(s_t1 + C_HID);
+  TileInfo* s_ti = reinterpret_cast<TileInfo*>(smem_gen + Cfg::OFF_TI);
+  float2* s_red = reinterpret_cast<float2*>(smem_gen + Cfg::OFF_RED);  // [2][16]
+  const uint32_t bar0 = smem_base + Cfg::OFF_BAR;
+  auto raw_full = [&](int s) { return bar0 + 8u * s; };
+  auto raw_empty = [&](int s) { return bar0 + 8u * (2 + s); };
+  auto ab_full = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto ab_empty = [&](int s) { return bar0 + 8u * (6 + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (8 + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (10 + s); };
+  const uint32_t tmem_ptr_smem = bar0 + 8u * 12;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n_tiles = tb.n_tiles;
+  const int d = (D > 0) ? D : p.dilation;
+  const int hw = (D > 0) ? 8 : d;  // halo width in frames (multiple of 8, <= 128)
 
-  if (warp == 4 && lane == 0) tma_prefetch_desc(&tm_b);
-  if (warp == 5) {
+  // static tables -> shared memory
+  for (int i = threadIdx.x; i < C_HID; i += Cfg::THREADS) {
+    s_t0[i] = __ldg(p.t0 + i);
+    s_t1[i] = __ldg(p.t1 + i);
+    s_cb[i] = __ldg(p.cb + i);
+  }
+  ti_cache_fill(s_ti, tb, threadIdx.x);
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&tm_hc); tma_prefetch_desc(&tm_hh); }
+  if (warp == 5 && lane == 0) tma_prefetch_desc(&tm_b);
+  if (warp == 6) {
     if (lane == 0) {
-      for (int s = 0; s < Cfg::STAGES; ++s) {
-        mbar_init(full_bar(s), Cfg::PROD_WARPS * 32 + 1);
-        mbar_init(empty_bar(s), 1);
-      }
       for (int s = 0; s < 2; ++s) {
+        mbar_init(raw_full(s), 1);
+        mbar_init(raw_empty(s), Cfg::PROD_WARPS * 32);
+        mbar_init(ab_full(s), Cfg::PROD_WARPS * 32 + 1);
+        mbar_init(ab_empty(s), 1);
         mbar_init(tfull_bar(s), 1);
         mbar_init(tempty_bar(s), 32 * Cfg::EPI_WARPS);
       }
@@ -243,35 +270,60 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __half* __restrict_
       mbar_wait_b(tfull_bar(as), aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-      __half* __restrict__ dst = g + tt_index(w, BN, 0, r);
+      __half* __restrict__ d_res = g_res + tt_index(w, C_BN, 0, r);
+      __half* __restrict__ d_skip = g_skip + tt_index(w, C_SKIP, 0, r);
       float v[2][32];
       tmem_ld32(taddr, v[0]);
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         tmem_ld_wait();
         if (c + 1 < NCH) tmem_ld32(taddr + (uint32_t)((c + 1) * 32), v[(c + 1) & 1]);
+        // BN == 256: columns 0-127 = residual conv, 128-255 = skip conv; BN == 128 (last block): skip only
+        __half* __restrict__ dst = (BN == 256 && c < 4) ? d_res + (size_t)(c * 32) * TILE_M
+                                                        : d_skip + (size_t)((BN == 256 ? c - 4 : c) * 32) * TILE_M;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dst[(size_t)(c * 32 + j) * TILE_M] = __float2half_rn(v[c & 1][j]);
+        for (int j = 0; j < 32; ++j) dst[(size_t)j * TILE_M] = __float2half_rn(v[c & 1][j]);
       }
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(as));
     }
   } else if (warp == 4) {
-    // ================================ TMA producer (weights) ======================================
+    // ================================ TMA producer: raw h1 k-blocks + halos =======================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint32_t bytes = (uint32_t)(64 * (TILE_M + 2 * hw) * 2);
       for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
         for (int kb = 0; kb < 8; ++kb) {
-          mbar_wait_b(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), Cfg::B_STAGE);
-          tma_load_2d(stage_b(stage), &tm_b, full_bar(stage), kb * 64, 0);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          mbar_wait_b(raw_empty(stage), phase ^ 1u);
+          mbar_expect_tx(raw_full(stage), bytes);
+          const uint32_t dst = raw_st(stage);
+          tma_load_2d(dst, &tm_hc, raw_full(stage), 0, w * C_HID + kb * 64);
+          // frames [t0 - hw, t0) live at the end of the previous m-tile, [t0 + 128, t0 + 128 + hw) at the
+          // start of the next; rows outside the tensor are zero-filled by the TMA unit
+          tma_load_2d(dst + 16384u, &tm_hh, raw_full(stage), TILE_M - hw, (w - 1) * C_HID + kb * 64);
+          tma_load_2d(dst + 32768u, &tm_hh, raw_full(stage), 0, (w + 1) * C_HID + kb * 64);
+          if (++stage == Cfg::RAW_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
     __syncwarp();
   } else if (warp == 5) {
+    // ================================ TMA producer: weights =======================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
+        for (int kb = 0; kb < 8; ++kb) {
+          mbar_wait_b(ab_empty(stage), phase ^ 1u);
+          mbar_expect_tx(ab_full(stage), Cfg::B_STAGE);
+          tma_load_2d(stage_b(stage), &tm_b, ab_full(stage), kb * 64, 0);
+          if (++stage == Cfg::AB_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 6) {
     // ================================ MMA issuer ==================================================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN);
@@ -285,7 +337,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __half* __restrict_
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < 8; ++kb) {
-          mbar_wait_b(full_bar(stage), phase);
+          mbar_wait_b(ab_full(stage), phase);
           tcgen05_fence_after();
           const uint32_t sa = stage_a(stage), sb = stage_b(stage);
 #pragma unroll
@@ -294,74 +346,86 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __half* __restrict_
             const uint64_t db = make_smem_desc(sb + j * 32u, 16u, 1024u);
             umma_f16(tmem_d, da, db, idesc, (uint32_t)((kb | j) != 0));
           }
-          umma_commit(empty_bar(stage));
+          umma_commit(ab_empty(stage));
           if (kb == 7) umma_commit(tfull_bar(as));
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == Cfg::AB_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
     __syncwarp();
   } else {
     // ================================ depthwise producers =========================================
-    const int pw = warp - 6;              // 0..15
-    const int ptid = pw * 32 + lane;      // 0..511
+    const int pw = warp - 7;              // 0..15
     const int sub = lane >> 4, lane16 = lane & 15;
-    const int c0 = pw * 2 + sub;          // channel of step 0; step n handles channel c0 + 32 n
-    const int d = (D > 0) ? D : p.dilation;
+    const int row0 = pw * 2 + sub;        // k-row of step 0 inside a k-block; step 1 = row0 + 32
     const float alpha = p.alpha2;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
-      const TileInfo ti = load_tile_info(tb.tile_info + w);
-      const int tile0 = ti.tile0, ntiles = ti.ntiles, F = ti.F, tile_t0 = ti.t0;
-      float mean, rstd;
-      warp_seg_stats(part1, tile0, ntiles, slots1, ti.inv_count, mean, rstd);
-      named_bar_sync(1, Cfg::PROD_WARPS * 32);  // nobody still reads the previous tile's table
-      {
-        const int c = ptid;
-        const float a = __ldg(p.gamma1 + c) * rstd;
-        const float b = __ldg(p.beta1 + c) - a * mean;  // y = a*h + b
-        const float w0 = __ldg(p.w + c * 3 + 0), w1 = __ldg(p.w + c * 3 + 1), w2 = __ldg(p.w + c * 3 + 2);
-        const float bias = __ldg(p.bias + c);
-        s_par[c * 2 + 0] = make_float4(w0 * a, w1 * a, w2 * a, bias + (w0 + w1 + w2) * b);
-        s_par[c * 2 + 1] = make_float4(w0 * b, w1 * b, w2 * b, bias);
-      }
-      named_bar_sync(1, Cfg::PROD_WARPS * 32);
+    // shared-memory offsets (inside a raw stage) of this thread's centre / left / right vectors
+    const int sv = (D > 0) ? 1 : (d >> 3);  // tap distance in 8-frame vectors
+    const int hv = hw >> 3;                 // halo width in vectors
+    const uint32_t c_off = (uint32_t)(lane16 * 16), c_pitch = 256u;
+    uint32_t l_off, l_pitch, r_off, r_pitch;
+    if (lane16 - sv >= 0) { l_off = (uint32_t)((lane16 - sv) * 16); l_pitch = 256u; }
+    else { l_off = 16384u + (uint32_t)((lane16 - sv + hv) * 16); l_pitch = (uint32_t)(hw * 2); }
+    if (lane16 + sv < 16) { r_off = (uint32_t)((lane16 + sv) * 16); r_pitch = 256u; }
+    else { r_off = 32768u + (uint32_t)((lane16 + sv - 16) * 16); r_pitch = (uint32_t)(hw * 2); }
 
+    int rs_ = 0, as_ = 0;
+    uint32_t rphase = 0, aphase = 0;
+    int it = 0;
+    float2 pre = make_float2(0.f, 0.f);
+    if ((int)blockIdx.x < n_tiles) pre = part_prefetch(part1, ti_get(s_ti, tb, 0, blockIdx.x));
+    for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
+      const TileInfo ti = ti_get(s_ti, tb, it, w);
+      const int F = ti.F, tile_t0 = ti.t0;
+      float mean, rstd;
+      seg_stats_pre(part1, ti, pre, mean, rstd);
+      if (w + (int)gridDim.x < n_tiles) pre = part_prefetch(part1, ti_get(s_ti, tb, it + 1, w + gridDim.x));
+      const float rm = rstd * mean;
       const int t_base = tile_t0 + lane16 * 8;
       const bool interior = (tile_t0 - d >= 0) && (tile_t0 + TILE_M - 1 + d < F);
       float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
       if (interior) {
-        auto ptr_at = [&](int t) { return h1 + tt_index(tile0 + (t >> 7), C_HID, c0, t & (TILE_M - 1)); };
-        const __half* pc = ptr_at(t_base);
-        const __half* pa_ = (D == 0) ? ptr_at(t_base - d) : ((lane16 == 0) ? ptr_at(t_base - 8) : pc);
-        const __half* pb_ = (D == 0) ? ptr_at(t_base + d) : ((lane16 == 15) ? ptr_at(t_base + 8) : pc);
-        constexpr size_t STRIDE = (size_t)32 * TILE_M;
-        auto load = [&](int n) {
-          DwLd r;
-          r.c = ldg_v4(pc + n * STRIDE);
-          if (D == 0 || lane16 == 0) r.a = ldg_v4(pa_ + n * STRIDE); else r.a = r.c;
-          if (D == 0 || lane16 == 15) r.b = ldg_v4(pb_ + n * STRIDE); else r.b = r.c;
-          return r;
-        };
-        DwLd cur = load(0);
-#pragma unroll 2
-        for (int n = 0; n < 16; ++n) {
-          const DwLd nxt = load(n < 15 ? n + 1 : 15);
-          if ((n & 1) == 0) mbar_wait_b(empty_bar(stage), phase ^ 1u);
-          const int row = (n & 1) * 32 + c0;
-          const float4 pa = s_par[(c0 + n * 32) * 2];
-          const uint4 o = dw_compute_interior<D, A01>(cur, pa, lane16, alpha, s2, q2);
-          st_shared_v4(stage_a(stage) + a_chunk_off(row, lane16 * 8), o);
-          if (n & 1) {
-            fence_proxy_async();
-            mbar_arrive(full_bar(stage));
-            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+#pragma unroll 1
+        for (int kb = 0; kb < 8; ++kb) {
+          mbar_wait_b(raw_full(rs_), rphase);
+          mbar_wait_b(ab_empty(as_), aphase ^ 1u);
+          const uint32_t raw = raw_st(rs_), sa = stage_a(as_);
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const int row = s * 32 + row0;
+            const int c = kb * 64 + row;
+            const uint4 vc = ld_shared_v4(raw + c_off + (uint32_t)row * c_pitch);
+            const uint4 va = ld_shared_v4(raw + l_off + (uint32_t)row * l_pitch);
+            const uint4 vb = ld_shared_v4(raw + r_off + (uint32_t)row * r_pitch);
+            const float4 t0 = s_t0[c];
+            const float cw = fmaf(-t0.w, rm, s_cb[c]);
+            float ctr[8], lft[8], rgt[8];
+            dw_taps<D>(vc, va, vb, ctr, lft, rgt);
+            const float wa0 = t0.x * rstd, wa1 = t0.y * rstd, wa2 = t0.z * rstd;
+            const float2 w0 = make_float2(wa0, wa0), w1 = make_float2(wa1, wa1), w2 = make_float2(wa2, wa2);
+            const float2 cw2 = make_float2(cw, cw);
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              float2 u = fma2(make_float2(lft[i], lft[i + 1]), w0,
+                              fma2(make_float2(ctr[i], ctr[i + 1]), w1, fma2(make_float2(rgt[i], rgt[i + 1]), w2, cw2)));
+              u = prelu2<A01>(u, alpha);
+              o[i] = u.x; o[i + 1] = u.y;
+              s2 = add2(s2, u);
+              q2 = fma2(u, u, q2);
+            }
+            st_shared_v4(sa + a_chunk_off(row, lane16 * 8), pack8(o));
           }
-          cur = nxt;
+          fence_proxy_async();
+          mbar_arrive(ab_full(as_));
+          mbar_arrive(raw_empty(rs_));
+          if (++rs_ == Cfg::RAW_STAGES) { rs_ = 0; rphase ^= 1u; }
+          if (++as_ == Cfg::AB_STAGES) { as_ = 0; aphase ^= 1u; }
         }
       } else {
-        DwEdgeMasks mk;
+        // taps and frames masked by segment-relative frame index (zero padding applies to the normalised
+        // signal at the TRUE segment ends); masked-out taps read finite values, so 0 * h is exactly 0
+        DwEdge mk;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int ta = t_base + 2 * k, tb2 = ta + 1;
@@ -369,52 +433,72 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __half* __restrict_
           mk.mc[k] = make_float2(ta < F ? 1.f : 0.f, tb2 < F ? 1.f : 0.f);
           mk.mr[k] = make_float2(ta + d < F ? 1.f : 0.f, tb2 + d < F ? 1.f : 0.f);
         }
-        auto load = [&](int n) {
-          const int c = c0 + n * 32;
-          DwLd r;
-          r.c = ld_group8(h1, tile0, ntiles, c, t_base);
-          if (D == 0) {
-            r.a = ld_group8(h1, tile0, ntiles, c, t_base - d);
-            r.b = ld_group8(h1, tile0, ntiles, c, t_base + d);
-          } else {
-            r.a = (lane16 == 0) ? ld_group8(h1, tile0, ntiles, c, t_base - 8) : r.c;
-            r.b = (lane16 == 15) ? ld_group8(h1, tile0, ntiles, c, t_base + 8) : r.c;
-          }
-          return r;
-        };
-        DwLd cur = load(0);
 #pragma unroll 1
-        for (int n = 0; n < 16; ++n) {
-          const DwLd nxt = load(n < 15 ? n + 1 : 15);
-          if ((n & 1) == 0) mbar_wait_b(empty_bar(stage), phase ^ 1u);
-          const int row = (n & 1) * 32 + c0;
-          const float4 pa = s_par[(c0 + n * 32) * 2], pb = s_par[(c0 + n * 32) * 2 + 1];
-          const uint4 o = dw_compute_edge<D, A01>(cur, pa, pb, mk, lane16, alpha, s2, q2);
-          st_shared_v4(stage_a(stage) + a_chunk_off(row, lane16 * 8), o);
-          if (n & 1) {
-            fence_proxy_async();
-            mbar_arrive(full_bar(stage));
-            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
+        for (int kb = 0; kb < 8; ++kb) {
+          mbar_wait_b(raw_full(rs_), rphase);
+          mbar_wait_b(ab_empty(as_), aphase ^ 1u);
+          const uint32_t raw = raw_st(rs_), sa = stage_a(as_);
+#pragma unroll 1
+          for (int s = 0; s < 2; ++s) {
+            const int row = s * 32 + row0;
+            const int c = kb * 64 + row;
+            const uint4 vc = ld_shared_v4(raw + c_off + (uint32_t)row * c_pitch);
+            const uint4 va = ld_shared_v4(raw + l_off + (uint32_t)row * l_pitch);
+            const uint4 vb = ld_shared_v4(raw + r_off + (uint32_t)row * r_pitch);
+            const float4 t0 = s_t0[c], t1 = s_t1[c];
+            float ctr[8], lft[8], rgt[8];
+            dw_taps<D>(vc, va, vb, ctr, lft, rgt);
+            const float wa0 = t0.x * rstd, wa1 = t0.y * rstd, wa2 = t0.z * rstd;
+            const float wb0 = fmaf(-t0.x, rm, t1.x), wb1 = fmaf(-t0.y, rm, t1.y), wb2 = fmaf(-t0.z, rm, t1.z);
+            const float2 a0 = make_float2(wa0, wa0), a1 = make_float2(wa1, wa1), a2 = make_float2(wa2, wa2);
+            const float2 b0 = make_float2(wb0, wb0), b1 = make_float2(wb1, wb1), b2 = make_float2(wb2, wb2);
+            const float2 bias = make_float2(t1.w, t1.w);
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const int k = i >> 1;
+              float2 u = fma2(fma2(make_float2(lft[i], lft[i + 1]), a0, b0), mk.ml[k], bias);
+              u = fma2(fma2(make_float2(ctr[i], ctr[i + 1]), a1, b1), mk.mc[k], u);
+              u = fma2(fma2(make_float2(rgt[i], rgt[i + 1]), a2, b2), mk.mr[k], u);
+              u = mul2(prelu2<A01>(u, alpha), mk.mc[k]);
+              o[i] = u.x; o[i + 1] = u.y;
+              s2 = add2(s2, u);
+              q2 = fma2(u, u, q2);
+            }
+            st_shared_v4(sa + a_chunk_off(row, lane16 * 8), pack8(o));
           }
-          cur = nxt;
+          fence_proxy_async();
+          mbar_arrive(ab_full(as_));
+          mbar_arrive(raw_empty(rs_));
+          if (++rs_ == Cfg::RAW_STAGES) { rs_ = 0; rphase ^= 1u; }
+          if (++as_ == Cfg::AB_STAGES) { as_ = 0; aphase ^= 1u; }
         }
       }
+      // gLN2 partial of this m-tile: fixed-order block reduction -> one slot per tile
       const float s_acc = warp_sum(s2.x + s2.y);
       const float q_acc = warp_sum(q2.x + q2.y);
-      if (lane == 0) part2[(size_t)w * Cfg::SLOTS + pw] = make_float2(s_acc, q_acc);
+      float2* red = s_red + (it & 1) * Cfg::PROD_WARPS;
+      if (lane == 0) red[pw] = make_float2(s_acc, q_acc);
+      named_bar_sync(1, Cfg::PROD_WARPS * 32);
+      if (pw == 0 && lane == 0) {
+        float ts = 0.f, tq = 0.f;
+#pragma unroll
+        for (int k = 0; k < Cfg::PROD_WARPS; ++k) { ts += red[k].x; tq += red[k].y; }
+        part2[w] = make_float2(ts, tq);
+      }
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 6) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
 // =================================================================================================
-// K_B: apply previous block's G (x += res, skip += skip) + in-conv GEMM -> h1
+// K_B: apply previous block's G_res (x += res) + in-conv GEMM -> h1
 // =================================================================================================
 struct KbCfg {
   static constexpr int W_BYTES = C_HID * C_BN * 2;      // 128 KiB: [2 k-blocks][512 rows][64 k]
@@ -422,19 +506,19 @@ struct KbCfg {
   static constexpr int EPI_WARPS = 8, PRO_WARPS = 8;
   static constexpr int THREADS = (EPI_WARPS + 1 + PRO_WARPS) * 32;  // 544
   static constexpr int TMEM_COLS = 512;                 // 4 chunks of 128 output channels
-  static constexpr int SMEM_BYTES = W_BYTES + 2 * XN_BYTES + 1024 + 256;
-  static constexpr int SLOTS = EPI_WARPS;               // gLN1 partial slots per m-tile
+  static constexpr int OFF_XN = W_BYTES;
+  static constexpr int OFF_TI = OFF_XN + 2 * XN_BYTES;
+  static constexpr int OFF_RED = OFF_TI + TI_CACHE * 32;
+  static constexpr int OFF_BAR = OFF_RED + 2 * EPI_WARPS * 8;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 };
 
 struct ApplyParams {
-  const __half* g;      // [nt][g_ch][128] raw [res | skip] of the previous block (nullptr: block 0)
-  const float2* part2;  // gLN2 partials of the previous block
-  int slots2;
-  const float* rs;      // [256] rowsum(W . gamma2) of the previous block
-  const float* cb;      // [256] W * beta2 + b
+  const __half* g;      // [nt][128][128] raw residual-conv output of the previous block (nullptr: block 0)
+  const float2* part2;  // [nt] gLN2 partials of the previous block
+  const float* rs;      // [>=128] rowsum(W_res . gamma2) of the previous block
+  const float* cb;      // [>=128] W_res * beta2 + b_res
   float* x;             // [nt][128][128] fp32 residual stream (updated in place)
-  float* skip;          // [nt][128][128] fp32 skip accumulator (updated in place)
-  int first;            // previous block was block 0: skip has no old value
 };
 
 template <bool A01>
@@ -443,9 +527,12 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
   using Cfg = KbCfg;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t smem_w = smem_base;
-  auto smem_xn = [&](int b) { return smem_base + (uint32_t)(Cfg::W_BYTES + b * Cfg::XN_BYTES); };
-  const uint32_t bar0 = smem_base + Cfg::W_BYTES + 2 * Cfg::XN_BYTES;
+  auto smem_xn = [&](int b) { return smem_base + (uint32_t)(Cfg::OFF_XN + b * Cfg::XN_BYTES); };
+  TileInfo* s_ti = reinterpret_cast<TileInfo*>(smem_gen + Cfg::OFF_TI);
+  float2* s_red = reinterpret_cast<float2*>(smem_gen + Cfg::OFF_RED);  // [2][8]
+  const uint32_t bar0 = smem_base + Cfg::OFF_BAR;
   const uint32_t w_bar = bar0;
   auto xn_full = [&](int b) { return bar0 + 8u * (1 + b); };
   auto xn_empty = [&](int b) { return bar0 + 8u * (3 + b); };
@@ -457,6 +544,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
   const int lane = threadIdx.x & 31;
   const int n_tiles = tb.n_tiles;
 
+  ti_cache_fill(s_ti, tb, threadIdx.x);
   if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_w);
@@ -491,8 +579,9 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
     const int r = quad * 32 + lane;
     int it = 0;
     for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
+      const TileInfo ti = ti_get(s_ti, tb, it, w);
       EpiState st;
-      epi.tile_begin(st, w, tb);
+      st.F = ti.F; st.t0 = ti.t0; st.s = 0.f; st.q = 0.f;
       const uint32_t ph = (uint32_t)it & 1u;
       float pre[32];  // unused by EpiIn
 #pragma unroll 1
@@ -511,7 +600,15 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
         epi.template apply<32>(st, w, r, n_base + 32, v[1], pre);
       }
       const float s = warp_sum(st.s), qq = warp_sum(st.q);
-      if (lane == 0) epi.part_out[(size_t)w * Cfg::SLOTS + ew] = make_float2(s, qq);
+      float2* red = s_red + (it & 1) * Cfg::EPI_WARPS;
+      if (lane == 0) red[ew] = make_float2(s, qq);
+      named_bar_sync(1, Cfg::EPI_WARPS * 32);
+      if (ew == 0 && lane == 0) {
+        float ts = 0.f, tq = 0.f;
+#pragma unroll
+        for (int k = 0; k < Cfg::EPI_WARPS; ++k) { ts += red[k].x; tq += red[k].y; }
+        epi.part_out[w] = make_float2(ts, tq);
+      }
     }
   } else if (warp == 8) {
     // ================================ MMA issuer ==================================================
@@ -544,65 +641,68 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
     }
     __syncwarp();
   } else {
-    // ================================ prologue: apply G, build the fp16 operand ===================
+    // ================================ prologue: apply G_res, build the fp16 operand ===============
     const int pt = (warp - 9) * 32 + lane;  // 0..255
     const int lane16 = pt & 15, crow = pt >> 4;
     const int f0 = lane16 * 8;
     const bool has_g = ap.g != nullptr;
     int it = 0;
+    float2 pre = make_float2(0.f, 0.f);
+    if (has_g && (int)blockIdx.x < n_tiles) pre = part_prefetch(ap.part2, ti_get(s_ti, tb, 0, blockIdx.x));
     for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
       const int b = it & 1;
-      const TileInfo ti = load_tile_info(tb.tile_info + w);
+      const TileInfo ti = ti_get(s_ti, tb, it, w);
       float mean = 0.f, rstd = 0.f;
-      if (has_g) warp_seg_stats(ap.part2, ti.tile0, ti.ntiles, ap.slots2, ti.inv_count, mean, rstd);
+      if (has_g) {
+        seg_stats_pre(ap.part2, ti, pre, mean, rstd);
+        if (w + (int)gridDim.x < n_tiles) pre = part_prefetch(ap.part2, ti_get(s_ti, tb, it + 1, w + gridDim.x));
+      }
       float2 vm[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         vm[k] = make_float2((ti.t0 + f0 + 2 * k) < ti.F ? 1.f : 0.f, (ti.t0 + f0 + 2 * k + 1) < ti.F ? 1.f : 0.f);
       const float nmr = -mean * rstd;
       const float2 rstd2 = make_float2(rstd, rstd);
-      mbar_wait_b(xn_empty(b), ((uint32_t)(it >> 1) & 1u) ^ 1u);
-      const uint32_t xn = smem_xn(b);
       float* __restrict__ xt = ap.x + tt_index(w, C_BN, 0, f0);
-      float* __restrict__ st_ = ap.skip + tt_index(w, C_BN, 0, f0);
-      const __half* __restrict__ gt = has_g ? ap.g + tt_index(w, 2 * C_BN, 0, f0) : nullptr;
-#pragma unroll 2
-      for (int ps = 0; ps < 8; ++ps) {
-        const int c = ps * 16 + crow;
-        const size_t off = (size_t)c * TILE_M;
-        float4 xa = *reinterpret_cast<const float4*>(xt + off), xb = *reinterpret_cast<const float4*>(xt + off + 4);
-        float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-        if (has_g) {
-          const uint4 gr = ldg_v4(gt + off);
-          const uint4 gs = ldg_v4(gt + (size_t)C_BN * TILE_M + off);
-          float sv[8];
-          if (!ap.first) {
-            const float4 sa4 = *reinterpret_cast<const float4*>(st_ + off), sb4 = *reinterpret_cast<const float4*>(st_ + off + 4);
-            sv[0] = sa4.x; sv[1] = sa4.y; sv[2] = sa4.z; sv[3] = sa4.w; sv[4] = sb4.x; sv[5] = sb4.y; sv[6] = sb4.z; sv[7] = sb4.w;
-          } else {
+      const __half* __restrict__ gt = has_g ? ap.g + tt_index(w, C_BN, 0, f0) : nullptr;
+      // all global loads of the tile are issued before the (possibly blocking) operand-buffer wait
+      constexpr int PASSES = 8;
+      uint32_t xn = 0;
+#pragma unroll 1
+      for (int p0 = 0; p0 < PASSES; p0 += 4) {
+        float4 xa[4], xb[4];
+        uint4 gr[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sv[i] = 0.f;
-          }
-          const float kr = fmaf(nmr, __ldg(ap.rs + c), __ldg(ap.cb + c));
-          const float ks = fmaf(nmr, __ldg(ap.rs + C_BN + c), __ldg(ap.cb + C_BN + c));
-          float gv[8], hv[8];
-          unpack8(gr, gv);
-          unpack8(gs, hv);
-#pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            const float2 dr = fma2(make_float2(gv[i], gv[i + 1]), rstd2, make_float2(kr, kr));
-            const float2 ds = fma2(make_float2(hv[i], hv[i + 1]), rstd2, make_float2(ks, ks));
-            const float2 nx = fma2(dr, vm[i >> 1], make_float2(xv[i], xv[i + 1]));
-            const float2 ns = fma2(ds, vm[i >> 1], make_float2(sv[i], sv[i + 1]));
-            xv[i] = nx.x; xv[i + 1] = nx.y;
-            sv[i] = ns.x; sv[i + 1] = ns.y;
-          }
-          *reinterpret_cast<float4*>(xt + off) = make_float4(xv[0], xv[1], xv[2], xv[3]);
-          *reinterpret_cast<float4*>(xt + off + 4) = make_float4(xv[4], xv[5], xv[6], xv[7]);
-          *reinterpret_cast<float4*>(st_ + off) = make_float4(sv[0], sv[1], sv[2], sv[3]);
-          *reinterpret_cast<float4*>(st_ + off + 4) = make_float4(sv[4], sv[5], sv[6], sv[7]);
+        for (int j = 0; j < 4; ++j) {
+          const size_t off = (size_t)((p0 + j) * 16 + crow) * TILE_M;
+          xa[j] = *reinterpret_cast<const float4*>(xt + off);
+          xb[j] = *reinterpret_cast<const float4*>(xt + off + 4);
+          if (has_g) gr[j] = ldg_v4(gt + off);
         }
-        st_shared_v4(xn + (uint32_t)((c >> 6) * 16384) + a_chunk_off(c & 63, f0), pack8(xv));
+        if (p0 == 0) {
+          mbar_wait_b(xn_empty(b), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+          xn = smem_xn(b);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = (p0 + j) * 16 + crow;
+          const size_t off = (size_t)c * TILE_M;
+          float xv[8] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w, xb[j].x, xb[j].y, xb[j].z, xb[j].w};
+          if (has_g) {
+            const float kr = fmaf(nmr, __ldg(ap.rs + c), __ldg(ap.cb + c));
+            float gv[8];
+            unpack8(gr[j], gv);
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const float2 dr = fma2(make_float2(gv[i], gv[i + 1]), rstd2, make_float2(kr, kr));
+              const float2 nx = fma2(dr, vm[i >> 1], make_float2(xv[i], xv[i + 1]));
+              xv[i] = nx.x; xv[i + 1] = nx.y;
+            }
+            *reinterpret_cast<float4*>(xt + off) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+            *reinterpret_cast<float4*>(xt + off + 4) = make_float4(xv[4], xv[5], xv[6], xv[7]);
+          }
+          st_shared_v4(xn + (uint32_t)((c >> 6) * 16384) + a_chunk_off(c & 63, f0), pack8(xv));
+        }
       }
       fence_proxy_async();
       mbar_arrive(xn_full(b));
@@ -618,39 +718,50 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
 }
 
 // =================================================================================================
-// After the last block: skip_sum += gLN2-scaled skip of the last block, PReLU (mask_net.0), fp16
-// operand of the mask GEMM.  grid = n_tiles, 256 threads: thread = (channel row, 8 frames).
+// After the last block: skip_sum = sum over blocks of the gLN2-scaled raw skip outputs, then PReLU
+// (mask_net.0) -> fp16 operand of the mask GEMM.  grid = n_tiles, 256 threads: thread = (channel row,
+// 8 frames).  stash[b] = raw G_skip of block b, part2[b] its gLN2 partials, rs/cb [n_layers][128].
 // =================================================================================================
-__global__ void __launch_bounds__(256) final_skip_kernel(const __half* __restrict__ g,  // [nt][128][128]
-                                                         const float2* __restrict__ part2, int slots2,
+constexpr int MAX_LAYERS = 64;
+__global__ void __launch_bounds__(256) skip_merge_kernel(const __half* __restrict__ stash, size_t stash_stride,
+                                                         const float2* __restrict__ part2, size_t part_stride,
                                                          const float* __restrict__ rs, const float* __restrict__ cb,
-                                                         const float* __restrict__ skip, __half* __restrict__ skipa,
-                                                         float alpha_mask, int first, Tables tb) {
+                                                         __half* __restrict__ skipa, float alpha_mask, int n_layers,
+                                                         Tables tb) {
+  __shared__ float2 s_stat[MAX_LAYERS];  // (rstd, -mean*rstd) per block
   const int w = blockIdx.x;
   const TileInfo ti = load_tile_info(tb.tile_info + w);
-  float mean, rstd;
-  warp_seg_stats(part2, ti.tile0, ti.ntiles, slots2, ti.inv_count, mean, rstd);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = warp; b < n_layers; b += 8) {
+    float mean, rstd;
+    warp_seg_stats(part2 + (size_t)b * part_stride, ti.tile0, ti.ntiles, 1, ti.inv_count, mean, rstd);
+    if (lane == 0) s_stat[b] = make_float2(rstd, -mean * rstd);
+  }
+  __syncthreads();
   const int lane16 = threadIdx.x & 15, crow = threadIdx.x >> 4;
   const int f0 = lane16 * 8;
-  const float nmr = -mean * rstd;
-#pragma unroll 2
+#pragma unroll 1
   for (int ps = 0; ps < 8; ++ps) {
     const int c = ps * 16 + crow;
     const size_t idx = tt_index(w, C_SKIP, c, f0);
-    float gv[8], sv[8], o[8];
-    unpack8(ldg_v4(g + idx), gv);
-    if (!first) {
-      const float4 a = *reinterpret_cast<const float4*>(skip + idx), b = *reinterpret_cast<const float4*>(skip + idx + 4);
-      sv[0] = a.x; sv[1] = a.y; sv[2] = a.z; sv[3] = a.w; sv[4] = b.x; sv[5] = b.y; sv[6] = b.z; sv[7] = b.w;
-    } else {
+    float acc[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sv[i] = 0.f;
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    float kc = 0.f;
+#pragma unroll 4
+    for (int b = 0; b < n_layers; ++b) {
+      const uint4 gv4 = ldg_v4(stash + (size_t)b * stash_stride + idx);
+      const float2 sb = s_stat[b];
+      kc += fmaf(sb.y, __ldg(rs + b * C_SKIP + c), __ldg(cb + b * C_SKIP + c));
+      float gv[8];
+      unpack8(gv4, gv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(gv[i], sb.x, acc[i]);
     }
-    const float ks = fmaf(nmr, __ldg(rs + c), __ldg(cb + c));
+    float o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float vmask = (ti.t0 + f0 + i) < ti.F ? 1.f : 0.f;
-      const float v = fmaf(fmaf(gv[i], rstd, ks), vmask, sv[i]);
+      const float v = ((ti.t0 + f0 + i) < ti.F) ? acc[i] + kc : 0.f;
       o[i] = fmaxf(v, 0.f) + alpha_mask * fminf(v, 0.f);
     }
     *reinterpret_cast<uint4*>(skipa + idx) = pack8(o);

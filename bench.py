@@ -163,16 +163,28 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-KERNEL_CLASSES = ["encoder", "bottleneck_gemm", "in_conv_gemm", "dwconv", "res_skip_gemm", "mask_gemm", "decoder"]
+KERNEL_CLASSES = ["encoder", "bottleneck_gemm", "in_conv_gemm", "dwconv", "res_skip_gemm", "apply_in_gemm", "dw_rs_gemm",
+                  "final_skip", "mask_gemm", "decoder"]
 
 
-def classify_launches(ms, n_layers):
+def launches_per_forward(n_layers, pipeline):
+    """pipeline 1 (fused fp16 tensor-core mode): encoder, bottleneck, (K_B, K_A) per block, final skip, mask,
+    decoder; pipeline 0: encoder, bottleneck, (in-conv, depthwise, res/skip) per block, mask, decoder."""
+    return 2 + 2 * n_layers + 1 + 2 if pipeline == 1 else 2 + 3 * n_layers + 2
+
+
+def classify_launches(ms, n_layers, pipeline=0):
     per = {k: [] for k in KERNEL_CLASSES}
-    if len(ms) != 2 + 3 * n_layers + 2:
+    if len(ms) != launches_per_forward(n_layers, pipeline):
         return per
     per["encoder"].append(ms[0]); per["bottleneck_gemm"].append(ms[1])
-    for i in range(n_layers):
-        per["in_conv_gemm"].append(ms[2 + 3 * i]); per["dwconv"].append(ms[3 + 3 * i]); per["res_skip_gemm"].append(ms[4 + 3 * i])
+    if pipeline == 1:
+        for i in range(n_layers):
+            per["apply_in_gemm"].append(ms[2 + 2 * i]); per["dw_rs_gemm"].append(ms[3 + 2 * i])
+        per["final_skip"].append(ms[-3])
+    else:
+        for i in range(n_layers):
+            per["in_conv_gemm"].append(ms[2 + 3 * i]); per["dwconv"].append(ms[3 + 3 * i]); per["res_skip_gemm"].append(ms[4 + 3 * i])
     per["mask_gemm"].append(ms[-2]); per["decoder"].append(ms[-1])
     return per
 
@@ -224,7 +236,9 @@ def main():
                             model_args=margs, precision=args.precision)
     eng = sep.engine
     n_layers = int(margs["n_blocks"]) * int(margs["n_repeats"])
-    launches_per_step = 2 + 3 * n_layers + 2
+    from b200sep import _native as nat
+    pipeline = int(nat.lib().b200sep_pipeline(eng._handle))
+    launches_per_step = launches_per_forward(n_layers, pipeline)
 
     # ---------------- device-resident timing (inputs already in HBM) ----------------
     d_mix = torch.from_numpy(np.concatenate(mixes)).to(dev)
@@ -283,7 +297,7 @@ def main():
         for _ in range(3):
             flush.zero_()
             eng.separate_device(d_mix, lens, out=d_out, workspace=ws)
-            per = classify_launches(eng.profile_read(), n_layers)
+            per = classify_launches(eng.profile_read(), n_layers, pipeline)
             for k, v in per.items():
                 acc[k].extend(v)
         eng.profile_last_call(False)
@@ -294,6 +308,12 @@ def main():
             "in_conv_gemm": ("tensor", 2 * frames * 128 * 512),
             "dwconv": ("hbm", 2 * 512 * frames * es),
             "res_skip_gemm": ("tensor", 2 * frames * 512 * 256),
+            # fused block kernels: HBM bytes per frame = G_res 256 + x r/w 1024 + h1 1024 (K_B); h1 1024 +
+            # G_res 256 + skip stash 256 (K_A); their GEMM FLOPs are reported beside as tensor_tflops;
+            # skip merge: one 256 B stash slot per block read once + the fp16 mask operand
+            "apply_in_gemm": ("hbm", 2304 * frames),
+            "dw_rs_gemm": ("hbm", 1536 * frames),
+            "final_skip": ("hbm", (256 * n_layers + 256) * frames),
             "mask_gemm": ("tensor", 2 * frames * 128 * 512 * N_SRC),
             "decoder": ("hbm", N_SRC * 512 * frames * es + 4 * N_SRC * total),
         }
@@ -309,6 +329,9 @@ def main():
                 ach, peak, unit = work / (avg * 1e-3) / 1e9, float(peaks["hbm_gbs"]), "GB/s"
             kernels[k] = {"launches_per_step": len(v) // 3, "avg_ms": avg, "share_of_step": (sum(v) / 3.0) / step_total,
                           "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak}
+            gemm_flops = {"apply_in_gemm": 2 * frames * 128 * 512, "dw_rs_gemm": 2 * frames * 512 * 256}.get(k)
+            if gemm_flops:
+                kernels[k]["tensor_tflops"] = gemm_flops / (avg * 1e-3) / 1e12
         dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
         kd = kernels[dom]
         roofline = {"kernel": dom, "bound": kd["bound"], "achieved": kd["achieved"], "peak": kd["peak"], "unit": kd["unit"],
@@ -333,7 +356,7 @@ def main():
             "dtype": "f16" if args.precision != "fp32" else "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: 64 synthetic 3-speaker overlap segments U[0.2,4.0] s per GPU, 8 kHz, ConvTasNet n_src=3 random-init",
                        "segments_per_gpu": len(lens), "audio_s_per_gpu": audio_s, "sample_rate": SR, "n_src": N_SRC,
-                       "precision": args.precision, "parallelism": f"replica x{world} (segments sharded, no data-path collective)",
+                       "precision": args.precision, "pipeline": "fused (2 kernels per TCN block)" if pipeline == 1 else "unfused (3 kernels per TCN block)", "parallelism": f"replica x{world} (segments sharded, no data-path collective)",
                        "l2": "L2 flushed (256 MiB write) between timed steps; per-step activation working set ~1 GB > 126 MB L2"},
             "model_tflops": whole_flops / (ms_max * 1e-3) / 1e12,
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,

@@ -6,8 +6,10 @@ import b200sep
 from b200sep import synth, weights
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import classify_launches, KERNEL_CLASSES
+from b200sep import _native as nat
 sd, args = weights.random_state_dict(3, 0)
 eng = b200sep.SeparationEngine(sd, args, 0, "fp16")
+pipeline = int(nat.lib().b200sep_pipeline(eng._handle))
 lens = synth.segment_lengths(64, 2)
 total = sum(lens)
 d_mix = torch.randn(total, device="cuda") * 0.05
@@ -25,7 +27,7 @@ eng.profile_last_call(True)
 acc = {k: [] for k in KERNEL_CLASSES}
 for _ in range(3):
     eng.separate_device(d_mix, lens, out=out, workspace=ws)
-    for k, v in classify_launches(eng.profile_read(), 24).items():
+    for k, v in classify_launches(eng.profile_read(), 24, pipeline).items():
         acc[k].extend(v)
 print(os.path.basename(os.environ.get("B200SEP_LIB", "default")), f"{min(ts):.3f} ms",
-      " ".join(f"{k}={1e3*sum(v)/len(v):.1f}" for k, v in acc.items()), flush=True)
+      " ".join(f"{k}={1e3*sum(v)/len(v):.1f}" for k, v in acc.items() if v), "abort=", nat.abort_flag(), flush=True)
