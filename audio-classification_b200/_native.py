@@ -26,7 +26,7 @@ EXPORTS = [
     "b200sep_workspace_bytes", "b200sep_separate_batch", "b200sep_pit_workspace_bytes",
     "b200sep_pit_sisdr_batch", "b200sep_debug_gemm", "b200sep_debug_set_stop",
     "b200sep_debug_layout", "b200sep_profile_enable", "b200sep_profile_read",
-    "b200sep_debug_abort_flag", "b200sep_pipeline",
+    "b200sep_debug_abort_flag", "b200sep_pipeline", "b200sep_debug_timeline",
 ]
 
 
@@ -101,6 +101,8 @@ def lib() -> C.CDLL:
         L.b200sep_profile_read.argtypes = [vp, C.POINTER(C.c_float), i32, i32p]
         L.b200sep_debug_abort_flag.restype = C.c_int
         L.b200sep_debug_abort_flag.argtypes = [i32p, i32]
+        L.b200sep_debug_timeline.restype = C.c_int
+        L.b200sep_debug_timeline.argtypes = [vp]
         L.b200sep_pipeline.restype = C.c_int
         L.b200sep_pipeline.argtypes = [vp]
         _lib = L

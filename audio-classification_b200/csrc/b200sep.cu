@@ -767,6 +767,14 @@ int b200sep_debug_abort_flag(int32_t* out, int32_t reset) {
   return 0;
 }
 
+// Registers (or, with nullptr, removes) a device buffer of 148 * 8 * 128 int64 the fused kernels stamp with
+// clock64 values per (CTA, tile visit, slot) -- see tl_stamp in fused_block.cuh.  Debug only.
+int b200sep_debug_timeline(void* d_buf) {
+  long long* p = static_cast<long long*>(d_buf);
+  CK(cudaMemcpyToSymbol(b200sep::c_timeline, &p, sizeof(p)));
+  return 0;
+}
+
 // Launch sequence the model runs: 0 = unfused (encoder, bottleneck, 3 kernels per block, mask, decoder),
 // 1 = fused (encoder, bottleneck, 2 kernels per block, final skip, mask, decoder).
 int b200sep_pipeline(const b200sep_model* m) { return (m && m->half && m->use_tc && m->fused) ? 1 : 0; }

@@ -31,6 +31,14 @@ namespace b200sep {
 
 __device__ int g_abort = 0;  // set when a bounded wait ran out (read by b200sep_debug_abort_flag)
 
+// Optional in-kernel timeline (b200sep_debug_timeline): clock64 stamps per (CTA, tile visit, slot).
+constexpr int TL_TILES = 8, TL_SLOTS = 128;
+__constant__ long long* c_timeline = nullptr;
+__device__ __forceinline__ void tl_stamp(int it, int slot) {
+  long long* tl = c_timeline;
+  if (tl != nullptr && it < TL_TILES) tl[((size_t)blockIdx.x * TL_TILES + it) * TL_SLOTS + slot] = clock64();
+}
+
 namespace fb {
 using namespace tc;
 
@@ -56,6 +64,39 @@ __device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity) {
     if ((i & 31u) == 31u && *reinterpret_cast<volatile int*>(&g_abort) != 0) return;
   }
   *reinterpret_cast<volatile int*>(&g_abort) = 1;
+}
+// L2 prefetch of a contiguous global range (bytes % 16 == 0) / of a TMA box
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_tma_2d(const void* desc, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(desc)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+// Wait-free block reduction of per-warp (sum, sumsq) partials of one m-tile: every warp publishes its pair
+// and bumps a shared counter; whichever warp arrives last adds the n_warps pairs in index order (so the
+// result does not depend on who that is) and writes the tile's single partial.  `red` / `cnt` are double-
+// buffered by tile parity by the caller; warps of one role are never two tiles apart (they meet at the
+// pipeline mbarriers every chunk), so a buffer is free again when it is reused.  (A bar.arrive / bar.sync
+// pair is NOT safe here: a fast warp can arrive twice in one barrier phase and hang the waiting warp.)
+__device__ __forceinline__ void tile_partial_reduce(float2* red, int* cnt, int n_warps, int my_warp, float s, float q,
+                                                    float2* out) {
+  if ((threadIdx.x & 31) == 0) {
+    red[my_warp] = make_float2(s, q);
+    __threadfence_block();
+    const int prev = atomicAdd(cnt, 1);
+    if (prev == n_warps - 1) {
+      __threadfence_block();
+      float ts = 0.f, tq = 0.f;
+      for (int k = 0; k < n_warps; ++k) {
+        const volatile float* v = reinterpret_cast<const volatile float*>(red + k);
+        ts += v[0]; tq += v[1];
+      }
+      *cnt = 0;
+      *out = make_float2(ts, tq);
+    }
+  }
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -155,8 +196,10 @@ struct DwTab {
 
 template <int BN>
 struct KaCfg {
-  static constexpr int RAW_STAGES = 2, AB_STAGES = 2;
-  static constexpr int RAW_STAGE = 3 * 16384;        // centre 64 x 128, left halo, right halo (<= 64 x 128 each)
+  static constexpr int AB_STAGES = 2;
+  // raw h1 ring: a 110 KiB pool cut into as many stages as fit (stage = 64 channels x (128 + 2 hw) frames:
+  // centre box, left halo, right halo); 6 stages at hw = 8 ... 2 stages at hw = 128
+  static constexpr int RAW_POOL = 110 * 1024, RAW_MAX_STAGES = 8;
   static constexpr int A_STAGE = TILE_M * 64 * 2;    // 16 KiB
   static constexpr int B_STAGE = BN * 64 * 2;        // 32 / 16 KiB
   static constexpr int AB_STAGE = A_STAGE + 32768;
@@ -164,12 +207,14 @@ struct KaCfg {
   static constexpr int EPI_WARPS = 4, PROD_WARPS = 16;
   static constexpr int THREADS = (EPI_WARPS + 3 + PROD_WARPS) * 32;  // 736
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int OFF_AB = RAW_STAGES * RAW_STAGE;
+  static constexpr int OFF_AB = RAW_POOL;
   static constexpr int OFF_TAB = OFF_AB + AB_STAGES * AB_STAGE;
   static constexpr int OFF_TI = OFF_TAB + TAB_BYTES;
   static constexpr int OFF_RED = OFF_TI + TI_CACHE * 32;
-  static constexpr int OFF_BAR = OFF_RED + 2 * PROD_WARPS * 8;
+  static constexpr int OFF_CNT = OFF_RED + 2 * PROD_WARPS * 8;
+  static constexpr int OFF_BAR = OFF_CNT + 16;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024 /*align*/;
+  static_assert(SMEM_BYTES <= 232448, "K_A shared memory over the 227 KiB limit");
 };
 
 struct DwEdge { float2 ml[4], mc[4], mr[4]; };
@@ -196,6 +241,52 @@ __device__ __forceinline__ void dw_taps(const uint4 vc, const uint4 va, const ui
   }
 }
 
+// Interior-tile producer step in packed half arithmetic: 8 outputs of one channel from the three 8-frame
+// vectors.  Taps, PReLU and the operand rounding happen in fp16 (HFMA2 / HMUL2 / HMNMX2: no fp16 -> fp32
+// conversions on the tap path); only the gLN2 statistics are accumulated in fp32.
+__device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+template <int D, bool A01>
+__device__ __forceinline__ uint4 dw_step_h2(const uint4 vc, const uint4 va, const uint4 vb, const float4 t0,
+                                            const float cb, const float rstd, const float rm, const __half2 alpha2,
+                                            float2& s2, float2& q2) {
+  const uint32_t c[4] = {vc.x, vc.y, vc.z, vc.w};
+  const uint32_t pv[4] = {va.x, va.y, va.z, va.w};
+  const uint32_t nv[4] = {vb.x, vb.y, vb.z, vb.w};
+  uint32_t l[4], r[4];
+  if (D == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { l[i] = pv[i]; r[i] = nv[i]; }
+  } else if (D == 1) {
+    // pairs shifted by one frame: (hi of word i-1, lo of word i)
+    const uint32_t m0 = __byte_perm(pv[3], c[0], 0x5432), m1 = __byte_perm(c[0], c[1], 0x5432);
+    const uint32_t m2 = __byte_perm(c[1], c[2], 0x5432), m3 = __byte_perm(c[2], c[3], 0x5432);
+    const uint32_t m4 = __byte_perm(c[3], nv[0], 0x5432);
+    l[0] = m0; l[1] = m1; l[2] = m2; l[3] = m3;
+    r[0] = m1; r[1] = m2; r[2] = m3; r[3] = m4;
+  } else if (D == 2) {
+    l[0] = pv[3]; l[1] = c[0]; l[2] = c[1]; l[3] = c[2];
+    r[0] = c[1]; r[1] = c[2]; r[2] = c[3]; r[3] = nv[0];
+  } else {  // D == 4
+    l[0] = pv[2]; l[1] = pv[3]; l[2] = c[0]; l[3] = c[1];
+    r[0] = c[2]; r[1] = c[3]; r[2] = nv[0]; r[3] = nv[1];
+  }
+  const __half2 w0 = __float2half2_rn(t0.x * rstd), w1 = __float2half2_rn(t0.y * rstd);
+  const __half2 w2 = __float2half2_rn(t0.z * rstd), cw = __float2half2_rn(fmaf(-t0.w, rm, cb));
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 u = __hfma2(u32_as_h2(l[i]), w0, __hfma2(u32_as_h2(c[i]), w1, __hfma2(u32_as_h2(r[i]), w2, cw)));
+    if (A01) u = __hmax2(u, __hmul2(u, alpha2));
+    else u = __hadd2(__hmax2(u, __float2half2_rn(0.f)), __hmul2(alpha2, __hmin2(u, __float2half2_rn(0.f))));
+    o[i] = h2_as_u32(u);
+    const float2 f = __half22float2(u);
+    s2 = add2(s2, f);
+    q2 = fma2(f, f, q2);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 template <int BN, int D, bool A01>
 __global__ void __launch_bounds__(736, 1)
 dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_hc,
@@ -205,7 +296,6 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  auto raw_st = [&](int s) { return smem_base + (uint32_t)(s * Cfg::RAW_STAGE); };
   auto stage_a = [&](int s) { return smem_base + (uint32_t)(Cfg::OFF_AB + s * Cfg::AB_STAGE); };
   auto stage_b = [&](int s) { return smem_base + (uint32_t)(Cfg::OFF_AB + s * Cfg::AB_STAGE + Cfg::A_STAGE); };
   float4* s_t0 = reinterpret_cast<float4*>(smem_gen + Cfg::OFF_TAB);
@@ -213,20 +303,25 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   float* s_cb = reinterpret_cast<float*>(s_t1 + C_HID);
   TileInfo* s_ti = reinterpret_cast<TileInfo*>(smem_gen + Cfg::OFF_TI);
   float2* s_red = reinterpret_cast<float2*>(smem_gen + Cfg::OFF_RED);  // [2][16]
+  int* s_cnt = reinterpret_cast<int*>(smem_gen + Cfg::OFF_CNT);          // [2]
   const uint32_t bar0 = smem_base + Cfg::OFF_BAR;
   auto raw_full = [&](int s) { return bar0 + 8u * s; };
-  auto raw_empty = [&](int s) { return bar0 + 8u * (2 + s); };
-  auto ab_full = [&](int s) { return bar0 + 8u * (4 + s); };
-  auto ab_empty = [&](int s) { return bar0 + 8u * (6 + s); };
-  auto tfull_bar = [&](int s) { return bar0 + 8u * (8 + s); };
-  auto tempty_bar = [&](int s) { return bar0 + 8u * (10 + s); };
-  const uint32_t tmem_ptr_smem = bar0 + 8u * 12;
+  auto raw_empty = [&](int s) { return bar0 + 8u * (8 + s); };
+  auto ab_full = [&](int s) { return bar0 + 8u * (16 + s); };
+  auto ab_empty = [&](int s) { return bar0 + 8u * (18 + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (20 + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (22 + s); };
+  const uint32_t tmem_ptr_smem = bar0 + 8u * 24;
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n_tiles = tb.n_tiles;
   const int d = (D > 0) ? D : p.dilation;
   const int hw = (D > 0) ? 8 : d;  // halo width in frames (multiple of 8, <= 128)
+  const uint32_t halo_bytes = (uint32_t)(64 * hw * 2);
+  const uint32_t raw_stage_bytes = (16384u + 2u * halo_bytes + 1023u) & ~1023u;
+  const int raw_stages = min((int)(Cfg::RAW_POOL / raw_stage_bytes), Cfg::RAW_MAX_STAGES);
+  auto raw_st = [&](int s) { return smem_base + (uint32_t)s * raw_stage_bytes; };
 
   // static tables -> shared memory
   for (int i = threadIdx.x; i < C_HID; i += Cfg::THREADS) {
@@ -235,14 +330,17 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
     s_cb[i] = __ldg(p.cb + i);
   }
   ti_cache_fill(s_ti, tb, threadIdx.x);
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
   if (warp == 4 && lane == 0) { tma_prefetch_desc(&tm_hc); tma_prefetch_desc(&tm_hh); }
   if (warp == 5 && lane == 0) tma_prefetch_desc(&tm_b);
   if (warp == 6) {
     if (lane == 0) {
-      for (int s = 0; s < 2; ++s) {
+      for (int s = 0; s < Cfg::RAW_MAX_STAGES; ++s) {
         mbar_init(raw_full(s), 1);
-        mbar_init(raw_empty(s), Cfg::PROD_WARPS * 32);
-        mbar_init(ab_full(s), Cfg::PROD_WARPS * 32 + 1);
+        mbar_init(raw_empty(s), Cfg::PROD_WARPS * 16);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(ab_full(s), Cfg::PROD_WARPS * 16 + 1);
         mbar_init(ab_empty(s), 1);
         mbar_init(tfull_bar(s), 1);
         mbar_init(tempty_bar(s), 32 * Cfg::EPI_WARPS);
@@ -269,6 +367,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       mbar_wait_b(tfull_bar(as), aphase);
       tcgen05_fence_after();
+      if (threadIdx.x == 0) tl_stamp(it, 80);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
       __half* __restrict__ d_res = g_res + tt_index(w, C_BN, 0, r);
       __half* __restrict__ d_skip = g_skip + tt_index(w, C_SKIP, 0, r);
@@ -286,6 +385,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       }
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(as));
+      if (threadIdx.x == 0) tl_stamp(it, 81);
     }
   } else if (warp == 4) {
     // ================================ TMA producer: raw h1 k-blocks + halos =======================
@@ -295,15 +395,18 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       const uint32_t bytes = (uint32_t)(64 * (TILE_M + 2 * hw) * 2);
       for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
         for (int kb = 0; kb < 8; ++kb) {
+          // pull the same k-block of the NEXT tile this CTA visits into L2 (a whole tile ahead of its use)
+          if (w + (int)gridDim.x < n_tiles) l2_prefetch_tma_2d(&tm_hc, 0, (w + (int)gridDim.x) * C_HID + kb * 64);
           mbar_wait_b(raw_empty(stage), phase ^ 1u);
+          tl_stamp((w - (int)blockIdx.x) / (int)gridDim.x, 88 + kb);
           mbar_expect_tx(raw_full(stage), bytes);
           const uint32_t dst = raw_st(stage);
           tma_load_2d(dst, &tm_hc, raw_full(stage), 0, w * C_HID + kb * 64);
           // frames [t0 - hw, t0) live at the end of the previous m-tile, [t0 + 128, t0 + 128 + hw) at the
           // start of the next; rows outside the tensor are zero-filled by the TMA unit
           tma_load_2d(dst + 16384u, &tm_hh, raw_full(stage), TILE_M - hw, (w - 1) * C_HID + kb * 64);
-          tma_load_2d(dst + 32768u, &tm_hh, raw_full(stage), 0, (w + 1) * C_HID + kb * 64);
-          if (++stage == Cfg::RAW_STAGES) { stage = 0; phase ^= 1u; }
+          tma_load_2d(dst + 16384u + halo_bytes, &tm_hh, raw_full(stage), 0, (w + 1) * C_HID + kb * 64);
+          if (++stage == raw_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -335,10 +438,12 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait_b(tempty_bar(as), aphase ^ 1u);
         tcgen05_fence_after();
+        tl_stamp(it, 64);
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < 8; ++kb) {
           mbar_wait_b(ab_full(stage), phase);
           tcgen05_fence_after();
+          tl_stamp(it, 65 + kb);
           const uint32_t sa = stage_a(stage), sb = stage_b(stage);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -355,77 +460,63 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
     __syncwarp();
   } else {
     // ================================ depthwise producers =========================================
+    // Two groups of 8 warps; group g produces the k-blocks kb = g, g+2, ... (and owns A/B stage g), so
+    // the groups run out of phase: while one waits on its barriers the other keeps the issue slots busy.
+    // A warp-step = 2 channels x 128 frames; a group covers a k-block in 4 steps per warp.
     const int pw = warp - 7;              // 0..15
+    const int grp = pw >> 3, gw = pw & 7;
     const int sub = lane >> 4, lane16 = lane & 15;
-    const int row0 = pw * 2 + sub;        // k-row of step 0 inside a k-block; step 1 = row0 + 32
+    const int row0 = gw * 2 + sub;        // k-row of step 0 inside a k-block; step j = row0 + 16 j
     const float alpha = p.alpha2;
     // shared-memory offsets (inside a raw stage) of this thread's centre / left / right vectors
     const int sv = (D > 0) ? 1 : (d >> 3);  // tap distance in 8-frame vectors
     const int hv = hw >> 3;                 // halo width in vectors
-    const uint32_t c_off = (uint32_t)(lane16 * 16), c_pitch = 256u;
+    const uint32_t c_pitch = 256u;
     uint32_t l_off, l_pitch, r_off, r_pitch;
     if (lane16 - sv >= 0) { l_off = (uint32_t)((lane16 - sv) * 16); l_pitch = 256u; }
     else { l_off = 16384u + (uint32_t)((lane16 - sv + hv) * 16); l_pitch = (uint32_t)(hw * 2); }
     if (lane16 + sv < 16) { r_off = (uint32_t)((lane16 + sv) * 16); r_pitch = 256u; }
-    else { r_off = 32768u + (uint32_t)((lane16 + sv - 16) * 16); r_pitch = (uint32_t)(hw * 2); }
+    else { r_off = 16384u + halo_bytes + (uint32_t)((lane16 + sv - 16) * 16); r_pitch = (uint32_t)(hw * 2); }
+    // step 0 addresses of this thread (step j = + 16 j rows)
+    const uint32_t c_base = (uint32_t)(lane16 * 16) + (uint32_t)row0 * c_pitch;
+    const uint32_t l_base = l_off + (uint32_t)row0 * l_pitch, r_base = r_off + (uint32_t)row0 * r_pitch;
+    const uint32_t c_step = 16u * c_pitch, l_step = 16u * l_pitch, r_step = 16u * r_pitch;
+    const uint32_t a_off0 = a_chunk_off(row0, lane16 * 8);  // (row & 7) is the same for every step; step j = + 2048 j
+    const uint32_t sa = stage_a(grp) + a_off0;
+    const uint32_t my_ab_full = ab_full(grp), my_ab_empty = ab_empty(grp);
+    const __half2 alpha_h2 = __float2half2_rn(alpha);
+    const bool tl_on = (gw == 0 && lane == 0);
+    const int tl_base = grp ? 100 : 40;  // timeline slots: group 0 40.., group 1 100..
 
-    int rs_ = 0, as_ = 0;
-    uint32_t rphase = 0, aphase = 0;
+    int rs_ = grp % raw_stages;  // raw stage / phase of this group's next k-block (advances by 2 k-blocks)
+    uint32_t rphase = (uint32_t)(grp / raw_stages) & 1u;
+    uint32_t aphase = 0;
     int it = 0;
-    float2 pre = make_float2(0.f, 0.f);
-    if ((int)blockIdx.x < n_tiles) pre = part_prefetch(part1, ti_get(s_ti, tb, 0, blockIdx.x));
+    float nmean = 0.f, nrstd = 0.f;  // statistics of the NEXT tile's segment (computed mid-tile)
+    if ((int)blockIdx.x < n_tiles) {
+      const TileInfo t0i = ti_get(s_ti, tb, 0, blockIdx.x);
+      seg_stats_pre(part1, t0i, part_prefetch(part1, t0i), nmean, nrstd);
+    }
     for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
       const TileInfo ti = ti_get(s_ti, tb, it, w);
       const int F = ti.F, tile_t0 = ti.t0;
-      float mean, rstd;
-      seg_stats_pre(part1, ti, pre, mean, rstd);
-      if (w + (int)gridDim.x < n_tiles) pre = part_prefetch(part1, ti_get(s_ti, tb, it + 1, w + gridDim.x));
+      const float mean = nmean, rstd = nrstd;
+      const bool has_next = w + (int)gridDim.x < n_tiles;
+      TileInfo tn = ti;
+      float2 pre = make_float2(0.f, 0.f);
+      if (has_next) {
+        tn = ti_get(s_ti, tb, it + 1, w + gridDim.x);
+        pre = part_prefetch(part1, tn);
+      }
       const float rm = rstd * mean;
+      if (tl_on) tl_stamp(it, 32 + grp);
       const int t_base = tile_t0 + lane16 * 8;
       const bool interior = (tile_t0 - d >= 0) && (tile_t0 + TILE_M - 1 + d < F);
       float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
-      if (interior) {
-#pragma unroll 1
-        for (int kb = 0; kb < 8; ++kb) {
-          mbar_wait_b(raw_full(rs_), rphase);
-          mbar_wait_b(ab_empty(as_), aphase ^ 1u);
-          const uint32_t raw = raw_st(rs_), sa = stage_a(as_);
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const int row = s * 32 + row0;
-            const int c = kb * 64 + row;
-            const uint4 vc = ld_shared_v4(raw + c_off + (uint32_t)row * c_pitch);
-            const uint4 va = ld_shared_v4(raw + l_off + (uint32_t)row * l_pitch);
-            const uint4 vb = ld_shared_v4(raw + r_off + (uint32_t)row * r_pitch);
-            const float4 t0 = s_t0[c];
-            const float cw = fmaf(-t0.w, rm, s_cb[c]);
-            float ctr[8], lft[8], rgt[8];
-            dw_taps<D>(vc, va, vb, ctr, lft, rgt);
-            const float wa0 = t0.x * rstd, wa1 = t0.y * rstd, wa2 = t0.z * rstd;
-            const float2 w0 = make_float2(wa0, wa0), w1 = make_float2(wa1, wa1), w2 = make_float2(wa2, wa2);
-            const float2 cw2 = make_float2(cw, cw);
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-              float2 u = fma2(make_float2(lft[i], lft[i + 1]), w0,
-                              fma2(make_float2(ctr[i], ctr[i + 1]), w1, fma2(make_float2(rgt[i], rgt[i + 1]), w2, cw2)));
-              u = prelu2<A01>(u, alpha);
-              o[i] = u.x; o[i + 1] = u.y;
-              s2 = add2(s2, u);
-              q2 = fma2(u, u, q2);
-            }
-            st_shared_v4(sa + a_chunk_off(row, lane16 * 8), pack8(o));
-          }
-          fence_proxy_async();
-          mbar_arrive(ab_full(as_));
-          mbar_arrive(raw_empty(rs_));
-          if (++rs_ == Cfg::RAW_STAGES) { rs_ = 0; rphase ^= 1u; }
-          if (++as_ == Cfg::AB_STAGES) { as_ = 0; aphase ^= 1u; }
-        }
-      } else {
+      DwEdge mk;
+      if (!interior) {
         // taps and frames masked by segment-relative frame index (zero padding applies to the normalised
         // signal at the TRUE segment ends); masked-out taps read finite values, so 0 * h is exactly 0
-        DwEdge mk;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int ta = t_base + 2 * k, tb2 = ta + 1;
@@ -433,18 +524,41 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
           mk.mc[k] = make_float2(ta < F ? 1.f : 0.f, tb2 < F ? 1.f : 0.f);
           mk.mr[k] = make_float2(ta + d < F ? 1.f : 0.f, tb2 + d < F ? 1.f : 0.f);
         }
+      }
 #pragma unroll 1
-        for (int kb = 0; kb < 8; ++kb) {
-          mbar_wait_b(raw_full(rs_), rphase);
-          mbar_wait_b(ab_empty(as_), aphase ^ 1u);
-          const uint32_t raw = raw_st(rs_), sa = stage_a(as_);
+      for (int kb = grp; kb < 8; kb += 2) {
+        mbar_wait_b(raw_full(rs_), rphase);
+        if (tl_on) tl_stamp(it, tl_base + 3 * (kb >> 1));
+        const uint32_t raw = raw_st(rs_);
+        const int ch0 = kb * 64 + row0;
+        if (interior) {
+#pragma unroll
+          for (int jj = 0; jj < 4; jj += 2) {
+            // both steps' vectors and table entries first (independent shared-memory loads in flight) ...
+            const uint4 vc0 = ld_shared_v4(raw + c_base + jj * c_step), va0 = ld_shared_v4(raw + l_base + jj * l_step);
+            const uint4 vb0 = ld_shared_v4(raw + r_base + jj * r_step);
+            const uint4 vc1 = ld_shared_v4(raw + c_base + (jj + 1) * c_step), va1 = ld_shared_v4(raw + l_base + (jj + 1) * l_step);
+            const uint4 vb1 = ld_shared_v4(raw + r_base + (jj + 1) * r_step);
+            const float4 ta = s_t0[ch0 + jj * 16], tb_ = s_t0[ch0 + jj * 16 + 16];
+            const float cba = s_cb[ch0 + jj * 16], cbb = s_cb[ch0 + jj * 16 + 16];
+            // ... then the arithmetic; the (single) A stage of this group is only needed for the stores, so the
+            // tensor core drains the previous k-block of the group while the first two steps are computed
+            const uint4 o0 = dw_step_h2<D, A01>(vc0, va0, vb0, ta, cba, rstd, rm, alpha_h2, s2, q2);
+            const uint4 o1 = dw_step_h2<D, A01>(vc1, va1, vb1, tb_, cbb, rstd, rm, alpha_h2, s2, q2);
+            if (jj == 0) {
+              mbar_wait_b(my_ab_empty, aphase ^ 1u);
+              if (tl_on) tl_stamp(it, tl_base + 3 * (kb >> 1) + 1);
+            }
+            st_shared_v4(sa + jj * 2048u, o0);
+            st_shared_v4(sa + (jj + 1) * 2048u, o1);
+          }
+        } else {
 #pragma unroll 1
-          for (int s = 0; s < 2; ++s) {
-            const int row = s * 32 + row0;
-            const int c = kb * 64 + row;
-            const uint4 vc = ld_shared_v4(raw + c_off + (uint32_t)row * c_pitch);
-            const uint4 va = ld_shared_v4(raw + l_off + (uint32_t)row * l_pitch);
-            const uint4 vb = ld_shared_v4(raw + r_off + (uint32_t)row * r_pitch);
+          for (int j = 0; j < 4; ++j) {
+            const int c = ch0 + j * 16;
+            const uint4 vc = ld_shared_v4(raw + c_base + j * c_step);
+            const uint4 va = ld_shared_v4(raw + l_base + j * l_step);
+            const uint4 vb = ld_shared_v4(raw + r_base + j * r_step);
             const float4 t0 = s_t0[c], t1 = s_t1[c];
             float ctr[8], lft[8], rgt[8];
             dw_taps<D>(vc, va, vb, ctr, lft, rgt);
@@ -465,27 +579,26 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
               s2 = add2(s2, u);
               q2 = fma2(u, u, q2);
             }
-            st_shared_v4(sa + a_chunk_off(row, lane16 * 8), pack8(o));
+            if (j == 0) mbar_wait_b(my_ab_empty, aphase ^ 1u);
+            st_shared_v4(sa + j * 2048u, pack8(o));
           }
-          fence_proxy_async();
-          mbar_arrive(ab_full(as_));
-          mbar_arrive(raw_empty(rs_));
-          if (++rs_ == Cfg::RAW_STAGES) { rs_ = 0; rphase ^= 1u; }
-          if (++as_ == Cfg::AB_STAGES) { as_ = 0; aphase ^= 1u; }
         }
+        fence_proxy_async();
+        mbar_arrive(my_ab_full);
+        mbar_arrive(raw_empty(rs_));
+        if (tl_on) tl_stamp(it, tl_base + 3 * (kb >> 1) + 2);
+        rs_ += 2;
+        if (rs_ >= raw_stages) { rs_ -= raw_stages; rphase ^= 1u; }
+        aphase ^= 1u;
+        // statistics of the next tile's segment, off the tile-boundary critical path
+        if (kb == 4 + grp && has_next) seg_stats_pre(part1, tn, pre, nmean, nrstd);
       }
       // gLN2 partial of this m-tile: fixed-order block reduction -> one slot per tile
       const float s_acc = warp_sum(s2.x + s2.y);
       const float q_acc = warp_sum(q2.x + q2.y);
-      float2* red = s_red + (it & 1) * Cfg::PROD_WARPS;
-      if (lane == 0) red[pw] = make_float2(s_acc, q_acc);
-      named_bar_sync(1, Cfg::PROD_WARPS * 32);
-      if (pw == 0 && lane == 0) {
-        float ts = 0.f, tq = 0.f;
-#pragma unroll
-        for (int k = 0; k < Cfg::PROD_WARPS; ++k) { ts += red[k].x; tq += red[k].y; }
-        part2[w] = make_float2(ts, tq);
-      }
+      tile_partial_reduce(s_red + (it & 1) * Cfg::PROD_WARPS, s_cnt + (it & 1), Cfg::PROD_WARPS, pw, s_acc, q_acc,
+                          part2 + w);
+      if (tl_on) tl_stamp(it, 34 + grp);
     }
   }
 
@@ -503,13 +616,14 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
 struct KbCfg {
   static constexpr int W_BYTES = C_HID * C_BN * 2;      // 128 KiB: [2 k-blocks][512 rows][64 k]
   static constexpr int XN_BYTES = TILE_M * C_BN * 2;    // 32 KiB: [2 k-blocks][64 k][128 m]
-  static constexpr int EPI_WARPS = 8, PRO_WARPS = 8;
+  static constexpr int EPI_WARPS = 8, PRO_WARPS = 8;  // EPI_WARPS / 4 epilogue warps per TMEM lane quadrant
   static constexpr int THREADS = (EPI_WARPS + 1 + PRO_WARPS) * 32;  // 544
   static constexpr int TMEM_COLS = 512;                 // 4 chunks of 128 output channels
   static constexpr int OFF_XN = W_BYTES;
   static constexpr int OFF_TI = OFF_XN + 2 * XN_BYTES;
   static constexpr int OFF_RED = OFF_TI + TI_CACHE * 32;
-  static constexpr int OFF_BAR = OFF_RED + 2 * EPI_WARPS * 8;
+  static constexpr int OFF_CNT = OFF_RED + 2 * EPI_WARPS * 8;
+  static constexpr int OFF_BAR = OFF_CNT + 16;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 };
 
@@ -522,7 +636,7 @@ struct ApplyParams {
 };
 
 template <bool A01>
-__global__ void __launch_bounds__(544, 1)
+__global__ void __launch_bounds__(KbCfg::THREADS, 1)
 apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<__half, A01> epi, Tables tb) {
   using Cfg = KbCfg;
   extern __shared__ uint8_t smem_raw[];
@@ -531,7 +645,8 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
   const uint32_t smem_w = smem_base;
   auto smem_xn = [&](int b) { return smem_base + (uint32_t)(Cfg::OFF_XN + b * Cfg::XN_BYTES); };
   TileInfo* s_ti = reinterpret_cast<TileInfo*>(smem_gen + Cfg::OFF_TI);
-  float2* s_red = reinterpret_cast<float2*>(smem_gen + Cfg::OFF_RED);  // [2][8]
+  float2* s_red = reinterpret_cast<float2*>(smem_gen + Cfg::OFF_RED);  // [2][EPI_WARPS]
+  int* s_cnt = reinterpret_cast<int*>(smem_gen + Cfg::OFF_CNT);          // [2]
   const uint32_t bar0 = smem_base + Cfg::OFF_BAR;
   const uint32_t w_bar = bar0;
   auto xn_full = [&](int b) { return bar0 + 8u * (1 + b); };
@@ -544,8 +659,10 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
   const int lane = threadIdx.x & 31;
   const int n_tiles = tb.n_tiles;
 
+  constexpr int MMA_WARP = Cfg::EPI_WARPS;
   ti_cache_fill(s_ti, tb, threadIdx.x);
-  if (warp == 8) {
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  if (warp == MMA_WARP) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_w);
       mbar_init(w_bar, 1);
@@ -573,9 +690,10 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
-  if (warp < 8) {
+  if (warp < MMA_WARP) {
     // ================================ epilogue: bias + PReLU -> h1, gLN1 partials ==================
-    const int ew = warp, quad = ew & 3, half = ew >> 2;
+    // warp = (TMEM lane quadrant, column group of the 128-column chunk)
+    const int ew = warp, quad = ew & 3, cg = ew >> 2;
     const int r = quad * 32 + lane;
     int it = 0;
     for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
@@ -588,29 +706,25 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
       for (int q = 0; q < 4; ++q) {
         mbar_wait_b(tfull_bar(q), ph);
         tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(q * 128 + half * 64);
-        const int n_base = q * 128 + half * 64;
+        if (threadIdx.x == 0) tl_stamp(it, 16 + q);
+        constexpr int COLS = 128 / (Cfg::EPI_WARPS / 4);  // columns of the chunk this warp owns
+        const int n_base = q * 128 + cg * COLS;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)n_base;
         float v[2][32];
         tmem_ld32(taddr, v[0]);
-        tmem_ld32(taddr + 32u, v[1]);
+        if (COLS > 32) tmem_ld32(taddr + 32u, v[1]);
         tmem_ld_wait();
         tcgen05_fence_before();
-        mbar_arrive(tempty_bar(q));  // accumulator chunk is in registers: the MMA may overwrite it
+        mbar_arrive(tempty_bar(q));  // the warp's part of the chunk is in registers: the MMA may overwrite it
         epi.template apply<32>(st, w, r, n_base, v[0], pre);
-        epi.template apply<32>(st, w, r, n_base + 32, v[1], pre);
+        if (COLS > 32) epi.template apply<32>(st, w, r, n_base + 32, v[1], pre);
+        if (threadIdx.x == 0) tl_stamp(it, 20 + q);
       }
       const float s = warp_sum(st.s), qq = warp_sum(st.q);
-      float2* red = s_red + (it & 1) * Cfg::EPI_WARPS;
-      if (lane == 0) red[ew] = make_float2(s, qq);
-      named_bar_sync(1, Cfg::EPI_WARPS * 32);
-      if (ew == 0 && lane == 0) {
-        float ts = 0.f, tq = 0.f;
-#pragma unroll
-        for (int k = 0; k < Cfg::EPI_WARPS; ++k) { ts += red[k].x; tq += red[k].y; }
-        epi.part_out[w] = make_float2(ts, tq);
-      }
+      tile_partial_reduce(s_red + (it & 1) * Cfg::EPI_WARPS, s_cnt + (it & 1), Cfg::EPI_WARPS, ew, s, qq,
+                          epi.part_out + w);
     }
-  } else if (warp == 8) {
+  } else if (warp == MMA_WARP) {
     // ================================ MMA issuer ==================================================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(128);
@@ -620,10 +734,12 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
         const int b = it & 1;
         mbar_wait_b(xn_full(b), (uint32_t)(it >> 1) & 1u);
         tcgen05_fence_after();
+        tl_stamp(it, 8);
         const uint32_t sa = smem_xn(b);
         for (int q = 0; q < 4; ++q) {
           mbar_wait_b(tempty_bar(q), ((uint32_t)it & 1u) ^ 1u);
           tcgen05_fence_after();
+          tl_stamp(it, 9 + q);
           const uint32_t tmem_d = tmem_base + (uint32_t)(q * 128);
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb) {
@@ -642,7 +758,8 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
     __syncwarp();
   } else {
     // ================================ prologue: apply G_res, build the fp16 operand ===============
-    const int pt = (warp - 9) * 32 + lane;  // 0..255
+    const int pt = (warp - MMA_WARP - 1) * 32 + lane;  // 0..PRO_WARPS*32-1
+    constexpr int ROWS = Cfg::PRO_WARPS * 2;  // channel rows covered per pass
     const int lane16 = pt & 15, crow = pt >> 4;
     const int f0 = lane16 * 8;
     const bool has_g = ap.g != nullptr;
@@ -663,29 +780,42 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
         vm[k] = make_float2((ti.t0 + f0 + 2 * k) < ti.F ? 1.f : 0.f, (ti.t0 + f0 + 2 * k + 1) < ti.F ? 1.f : 0.f);
       const float nmr = -mean * rstd;
       const float2 rstd2 = make_float2(rstd, rstd);
+      if (pt == 0) tl_stamp(it, 0);
+      if (pt == 0 && w + (int)gridDim.x < n_tiles) {  // next tile's x / G_res -> L2 while this tile is processed
+        const size_t nidx = tt_index(w + gridDim.x, C_BN, 0, 0);
+        l2_prefetch_bulk(ap.x + nidx, TILE_M * C_BN * 4);
+        if (has_g) l2_prefetch_bulk(ap.g + nidx, TILE_M * C_BN * 2);
+      }
       float* __restrict__ xt = ap.x + tt_index(w, C_BN, 0, f0);
       const __half* __restrict__ gt = has_g ? ap.g + tt_index(w, C_BN, 0, f0) : nullptr;
       // all global loads of the tile are issued before the (possibly blocking) operand-buffer wait
-      constexpr int PASSES = 8;
+      constexpr int PASSES = C_BN / ROWS;
       uint32_t xn = 0;
 #pragma unroll 1
-      for (int p0 = 0; p0 < PASSES; p0 += 4) {
-        float4 xa[4], xb[4];
-        uint4 gr[4];
+      constexpr int RND = 4;  // passes per round (global loads in flight per thread: 3 x RND vectors)
+      static_assert(PASSES % RND == 0, "prologue rounds");
+      for (int p0 = 0; p0 < PASSES; p0 += RND) {
+        float4 xa[RND], xb[RND];
+        uint4 gr[RND];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const size_t off = (size_t)((p0 + j) * 16 + crow) * TILE_M;
+        for (int j = 0; j < RND; ++j) {
+          const size_t off = (size_t)((p0 + j) * ROWS + crow) * TILE_M;
+#ifndef B200SEP_EXP_NO_PRO_IO
           xa[j] = *reinterpret_cast<const float4*>(xt + off);
           xb[j] = *reinterpret_cast<const float4*>(xt + off + 4);
           if (has_g) gr[j] = ldg_v4(gt + off);
+#else
+          xa[j] = make_float4(0.1f, 0.2f, 0.3f, (float)off); xb[j] = xa[j]; gr[j] = make_uint4(0, 0, 0, 0);
+#endif
         }
         if (p0 == 0) {
           mbar_wait_b(xn_empty(b), ((uint32_t)(it >> 1) & 1u) ^ 1u);
           xn = smem_xn(b);
+          if (pt == 0) tl_stamp(it, 1);
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = (p0 + j) * 16 + crow;
+        for (int j = 0; j < RND; ++j) {
+          const int c = (p0 + j) * ROWS + crow;
           const size_t off = (size_t)c * TILE_M;
           float xv[8] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w, xb[j].x, xb[j].y, xb[j].z, xb[j].w};
           if (has_g) {
@@ -698,20 +828,23 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
               const float2 nx = fma2(dr, vm[i >> 1], make_float2(xv[i], xv[i + 1]));
               xv[i] = nx.x; xv[i + 1] = nx.y;
             }
+#ifndef B200SEP_EXP_NO_PRO_IO
             *reinterpret_cast<float4*>(xt + off) = make_float4(xv[0], xv[1], xv[2], xv[3]);
             *reinterpret_cast<float4*>(xt + off + 4) = make_float4(xv[4], xv[5], xv[6], xv[7]);
+#endif
           }
           st_shared_v4(xn + (uint32_t)((c >> 6) * 16384) + a_chunk_off(c & 63, f0), pack8(xv));
         }
       }
       fence_proxy_async();
       mbar_arrive(xn_full(b));
+      if (pt == 0) tl_stamp(it, 2);
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }

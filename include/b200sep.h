@@ -187,6 +187,10 @@ int b200sep_debug_layout(const b200sep_model* m, const int32_t* lens, int32_t n_
  * synchronises the device; `reset` != 0 clears the flag. */
 int b200sep_debug_abort_flag(int32_t* out, int32_t reset);
 
+/* Debug: register (nullptr: remove) a device buffer of n_sm * 8 * 128 int64 that the fused kernels stamp
+ * with clock64 values per (CTA, tile visit, slot); used by tests/timeline.py to see the pipeline. */
+int b200sep_debug_timeline(void* d_buf);
+
 /* Launch sequence of the model: 0 = encoder, bottleneck GEMM, per TCN block (in-conv GEMM, depthwise
  * conv, res/skip GEMM), mask GEMM, decoder; 1 = encoder, bottleneck GEMM, per TCN block (apply + in-conv
  * GEMM, depthwise + res/skip GEMM), final skip, mask GEMM, decoder (fused fp16 tensor-core mode). */
