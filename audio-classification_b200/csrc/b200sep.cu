@@ -23,6 +23,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "fused_block.cuh"
+#include "tail_kernel.cuh"
 #include "pit.cuh"
 
 using namespace b200sep;
@@ -164,6 +165,9 @@ struct b200sep_model {
   int n_layers = 0;
   bool half = true, use_tc = true;
   bool fused = true;  // fp16 tensor-core mode: two fused kernels per TCN block (fused_block.cuh)
+  bool fused_tail = true;  // ... and mask GEMM + mask application + decoder in one kernel (tail_kernel.cuh)
+  void* dec_w16 = nullptr;  // [L][512] fp16 decoder filterbank (B operand of the decoder MMA)
+  CUtensorMap tm_mask128, tm_wd;
   std::vector<void*> allocs;
   float *enc_w = nullptr, *dec_w = nullptr;
   void* bn_w = nullptr;
@@ -298,6 +302,12 @@ static int build_weights(b200sep_model* m, const b200sep_weights* w) {
   }
   if (dev_upload_f(m, skip_rs, &m->skip_rs)) return 1;
   if (dev_upload_f(m, skip_cb, &m->skip_cb)) return 1;
+  {  // decoder filterbank as a K-major fp16 B operand: [L][512]
+    std::vector<__half> wd((size_t)L * C_ENC);
+    for (int n = 0; n < C_ENC; ++n)
+      for (int l = 0; l < L; ++l) wd[(size_t)l * C_ENC + n] = __float2half_rn(w->dec_filters[(size_t)n * L + l]);
+    if (dev_upload(m, wd.data(), wd.size() * sizeof(__half), &m->dec_w16)) return 1;
+  }
   m->alpha_mask = w->mask_prelu[0];
   if (upload_cvt<T>(m, w->mask_weight, (size_t)S * C_ENC * C_SKIP, &m->mask_w)) return 1;
   if (dev_upload(m, w->mask_bias, (size_t)S * C_ENC * 4, reinterpret_cast<void**>(&m->mask_b))) return 1;
@@ -446,6 +456,7 @@ struct KaArgs {
   const CUtensorMap* tm_hh;
   __half* g_res;
   __half* g_skip;
+  size_t skip_tile_stride;
   const float2* p1;
   float2* p2;
   fb::DwTab tab;
@@ -461,7 +472,7 @@ static int launch_dw_rs(const b200sep_model* m, const KaArgs& a, const Tables& t
   }
   const int grid = std::min(tb.n_tiles, m->n_sm);
   CK(launch_k(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, *a.tm_b, *a.tm_hc, *a.tm_hh, a.g_res, a.g_skip,
-              a.p1, a.p2, a.tab, tb));
+              a.skip_tile_stride, a.p1, a.p2, a.tab, tb));
   return 0;
 }
 template <int BN, bool A01>
@@ -582,7 +593,9 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
         if (stop()) return 0;
         int hk = 0;  // halo box: 8 frames for d < 8, else d frames
         while ((8 << hk) < b.dilation) ++hk;
-        KaArgs ka{&b.tm_rs, &tm_hc, &tm_hh[hk], gbuf, stash + (size_t)i * lo.stash_stride, p1,
+        // stash layout [tile][block][128][128]
+        KaArgs ka{&b.tm_rs, &tm_hc, &tm_hh[hk], gbuf, stash + (size_t)i * (C_SKIP * TILE_M),
+                  (size_t)m->n_layers * C_SKIP * TILE_M, p1,
                   p2 + (size_t)i * lo.part2_stride, fb::DwTab{b.dw_t0, b.dw_t1, b.dw_cb, b.a2, b.dilation}};
         const bool a01 = b.a2 >= 0.f && b.a2 <= 1.f;
         if (!last) rc = a01 ? launch_dw_rs_d<256, true>(m, ka, tb, st) : launch_dw_rs_d<256, false>(m, ka, tb, st);
@@ -591,7 +604,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
         if (stop()) return 0;
       }
       if (m->n_layers > fb::MAX_LAYERS) return fail("fused path supports up to %d TCN blocks", fb::MAX_LAYERS);
-      CK(launch_k(fb::skip_merge_kernel, dim3(nt), dim3(256), 0, st, (const __half*)stash, lo.stash_stride,
+      CK(launch_k(fb::skip_merge_kernel, dim3(nt), dim3(256), 0, st, (const __half*)stash,
                   (const float2*)p2, lo.part2_stride, (const float*)m->skip_rs, (const float*)m->skip_cb, skipa,
                   m->alpha_mask, m->n_layers, tb));
       if (stop()) return 0;
@@ -642,6 +655,23 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
     if (stop()) return 0;
   }
 
+  // 4+5 fused: mask net + mask application + decoder + overlap-add (d_out was zero-filled by the caller)
+  if constexpr (kHalf) {
+    if (fused_mode && m->fused_tail) {
+      using Cfg = tail::TailCfg<L>;
+      auto kern = tail::mask_dec_kernel<L>;
+      static bool configured = false;  // per template instantiation
+      if (!configured) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+      }
+      tail::TailParams tp{m->mask_b, enc, d_out, c.n_src, c.mask_act};
+      CK(launch_k(kern, dim3(std::min(nt, m->n_sm)), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tm_skipa, m->tm_mask128,
+                  m->tm_wd, tp, tb));
+      prof_mark();
+      return 0;
+    }
+  }
   // 4. mask net + mask application
   {
     const int n_total = c.n_src * C_ENC;
@@ -717,6 +747,7 @@ int b200sep_model_create(const b200sep_config* cfg, const b200sep_weights* w, in
   m->half = (c.precision != B200SEP_PREC_FP32);
   m->use_tc = (c.precision == B200SEP_PREC_FP16_TC);
   if (const char* f = getenv("B200SEP_FUSED")) m->fused = atoi(f) != 0;
+  if (const char* f = getenv("B200SEP_FUSED_TAIL")) m->fused_tail = atoi(f) != 0;
   const char* dbg = getenv("B200SEP_DEBUG_STOP_AFTER");
   if (dbg) m->debug_stop_after = atoi(dbg);
   int rc = m->half ? build_weights<__half>(m, w) : build_weights<float>(m, w);
@@ -728,6 +759,8 @@ int b200sep_model_create(const b200sep_config* cfg, const b200sep_weights* w, in
       if (!rc) rc = make_tmap_w(&b.tm_rs, b.w_rs, b.n_out, C_HID, b.n_out == 256 ? 256 : 128);
     }
     if (!rc) rc = make_tmap_w(&m->tm_mask, m->mask_w, c.n_src * C_ENC, C_SKIP, 256);
+    if (!rc) rc = make_tmap_w(&m->tm_mask128, m->mask_w, c.n_src * C_ENC, C_SKIP, 128);
+    if (!rc) rc = make_tmap_w(&m->tm_wd, m->dec_w16, c.kernel_size, C_ENC, c.kernel_size);
   }
   if (rc) {
     std::string keep = g_err;
@@ -776,8 +809,12 @@ int b200sep_debug_timeline(void* d_buf) {
 }
 
 // Launch sequence the model runs: 0 = unfused (encoder, bottleneck, 3 kernels per block, mask, decoder),
-// 1 = fused (encoder, bottleneck, 2 kernels per block, final skip, mask, decoder).
-int b200sep_pipeline(const b200sep_model* m) { return (m && m->half && m->use_tc && m->fused) ? 1 : 0; }
+// 1 = fused (encoder, bottleneck, 2 kernels per block, skip merge, mask, decoder),
+// 2 = fused + fused tail (encoder, bottleneck, 2 kernels per block, skip merge, mask+decoder).
+int b200sep_pipeline(const b200sep_model* m) {
+  if (!(m && m->half && m->use_tc && m->fused)) return 0;
+  return m->fused_tail ? 2 : 1;
+}
 
 int b200sep_profile_enable(b200sep_model* m, int on) {
   if (!m) return fail("null model");

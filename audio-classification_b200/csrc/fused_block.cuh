@@ -244,6 +244,12 @@ __device__ __forceinline__ void dw_taps(const uint4 vc, const uint4 va, const ui
 // Interior-tile producer step in packed half arithmetic: 8 outputs of one channel from the three 8-frame
 // vectors.  Taps, PReLU and the operand rounding happen in fp16 (HFMA2 / HMUL2 / HMNMX2: no fp16 -> fp32
 // conversions on the tap path); only the gLN2 statistics are accumulated in fp32.
+// d = a * b + c with fp16 a, b and fp32 c, d (sm_100 mixed-precision FMA: no conversion instruction)
+__device__ __forceinline__ float fma_f32_f16(uint16_t a, uint16_t b, float c) {
+  float d;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 template <int D, bool A01>
@@ -271,8 +277,13 @@ __device__ __forceinline__ uint4 dw_step_h2(const uint4 vc, const uint4 va, cons
     l[0] = pv[2]; l[1] = pv[3]; l[2] = c[0]; l[3] = c[1];
     r[0] = c[2]; r[1] = c[3]; r[2] = nv[0]; r[3] = nv[1];
   }
+#ifndef B200SEP_EXP_NO_COEF_CVT
   const __half2 w0 = __float2half2_rn(t0.x * rstd), w1 = __float2half2_rn(t0.y * rstd);
   const __half2 w2 = __float2half2_rn(t0.z * rstd), cw = __float2half2_rn(fmaf(-t0.w, rm, cb));
+#else  // timing experiment only (wrong numbers): no XU-pipe conversions on the step path
+  const __half2 w0 = u32_as_h2(__float_as_uint(t0.x * rstd) & 0x3c003c00u), w1 = u32_as_h2(__float_as_uint(t0.y * rstd) & 0x3c003c00u);
+  const __half2 w2 = u32_as_h2(__float_as_uint(t0.z * rstd) & 0x3c003c00u), cw = u32_as_h2(__float_as_uint(fmaf(-t0.w, rm, cb)) & 0x3c003c00u);
+#endif
   uint32_t o[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -280,9 +291,12 @@ __device__ __forceinline__ uint4 dw_step_h2(const uint4 vc, const uint4 va, cons
     if (A01) u = __hmax2(u, __hmul2(u, alpha2));
     else u = __hadd2(__hmax2(u, __float2half2_rn(0.f)), __hmul2(alpha2, __hmin2(u, __float2half2_rn(0.f))));
     o[i] = h2_as_u32(u);
-    const float2 f = __half22float2(u);
-    s2 = add2(s2, f);
-    q2 = fma2(f, f, q2);
+    // gLN2 statistics of the ROUNDED outputs, fp32 accumulation, straight from the packed halves
+    const uint16_t lo = (uint16_t)(o[i] & 0xffffu), hi = (uint16_t)(o[i] >> 16);
+    s2.x = fma_f32_f16(lo, (uint16_t)0x3c00u, s2.x);  // + lo * 1.0
+    s2.y = fma_f32_f16(hi, (uint16_t)0x3c00u, s2.y);
+    q2.x = fma_f32_f16(lo, lo, q2.x);
+    q2.y = fma_f32_f16(hi, hi, q2.y);
   }
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
@@ -291,7 +305,8 @@ template <int BN, int D, bool A01>
 __global__ void __launch_bounds__(736, 1)
 dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_hc,
              const __grid_constant__ CUtensorMap tm_hh, __half* __restrict__ g_res, __half* __restrict__ g_skip,
-             const float2* __restrict__ part1, float2* __restrict__ part2, DwTab p, Tables tb) {
+             size_t skip_tile_stride, const float2* __restrict__ part1, float2* __restrict__ part2, DwTab p,
+             Tables tb) {
   using Cfg = KaCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -370,7 +385,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       if (threadIdx.x == 0) tl_stamp(it, 80);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
       __half* __restrict__ d_res = g_res + tt_index(w, C_BN, 0, r);
-      __half* __restrict__ d_skip = g_skip + tt_index(w, C_SKIP, 0, r);
+      __half* __restrict__ d_skip = g_skip + (size_t)w * skip_tile_stride + r;  // stash: [tile][block][128][128]
       float v[2][32];
       tmem_ld32(taddr, v[0]);
 #pragma unroll
@@ -381,7 +396,11 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         __half* __restrict__ dst = (BN == 256 && c < 4) ? d_res + (size_t)(c * 32) * TILE_M
                                                         : d_skip + (size_t)((BN == 256 ? c - 4 : c) * 32) * TILE_M;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dst[(size_t)j * TILE_M] = __float2half_rn(v[c & 1][j]);
+        for (int j = 0; j < 32; j += 2) {  // one packed conversion per two channels
+          const __half2 h = __floats2half2_rn(v[c & 1][j], v[c & 1][j + 1]);
+          dst[(size_t)j * TILE_M] = __low2half(h);
+          dst[(size_t)(j + 1) * TILE_M] = __high2half(h);
+        }
       }
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(as));
@@ -778,8 +797,11 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         vm[k] = make_float2((ti.t0 + f0 + 2 * k) < ti.F ? 1.f : 0.f, (ti.t0 + f0 + 2 * k + 1) < ti.F ? 1.f : 0.f);
-      const float nmr = -mean * rstd;
-      const float2 rstd2 = make_float2(rstd, rstd);
+      // rstd2 rounded to fp16: multiplier of the mixed-precision FMA on the fp16 G_res (the constant term uses the
+      // same rounded value)
+      const __half rstd_hh = __float2half_rn(rstd);
+      const uint16_t rstd_h = __half_as_ushort(rstd_hh);
+      const float nmr = -mean * __half2float(rstd_hh);
       if (pt == 0) tl_stamp(it, 0);
       if (pt == 0 && w + (int)gridDim.x < n_tiles) {  // next tile's x / G_res -> L2 while this tile is processed
         const size_t nidx = tt_index(w + gridDim.x, C_BN, 0, 0);
@@ -791,9 +813,9 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
       // all global loads of the tile are issued before the (possibly blocking) operand-buffer wait
       constexpr int PASSES = C_BN / ROWS;
       uint32_t xn = 0;
-#pragma unroll 1
       constexpr int RND = 4;  // passes per round (global loads in flight per thread: 3 x RND vectors)
       static_assert(PASSES % RND == 0, "prologue rounds");
+#pragma unroll 1
       for (int p0 = 0; p0 < PASSES; p0 += RND) {
         float4 xa[RND], xb[RND];
         uint4 gr[RND];
@@ -820,11 +842,11 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
           float xv[8] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w, xb[j].x, xb[j].y, xb[j].z, xb[j].w};
           if (has_g) {
             const float kr = fmaf(nmr, __ldg(ap.rs + c), __ldg(ap.cb + c));
-            float gv[8];
-            unpack8(gr[j], gv);
+            const uint32_t gw[4] = {gr[j].x, gr[j].y, gr[j].z, gr[j].w};
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
-              const float2 dr = fma2(make_float2(gv[i], gv[i + 1]), rstd2, make_float2(kr, kr));
+              const float2 dr = make_float2(fma_f32_f16((uint16_t)(gw[i >> 1] & 0xffffu), rstd_h, kr),
+                                            fma_f32_f16((uint16_t)(gw[i >> 1] >> 16), rstd_h, kr));
               const float2 nx = fma2(dr, vm[i >> 1], make_float2(xv[i], xv[i + 1]));
               xv[i] = nx.x; xv[i + 1] = nx.y;
             }
@@ -856,19 +878,26 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
 // 8 frames).  stash[b] = raw G_skip of block b, part2[b] its gLN2 partials, rs/cb [n_layers][128].
 // =================================================================================================
 constexpr int MAX_LAYERS = 64;
-__global__ void __launch_bounds__(256) skip_merge_kernel(const __half* __restrict__ stash, size_t stash_stride,
+__global__ void __launch_bounds__(256) skip_merge_kernel(const __half* __restrict__ stash,
                                                          const float2* __restrict__ part2, size_t part_stride,
                                                          const float* __restrict__ rs, const float* __restrict__ cb,
                                                          __half* __restrict__ skipa, float alpha_mask, int n_layers,
                                                          Tables tb) {
-  __shared__ float2 s_stat[MAX_LAYERS];  // (rstd, -mean*rstd) per block
+  __shared__ float2 s_stat[MAX_LAYERS];    // (rstd, -mean*rstd) per block
+  __shared__ uint16_t s_rstd_h[MAX_LAYERS];  // rstd rounded to fp16: multiplier of the mixed-precision FMA
   const int w = blockIdx.x;
   const TileInfo ti = load_tile_info(tb.tile_info + w);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int b = warp; b < n_layers; b += 8) {
     float mean, rstd;
     warp_seg_stats(part2 + (size_t)b * part_stride, ti.tile0, ti.ntiles, 1, ti.inv_count, mean, rstd);
-    if (lane == 0) s_stat[b] = make_float2(rstd, -mean * rstd);
+    if (lane == 0) {
+      // the constant term uses the SAME rounded rstd, so sum_b rstd_b * (G_b - mean_b * rs_b) stays consistent
+      const __half rh = __float2half_rn(rstd);
+      s_rstd_h[b] = __half_as_ushort(rh);
+      const float rr = __half2float(rh);
+      s_stat[b] = make_float2(rr, -mean * rr);
+    }
   }
   __syncthreads();
   const int lane16 = threadIdx.x & 15, crow = threadIdx.x >> 4;
@@ -877,19 +906,24 @@ __global__ void __launch_bounds__(256) skip_merge_kernel(const __half* __restric
   for (int ps = 0; ps < 8; ++ps) {
     const int c = ps * 16 + crow;
     const size_t idx = tt_index(w, C_SKIP, c, f0);
+    // stash layout [tile][block][128][128]: the n_layers slots of an m-tile are contiguous
+    const __half* __restrict__ sp = stash + ((size_t)w * n_layers * C_SKIP + c) * TILE_M + f0;
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     float kc = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int b = 0; b < n_layers; ++b) {
-      const uint4 gv4 = ldg_v4(stash + (size_t)b * stash_stride + idx);
+      const uint4 gv4 = ldg_v4(sp + (size_t)b * (C_SKIP * TILE_M));
       const float2 sb = s_stat[b];
+      const uint16_t rh = s_rstd_h[b];
       kc += fmaf(sb.y, __ldg(rs + b * C_SKIP + c), __ldg(cb + b * C_SKIP + c));
-      float gv[8];
-      unpack8(gv4, gv);
+      const uint32_t gw[4] = {gv4.x, gv4.y, gv4.z, gv4.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(gv[i], sb.x, acc[i]);
+      for (int i = 0; i < 4; ++i) {  // fp16 x fp16 + fp32 (no conversion instructions)
+        acc[2 * i] = fma_f32_f16((uint16_t)(gw[i] & 0xffffu), rh, acc[2 * i]);
+        acc[2 * i + 1] = fma_f32_f16((uint16_t)(gw[i] >> 16), rh, acc[2 * i + 1]);
+      }
     }
     float o[8];
 #pragma unroll

@@ -1,0 +1,328 @@
+// Fused mask net + mask application + decoder (sm_100a, fp16 tensor-core mode): the `masked` tensor
+// (n_src x 512 x F, the largest activation of the forward) never leaves the SM.
+//
+//   per m-tile (128 frames), for every source s and every 128-filter chunk c of its 512 filters:
+//     MMA 1 : score[frame][n] = sum_k PReLU(skip_sum)[frame][k] * W_mask[s*512 + c*128 + n][k]   (K = 128)
+//     epi 1 : masked = act(score + b) * tf_rep[c*128 + n][frame]  -> fp16 -> swizzled K-major smem operand
+//     MMA 2 : dec[frame][l] += sum_n masked[frame][n] * W_dec[c*128 + n][l]      (N = L taps, K = 128 / chunk)
+//   after the 4 chunks of a source:
+//     epi 2 : overlap-add of the L taps of the 128 frames (stride L/2) + zero tail (pad_x_to_y) -> d_out
+//
+// (asteroid: mask_net + output_act, `est_masks * tf_rep.unsqueeze(1)`, Decoder(FreeFB) = conv_transpose1d;
+//  SURVEY.md A.2.)  Warp roles as in gemm_tc.cuh: warp 0 TMA, warp 1 MMA issuer (both MMAs), warp 2 TMEM
+// allocator, warps 4-11 epilogue (lane = frame).  TMEM: 2 x 128 score columns (double-buffered) + n_src x L
+// decoder columns.  d_out must be zero-filled by the caller (the two hops shared with the neighbouring
+// m-tiles are accumulated with atomicAdd: two addends onto zero, order-independent).
+#pragma once
+#include "common.cuh"
+#include "fused_block.cuh"
+#include "gemm_tc.cuh"
+
+namespace b200sep {
+namespace tail {
+using namespace tc;
+using fb::mbar_wait_b;
+using fb::st_shared_v4;
+
+template <int L>
+struct TailCfg {
+  static constexpr int A_BYTES = TILE_M * C_SKIP * 2;     // 32 KiB: PReLU(skip_sum) tile, 2 k-blocks
+  static constexpr int B_STAGE = 128 * C_SKIP * 2;        // 32 KiB: 128 mask-conv rows x 128 k
+  static constexpr int B_STAGES = 2;
+  static constexpr int WD_BYTES = L * C_ENC * 2;          // decoder filterbank [L][512] fp16, 8 k-blocks
+  static constexpr int ST_BYTES = TILE_M * 128 * 2;       // 32 KiB: masked chunk [128 frames][128 filters]
+  static constexpr int ST_STAGES = 2;
+  static constexpr int OLA_BYTES = TILE_M * (L + 1) * 4;
+  static constexpr int OFF_B = A_BYTES;
+  static constexpr int OFF_WD = OFF_B + B_STAGES * B_STAGE;
+  static constexpr int OFF_ST = OFF_WD + WD_BYTES;
+  static constexpr int OFF_OLA = OFF_ST + ST_STAGES * ST_BYTES;
+  static constexpr int OFF_BAR = (OFF_OLA + OLA_BYTES + 15) / 16 * 16;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int THREADS = 384;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int DEC_COL0 = 256;                    // decoder accumulators start here
+  static_assert(SMEM_BYTES <= 232448, "tail kernel shared memory over the 227 KiB limit");
+};
+
+// kind::f16 instruction descriptor, D = fp32, A = B = fp16, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t make_idesc_kk(int n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+struct TailParams {
+  const float* bias;   // [S*512] mask conv bias
+  const __half* enc;   // [nt][512][128] encoder output
+  float* out;          // separated waveforms (zero-filled)
+  int n_src;
+  int act;             // 0 sigmoid, 1 relu
+};
+
+template <int L>
+__global__ void __launch_bounds__(384, 1)
+mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                const __grid_constant__ CUtensorMap tm_wd, TailParams p, Tables tb) {
+  using Cfg = TailCfg<L>;
+  constexpr int S = L / 2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t smem_a = smem_base;
+  auto smem_b = [&](int s) { return smem_base + (uint32_t)(Cfg::OFF_B + s * Cfg::B_STAGE); };
+  const uint32_t smem_wd = smem_base + Cfg::OFF_WD;
+  auto smem_st = [&](int s) { return smem_base + (uint32_t)(Cfg::OFF_ST + s * Cfg::ST_BYTES); };
+  float (*s_ola)[L + 1] = reinterpret_cast<float (*)[L + 1]>(smem_gen + Cfg::OFF_OLA);
+  const uint32_t bar0 = smem_base + Cfg::OFF_BAR;
+  const uint32_t wd_bar = bar0;                                  // decoder filterbank landed (once)
+  const uint32_t a_full = bar0 + 8u, a_empty = bar0 + 16u;       // skip operand of the m-tile
+  auto b_full = [&](int s) { return bar0 + 8u * (3 + s); };
+  auto b_empty = [&](int s) { return bar0 + 8u * (5 + s); };
+  auto acc_full = [&](int s) { return bar0 + 8u * (7 + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (9 + s); };
+  auto st_full = [&](int s) { return bar0 + 8u * (11 + s); };
+  auto st_empty = [&](int s) { return bar0 + 8u * (13 + s); };
+  const uint32_t dec_full = bar0 + 8u * 15;                      // decoder accumulator of a source complete
+  const uint32_t dec_empty = bar0 + 8u * 16;                     // ... drained by the overlap-add
+  const uint32_t tmem_ptr_smem = bar0 + 8u * 17;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = tb.n_tiles;
+  const int n_chunks = p.n_src * 4;  // 128-filter chunks per m-tile
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_wd);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(wd_bar, 1);
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(b_empty(s), 1);
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 256);
+      mbar_init(st_full(s), 256);
+      mbar_init(st_empty(s), 1);
+    }
+    mbar_init(dec_full, 1);
+    mbar_init(dec_empty, 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================================
+    if (lane == 0) {
+      mbar_expect_tx(wd_bar, Cfg::WD_BYTES);
+      for (int kb = 0; kb < 8; ++kb) tma_load_2d(smem_wd + (uint32_t)(kb * L * 128), &tm_wd, wd_bar, kb * 64, 0);
+      int bs = 0;
+      uint32_t bphase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
+        mbar_wait_b(a_empty, ((uint32_t)it & 1u) ^ 1u);
+        mbar_expect_tx(a_full, Cfg::A_BYTES);
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_2d(smem_a + (uint32_t)(kb * 16384), &tm_a, a_full, 0, w * C_SKIP + kb * 64);
+          tma_load_2d(smem_a + (uint32_t)(kb * 16384 + 8192), &tm_a, a_full, 64, w * C_SKIP + kb * 64);
+        }
+        for (int c = 0; c < n_chunks; ++c) {
+          mbar_wait_b(b_empty(bs), bphase ^ 1u);
+          mbar_expect_tx(b_full(bs), Cfg::B_STAGE);
+          tma_load_2d(smem_b(bs), &tm_b, b_full(bs), 0, c * 128);
+          tma_load_2d(smem_b(bs) + 16384u, &tm_b, b_full(bs), 64, c * 128);
+          if (++bs == Cfg::B_STAGES) { bs = 0; bphase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================ MMA issuer (mask GEMM + decoder GEMM) =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc_mask = make_idesc(128);     // A MN-major (tile-transposed skip operand)
+      constexpr uint32_t idesc_dec = make_idesc_kk(L);     // A K-major (masked chunk written by the epilogue)
+      mbar_wait_b(wd_bar, 0);
+      int bs = 0;
+      uint32_t bphase = 0;
+      int n_acc = 0, n_st = 0, n_dec = 0;  // running counters -> stage / phase
+      auto issue_mask = [&](int c) {
+        (void)c;
+        const int as = n_acc & 1;
+        mbar_wait_b(acc_empty(as), (((uint32_t)n_acc >> 1) & 1u) ^ 1u);
+        mbar_wait_b(b_full(bs), bphase);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * 128);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t da = make_smem_desc(smem_a + (uint32_t)(kb * 16384 + j * 2048), 8192u, 1024u);
+            const uint64_t db = make_smem_desc(smem_b(bs) + (uint32_t)(kb * 16384 + j * 32), 16u, 1024u);
+            umma_f16(tmem_d, da, db, idesc_mask, (uint32_t)((kb | j) != 0));
+          }
+        }
+        umma_commit(b_empty(bs));
+        umma_commit(acc_full(as));
+        if (++bs == Cfg::B_STAGES) { bs = 0; bphase ^= 1u; }
+        ++n_acc;
+      };
+      int it = 0;
+      for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
+        mbar_wait_b(a_full, (uint32_t)it & 1u);
+        issue_mask(0);
+        for (int c = 0; c < n_chunks; ++c) {
+          if (c + 1 < n_chunks) issue_mask(c + 1);  // keeps the tensor core busy while chunk c is in its epilogue
+          else umma_commit(a_empty);                // all mask MMAs of this m-tile issued: operand reusable when done
+          const int src = c >> 2, cc = c & 3;
+          const int ss = n_st & 1;
+          if (cc == 0) mbar_wait_b(dec_empty, ((uint32_t)n_dec & 1u) ^ 1u);  // overlap-add drained the accumulator
+          mbar_wait_b(st_full(ss), ((uint32_t)n_st >> 1) & 1u);
+          tcgen05_fence_after();
+          const uint32_t tmem_dec = tmem_base + (uint32_t)(Cfg::DEC_COL0 + (src & 1) * L);
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t da = make_smem_desc(smem_st(ss) + (uint32_t)(kb * 16384 + j * 32), 16u, 1024u);
+              const uint64_t db = make_smem_desc(smem_wd + (uint32_t)((cc * 2 + kb) * L * 128 + j * 32), 16u, 1024u);
+              umma_f16(tmem_dec, da, db, idesc_dec, (uint32_t)((cc | kb | j) != 0));
+            }
+          }
+          umma_commit(st_empty(ss));
+          if (cc == 3) { umma_commit(dec_full); ++n_dec; }
+          ++n_st;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ================================ epilogue ====================================================
+    const int ew = warp - 4, quad = ew & 3, half = ew >> 2;
+    const int r = quad * 32 + lane;  // frame within the m-tile == TMEM lane
+    int n_acc = 0, n_st = 0, n_dec = 0;
+    for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
+      const TileInfo ti = load_tile_info(tb.tile_info + w);
+      const int seg = ti.seg, t0 = ti.t0, F = ti.F;
+      const int T_len = tb.seg_len[seg];
+      const bool fvalid = (t0 + r) < F;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int src = c >> 2, cc = c & 3;
+        const int as = n_acc & 1, ss = n_st & 1;
+        const int ch0 = cc * 128 + half * 64;           // first filter of this warp's 64 columns
+        const __half* __restrict__ ep = p.enc + tt_index(w, C_ENC, ch0, r);
+        const float* __restrict__ bp = p.bias + src * C_ENC + ch0;
+        mbar_wait_b(acc_full(as), ((uint32_t)n_acc >> 1) & 1u);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 128 + half * 64);
+        float v[2][32];
+        tmem_ld32(taddr, v[0]);
+        tmem_ld32(taddr + 32u, v[1]);
+        uint32_t pk[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // two halves of 32 filters: keeps the live register set small
+          float e[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) e[j] = __half2float(ep[(size_t)(h * 32 + j) * TILE_M]);
+          if (h == 0) {
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            mbar_arrive(acc_empty(as));  // both halves are in registers: the next mask MMA may overwrite the buffer
+            ++n_acc;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float2 b2 = __ldg(reinterpret_cast<const float2*>(bp + h * 32 + j));
+            const float a0 = v[h][j] + b2.x, a1 = v[h][j + 1] + b2.y;
+            float m0, m1;
+            if (p.act == 0) {
+              // sigmoid(v) = 0.5 * tanh(0.5 v) + 0.5 (one MUFU op per element)
+              float t0_, t1_;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t0_) : "f"(0.5f * a0));
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t1_) : "f"(0.5f * a1));
+              m0 = fmaf(t0_, 0.5f, 0.5f) * e[j];
+              m1 = fmaf(t1_, 0.5f, 0.5f) * e[j + 1];
+            } else {
+              m0 = fmaxf(a0, 0.f) * e[j];
+              m1 = fmaxf(a1, 0.f) * e[j + 1];
+            }
+            if (!fvalid) { m0 = 0.f; m1 = 0.f; }  // frames beyond the segment end contribute nothing
+            const __half2 hh2 = __floats2half2_rn(m0, m1);
+            pk[h * 16 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&hh2);
+          }
+        }
+        // masked chunk -> K-major SWIZZLE_128B operand: k-block = half, row = frame, 8 filters per 16-byte chunk
+        mbar_wait_b(st_empty(ss), (((uint32_t)n_st >> 1) & 1u) ^ 1u);
+        const uint32_t row_base = smem_st(ss) + (uint32_t)(half * 16384 + r * 128);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st_shared_v4(row_base + (uint32_t)((q ^ (r & 7)) << 4), make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]));
+        fence_proxy_async();
+        mbar_arrive(st_full(ss));
+        ++n_st;
+
+        if (cc == 3) {
+          // ---- decoder output of source `src`: taps -> overlap-add -> global (4 warps, one per lane quadrant)
+          if (half == 0) {
+            mbar_wait_b(dec_full, (uint32_t)n_dec & 1u);
+            tcgen05_fence_after();
+            float taps[32];
+            const uint32_t daddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::DEC_COL0 + (src & 1) * L);
+            if (L == 16) {
+              uint32_t* u = reinterpret_cast<uint32_t*>(taps);
+              asm volatile(
+                  "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                  : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+                    "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                  : "r"(daddr)
+                  : "memory");
+            } else {
+              tmem_ld32(daddr, taps);
+            }
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            mbar_arrive(dec_empty);
+#pragma unroll
+            for (int l = 0; l < L; ++l) s_ola[r][l] = taps[l];
+            fb::named_bar_sync(2, 128);
+            float* o = p.out + tb.seg_out_off[seg] + (size_t)src * T_len;
+            const int tid = quad * 32 + lane;
+            // hops hh = 0..128 of this tile: sample (t0 + hh) * S + l gets frame hh's first half and frame
+            // hh-1's second half
+            for (int i = tid; i < (TILE_M + 1) * S; i += 128) {
+              const int hh = i / S, l = i % S;
+              const int f_hi = t0 + hh, f_lo = t0 + hh - 1;
+              float val = 0.f;
+              bool any = false;
+              if (hh < TILE_M && f_hi < F) { val += s_ola[hh][l]; any = true; }
+              if (hh >= 1 && f_lo < F) { val += s_ola[hh - 1][S + l]; any = true; }
+              if (!any) continue;
+              const size_t idx = (size_t)(t0 + hh) * S + l;
+              if (hh == 0 || hh == TILE_M) atomicAdd(o + idx, val);
+              else o[idx] = val;
+            }
+            fb::named_bar_sync(2, 128);  // s_ola is reused by the next source
+          }
+          ++n_dec;
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace tail
+}  // namespace b200sep

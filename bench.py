@@ -164,12 +164,14 @@ def run_reference(args, rank, world):
 
 
 KERNEL_CLASSES = ["encoder", "bottleneck_gemm", "in_conv_gemm", "dwconv", "res_skip_gemm", "apply_in_gemm", "dw_rs_gemm",
-                  "final_skip", "mask_gemm", "decoder"]
+                  "final_skip", "mask_gemm", "decoder", "mask_dec"]
 
 
 def launches_per_forward(n_layers, pipeline):
     """pipeline 1 (fused fp16 tensor-core mode): encoder, bottleneck, (K_B, K_A) per block, final skip, mask,
     decoder; pipeline 0: encoder, bottleneck, (in-conv, depthwise, res/skip) per block, mask, decoder."""
+    if pipeline == 2:  # ... and mask GEMM + decoder fused into one kernel
+        return 2 + 2 * n_layers + 1 + 1
     return 2 + 2 * n_layers + 1 + 2 if pipeline == 1 else 2 + 3 * n_layers + 2
 
 
@@ -178,9 +180,12 @@ def classify_launches(ms, n_layers, pipeline=0):
     if len(ms) != launches_per_forward(n_layers, pipeline):
         return per
     per["encoder"].append(ms[0]); per["bottleneck_gemm"].append(ms[1])
-    if pipeline == 1:
+    if pipeline in (1, 2):
         for i in range(n_layers):
             per["apply_in_gemm"].append(ms[2 + 2 * i]); per["dw_rs_gemm"].append(ms[3 + 2 * i])
+        if pipeline == 2:
+            per["final_skip"].append(ms[-2]); per["mask_dec"].append(ms[-1])
+            return per
         per["final_skip"].append(ms[-3])
     else:
         for i in range(n_layers):
@@ -315,6 +320,7 @@ def main():
             "dw_rs_gemm": ("hbm", 1536 * frames),
             "final_skip": ("hbm", (256 * n_layers + 256) * frames),
             "mask_gemm": ("tensor", 2 * frames * 128 * 512 * N_SRC),
+            "mask_dec": ("tensor", 2 * frames * (128 * 512 * N_SRC + 512 * 16 * N_SRC)),
             "decoder": ("hbm", N_SRC * 512 * frames * es + 4 * N_SRC * total),
         }
         step_total = sum(sum(v) / 3.0 for v in acc.values() if v)
@@ -356,7 +362,7 @@ def main():
             "dtype": "f16" if args.precision != "fp32" else "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: 64 synthetic 3-speaker overlap segments U[0.2,4.0] s per GPU, 8 kHz, ConvTasNet n_src=3 random-init",
                        "segments_per_gpu": len(lens), "audio_s_per_gpu": audio_s, "sample_rate": SR, "n_src": N_SRC,
-                       "precision": args.precision, "pipeline": "fused (2 kernels per TCN block)" if pipeline == 1 else "unfused (3 kernels per TCN block)", "parallelism": f"replica x{world} (segments sharded, no data-path collective)",
+                       "precision": args.precision, "pipeline": {0: "unfused (3 kernels per TCN block)", 1: "fused (2 kernels per TCN block)", 2: "fused (2 kernels per TCN block; mask GEMM + decoder in one kernel)"}[pipeline], "parallelism": f"replica x{world} (segments sharded, no data-path collective)",
                        "l2": "L2 flushed (256 MiB write) between timed steps; per-step activation working set ~1 GB > 126 MB L2"},
             "model_tflops": whole_flops / (ms_max * 1e-3) / 1e12,
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,

@@ -1,0 +1,3 @@
+cd $GRAFT_REPO_ROOT
+timeout 100 python tests/variant_time.py 2>&1 | tail -1
+timeout 100 python tests/gpu_diag.py e2e 2>&1 | grep "fp16 " 
