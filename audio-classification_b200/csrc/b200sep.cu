@@ -381,18 +381,21 @@ static int compute_layout(const b200sep_config& c, bool half, bool fused, const 
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-// EXPERIMENTAL, off by default (B200SEP_PDL=1 enables): with overlapping launches the per-SM L1 can
-// keep lines of a buffer that a later kernel rewrites (activations are re-used at fixed workspace
-// addresses every TCN block), and L1-cached / non-coherent loads then read stale data -- observed on
-// B200 in the fp32 mode.  Measured gain when it happens to be correct: ~3 %.
-static bool pdl_enabled() {
+// Programmatic dependent launch.  Used by the fused fp16 pipeline only (B200SEP_PDL=0 disables): its kernels
+// touch nothing but constants before griddepcontrol.wait, read activations written by other SMs through TMA
+// / L2 or after the wait, and at most two consecutive kernels ever overlap.  The unfused pipelines keep
+// plain stream order: with overlapping launches they were observed (fp32 mode) to read stale per-SM L1 lines
+// of buffers that are rewritten in place at fixed workspace addresses.
+static bool pdl_env() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200SEP_PDL");
-    v = (e && atoi(e) == 1) ? 1 : 0;
+    v = (e && atoi(e) == 0) ? 0 : 1;
   }
   return v == 1;
 }
+static thread_local bool g_pdl_on = false;  // set per forward() call
+static bool pdl_enabled() { return g_pdl_on; }
 
 // Launch with programmatic stream serialisation (PDL): the kernel may start while its predecessor
 // drains; every kernel orders itself with griddepcontrol.wait (pdl_enter) before touching global data.
@@ -518,6 +521,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
   float2* p2 = reinterpret_cast<float2*>(ws + lo.o_p2);
   constexpr bool kHalf = std::is_same<T, __half>::value;
   const bool fused_mode = kHalf && m->use_tc && m->fused;
+  g_pdl_on = fused_mode && pdl_env();
   T* xa_or_null = (kHalf && !fused_mode) ? xa : nullptr;
   const T* a_x = kHalf ? xa : reinterpret_cast<const T*>(x);  // A operand of the in-conv
 

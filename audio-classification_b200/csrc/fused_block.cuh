@@ -328,6 +328,9 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   auto tempty_bar = [&](int s) { return bar0 + 8u * (22 + s); };
   const uint32_t tmem_ptr_smem = bar0 + 8u * 24;
 
+  // PDL: everything up to the prologue barrier touches only constants (weights, tap tables, per-call layout
+  // tables), so it may overlap the previous kernel's tail; activations are read after pdl_wait().
+  pdl_launch_dependents();
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n_tiles = tb.n_tiles;
@@ -368,6 +371,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
@@ -674,6 +678,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
   auto tempty_bar = [&](int q) { return bar0 + 8u * (9 + q); };
   const uint32_t tmem_ptr_smem = bar0 + 8u * 13;
 
+  pdl_launch_dependents();  // PDL: the prologue below (barriers, TMEM, resident W_in, layout tables) reads constants only
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n_tiles = tb.n_tiles;
@@ -706,6 +711,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
@@ -885,6 +891,7 @@ __global__ void __launch_bounds__(256) skip_merge_kernel(const __half* __restric
                                                          Tables tb) {
   __shared__ float2 s_stat[MAX_LAYERS];    // (rstd, -mean*rstd) per block
   __shared__ uint16_t s_rstd_h[MAX_LAYERS];  // rstd rounded to fp16: multiplier of the mixed-precision FMA
+  pdl_enter();
   const int w = blockIdx.x;
   const TileInfo ti = load_tile_info(tb.tile_info + w);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

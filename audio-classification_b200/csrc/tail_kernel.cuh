@@ -86,6 +86,7 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const uint32_t dec_empty = bar0 + 8u * 16;                     // ... drained by the overlap-add
   const uint32_t tmem_ptr_smem = bar0 + 8u * 17;
 
+  pdl_launch_dependents();  // PDL: the prologue reads constants only (see fused_block.cuh)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n_tiles = tb.n_tiles;
@@ -116,6 +117,7 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 

@@ -158,31 +158,33 @@ class SeparationEngine:
         total = int(sum(lens))
         S = self.n_src
         dev = torch.device("cuda", self.device)
-        with self._lock:  # pinned staging buffers are shared; serialise the boundary per engine
+        # Input staging buffer is shared (serialised per engine); the OUTPUT pinned buffer is allocated per call
+        # (torch's caching host allocator makes that cheap) and handed to the caller as numpy views, so the
+        # 4 * S * T bytes of results are never copied a second time on the host.
+        with self._lock:
             if self._pinned_in is None or self._pinned_in.numel() < total:
                 self._pinned_in = torch.empty(max(total, 1 << 16), dtype=torch.float32, pin_memory=True)
-            if self._pinned_out is None or self._pinned_out.numel() < total * S:
-                self._pinned_out = torch.empty(max(total * S, 1 << 18), dtype=torch.float32, pin_memory=True)
             hin = self._pinned_in.numpy()
             o = 0
             for c, n in zip(chunks, lens):
                 hin[o:o + n] = np.asarray(c, dtype=np.float32).reshape(-1)
                 o += n
+            pinned_out = torch.empty(total * S, dtype=torch.float32, pin_memory=True)
             with torch.cuda.device(dev):
                 d_mix = torch.empty(total, dtype=torch.float32, device=dev)
                 d_mix.copy_(self._pinned_in[:total], non_blocking=True)
                 d_out = self.separate_device(d_mix, lens)
-                self._pinned_out[:total * S].copy_(d_out, non_blocking=True)
+                pinned_out.copy_(d_out, non_blocking=True)
                 torch.cuda.current_stream(dev).synchronize()
                 if nat.abort_flag():
                     raise RuntimeError("b200sep: a device-side pipeline wait timed out; results are invalid")
-            hout = self._pinned_out.numpy()
-            res: List[List[np.ndarray]] = []
-            o = 0
-            for n in lens:
-                seg = np.array(hout[o * S:(o + n) * S], dtype=np.float32, copy=True).reshape(S, n)
-                res.append([seg[s] for s in range(S)])
-                o += n
+        hout = pinned_out.numpy()  # views keep the pinned block alive until the caller drops them
+        res: List[List[np.ndarray]] = []
+        o = 0
+        for n in lens:
+            seg = hout[o * S:(o + n) * S].reshape(S, n)
+            res.append([seg[s] for s in range(S)])
+            o += n
         return res
 
 

@@ -303,7 +303,11 @@ def test_device_resident_pipeline_and_profile_hooks(b200, model3):
     eng.profile_last_call(True)
     d_out = eng.separate_device(d_mix, lens)
     ms = eng.profile_read()
-    assert len(ms) == 2 + 3 * 24 + 2 and all(m >= 0 for m in ms)
+    from b200sep import _native as nat
+    from bench import launches_per_forward
+    pipeline = int(nat.lib().b200sep_pipeline(eng._handle))
+    assert pipeline == 2  # fp16 tensor-core mode runs the fused pipeline
+    assert len(ms) == launches_per_forward(24, pipeline) and all(m >= 0 for m in ms)
     eng.profile_last_call(False)
     host = eng.separate_batch(mixes)
     o = 0
@@ -312,3 +316,47 @@ def test_device_resident_pipeline_and_profile_hooks(b200, model3):
         assert np.array_equal(got[o * 3:(o + n) * 3].reshape(3, n), np.stack(h))
         o += n
     eng.close()
+
+
+def test_fused_pipeline_many_tiles_per_cta_and_batch_independence(b200, model3):
+    """> 148 m-tiles: every persistent CTA of the fused kernels visits several tiles (pipeline phases wrap,
+    TileInfo cache, cross-tile statistics prefetch).  Results must be bit-identical to the same segments
+    run in small batches (per-segment arithmetic is independent of batch composition), stay >= 40 dB from
+    the oracle, and no bounded device wait may time out."""
+    from b200sep import _native as nat, synth
+    sd, args, model = model3
+    eng = b200.SeparationEngine(sd, args, 0, "fp16")
+    lens = [32000, 1600, 31999, 12345, 16, 24000, 8191, 30000] * 5 + [28000] * 4   # ~ 1100 m-tiles
+    mixes = [synth.make_mixture(300 + i, n, 3)[0] for i, n in enumerate(lens)]
+    big = eng.separate_batch(mixes)
+    assert nat.abort_flag() == 0
+    for i in (0, 1, 4, 7, 20, 43):
+        small = eng.separate_batch([mixes[i]])[0]
+        for s_ in range(3):
+            assert np.array_equal(big[i][s_], small[s_]), (i, s_)
+    for i in (0, 3, 21):
+        ref = oracle_separate(model, mixes[i])
+        assert min_sisdr(ref, np.stack(big[i])) >= GATE_FP16_DB
+    eng.close()
+
+
+def test_fused_and_unfused_pipelines_agree(b200, model3, monkeypatch):
+    """The fused kernels (fused_block.cuh / tail_kernel.cuh) against the unfused three-kernels-per-block
+    pipeline of the same precision mode: both within the gate of the oracle, and within 50 dB of each other."""
+    from b200sep import _native as nat, synth
+    sd, args, model = model3
+    lens = [16000, 2400, 9000, 31000]
+    mixes = [synth.make_mixture(400 + i, n, 3)[0] for i, n in enumerate(lens)]
+    outs = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("B200SEP_FUSED", fused)
+        eng = b200.SeparationEngine(sd, args, 0, "fp16")
+        assert int(nat.lib().b200sep_pipeline(eng._handle)) == (2 if fused == "1" else 0)
+        outs[fused] = eng.separate_batch(mixes)
+        eng.close()
+    assert nat.abort_flag() == 0
+    for i, m in enumerate(mixes):
+        ref = oracle_separate(model, m)
+        for fused in ("1", "0"):
+            assert min_sisdr(ref, np.stack(outs[fused][i])) >= GATE_FP16_DB
+        assert min_sisdr(np.stack(outs["0"][i]), np.stack(outs["1"][i])) >= 50.0
