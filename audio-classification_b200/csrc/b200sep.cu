@@ -381,16 +381,15 @@ static int compute_layout(const b200sep_config& c, bool half, bool fused, const 
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-// Programmatic dependent launch.  Used by the fused fp16 pipeline only (B200SEP_PDL=0 disables): its kernels
-// touch nothing but constants before griddepcontrol.wait, read activations written by other SMs through TMA
-// / L2 or after the wait, and at most two consecutive kernels ever overlap.  The unfused pipelines keep
-// plain stream order: with overlapping launches they were observed (fp32 mode) to read stale per-SM L1 lines
-// of buffers that are rewritten in place at fixed workspace addresses.
+// Programmatic dependent launch: EXPERIMENTAL, off by default (B200SEP_PDL=1 enables it for the fused fp16
+// pipeline only).  Measured on B200: ~0.5 % faster, but 1 of 6 bench processes ended in "unspecified launch
+// failure" with it on and 0 of 6 with it off (cause not found; the unfused pipelines additionally showed stale
+// per-SM L1 lines under overlapping launches).  Plain stream order is the shipped behaviour.
 static bool pdl_env() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B200SEP_PDL");
-    v = (e && atoi(e) == 0) ? 0 : 1;
+    v = (e && atoi(e) == 1) ? 1 : 0;
   }
   return v == 1;
 }

@@ -199,7 +199,10 @@ struct KaCfg {
   static constexpr int AB_STAGES = 2;
   // raw h1 ring: a 110 KiB pool cut into as many stages as fit (stage = 64 channels x (128 + 2 hw) frames:
   // centre box, left halo, right halo); 6 stages at hw = 8 ... 2 stages at hw = 128
-  static constexpr int RAW_POOL = 110 * 1024, RAW_MAX_STAGES = 8;
+#ifndef B200SEP_EXP_KA_MAX_STAGES
+#define B200SEP_EXP_KA_MAX_STAGES 8
+#endif
+  static constexpr int RAW_POOL = 110 * 1024, RAW_MAX_STAGES = B200SEP_EXP_KA_MAX_STAGES;
   static constexpr int A_STAGE = TILE_M * 64 * 2;    // 16 KiB
   static constexpr int B_STAGE = BN * 64 * 2;        // 32 / 16 KiB
   static constexpr int AB_STAGE = A_STAGE + 32768;
@@ -419,7 +422,9 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
         for (int kb = 0; kb < 8; ++kb) {
           // pull the same k-block of the NEXT tile this CTA visits into L2 (a whole tile ahead of its use)
+#ifndef B200SEP_EXP_KA_NO_L2PF
           if (w + (int)gridDim.x < n_tiles) l2_prefetch_tma_2d(&tm_hc, 0, (w + (int)gridDim.x) * C_HID + kb * 64);
+#endif
           mbar_wait_b(raw_empty(stage), phase ^ 1u);
           tl_stamp((w - (int)blockIdx.x) / (int)gridDim.x, 88 + kb);
           mbar_expect_tx(raw_full(stage), bytes);
@@ -442,8 +447,12 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
         for (int kb = 0; kb < 8; ++kb) {
           mbar_wait_b(ab_empty(stage), phase ^ 1u);
+#ifndef B200SEP_EXP_KA_NO_B_TMA
           mbar_expect_tx(ab_full(stage), Cfg::B_STAGE);
           tma_load_2d(stage_b(stage), &tm_b, ab_full(stage), kb * 64, 0);
+#else  // timing experiment: no weight traffic into shared memory
+          mbar_arrive(ab_full(stage));
+#endif
           if (++stage == Cfg::AB_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -452,7 +461,11 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   } else if (warp == 6) {
     // ================================ MMA issuer ==================================================
     if (lane == 0) {
+#ifndef B200SEP_EXP_KA_HALF_N
       constexpr uint32_t idesc = make_idesc(BN);
+#else  // timing experiment: half the B operand reads
+      constexpr uint32_t idesc = make_idesc(BN / 2);
+#endif
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;

@@ -1,0 +1,5 @@
+cd $GRAFT_REPO_ROOT
+for v in KA_NO_L2PF KA_ST3 KA_ST3_NOPF; do
+B200SEP_LIB=$PWD/audio-classification_b200/variants/lib_$v.so timeout 100 python tests/variant_time.py 2>&1 | tail -1
+done
+timeout 100 python tests/variant_time.py 2>&1 | tail -1
