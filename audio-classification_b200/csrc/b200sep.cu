@@ -381,10 +381,11 @@ static int compute_layout(const b200sep_config& c, bool half, bool fused, const 
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-// Programmatic dependent launch: EXPERIMENTAL, off by default (B200SEP_PDL=1 enables it for the fused fp16
-// pipeline only).  Measured on B200: ~0.5 % faster, but 1 of 6 bench processes ended in "unspecified launch
-// failure" with it on and 0 of 6 with it off (cause not found; the unfused pipelines additionally showed stale
-// per-SM L1 lines under overlapping launches).  Plain stream order is the shipped behaviour.
+// Programmatic dependent launch: optional (B200SEP_PDL=1 enables it for the fused fp16 pipeline only).  Measured
+// on B200: within +-0.5 % of plain stream order, so it is off by default.  (An intermittent launch failure first
+// attributed to it was a parity-aliasing bug of the odd-length raw ring in K_A -- see fused_block.cuh -- and
+// did not recur in 26 stress runs after that fix.)  The unfused pipelines keep plain stream order: with
+// overlapping launches they showed stale per-SM L1 lines of buffers rewritten in place.
 static bool pdl_env() {
   static int v = -1;
   if (v < 0) {
@@ -487,7 +488,7 @@ static int launch_dw_rs_d(const b200sep_model* m, const KaArgs& a, const Tables&
   }
 }
 template <bool A01>
-static int launch_apply_in(const b200sep_model* m, const CUtensorMap& tmw, const fb::ApplyParams& ap,
+static int launch_apply_in(const b200sep_model* m, const CUtensorMap& tmw, const CUtensorMap& tmh1, const fb::ApplyParams& ap,
                            const EpiIn<__half, A01>& epi, const Tables& tb, cudaStream_t st) {
   using Cfg = fb::KbCfg;
   auto kern = fb::apply_in_kernel<A01>;
@@ -497,7 +498,7 @@ static int launch_apply_in(const b200sep_model* m, const CUtensorMap& tmw, const
     configured = true;
   }
   const int grid = std::min(tb.n_tiles, m->n_sm);
-  CK(launch_k(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmw, ap, epi, tb));
+  CK(launch_k(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmw, tmh1, ap, epi, tb));
   return 0;
 }
 
@@ -543,15 +544,28 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
     cudaEventRecord(m->prof_ev[m->prof_n++], st);
   };
   prof_mark();
+  static const bool sync_debug = getenv("B200SEP_SYNC_DEBUG") != nullptr;  // debug: localise a faulting launch
+  int launch_no = 0;
+  bool sync_failed = false;
   auto stop = [&]() {
     prof_mark();
+    ++launch_no;
+    if (sync_debug) {
+      const cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) {
+        fail("launch #%d of the forward failed: %s", launch_no, cudaGetErrorString(e));
+        fprintf(stderr, "[b200sep] launch #%d of the forward failed: %s\n", launch_no, cudaGetErrorString(e));
+        sync_failed = true;
+        return true;
+      }
+    }
     return m->debug_stop_after > 0 && ++launches >= m->debug_stop_after;
   };
   const int slots1 = (kHalf && m->use_tc) ? C_HID / 256 : C_HID / 128;  // partial slots the in-conv GEMM writes
 
   // 1. encoder (+ bottleneck-gLN partials)
   CK(launch_k(encoder_kernel<T, L>, dim3(nt, 2), dim3(256), 0, st, d_mix, (const float*)m->enc_w, enc, p0, tb));
-  if (stop()) return 0;
+  if (stop()) return sync_failed ? 1 : 0;
 
   // 2. bottleneck: x = Wb . gLN(tf_rep) + bb
   {
@@ -559,7 +573,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
     if (run_gemm<T, 128, C_ENC>(m, enc, &tm_enc, reinterpret_cast<const T*>(m->bn_w), &m->tm_bn, nt, C_BN, e, tb, st))
       return 1;
   }
-  if (stop()) return 0;
+  if (stop()) return sync_failed ? 1 : 0;
 
   // 3. TCN blocks
   bool fused_done = false;
@@ -569,6 +583,8 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
       // GEMM -> raw G_res + skip stash slot); after the last block the stash is merged into the mask operand
       __half* stash = reinterpret_cast<__half*>(ws + lo.o_stash);
       CUtensorMap tm_hc, tm_hh[5];  // raw h1 views: centre box and halo boxes of 8..128 frames
+      CUtensorMap tm_h1s;  // swizzled 64 x 64 store boxes of h1 (K_B epilogue)
+      if (make_tmap_act(&tm_h1s, h1, nt, C_HID)) return 1;
       if (make_tmap_act_raw(&tm_hc, h1, nt, C_HID, TILE_M)) return 1;
       for (int k = 0; k < 5; ++k)
         if (make_tmap_act_raw(&tm_hh[k], h1, nt, C_HID, 8 << k)) return 1;
@@ -587,13 +603,13 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
         int rc;
         if (b.a1 >= 0.f && b.a1 <= 1.f) {
           EpiIn<__half, true> e{b.b_in, b.a1, h1, p1};
-          rc = launch_apply_in<true>(m, b.tm_in, ap, e, tb, st);
+          rc = launch_apply_in<true>(m, b.tm_in, tm_h1s, ap, e, tb, st);
         } else {
           EpiIn<__half, false> e{b.b_in, b.a1, h1, p1};
-          rc = launch_apply_in<false>(m, b.tm_in, ap, e, tb, st);
+          rc = launch_apply_in<false>(m, b.tm_in, tm_h1s, ap, e, tb, st);
         }
         if (rc) return 1;
-        if (stop()) return 0;
+        if (stop()) return sync_failed ? 1 : 0;
         int hk = 0;  // halo box: 8 frames for d < 8, else d frames
         while ((8 << hk) < b.dilation) ++hk;
         // stash layout [tile][block][128][128]
@@ -604,13 +620,13 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
         if (!last) rc = a01 ? launch_dw_rs_d<256, true>(m, ka, tb, st) : launch_dw_rs_d<256, false>(m, ka, tb, st);
         else rc = a01 ? launch_dw_rs_d<128, true>(m, ka, tb, st) : launch_dw_rs_d<128, false>(m, ka, tb, st);
         if (rc) return 1;
-        if (stop()) return 0;
+        if (stop()) return sync_failed ? 1 : 0;
       }
       if (m->n_layers > fb::MAX_LAYERS) return fail("fused path supports up to %d TCN blocks", fb::MAX_LAYERS);
       CK(launch_k(fb::skip_merge_kernel, dim3(nt), dim3(256), 0, st, (const __half*)stash,
                   (const float2*)p2, lo.part2_stride, (const float*)m->skip_rs, (const float*)m->skip_cb, skipa,
                   m->alpha_mask, m->n_layers, tb));
-      if (stop()) return 0;
+      if (stop()) return sync_failed ? 1 : 0;
       fused_done = true;
     }
   }
@@ -628,7 +644,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
       }
       if (rc) return 1;
     }
-    if (stop()) return 0;
+    if (stop()) return sync_failed ? 1 : 0;
     {
       DwParams p{b.g1, b.be1, b.wd, b.bd, b.a2, b.dilation};
       const dim3 g(DW_SLOTS, nt);
@@ -644,7 +660,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
       else DW_LAUNCH(0);
 #undef DW_LAUNCH
     }
-    if (stop()) return 0;
+    if (stop()) return sync_failed ? 1 : 0;
     {
       EpiResSkip<T> e{p2, DW_SLOTS, b.rs, b.cb, x, xa_or_null, skip, skipa, m->alpha_mask, last ? 0 : 1, first ? 1 : 0,
                       last ? 1 : 0};
@@ -655,7 +671,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
         rc = run_gemm<T, 128, C_HID>(m, h2, &tm_h2, reinterpret_cast<const T*>(b.w_rs), &b.tm_rs, nt, C_SKIP, e, tb, st);
       if (rc) return 1;
     }
-    if (stop()) return 0;
+    if (stop()) return sync_failed ? 1 : 0;
   }
 
   // 4+5 fused: mask net + mask application + decoder + overlap-add (d_out was zero-filled by the caller)
@@ -671,8 +687,8 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
       tail::TailParams tp{m->mask_b, enc, d_out, c.n_src, c.mask_act};
       CK(launch_k(kern, dim3(std::min(nt, m->n_sm)), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tm_skipa, m->tm_mask128,
                   m->tm_wd, tp, tb));
-      prof_mark();
-      return 0;
+      stop();
+      return sync_failed ? 1 : 0;
     }
   }
   // 4. mask net + mask application
@@ -690,7 +706,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
         return 1;
     }
   }
-  if (stop()) return 0;
+  if (stop()) return sync_failed ? 1 : 0;
 
   // 5. decoder + overlap-add (d_out was zero-filled by the caller of forward())
   {

@@ -98,6 +98,19 @@ __device__ __forceinline__ void tile_partial_reduce(float2* red, int* cnt, int n
     }
   }
 }
+// TMA tile store shared -> global (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const void* desc, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(desc)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -330,6 +343,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   auto tfull_bar = [&](int s) { return bar0 + 8u * (20 + s); };
   auto tempty_bar = [&](int s) { return bar0 + 8u * (22 + s); };
   const uint32_t tmem_ptr_smem = bar0 + 8u * 24;
+  const uint32_t done_bar = bar0 + 8u * 25;  // final tcgen05.commit: no async mbarrier arrive may outlive the CTA
 
   // PDL: everything up to the prologue barrier touches only constants (weights, tap tables, per-call layout
   // tables), so it may overlap the previous kernel's tail; activations are read after pdl_wait().
@@ -341,7 +355,10 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   const int hw = (D > 0) ? 8 : d;  // halo width in frames (multiple of 8, <= 128)
   const uint32_t halo_bytes = (uint32_t)(64 * hw * 2);
   const uint32_t raw_stage_bytes = (16384u + 2u * halo_bytes + 1023u) & ~1023u;
-  const int raw_stages = min((int)(Cfg::RAW_POOL / raw_stage_bytes), Cfg::RAW_MAX_STAGES);
+  // EVEN stage count: the two producer groups consume alternate k-blocks, so with an even ring every stage (and
+  // its mbarriers) belongs to one group and a parity wait is never more than one phase ahead.  (An odd ring lets
+  // a group revisit a barrier two phases later, where the parity test can be satisfied by a stale phase.)
+  const int raw_stages = min((int)(Cfg::RAW_POOL / raw_stage_bytes), Cfg::RAW_MAX_STAGES) & ~1;
   auto raw_st = [&](int s) { return smem_base + (uint32_t)s * raw_stage_bytes; };
 
   // static tables -> shared memory
@@ -366,6 +383,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         mbar_init(tfull_bar(s), 1);
         mbar_init(tempty_bar(s), 32 * Cfg::EPI_WARPS);
       }
+      mbar_init(done_bar, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -492,6 +510,9 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
           if (++stage == Cfg::AB_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
+      // the last ab_empty arrivals have no waiter: make sure every asynchronous arrive has landed before exit
+      umma_commit(done_bar);
+      mbar_wait_b(done_bar, 0);
     }
     __syncwarp();
   } else {
@@ -655,12 +676,18 @@ struct KbCfg {
   static constexpr int EPI_WARPS = 8, PRO_WARPS = 8;  // EPI_WARPS / 4 epilogue warps per TMEM lane quadrant
   static constexpr int THREADS = (EPI_WARPS + 1 + PRO_WARPS) * 32;  // 544
   static constexpr int TMEM_COLS = 512;                 // 4 chunks of 128 output channels
+#ifndef B200SEP_KB_TMA_STORE
+#define B200SEP_KB_TMA_STORE 0  // 1: h1 through a shared-memory staging tile + TMA stores (measured slower)
+#endif
+  static constexpr int ST_BYTES = B200SEP_KB_TMA_STORE ? TILE_M * 128 * 2 : 0;  // h1 staging of one 128-channel chunk
   static constexpr int OFF_XN = W_BYTES;
-  static constexpr int OFF_TI = OFF_XN + 2 * XN_BYTES;
+  static constexpr int OFF_ST = OFF_XN + 2 * XN_BYTES;
+  static constexpr int OFF_TI = OFF_ST + ST_BYTES;
   static constexpr int OFF_RED = OFF_TI + TI_CACHE * 32;
   static constexpr int OFF_CNT = OFF_RED + 2 * EPI_WARPS * 8;
   static constexpr int OFF_BAR = OFF_CNT + 16;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static_assert(SMEM_BYTES <= 232448, "K_B shared memory over the 227 KiB limit");
 };
 
 struct ApplyParams {
@@ -673,7 +700,8 @@ struct ApplyParams {
 
 template <bool A01>
 __global__ void __launch_bounds__(KbCfg::THREADS, 1)
-apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<__half, A01> epi, Tables tb) {
+apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_h1, ApplyParams ap,
+                EpiIn<__half, A01> epi, Tables tb) {
   using Cfg = KbCfg;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -690,6 +718,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
   auto tfull_bar = [&](int q) { return bar0 + 8u * (5 + q); };
   auto tempty_bar = [&](int q) { return bar0 + 8u * (9 + q); };
   const uint32_t tmem_ptr_smem = bar0 + 8u * 13;
+  const uint32_t done_bar = bar0 + 8u * 14;  // final tcgen05.commit: no async mbarrier arrive may outlive the CTA
 
   pdl_launch_dependents();  // PDL: the prologue below (barriers, TMEM, resident W_in, layout tables) reads constants only
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -702,6 +731,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
   if (warp == MMA_WARP) {
     if (lane == 0) {
       tma_prefetch_desc(&tm_w);
+      tma_prefetch_desc(&tm_h1);
       mbar_init(w_bar, 1);
       for (int b = 0; b < 2; ++b) {
         mbar_init(xn_full(b), Cfg::PRO_WARPS * 32);
@@ -711,6 +741,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
         mbar_init(tfull_bar(q), 1);
         mbar_init(tempty_bar(q), Cfg::EPI_WARPS * 32);
       }
+      mbar_init(done_bar, 1);
       fence_barrier_init();
       // resident weights: k-block kb at +64 KiB, rows 0-255 / 256-511 as two boxes of 64(k) x 256
       mbar_expect_tx(w_bar, Cfg::W_BYTES);
@@ -730,38 +761,113 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
 
   if (warp < MMA_WARP) {
     // ================================ epilogue: bias + PReLU -> h1, gLN1 partials ==================
-    // warp = (TMEM lane quadrant, column group of the 128-column chunk)
-    const int ew = warp, quad = ew & 3, cg = ew >> 2;
+    // warp = (TMEM lane quadrant, 64-channel half of the 128-channel chunk).  h1 goes through a swizzled
+    // shared-memory staging tile (2-byte st.shared, 32 lanes = 64 contiguous bytes: conflict-free) and is
+    // written to HBM by TMA tile stores -- not by 65 k two-byte global stores per m-tile through the LSU.
+    static_assert(Cfg::EPI_WARPS == 8, "epilogue mapping assumes two warps per TMEM lane quadrant");
+    const int ew = warp, quad = ew & 3, half = ew >> 2;
     const int r = quad * 32 + lane;
+    // staging offsets of this thread's frame: [k64-block = half][frame half][row = channel][128 B], chunk ^ (row & 7)
+    const uint32_t st_base = smem_base + (uint32_t)(Cfg::OFF_ST + half * 16384 + (r >> 6) * 8192 + (r & 7) * 2);
+    uint32_t st_x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) st_x[k] = st_base + (uint32_t)(((((r & 63) >> 3) ^ k)) << 4);
+    const bool issuer = (quad == 0 && lane == 0);  // one thread per half issues that half's TMA stores
+    const float alpha = epi.alpha;
     int it = 0;
     for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
       const TileInfo ti = ti_get(s_ti, tb, it, w);
-      EpiState st;
-      st.F = ti.F; st.t0 = ti.t0; st.s = 0.f; st.q = 0.f;
+      const float vm = ((ti.t0 + r) < ti.F) ? 1.f : 0.f;  // statistics exclude frames beyond the segment end
+      const float2 vm2 = make_float2(vm, vm);
+      float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
       const uint32_t ph = (uint32_t)it & 1u;
-      float pre[32];  // unused by EpiIn
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        mbar_wait_b(tfull_bar(q), ph);
-        tcgen05_fence_after();
-        if (threadIdx.x == 0) tl_stamp(it, 16 + q);
-        constexpr int COLS = 128 / (Cfg::EPI_WARPS / 4);  // columns of the chunk this warp owns
-        const int n_base = q * 128 + cg * COLS;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)n_base;
-        float v[2][32];
-        tmem_ld32(taddr, v[0]);
-        if (COLS > 32) tmem_ld32(taddr + 32u, v[1]);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        mbar_arrive(tempty_bar(q));  // the warp's part of the chunk is in registers: the MMA may overwrite it
-        epi.template apply<32>(st, w, r, n_base, v[0], pre);
-        if (COLS > 32) epi.template apply<32>(st, w, r, n_base + 32, v[1], pre);
-        if (threadIdx.x == 0) tl_stamp(it, 20 + q);
+      __half* __restrict__ gdst = epi.h1 + tt_index(w, C_HID, half * 64, r);
+      // 8 pieces of 32 columns per m-tile (4 chunks x 2); the tcgen05.ld of piece i+1 is in flight while piece i
+      // is processed (TMEM drains at ~64 B/cycle/SM: loads and arithmetic must overlap inside a warp)
+      float v[2][32];
+      mbar_wait_b(tfull_bar(0), ph);
+      tcgen05_fence_after();
+      if (threadIdx.x == 0) tl_stamp(it, 16);
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64), v[0]);
+#pragma unroll
+      for (int pi = 0; pi < 8; ++pi) {
+        const int q = pi >> 1, hh = pi & 1;
+        tmem_ld_wait();  // piece pi is in v[pi & 1]
+        if (hh == 1) {
+          tcgen05_fence_before();
+          mbar_arrive(tempty_bar(q));  // the warp's part of chunk q is in registers: the MMA may overwrite it
+        }
+        if (pi + 1 < 8) {
+          const int qn = (pi + 1) >> 1;
+          if (((pi + 1) & 1) == 0) {
+            mbar_wait_b(tfull_bar(qn), ph);
+            tcgen05_fence_after();
+            if (threadIdx.x == 0) tl_stamp(it, 16 + qn);
+          }
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qn * 128 + half * 64 + ((pi + 1) & 1) * 32),
+                    v[(pi + 1) & 1]);
+        }
+        const int n_base = q * 128 + half * 64 + hh * 32;
+#if B200SEP_KB_TMA_STORE
+        if (hh == 0) {
+          // the previous chunk's TMA stores must have finished READING the staging half before it is rewritten
+          if (issuer) bulk_wait_read0();
+          named_bar_sync(1 + half, 128);
+        }
+#endif
+#ifdef B200SEP_EXP_KB_TMEM_ONLY  // timing experiment: drain TMEM only
+        s2.x += v[pi & 1][0] + v[pi & 1][31];
+        if (s2.x == 123.456f) gdst[0] = __float2half(q2.x);
+#else
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = ldg4(epi.bias + n_base + j);
+          float2 v0 = add2(make_float2(v[pi & 1][j], v[pi & 1][j + 1]), make_float2(b4.x, b4.y));
+          float2 v1 = add2(make_float2(v[pi & 1][j + 2], v[pi & 1][j + 3]), make_float2(b4.z, b4.w));
+          v0 = prelu2<A01>(v0, alpha);
+          v1 = prelu2<A01>(v1, alpha);
+          const __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1v = __floats2half2_rn(v1.x, v1.y);
+#if B200SEP_KB_TMA_STORE
+          const uint32_t u0 = h2_as_u32(h0), u1 = h2_as_u32(h1v);
+          const int cc = hh * 32 + j;  // channel inside the 64-channel half (row of the staging block)
+          st_shared_u16(st_x[(cc + 0) & 7] + (uint32_t)((cc + 0) * 128), (uint16_t)(u0 & 0xffffu));
+          st_shared_u16(st_x[(cc + 1) & 7] + (uint32_t)((cc + 1) * 128), (uint16_t)(u0 >> 16));
+          st_shared_u16(st_x[(cc + 2) & 7] + (uint32_t)((cc + 2) * 128), (uint16_t)(u1 & 0xffffu));
+          st_shared_u16(st_x[(cc + 3) & 7] + (uint32_t)((cc + 3) * 128), (uint16_t)(u1 >> 16));
+#else
+          __half* __restrict__ d = gdst + (size_t)(q * 128 + hh * 32 + j) * TILE_M;
+          d[0] = __low2half(h0);
+          d[TILE_M] = __high2half(h0);
+          d[2 * TILE_M] = __low2half(h1v);
+          d[3 * TILE_M] = __high2half(h1v);
+#endif
+          const float2 m0 = mul2(v0, vm2), m1 = mul2(v1, vm2);
+          s2 = add2(s2, add2(m0, m1));
+          q2 = fma2(m0, v0, fma2(m1, v1, q2));
+        }
+#endif
+#if B200SEP_KB_TMA_STORE
+        if (hh == 1) {
+          fence_proxy_async();
+          named_bar_sync(1 + half, 128);
+          if (issuer) {
+            const uint32_t src = smem_base + (uint32_t)(Cfg::OFF_ST + half * 16384);
+            const int row = w * C_HID + q * 128 + half * 64;
+            tma_store_2d(&tm_h1, src, 0, row);
+            tma_store_2d(&tm_h1, src + 8192u, 64, row);
+            bulk_commit();
+          }
+        }
+#endif
+        if (hh == 1 && threadIdx.x == 0) tl_stamp(it, 20 + q);
       }
-      const float s = warp_sum(st.s), qq = warp_sum(st.q);
+      const float s = warp_sum(s2.x + s2.y), qq = warp_sum(q2.x + q2.y);
       tile_partial_reduce(s_red + (it & 1) * Cfg::EPI_WARPS, s_cnt + (it & 1), Cfg::EPI_WARPS, ew, s, qq,
                           epi.part_out + w);
     }
+#if B200SEP_KB_TMA_STORE
+    if (issuer) bulk_wait0();  // all h1 tile stores complete before the CTA exits
+#endif
   } else if (warp == MMA_WARP) {
     // ================================ MMA issuer ==================================================
     if (lane == 0) {
@@ -792,6 +898,8 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, ApplyParams ap, EpiIn<
         }
         umma_commit(xn_empty(b));
       }
+      umma_commit(done_bar);  // the last xn_empty arrivals have no waiter
+      mbar_wait_b(done_bar, 0);
     }
     __syncwarp();
   } else {

@@ -155,6 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * Cfg::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * Cfg::STAGES + 2 + s); };
   const uint32_t tmem_ptr_smem = bar0 + 8u * (2 * Cfg::STAGES + 4);
+  const uint32_t done_bar = bar0 + 8u * (2 * Cfg::STAGES + 5);  // final tcgen05.commit (see below)
   const uint32_t red_smem = bar0 + 256u;  // [2][8] float2 block-level stat reduction
 
   // warp index broadcast through a shuffle so the compiler can prove it warp-uniform (keeps the
@@ -176,6 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 32 * Cfg::EPI_WARPS);
     }
+    mbar_init(done_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
@@ -237,6 +239,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1u; }
         }
       }
+      // The last empty-barrier arrivals have no waiter; a CTA must not exit while an asynchronous mbarrier
+      // arrive of tcgen05.commit is still in flight (it would land in the shared memory of the next CTA).
+      umma_commit(done_bar);
+      mbar_wait(done_bar, 0);
     }
     __syncwarp();
   } else if (warp >= 4) {

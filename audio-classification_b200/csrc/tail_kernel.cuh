@@ -85,6 +85,7 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const uint32_t dec_full = bar0 + 8u * 15;                      // decoder accumulator of a source complete
   const uint32_t dec_empty = bar0 + 8u * 16;                     // ... drained by the overlap-add
   const uint32_t tmem_ptr_smem = bar0 + 8u * 17;
+  const uint32_t done_bar = bar0 + 8u * 18;  // final tcgen05.commit: no async mbarrier arrive may outlive the CTA
 
   pdl_launch_dependents();  // PDL: the prologue reads constants only (see fused_block.cuh)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -111,6 +112,7 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     }
     mbar_init(dec_full, 1);
     mbar_init(dec_empty, 128);
+    mbar_init(done_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
@@ -203,6 +205,8 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           ++n_st;
         }
       }
+      umma_commit(done_bar);  // the last b_empty / st_empty / a_empty arrivals have no waiter
+      mbar_wait_b(done_bar, 0);
     }
     __syncwarp();
   } else if (warp >= 4) {
