@@ -153,7 +153,7 @@ struct BlockW {
   float *rs = nullptr, *cb = nullptr;
   int dilation = 1;
   int n_out = 256;
-  CUtensorMap tm_in, tm_rs;
+  CUtensorMap tm_in, tm_rs, tm_rs_half;
   float4 *dw_t0 = nullptr, *dw_t1 = nullptr;  // folded depthwise tap tables (fused_block.cuh DwTab)
   float* dw_cb = nullptr;
 };
@@ -473,9 +473,27 @@ static int launch_dw_rs(const b200sep_model* m, const KaArgs& a, const Tables& t
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
+  // 2-CTA clusters (each CTA multicasts half of every weight stage to its peer): even grid, one pair per SM pair
+#if B200SEP_KA_CLUSTER
+  const int n_pairs = std::min((tb.n_tiles + 1) / 2, m->n_sm / 2);
+  const int grid = 2 * n_pairs;
+#else
   const int grid = std::min(tb.n_tiles, m->n_sm);
-  CK(launch_k(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, *a.tm_b, *a.tm_hc, *a.tm_hh, a.g_res, a.g_skip,
-              a.skip_tile_stride, a.p1, a.p2, a.tab, tb));
+#endif
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = B200SEP_KA_CLUSTER ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  CK(cudaLaunchKernelEx(&cfg, kern, *a.tm_b, *a.tm_hc, *a.tm_hh, a.g_res, a.g_skip, a.skip_tile_stride, a.p1, a.p2, a.tab,
+                        tb));
   return 0;
 }
 template <int BN, bool A01>
@@ -613,7 +631,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
         int hk = 0;  // halo box: 8 frames for d < 8, else d frames
         while ((8 << hk) < b.dilation) ++hk;
         // stash layout [tile][block][128][128]
-        KaArgs ka{&b.tm_rs, &tm_hc, &tm_hh[hk], gbuf, stash + (size_t)i * (C_SKIP * TILE_M),
+        KaArgs ka{B200SEP_KA_CLUSTER ? &b.tm_rs_half : &b.tm_rs, &tm_hc, &tm_hh[hk], gbuf, stash + (size_t)i * (C_SKIP * TILE_M),
                   (size_t)m->n_layers * C_SKIP * TILE_M, p1,
                   p2 + (size_t)i * lo.part2_stride, fb::DwTab{b.dw_t0, b.dw_t1, b.dw_cb, b.a2, b.dilation}};
         const bool a01 = b.a2 >= 0.f && b.a2 <= 1.f;
@@ -776,6 +794,7 @@ int b200sep_model_create(const b200sep_config* cfg, const b200sep_weights* w, in
       BlockW& b = m->blocks[i];
       rc = make_tmap_w(&b.tm_in, b.w_in, C_HID, C_BN, 256);
       if (!rc) rc = make_tmap_w(&b.tm_rs, b.w_rs, b.n_out, C_HID, b.n_out == 256 ? 256 : 128);
+      if (!rc) rc = make_tmap_w(&b.tm_rs_half, b.w_rs, b.n_out, C_HID, b.n_out / 2);  // K_A: per-CTA half of a stage
     }
     if (!rc) rc = make_tmap_w(&m->tm_mask, m->mask_w, c.n_src * C_ENC, C_SKIP, 256);
     if (!rc) rc = make_tmap_w(&m->tm_mask128, m->mask_w, c.n_src * C_ENC, C_SKIP, 128);

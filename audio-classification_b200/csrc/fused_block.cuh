@@ -94,10 +94,40 @@ __device__ __forceinline__ void tile_partial_reduce(float2* red, int* cnt, int n
         ts += v[0]; tq += v[1];
       }
       *cnt = 0;
-      *out = make_float2(ts, tq);
+      if (out != nullptr) *out = make_float2(ts, tq);
     }
   }
 }
+#ifndef B200SEP_KA_CLUSTER
+#define B200SEP_KA_CLUSTER 0  // 1: K_A runs as 2-CTA clusters, each CTA multicasts half of every weight stage (measured slower)
+#endif
+// ---- 2-CTA cluster helpers (K_A: each CTA TMA-multicasts half of every weight stage to both CTAs) ----------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA tile load delivered to the same shared-memory offset of every CTA in `mask`; each destination CTA's mbarrier at
+// the given offset receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const void* desc, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit whose mbarrier arrive lands on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+
 // TMA tile store shared -> global (bulk async group of the issuing thread)
 __device__ __forceinline__ void tma_store_2d(const void* desc, uint32_t smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -209,28 +239,29 @@ struct DwTab {
 
 template <int BN>
 struct KaCfg {
-  static constexpr int AB_STAGES = 2;
-  // raw h1 ring: a 110 KiB pool cut into as many stages as fit (stage = 64 channels x (128 + 2 hw) frames:
-  // centre box, left halo, right halo); 6 stages at hw = 8 ... 2 stages at hw = 128
-#ifndef B200SEP_EXP_KA_MAX_STAGES
-#define B200SEP_EXP_KA_MAX_STAGES 8
-#endif
-  static constexpr int RAW_POOL = 110 * 1024, RAW_MAX_STAGES = B200SEP_EXP_KA_MAX_STAGES;
+  // Shared-memory plan (dynamic, always the full 227 KiB; offsets from the 1 KiB-aligned base):
+  //   [A ring: 2 x 16 KiB, one stage per producer group][tap tables 18 KiB][TileInfo cache][reduction scratch]
+  //   [barriers] then [raw h1 ring: 2 stages of 64 ch x (128 + 2 hw) frames][B ring: as many 64-k weight stages
+  //   as still fit, 2..4].
+  // The B ring is decoupled from the A ring and as deep as possible: a weight stage can only be re-requested
+  // when the MMA that read it has completed, and its L2 -> shared-memory latency (~1.7 k cycles) is three times
+  // the MMA time of a k-block (512 cycles); with 2 stages that latency, not the work, paced the kernel.
   static constexpr int A_STAGE = TILE_M * 64 * 2;    // 16 KiB
   static constexpr int B_STAGE = BN * 64 * 2;        // 32 / 16 KiB
-  static constexpr int AB_STAGE = A_STAGE + 32768;
+  static constexpr int B_MAX_STAGES = 4;
   static constexpr int TAB_BYTES = C_HID * (16 + 16 + 4);  // 18 KiB
   static constexpr int EPI_WARPS = 4, PROD_WARPS = 16;
   static constexpr int THREADS = (EPI_WARPS + 3 + PROD_WARPS) * 32;  // 736
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int OFF_AB = RAW_POOL;
-  static constexpr int OFF_TAB = OFF_AB + AB_STAGES * AB_STAGE;
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_TAB = OFF_A + 2 * A_STAGE;
   static constexpr int OFF_TI = OFF_TAB + TAB_BYTES;
   static constexpr int OFF_RED = OFF_TI + TI_CACHE * 32;
   static constexpr int OFF_CNT = OFF_RED + 2 * PROD_WARPS * 8;
   static constexpr int OFF_BAR = OFF_CNT + 16;
-  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024 /*align*/;
-  static_assert(SMEM_BYTES <= 232448, "K_A shared memory over the 227 KiB limit");
+  static constexpr int OFF_RAW = (OFF_BAR + 512 + 1023) / 1024 * 1024;  // raw ring, then B ring
+  static constexpr int SMEM_BYTES = 232448;          // everything an SM offers to one CTA
+  static constexpr int SMEM_USABLE = SMEM_BYTES - 1024 /*alignment slack*/;
 };
 
 struct DwEdge { float2 ml[4], mc[4], mr[4]; };
@@ -327,8 +358,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  auto stage_a = [&](int s) { return smem_base + (uint32_t)(Cfg::OFF_AB + s * Cfg::AB_STAGE); };
-  auto stage_b = [&](int s) { return smem_base + (uint32_t)(Cfg::OFF_AB + s * Cfg::AB_STAGE + Cfg::A_STAGE); };
+  auto stage_a = [&](int s) { return smem_base + (uint32_t)(Cfg::OFF_A + s * Cfg::A_STAGE); };
   float4* s_t0 = reinterpret_cast<float4*>(smem_gen + Cfg::OFF_TAB);
   float4* s_t1 = s_t0 + C_HID;
   float* s_cb = reinterpret_cast<float*>(s_t1 + C_HID);
@@ -336,14 +366,16 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   float2* s_red = reinterpret_cast<float2*>(smem_gen + Cfg::OFF_RED);  // [2][16]
   int* s_cnt = reinterpret_cast<int*>(smem_gen + Cfg::OFF_CNT);          // [2]
   const uint32_t bar0 = smem_base + Cfg::OFF_BAR;
-  auto raw_full = [&](int s) { return bar0 + 8u * s; };
-  auto raw_empty = [&](int s) { return bar0 + 8u * (8 + s); };
-  auto ab_full = [&](int s) { return bar0 + 8u * (16 + s); };
-  auto ab_empty = [&](int s) { return bar0 + 8u * (18 + s); };
-  auto tfull_bar = [&](int s) { return bar0 + 8u * (20 + s); };
-  auto tempty_bar = [&](int s) { return bar0 + 8u * (22 + s); };
-  const uint32_t tmem_ptr_smem = bar0 + 8u * 24;
-  const uint32_t done_bar = bar0 + 8u * 25;  // final tcgen05.commit: no async mbarrier arrive may outlive the CTA
+  auto raw_full = [&](int s) { return bar0 + 8u * s; };          // [2]  TMA -> producers (stage = group)
+  auto raw_empty = [&](int s) { return bar0 + 8u * (2 + s); };     // [2]
+  auto a_full = [&](int s) { return bar0 + 8u * (4 + s); };        // [2]  producers -> MMA (stage = group)
+  auto a_empty = [&](int s) { return bar0 + 8u * (6 + s); };       // [2]
+  auto b_full = [&](int s) { return bar0 + 8u * (8 + s); };        // [4]  TMA (weights) -> MMA
+  auto b_empty = [&](int s) { return bar0 + 8u * (12 + s); };      // [4]
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (16 + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (18 + s); };
+  const uint32_t tmem_ptr_smem = bar0 + 8u * 20;
+  const uint32_t done_bar = bar0 + 8u * 21;  // final tcgen05.commit: no async mbarrier arrive may outlive the CTA
 
   // PDL: everything up to the prologue barrier touches only constants (weights, tap tables, per-call layout
   // tables), so it may overlap the previous kernel's tail; activations are read after pdl_wait().
@@ -351,15 +383,37 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n_tiles = tb.n_tiles;
+  // 2-CTA clusters: the pair (2p, 2p+1) visits the tile pairs p, p + n_pairs, ...; rank r takes tile 2*pair_tile + r.
+  // Both CTAs of a pair make the same number of visits (each visit consumes 8 weight stages that the two CTAs load
+  // for each other); with an odd tile count the last visit of rank 1 re-processes the last tile without writing.
+#if B200SEP_KA_CLUSTER
+  const int crank = (int)cluster_ctarank();
+  const int n_pairs = (int)(gridDim.x >> 1), pair = (int)(blockIdx.x >> 1);
+  const int n_pair_tiles = (n_tiles + 1) >> 1;
+#else  // plain grid: "pair" = CTA, one tile per visit
+  const int n_pairs = (int)gridDim.x, pair = (int)blockIdx.x;
+  const int n_pair_tiles = n_tiles;
+#endif
+  const int n_visits = (pair < n_pair_tiles) ? (n_pair_tiles - pair + n_pairs - 1) / n_pairs : 0;
+  auto tile_at = [&](int it, bool& valid) {
+#if B200SEP_KA_CLUSTER
+    const int wr = (pair + it * n_pairs) * 2 + crank;
+#else
+    const int wr = pair + it * n_pairs;
+#endif
+    valid = wr < n_tiles;
+    return valid ? wr : n_tiles - 1;
+  };
   const int d = (D > 0) ? D : p.dilation;
   const int hw = (D > 0) ? 8 : d;  // halo width in frames (multiple of 8, <= 128)
   const uint32_t halo_bytes = (uint32_t)(64 * hw * 2);
   const uint32_t raw_stage_bytes = (16384u + 2u * halo_bytes + 1023u) & ~1023u;
-  // EVEN stage count: the two producer groups consume alternate k-blocks, so with an even ring every stage (and
-  // its mbarriers) belongs to one group and a parity wait is never more than one phase ahead.  (An odd ring lets
-  // a group revisit a barrier two phases later, where the parity test can be satisfied by a stale phase.)
-  const int raw_stages = min((int)(Cfg::RAW_POOL / raw_stage_bytes), Cfg::RAW_MAX_STAGES) & ~1;
-  auto raw_st = [&](int s) { return smem_base + (uint32_t)s * raw_stage_bytes; };
+  // two raw stages (one per producer group: every stage and its mbarriers belong to ONE group, so a parity wait is
+  // never more than one phase ahead), the rest of the shared memory is the weight ring
+  const uint32_t off_b = (uint32_t)Cfg::OFF_RAW + 2u * raw_stage_bytes;
+  const int b_stages = min((int)(((uint32_t)Cfg::SMEM_USABLE - off_b) / (uint32_t)Cfg::B_STAGE), Cfg::B_MAX_STAGES);
+  auto stage_b = [&](int s) { return smem_base + off_b + (uint32_t)(s * Cfg::B_STAGE); };
+  auto raw_st = [&](int s) { return smem_base + (uint32_t)Cfg::OFF_RAW + (uint32_t)s * raw_stage_bytes; };
 
   // static tables -> shared memory
   for (int i = threadIdx.x; i < C_HID; i += Cfg::THREADS) {
@@ -367,21 +421,26 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
     s_t1[i] = __ldg(p.t1 + i);
     s_cb[i] = __ldg(p.cb + i);
   }
-  ti_cache_fill(s_ti, tb, threadIdx.x);
+  if ((int)threadIdx.x < TI_CACHE && (int)threadIdx.x < n_visits) {
+    bool v_;
+    s_ti[threadIdx.x] = load_tile_info(tb.tile_info + tile_at(threadIdx.x, v_));
+  }
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
   if (warp == 4 && lane == 0) { tma_prefetch_desc(&tm_hc); tma_prefetch_desc(&tm_hh); }
   if (warp == 5 && lane == 0) tma_prefetch_desc(&tm_b);
   if (warp == 6) {
     if (lane == 0) {
-      for (int s = 0; s < Cfg::RAW_MAX_STAGES; ++s) {
+      for (int s = 0; s < 2; ++s) {
         mbar_init(raw_full(s), 1);
         mbar_init(raw_empty(s), Cfg::PROD_WARPS * 16);
-      }
-      for (int s = 0; s < 2; ++s) {
-        mbar_init(ab_full(s), Cfg::PROD_WARPS * 16 + 1);
-        mbar_init(ab_empty(s), 1);
+        mbar_init(a_full(s), Cfg::PROD_WARPS * 16);
+        mbar_init(a_empty(s), 1);
         mbar_init(tfull_bar(s), 1);
         mbar_init(tempty_bar(s), 32 * Cfg::EPI_WARPS);
+      }
+      for (int s = 0; s < Cfg::B_MAX_STAGES; ++s) {
+        mbar_init(b_full(s), 1);
+        mbar_init(b_empty(s), B200SEP_KA_CLUSTER ? 2 : 1);  // cluster: this CTA's and the peer's MMA both release a (multicast-filled) weight stage
       }
       mbar_init(done_bar, 1);
       fence_barrier_init();
@@ -391,6 +450,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (B200SEP_KA_CLUSTER) cluster_sync_all();  // both CTAs' mbarriers are initialised before either multicasts into the other
   tcgen05_fence_after();
   pdl_wait();
   uint32_t tmem_base;
@@ -401,8 +461,9 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
     const int quad = warp;
     const int r = quad * 32 + lane;
     constexpr int NCH = BN / 32;
-    int it = 0;
-    for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
+    for (int it = 0; it < n_visits; ++it) {
+      bool valid;
+      const int w = tile_at(it, valid);
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       mbar_wait_b(tfull_bar(as), aphase);
@@ -420,12 +481,17 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         // BN == 256: columns 0-127 = residual conv, 128-255 = skip conv; BN == 128 (last block): skip only
         __half* __restrict__ dst = (BN == 256 && c < 4) ? d_res + (size_t)(c * 32) * TILE_M
                                                         : d_skip + (size_t)((BN == 256 ? c - 4 : c) * 32) * TILE_M;
+#ifdef B200SEP_EXP_KA_NO_EPI_STORE  // timing experiment: drain TMEM only
+        if (v[c & 1][0] == 123.456f) dst[0] = __float2half(v[c & 1][31]);
+#else
+        if (valid)
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {  // one packed conversion per two channels
           const __half2 h = __floats2half2_rn(v[c & 1][j], v[c & 1][j + 1]);
           dst[(size_t)j * TILE_M] = __low2half(h);
           dst[(size_t)(j + 1) * TILE_M] = __high2half(h);
         }
+#endif
       }
       tcgen05_fence_before();
       mbar_arrive(tempty_bar(as));
@@ -437,14 +503,22 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t bytes = (uint32_t)(64 * (TILE_M + 2 * hw) * 2);
-      for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
+      for (int it = 0; it < n_visits; ++it) {
+        bool valid, nvalid = false;
+        const int w = tile_at(it, valid);
+        const int wn = (it + 1 < n_visits) ? tile_at(it + 1, nvalid) : 0;
         for (int kb = 0; kb < 8; ++kb) {
           // pull the same k-block of the NEXT tile this CTA visits into L2 (a whole tile ahead of its use)
 #ifndef B200SEP_EXP_KA_NO_L2PF
-          if (w + (int)gridDim.x < n_tiles) l2_prefetch_tma_2d(&tm_hc, 0, (w + (int)gridDim.x) * C_HID + kb * 64);
+          if (nvalid) l2_prefetch_tma_2d(&tm_hc, 0, wn * C_HID + kb * 64);
 #endif
           mbar_wait_b(raw_empty(stage), phase ^ 1u);
-          tl_stamp((w - (int)blockIdx.x) / (int)gridDim.x, 88 + kb);
+          tl_stamp(it, 88 + kb);
+#ifdef B200SEP_EXP_KA_NO_RAW_TMA  // timing experiment: no activation traffic into shared memory
+          mbar_arrive(raw_full(stage));
+          if (++stage == 2) { stage = 0; phase ^= 1u; }
+          continue;
+#endif
           mbar_expect_tx(raw_full(stage), bytes);
           const uint32_t dst = raw_st(stage);
           tma_load_2d(dst, &tm_hc, raw_full(stage), 0, w * C_HID + kb * 64);
@@ -452,7 +526,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
           // start of the next; rows outside the tensor are zero-filled by the TMA unit
           tma_load_2d(dst + 16384u, &tm_hh, raw_full(stage), TILE_M - hw, (w - 1) * C_HID + kb * 64);
           tma_load_2d(dst + 16384u + halo_bytes, &tm_hh, raw_full(stage), 0, (w + 1) * C_HID + kb * 64);
-          if (++stage == raw_stages) { stage = 0; phase ^= 1u; }
+          if (++stage == 2) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -462,16 +536,23 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
+      for (int it = 0; it < n_visits; ++it) {
         for (int kb = 0; kb < 8; ++kb) {
-          mbar_wait_b(ab_empty(stage), phase ^ 1u);
+          mbar_wait_b(b_empty(stage), phase ^ 1u);  // BOTH CTAs' MMAs are done with this stage
 #ifndef B200SEP_EXP_KA_NO_B_TMA
-          mbar_expect_tx(ab_full(stage), Cfg::B_STAGE);
-          tma_load_2d(stage_b(stage), &tm_b, ab_full(stage), kb * 64, 0);
-#else  // timing experiment: no weight traffic into shared memory
-          mbar_arrive(ab_full(stage));
+          // the whole stage lands here (own half + the peer's half); this CTA loads rows [crank * BN/2, +BN/2) of the
+          // k-block and multicasts them to the same offset of both CTAs
+          mbar_expect_tx(b_full(stage), Cfg::B_STAGE);
+#if B200SEP_KA_CLUSTER
+          tma_load_2d_mc(stage_b(stage) + (uint32_t)(crank * (Cfg::B_STAGE / 2)), &tm_b, b_full(stage), kb * 64,
+                         crank * (BN / 2), (uint16_t)0x3);
+#else
+          tma_load_2d(stage_b(stage), &tm_b, b_full(stage), kb * 64, 0);
 #endif
-          if (++stage == Cfg::AB_STAGES) { stage = 0; phase ^= 1u; }
+#else  // timing experiment: no weight traffic into shared memory
+          mbar_arrive(b_full(stage));
+#endif
+          if (++stage == b_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -484,10 +565,9 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
 #else  // timing experiment: half the B operand reads
       constexpr uint32_t idesc = make_idesc(BN / 2);
 #endif
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
+      int bs = 0;
+      uint32_t bphase = 0, gphase = 0;  // gphase: phase of the (per-group) A stages, flips every 2 k-blocks
+      for (int it = 0; it < n_visits; ++it) {
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait_b(tempty_bar(as), aphase ^ 1u);
@@ -495,19 +575,27 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         tl_stamp(it, 64);
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < 8; ++kb) {
-          mbar_wait_b(ab_full(stage), phase);
+          const int g = kb & 1;
+          mbar_wait_b(a_full(g), gphase);
+          mbar_wait_b(b_full(bs), bphase);
           tcgen05_fence_after();
           tl_stamp(it, 65 + kb);
-          const uint32_t sa = stage_a(stage), sb = stage_b(stage);
+          const uint32_t sa = stage_a(g), sb = stage_b(bs);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint64_t da = make_smem_desc(sa + j * 2048u, 8192u, 1024u);
             const uint64_t db = make_smem_desc(sb + j * 32u, 16u, 1024u);
             umma_f16(tmem_d, da, db, idesc, (uint32_t)((kb | j) != 0));
           }
-          umma_commit(ab_empty(stage));
+          umma_commit(a_empty(g));
+#if B200SEP_KA_CLUSTER
+          umma_commit_mc(b_empty(bs), (uint16_t)0x3);  // releases the stage in both CTAs
+#else
+          umma_commit(b_empty(bs));
+#endif
           if (kb == 7) umma_commit(tfull_bar(as));
-          if (++stage == Cfg::AB_STAGES) { stage = 0; phase ^= 1u; }
+          if (++bs == b_stages) { bs = 0; bphase ^= 1u; }
+          if (g == 1) gphase ^= 1u;
         }
       }
       // the last ab_empty arrivals have no waiter: make sure every asynchronous arrive has landed before exit
@@ -540,29 +628,32 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
     const uint32_t c_step = 16u * c_pitch, l_step = 16u * l_pitch, r_step = 16u * r_pitch;
     const uint32_t a_off0 = a_chunk_off(row0, lane16 * 8);  // (row & 7) is the same for every step; step j = + 2048 j
     const uint32_t sa = stage_a(grp) + a_off0;
-    const uint32_t my_ab_full = ab_full(grp), my_ab_empty = ab_empty(grp);
+    const uint32_t my_ab_full = a_full(grp), my_ab_empty = a_empty(grp);
     const __half2 alpha_h2 = __float2half2_rn(alpha);
     const bool tl_on = (gw == 0 && lane == 0);
     const int tl_base = grp ? 100 : 40;  // timeline slots: group 0 40.., group 1 100..
 
-    int rs_ = grp % raw_stages;  // raw stage / phase of this group's next k-block (advances by 2 k-blocks)
-    uint32_t rphase = (uint32_t)(grp / raw_stages) & 1u;
+    const int rs_ = grp;  // raw stage of this group
+    uint32_t rphase = 0;
     uint32_t aphase = 0;
-    int it = 0;
     float nmean = 0.f, nrstd = 0.f;  // statistics of the NEXT tile's segment (computed mid-tile)
-    if ((int)blockIdx.x < n_tiles) {
-      const TileInfo t0i = ti_get(s_ti, tb, 0, blockIdx.x);
+    if (n_visits > 0) {
+      bool v_;
+      const TileInfo t0i = ti_get(s_ti, tb, 0, tile_at(0, v_));
       seg_stats_pre(part1, t0i, part_prefetch(part1, t0i), nmean, nrstd);
     }
-    for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
+    for (int it = 0; it < n_visits; ++it) {
+      bool valid;
+      const int w = tile_at(it, valid);
       const TileInfo ti = ti_get(s_ti, tb, it, w);
       const int F = ti.F, tile_t0 = ti.t0;
       const float mean = nmean, rstd = nrstd;
-      const bool has_next = w + (int)gridDim.x < n_tiles;
+      const bool has_next = it + 1 < n_visits;
       TileInfo tn = ti;
       float2 pre = make_float2(0.f, 0.f);
       if (has_next) {
-        tn = ti_get(s_ti, tb, it + 1, w + gridDim.x);
+        bool v_;
+        tn = ti_get(s_ti, tb, it + 1, tile_at(it + 1, v_));
         pre = part_prefetch(part1, tn);
       }
       const float rm = rstd * mean;
@@ -600,8 +691,14 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
             const float cba = s_cb[ch0 + jj * 16], cbb = s_cb[ch0 + jj * 16 + 16];
             // ... then the arithmetic; the (single) A stage of this group is only needed for the stores, so the
             // tensor core drains the previous k-block of the group while the first two steps are computed
+#ifdef B200SEP_EXP_KA_NO_COMPUTE  // timing experiment: producers only move data
+            const uint4 o0 = make_uint4(vc0.x ^ va0.x, vc0.y ^ vb0.y, vc0.z, vc0.w);
+            const uint4 o1 = make_uint4(vc1.x ^ va1.x, vc1.y ^ vb1.y, vc1.z, vc1.w);
+            s2.x += ta.x + tb_.x + cba + cbb;
+#else
             const uint4 o0 = dw_step_h2<D, A01>(vc0, va0, vb0, ta, cba, rstd, rm, alpha_h2, s2, q2);
             const uint4 o1 = dw_step_h2<D, A01>(vc1, va1, vb1, tb_, cbb, rstd, rm, alpha_h2, s2, q2);
+#endif
             if (jj == 0) {
               mbar_wait_b(my_ab_empty, aphase ^ 1u);
               if (tl_on) tl_stamp(it, tl_base + 3 * (kb >> 1) + 1);
@@ -644,8 +741,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         mbar_arrive(my_ab_full);
         mbar_arrive(raw_empty(rs_));
         if (tl_on) tl_stamp(it, tl_base + 3 * (kb >> 1) + 2);
-        rs_ += 2;
-        if (rs_ >= raw_stages) { rs_ -= raw_stages; rphase ^= 1u; }
+        rphase ^= 1u;
         aphase ^= 1u;
         // statistics of the next tile's segment, off the tile-boundary critical path
         if (kb == 4 + grp && has_next) seg_stats_pre(part1, tn, pre, nmean, nrstd);
@@ -654,13 +750,14 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       const float s_acc = warp_sum(s2.x + s2.y);
       const float q_acc = warp_sum(q2.x + q2.y);
       tile_partial_reduce(s_red + (it & 1) * Cfg::PROD_WARPS, s_cnt + (it & 1), Cfg::PROD_WARPS, pw, s_acc, q_acc,
-                          part2 + w);
+                          valid ? part2 + w : nullptr);
       if (tl_on) tl_stamp(it, 34 + grp);
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
+  if (B200SEP_KA_CLUSTER) cluster_sync_all();  // the peer may multicast into / arrive on this CTA's shared memory until it is done too
   if (warp == 6) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -677,9 +774,12 @@ struct KbCfg {
   static constexpr int THREADS = (EPI_WARPS + 1 + PRO_WARPS) * 32;  // 544
   static constexpr int TMEM_COLS = 512;                 // 4 chunks of 128 output channels
 #ifndef B200SEP_KB_TMA_STORE
-#define B200SEP_KB_TMA_STORE 0  // 1: h1 through a shared-memory staging tile + TMA stores (measured slower)
+#define B200SEP_KB_TMA_STORE 0  // (lane = frame orientation only) 1: h1 via 2-byte st.shared staging + TMA stores: slower
 #endif
-  static constexpr int ST_BYTES = B200SEP_KB_TMA_STORE ? TILE_M * 128 * 2 : 0;  // h1 staging of one 128-channel chunk
+#ifndef B200SEP_KB_TRANSPOSED
+#define B200SEP_KB_TRANSPOSED 1  // in-conv GEMM as D[channel][frame]: epilogue thread = channel, 16-byte staging stores
+#endif
+  static constexpr int ST_BYTES = (B200SEP_KB_TMA_STORE || B200SEP_KB_TRANSPOSED) ? TILE_M * 128 * 2 : 0;  // h1 staging
   static constexpr int OFF_XN = W_BYTES;
   static constexpr int OFF_ST = OFF_XN + 2 * XN_BYTES;
   static constexpr int OFF_TI = OFF_ST + ST_BYTES;
@@ -759,6 +859,96 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
+#if B200SEP_KB_TRANSPOSED
+  if (warp < MMA_WARP) {
+    // ================================ epilogue: bias + PReLU -> h1, gLN1 partials ==================
+    // D[channel][frame]: TMEM lane = output channel of the 128-channel chunk, column = frame.  A thread owns 32
+    // consecutive frames of one channel per tcgen05.ld: the bias is a per-lane constant, eight frames pack into one
+    // 16-byte st.shared (swizzled like a TMA box, conflict-free), and h1 leaves the SM as 64 x 64 TMA tile stores --
+    // 1/8 of the LSU instructions of the lane = frame mapping (which needs one 2-byte store per value).
+    static_assert(Cfg::EPI_WARPS == 8, "epilogue mapping assumes two warps per TMEM lane quadrant");
+    const int ew = warp, quad = ew & 3, half = ew >> 2;   // half = frame half of the m-tile
+    const int cl = quad * 32 + lane;                       // channel inside the chunk
+    const int kb64 = cl >> 6, row = cl & 63;
+    const int grp = kb64 * 2 + half;                       // staging box = (64-channel block, frame half): 2 warps
+    const uint32_t st_box = smem_base + (uint32_t)(Cfg::OFF_ST + kb64 * 16384 + half * 8192);
+    const uint32_t st_row = st_box + (uint32_t)(row * 128);
+    const bool issuer = ((quad & 1) == 0 && lane == 0);    // one thread per box issues its TMA store
+    const float alpha = epi.alpha;
+    int it = 0;
+    for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
+      const TileInfo ti = ti_get(s_ti, tb, it, w);
+      const int nvalid = ti.F - ti.t0;                     // frames >= nvalid lie beyond the segment end
+      const bool full = nvalid >= TILE_M;
+      float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+      const uint32_t ph = (uint32_t)it & 1u;
+      float v[2][32];
+      mbar_wait_b(tfull_bar(0), ph);
+      tcgen05_fence_after();
+      if (threadIdx.x == 0) tl_stamp(it, 16);
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64), v[0]);
+      float bch = __ldg(epi.bias + cl);
+#pragma unroll
+      for (int pi = 0; pi < 8; ++pi) {
+        const int q = pi >> 1, hh = pi & 1;
+        tmem_ld_wait();  // piece pi (32 frames) is in v[pi & 1]
+        if (hh == 1) {
+          tcgen05_fence_before();
+          mbar_arrive(tempty_bar(q));  // the warp's part of chunk q is in registers: the MMA may overwrite it
+        }
+        float bnext = bch;
+        if (pi + 1 < 8) {
+          const int qn = (pi + 1) >> 1;
+          if (((pi + 1) & 1) == 0) {
+            mbar_wait_b(tfull_bar(qn), ph);
+            tcgen05_fence_after();
+            if (threadIdx.x == 0) tl_stamp(it, 16 + qn);
+            bnext = __ldg(epi.bias + qn * 128 + cl);
+          }
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qn * 128 + half * 64 + ((pi + 1) & 1) * 32),
+                    v[(pi + 1) & 1]);
+        }
+        if (hh == 0) {
+          // the previous chunk's TMA store must have finished READING this staging box before it is rewritten
+          if (issuer) bulk_wait_read0();
+          named_bar_sync(1 + grp, 64);
+        }
+        const float2 b2 = make_float2(bch, bch);
+        const int f0 = half * 64 + hh * 32;  // first frame of the piece inside the m-tile
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float2 u = add2(make_float2(v[pi & 1][j], v[pi & 1][j + 1]), b2);
+          u = prelu2<A01>(u, alpha);
+          pk[j >> 1] = h2_as_u32(__floats2half2_rn(u.x, u.y));
+          if (!full) {  // statistics exclude frames beyond the segment end
+            if (f0 + j >= nvalid) u.x = 0.f;
+            if (f0 + j + 1 >= nvalid) u.y = 0.f;
+          }
+          s2 = add2(s2, u);
+          q2 = fma2(u, u, q2);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          st_shared_v4(st_row + (uint32_t)((((hh * 4 + k) ^ (row & 7))) << 4),
+                       make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
+        if (hh == 1) {
+          fence_proxy_async();
+          named_bar_sync(1 + grp, 64);
+          if (issuer) {
+            tma_store_2d(&tm_h1, st_box, half * 64, w * C_HID + q * 128 + kb64 * 64);
+            bulk_commit();
+          }
+          if (threadIdx.x == 0) tl_stamp(it, 20 + q);
+        }
+        bch = bnext;
+      }
+      const float s = warp_sum(s2.x + s2.y), qq = warp_sum(q2.x + q2.y);
+      tile_partial_reduce(s_red + (it & 1) * Cfg::EPI_WARPS, s_cnt + (it & 1), Cfg::EPI_WARPS, ew, s, qq,
+                          epi.part_out + w);
+    }
+    if (issuer) bulk_wait0();  // all h1 tile stores complete before the CTA exits
+#else
   if (warp < MMA_WARP) {
     // ================================ epilogue: bias + PReLU -> h1, gLN1 partials ==================
     // warp = (TMEM lane quadrant, 64-channel half of the 128-channel chunk).  h1 goes through a swizzled
@@ -868,10 +1058,16 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
 #if B200SEP_KB_TMA_STORE
     if (issuer) bulk_wait0();  // all h1 tile stores complete before the CTA exits
 #endif
+#endif  // B200SEP_KB_TRANSPOSED
   } else if (warp == MMA_WARP) {
     // ================================ MMA issuer ==================================================
     if (lane == 0) {
+#if B200SEP_KB_TRANSPOSED
+      // A = W_in chunk (K-major), B = x operand (MN-major): bit 15 (A major) = 0, bit 16 (B major) = 1
+      constexpr uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+#else
       constexpr uint32_t idesc = make_idesc(128);
+#endif
       mbar_wait_b(w_bar, 0);
       int it = 0;
       for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
@@ -889,9 +1085,13 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
           for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint64_t da = make_smem_desc(sa + (uint32_t)(kb * 16384 + j * 2048), 8192u, 1024u);
-              const uint64_t db = make_smem_desc(smem_w + (uint32_t)(kb * 65536 + q * 16384 + j * 32), 16u, 1024u);
-              umma_f16(tmem_d, da, db, idesc, (uint32_t)((kb | j) != 0));
+              const uint64_t dx = make_smem_desc(sa + (uint32_t)(kb * 16384 + j * 2048), 8192u, 1024u);  // MN-major
+              const uint64_t dw = make_smem_desc(smem_w + (uint32_t)(kb * 65536 + q * 16384 + j * 32), 16u, 1024u);  // K-major
+#if B200SEP_KB_TRANSPOSED
+              umma_f16(tmem_d, dw, dx, idesc, (uint32_t)((kb | j) != 0));  // D[channel][frame] = W . x^T
+#else
+              umma_f16(tmem_d, dx, dw, idesc, (uint32_t)((kb | j) != 0));  // D[frame][channel] = x . W^T
+#endif
             }
           }
           umma_commit(tfull_bar(q));
@@ -930,11 +1130,13 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
       const uint16_t rstd_h = __half_as_ushort(rstd_hh);
       const float nmr = -mean * __half2float(rstd_hh);
       if (pt == 0) tl_stamp(it, 0);
+#ifndef B200SEP_EXP_KB_NO_L2PF
       if (pt == 0 && w + (int)gridDim.x < n_tiles) {  // next tile's x / G_res -> L2 while this tile is processed
         const size_t nidx = tt_index(w + gridDim.x, C_BN, 0, 0);
         l2_prefetch_bulk(ap.x + nidx, TILE_M * C_BN * 4);
         if (has_g) l2_prefetch_bulk(ap.g + nidx, TILE_M * C_BN * 2);
       }
+#endif
       float* __restrict__ xt = ap.x + tt_index(w, C_BN, 0, f0);
       const __half* __restrict__ gt = has_g ? ap.g + tt_index(w, C_BN, 0, f0) : nullptr;
       // all global loads of the tile are issued before the (possibly blocking) operand-buffer wait
