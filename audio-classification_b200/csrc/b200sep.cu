@@ -13,6 +13,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -182,6 +183,9 @@ struct b200sep_model {
   std::mutex mu;
   int debug_stop_after = 0;  // 0 = run everything; k = stop after k-th launch (tests)
   // optional per-launch CUDA-event timing (bench.py roofline pass)
+  // concurrent sub-batches (b200sep_separate_batch): auxiliary streams and fork / join events
+  cudaStream_t aux_st[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;
   int prof_n = 0;
@@ -815,6 +819,11 @@ void b200sep_model_destroy(b200sep_model* m) {
   cudaSetDevice(m->device);
   for (void* p : m->allocs) cudaFree(p);
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
+  for (int g = 0; g < 4; ++g) {
+    if (m->aux_st[g]) cudaStreamDestroy(m->aux_st[g]);
+    if (m->ev_join[g]) cudaEventDestroy(m->ev_join[g]);
+  }
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   delete m;
 }
 
@@ -886,24 +895,94 @@ int b200sep_debug_layout(const b200sep_model* m, const int32_t* lens, int32_t n_
   return 0;
 }
 
-size_t b200sep_workspace_bytes(const b200sep_model* m, const int32_t* lens, int32_t n_seg) {
-  if (!m) { fail("null model"); return 0; }
-  Layout lo;
-  if (compute_layout(m->cfg, m->half, m->half && m->use_tc && m->fused, lens, n_seg, &lo)) return 0;
-  return lo.total;
+// ---- concurrent sub-batches -------------------------------------------------------------------------------------
+// Every kernel of the forward is a persistent grid of one CTA per SM, so a batch of n m-tiles costs
+// ceil(n / n_sm) tile-times per launch (1050 tiles on 148 SMs: 8 rounds for 7.09 rounds of work), and its two
+// block kernels are bound by different units (K_B: HBM, K_A: shared memory).  Segments are independent, so a large
+// batch is cut into `split` tile-balanced sub-batches that run the whole forward on separate streams: the CTAs of
+// one sub-batch's launch fill the SMs the other's launch has already drained, and K_A / K_B of different
+// sub-batches overlap.  Results do not change (a segment's arithmetic never depends on its batch neighbours).
+static int split_env() {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("B200SEP_SPLIT");
+    v = e ? atoi(e) : -1;
+  }
+  return v;
+}
+static constexpr int MAX_SPLIT = 4;
+// Deterministic LPT partition of the segments into tile-balanced groups (original order kept inside a group).
+static int plan_split(const b200sep_model* m, const int32_t* lens, int n_seg, std::vector<std::vector<int>>* groups) {
+  long long tiles = 0;
+  std::vector<int> nt(n_seg);
+  for (int i = 0; i < n_seg; ++i) {
+    if (lens[i] < m->cfg.kernel_size)
+      return fail("segment %d has %d samples < kernel_size %d (conv1d would fail in the reference too)", i, lens[i],
+                  m->cfg.kernel_size);
+    const int F = (lens[i] - m->cfg.kernel_size) / m->cfg.stride + 1;
+    nt[i] = (F + TILE_M - 1) / TILE_M;
+    tiles += nt[i];
+  }
+  int S = 1;
+  const bool eligible = m->half && m->use_tc && m->fused && !m->prof_on && m->debug_stop_after == 0 &&
+                        getenv("B200SEP_SYNC_DEBUG") == nullptr;
+  if (eligible) {
+    const int e = split_env();
+    if (e >= 1) S = std::min(e, MAX_SPLIT);
+    else S = (tiles >= 3ll * m->n_sm) ? 2 : 1;  // default: two sub-batches once each still fills the GPU
+    S = std::max(1, std::min(S, n_seg));
+  }
+  groups->assign(S, {});
+  if (S == 1) {
+    (*groups)[0].resize(n_seg);
+    for (int i = 0; i < n_seg; ++i) (*groups)[0][i] = i;
+    return 0;
+  }
+  std::vector<int> order(n_seg);
+  for (int i = 0; i < n_seg; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nt[a] > nt[b]; });
+  std::vector<long long> load(S, 0);
+  for (int i : order) {
+    int best = 0;
+    for (int g = 1; g < S; ++g)
+      if (load[g] < load[best]) best = g;
+    (*groups)[best].push_back(i);
+    load[best] += nt[i];
+  }
+  for (auto& g : *groups) std::sort(g.begin(), g.end());
+  return 0;
 }
 
-int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* offsets, const int32_t* lens,
-                           int32_t n_seg, float* d_out, void* d_ws, size_t ws_bytes, void* stream) {
-  if (!m || !d_mix || !lens || !d_out || !d_ws) return fail("null argument");
-  if ((reinterpret_cast<uintptr_t>(d_ws) & 255u) != 0) return fail("d_ws must be 256-byte aligned");
+size_t b200sep_workspace_bytes(const b200sep_model* m, const int32_t* lens, int32_t n_seg) {
+  if (!m) { fail("null model"); return 0; }
+  if (n_seg <= 0 || !lens) { fail("empty batch"); return 0; }
+  // the larger of the unsplit and the split plan (the split decision may differ between this call and the run,
+  // e.g. when profiling is switched on in between)
+  Layout lo;
+  if (compute_layout(m->cfg, m->half, m->half && m->use_tc && m->fused, lens, n_seg, &lo)) return 0;
+  size_t total = lo.total;
+  std::vector<std::vector<int>> groups;
+  if (plan_split(m, lens, n_seg, &groups)) return 0;
+  if (groups.size() > 1) {
+    size_t sum = 0;
+    for (auto& g : groups) {
+      std::vector<int32_t> sl(g.size());
+      for (size_t k = 0; k < g.size(); ++k) sl[k] = lens[g[k]];
+      if (compute_layout(m->cfg, m->half, true, sl.data(), (int)sl.size(), &lo)) return 0;
+      sum += align_up(lo.total, 1024);
+    }
+    total = std::max(total, sum);
+  }
+  return total;
+}
+
+// One forward over the segments (offsets[i], lens[i]) on stream `st`, workspace `ws`.  The caller has zero-filled the
+// output span.  Error text is left in this thread's g_err.
+static int run_sub(b200sep_model* m, const float* d_mix, const int64_t* offsets, const int32_t* lens, int n_seg,
+                   float* d_out, uint8_t* ws, cudaStream_t st) {
   Layout lo;
   if (compute_layout(m->cfg, m->half, m->half && m->use_tc && m->fused, lens, n_seg, &lo)) return 1;
-  if (ws_bytes < lo.total) return fail("workspace too small: %zu < %zu bytes", ws_bytes, lo.total);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  std::lock_guard<std::mutex> lock(m->mu);
   CK(cudaSetDevice(m->device));
-
   // ---- tables -> pinned staging -> workspace head
   StagingSlot* slot = nullptr;
   {
@@ -921,14 +1000,10 @@ int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* 
   int32_t* h_nt = reinterpret_cast<int32_t*>(h + lo.t_ntiles);
   int32_t* h_ts = reinterpret_cast<int32_t*>(h + lo.t_tile_seg);
   TileInfo* h_ti = reinterpret_cast<TileInfo*>(h + lo.t_info);
-  int64_t run = 0, out_lo = INT64_MAX, out_hi = 0;
   int tile = 0;
   for (int i = 0; i < n_seg; ++i) {
-    const int64_t off = offsets ? offsets[i] : run;
-    if (off < 0) return fail("negative offset for segment %d", i);
-    run += lens[i];
-    h_in[i] = off;
-    h_out[i] = off * m->cfg.n_src;
+    h_in[i] = offsets[i];
+    h_out[i] = offsets[i] * m->cfg.n_src;
     h_len[i] = lens[i];
     const int F = (lens[i] - m->cfg.kernel_size) / m->cfg.stride + 1;
     h_fr[i] = F;
@@ -943,14 +1018,9 @@ int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* 
       ti.inv_count = h_inv[i];
     }
     tile += ntile;
-    out_lo = std::min(out_lo, h_out[i]);
-    out_hi = std::max(out_hi, h_out[i] + (int64_t)lens[i] * m->cfg.n_src);
   }
-  uint8_t* ws = static_cast<uint8_t*>(d_ws);
   CK(cudaMemcpyAsync(ws + lo.o_tables, h, lo.tables_bytes, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(slot->ev, st));
-  // zero-fill the output span (overlap-add boundary hops accumulate atomically; pad_x_to_y tail)
-  CK(cudaMemsetAsync(d_out + out_lo, 0, (size_t)(out_hi - out_lo) * sizeof(float), st));
 
   Tables tb;
   uint8_t* t = ws + lo.o_tables;
@@ -970,6 +1040,78 @@ int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* 
   if (m->half)
     return l16 ? forward<__half, 16>(m, lo, tb, d_mix, d_out, ws, st) : forward<__half, 32>(m, lo, tb, d_mix, d_out, ws, st);
   return l16 ? forward<float, 16>(m, lo, tb, d_mix, d_out, ws, st) : forward<float, 32>(m, lo, tb, d_mix, d_out, ws, st);
+}
+
+int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* offsets, const int32_t* lens,
+                           int32_t n_seg, float* d_out, void* d_ws, size_t ws_bytes, void* stream) {
+  if (!m || !d_mix || !lens || !d_out || !d_ws) return fail("null argument");
+  if ((reinterpret_cast<uintptr_t>(d_ws) & 255u) != 0) return fail("d_ws must be 256-byte aligned");
+  if (n_seg <= 0) return fail("empty batch");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lock(m->mu);
+  CK(cudaSetDevice(m->device));
+  std::vector<std::vector<int>> groups;
+  if (plan_split(m, lens, n_seg, &groups)) return 1;
+  const int S = (int)groups.size();
+
+  // absolute offsets + the output span
+  std::vector<int64_t> off(n_seg);
+  int64_t run = 0, out_lo = INT64_MAX, out_hi = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    off[i] = offsets ? offsets[i] : run;
+    if (off[i] < 0) return fail("negative offset for segment %d", i);
+    run += lens[i];
+    out_lo = std::min(out_lo, off[i] * m->cfg.n_src);
+    out_hi = std::max(out_hi, (off[i] + (int64_t)lens[i]) * m->cfg.n_src);
+  }
+  // per-group segment lists and workspace slices
+  std::vector<std::vector<int32_t>> g_len(S);
+  std::vector<std::vector<int64_t>> g_off(S);
+  std::vector<size_t> g_ws(S);
+  size_t need = 0;
+  for (int g = 0; g < S; ++g) {
+    for (int i : groups[g]) { g_len[g].push_back(lens[i]); g_off[g].push_back(off[i]); }
+    Layout lo;
+    if (compute_layout(m->cfg, m->half, m->half && m->use_tc && m->fused, g_len[g].data(), (int)g_len[g].size(), &lo))
+      return 1;
+    g_ws[g] = need;
+    need += align_up(lo.total, 1024);
+  }
+  if (ws_bytes < need) return fail("workspace too small: %zu < %zu bytes", ws_bytes, need);
+  uint8_t* ws = static_cast<uint8_t*>(d_ws);
+  // zero-fill the output span (overlap-add boundary hops accumulate atomically; pad_x_to_y tail)
+  CK(cudaMemsetAsync(d_out + out_lo, 0, (size_t)(out_hi - out_lo) * sizeof(float), st));
+  if (S == 1) return run_sub(m, d_mix, g_off[0].data(), g_len[0].data(), n_seg, d_out, ws, st);
+
+  // fork: sub-batch 0 on the caller's stream, the others on the model's auxiliary streams, launches issued by one
+  // host thread per sub-batch so that the streams fill at the same pace
+  if (!m->ev_fork) CK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+  for (int g = 1; g < S; ++g) {
+    if (!m->aux_st[g]) CK(cudaStreamCreateWithFlags(&m->aux_st[g], cudaStreamNonBlocking));
+    if (!m->ev_join[g]) CK(cudaEventCreateWithFlags(&m->ev_join[g], cudaEventDisableTiming));
+  }
+  CK(cudaEventRecord(m->ev_fork, st));
+  std::vector<int> rc(S, 0);
+  std::vector<std::string> err(S);
+  std::vector<std::thread> workers;
+  for (int g = 1; g < S; ++g) {
+    CK(cudaStreamWaitEvent(m->aux_st[g], m->ev_fork, 0));
+    workers.emplace_back([&, g]() {
+      rc[g] = run_sub(m, d_mix, g_off[g].data(), g_len[g].data(), (int)g_len[g].size(), d_out, ws + g_ws[g], m->aux_st[g]);
+      if (rc[g]) err[g] = g_err;
+    });
+  }
+  rc[0] = run_sub(m, d_mix, g_off[0].data(), g_len[0].data(), (int)g_len[0].size(), d_out, ws + g_ws[0], st);
+  if (rc[0]) err[0] = g_err;
+  for (auto& w : workers) w.join();
+  // join (also on failure: the caller's stream must not run ahead of work already queued on the auxiliary streams)
+  for (int g = 1; g < S; ++g) {
+    CK(cudaEventRecord(m->ev_join[g], m->aux_st[g]));
+    CK(cudaStreamWaitEvent(st, m->ev_join[g], 0));
+  }
+  for (int g = 0; g < S; ++g)
+    if (rc[g]) return fail("%s", err[g].c_str());
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------- PIT
