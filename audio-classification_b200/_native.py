@@ -27,6 +27,7 @@ EXPORTS = [
     "b200sep_pit_sisdr_batch", "b200sep_debug_gemm", "b200sep_debug_set_stop",
     "b200sep_debug_layout", "b200sep_profile_enable", "b200sep_profile_read",
     "b200sep_debug_abort_flag", "b200sep_pipeline", "b200sep_debug_timeline",
+    "b200sep_host_workspace_bytes", "b200sep_separate_batch_host", "b200sep_split_count",
 ]
 
 
@@ -84,6 +85,12 @@ def lib() -> C.CDLL:
         L.b200sep_workspace_bytes.argtypes = [vp, i32p, i32]
         L.b200sep_separate_batch.restype = C.c_int
         L.b200sep_separate_batch.argtypes = [vp, vp, i64p, i32p, i32, vp, vp, C.c_size_t, vp]
+        L.b200sep_split_count.restype = C.c_int
+        L.b200sep_split_count.argtypes = [vp, i32p, i32]
+        L.b200sep_host_workspace_bytes.restype = C.c_size_t
+        L.b200sep_host_workspace_bytes.argtypes = [vp, i32p, i32]
+        L.b200sep_separate_batch_host.restype = C.c_int
+        L.b200sep_separate_batch_host.argtypes = [vp, C.POINTER(vp), i32p, i32, vp, vp, C.c_size_t, vp]
         L.b200sep_pit_workspace_bytes.restype = C.c_size_t
         L.b200sep_pit_workspace_bytes.argtypes = [i32p, i32]
         L.b200sep_pit_sisdr_batch.restype = C.c_int

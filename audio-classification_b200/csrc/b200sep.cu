@@ -186,6 +186,9 @@ struct b200sep_model {
   // concurrent sub-batches (b200sep_separate_batch): auxiliary streams and fork / join events
   cudaStream_t aux_st[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* hin = nullptr;  // pinned input staging of b200sep_separate_batch_host
+  size_t hin_cap = 0;    // floats
+  cudaEvent_t hin_ev = nullptr;
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;
   int prof_n = 0;
@@ -824,6 +827,8 @@ void b200sep_model_destroy(b200sep_model* m) {
     if (m->ev_join[g]) cudaEventDestroy(m->ev_join[g]);
   }
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  if (m->hin_ev) cudaEventDestroy(m->hin_ev);
+  if (m->hin) cudaFreeHost(m->hin);
   delete m;
 }
 
@@ -976,6 +981,13 @@ size_t b200sep_workspace_bytes(const b200sep_model* m, const int32_t* lens, int3
   return total;
 }
 
+int b200sep_split_count(const b200sep_model* m, const int32_t* lens, int32_t n_seg) {
+  if (!m || !lens || n_seg <= 0) { fail("null / empty argument"); return -1; }
+  std::vector<std::vector<int>> groups;
+  if (plan_split(m, lens, n_seg, &groups)) return -1;
+  return (int)groups.size();
+}
+
 // One forward over the segments (offsets[i], lens[i]) on stream `st`, workspace `ws`.  The caller has zero-filled the
 // output span.  Error text is left in this thread's g_err.
 static int run_sub(b200sep_model* m, const float* d_mix, const int64_t* offsets, const int32_t* lens, int n_seg,
@@ -1109,6 +1121,132 @@ int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* 
     CK(cudaEventRecord(m->ev_join[g], m->aux_st[g]));
     CK(cudaStreamWaitEvent(st, m->ev_join[g], 0));
   }
+  for (int g = 0; g < S; ++g)
+    if (rc[g]) return fail("%s", err[g].c_str());
+  return 0;
+}
+
+// ---- host boundary: pageable / pinned host segments in, host waveforms out -------------------------------------
+// Device-side extras of the host entry point: the packed mixtures and the packed outputs live behind the forward's
+// own scratch.
+static size_t host_extra_bytes(const b200sep_model* m, const int32_t* lens, int n_seg, size_t* o_mix, size_t* o_out) {
+  size_t total = 0;
+  for (int i = 0; i < n_seg; ++i) total += (size_t)lens[i];
+  const size_t mix_b = align_up(total * 4, 1024), out_b = align_up(total * 4 * m->cfg.n_src, 1024);
+  if (o_mix) *o_mix = 0;
+  if (o_out) *o_out = mix_b;
+  return mix_b + out_b;
+}
+size_t b200sep_host_workspace_bytes(const b200sep_model* m, const int32_t* lens, int32_t n_seg) {
+  const size_t fw = b200sep_workspace_bytes(m, lens, n_seg);
+  if (fw == 0) return 0;
+  return align_up(fw, 1024) + host_extra_bytes(m, lens, n_seg, nullptr, nullptr);
+}
+
+int b200sep_separate_batch_host(b200sep_model* m, const float* const* h_segs, const int32_t* lens, int32_t n_seg,
+                                float* h_out, void* d_ws, size_t ws_bytes, void* stream) {
+  if (!m || !h_segs || !lens || !h_out || !d_ws) return fail("null argument");
+  if ((reinterpret_cast<uintptr_t>(d_ws) & 255u) != 0) return fail("d_ws must be 256-byte aligned");
+  if (n_seg <= 0) return fail("empty batch");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lock(m->mu);
+  CK(cudaSetDevice(m->device));
+  std::vector<std::vector<int>> groups;
+  if (plan_split(m, lens, n_seg, &groups)) return 1;
+  const int S = (int)groups.size(), NS = m->cfg.n_src;
+
+  // device packing: group-contiguous (each group's H2D is one copy); the host output keeps the caller's order
+  std::vector<int64_t> h_off(n_seg), d_off(n_seg);
+  int64_t total = 0;
+  for (int i = 0; i < n_seg; ++i) { h_off[i] = total; total += lens[i]; }
+  std::vector<std::vector<int32_t>> g_len(S);
+  std::vector<std::vector<int64_t>> g_off(S);
+  std::vector<int64_t> g_begin(S), g_end(S);
+  std::vector<size_t> g_ws(S);
+  size_t fw_need = 0;
+  int64_t run = 0;
+  for (int g = 0; g < S; ++g) {
+    g_begin[g] = run;
+    for (int i : groups[g]) {
+      d_off[i] = run;
+      g_len[g].push_back(lens[i]);
+      g_off[g].push_back(run);
+      run += lens[i];
+    }
+    g_end[g] = run;
+    Layout lo;
+    if (compute_layout(m->cfg, m->half, m->half && m->use_tc && m->fused, g_len[g].data(), (int)g_len[g].size(), &lo))
+      return 1;
+    g_ws[g] = fw_need;
+    fw_need += align_up(lo.total, 1024);
+  }
+  size_t o_mix, o_out;
+  const size_t extra = host_extra_bytes(m, lens, n_seg, &o_mix, &o_out);
+  if (ws_bytes < fw_need + extra) return fail("workspace too small: %zu < %zu bytes", ws_bytes, fw_need + extra);
+  uint8_t* ws = static_cast<uint8_t*>(d_ws);
+  float* d_mix = reinterpret_cast<float*>(ws + fw_need + o_mix);
+  float* d_out = reinterpret_cast<float*>(ws + fw_need + o_out);
+
+  // pinned input staging (grown on demand); its previous H2D copies must have completed before it is rewritten
+  if (m->hin_cap < (size_t)total) {
+    if (m->hin_ev) CK(cudaEventSynchronize(m->hin_ev));
+    if (m->hin) CK(cudaFreeHost(m->hin));
+    m->hin = nullptr; m->hin_cap = 0;
+    const size_t cap = std::max<size_t>((size_t)total * 2, 1 << 16);
+    CK(cudaHostAlloc(reinterpret_cast<void**>(&m->hin), cap * sizeof(float), cudaHostAllocDefault));
+    m->hin_cap = cap;
+  }
+  if (!m->hin_ev) CK(cudaEventCreateWithFlags(&m->hin_ev, cudaEventDisableTiming));
+  else CK(cudaEventSynchronize(m->hin_ev));
+
+  CK(cudaMemsetAsync(d_out, 0, (size_t)total * NS * sizeof(float), st));
+  if (!m->ev_fork) CK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+  for (int g = 1; g < S; ++g) {
+    if (!m->aux_st[g]) CK(cudaStreamCreateWithFlags(&m->aux_st[g], cudaStreamNonBlocking));
+    if (!m->ev_join[g]) CK(cudaEventCreateWithFlags(&m->ev_join[g], cudaEventDisableTiming));
+  }
+  CK(cudaEventRecord(m->ev_fork, st));
+  for (int g = 1; g < S; ++g) CK(cudaStreamWaitEvent(m->aux_st[g], m->ev_fork, 0));
+
+  // per group: gather -> H2D -> forward -> D2H, everything of a group on its own stream and host thread, so the
+  // gather / copies of one group overlap the kernels of the other
+  auto run_group = [&](int g, cudaStream_t gs) -> int {
+    CK(cudaSetDevice(m->device));
+    for (int i : groups[g]) memcpy(m->hin + d_off[i], h_segs[i], (size_t)lens[i] * sizeof(float));
+    CK(cudaMemcpyAsync(d_mix + g_begin[g], m->hin + g_begin[g], (size_t)(g_end[g] - g_begin[g]) * sizeof(float),
+                       cudaMemcpyHostToDevice, gs));
+    if (run_sub(m, d_mix, g_off[g].data(), g_len[g].data(), (int)g_len[g].size(), d_out, ws + g_ws[g], gs)) return 1;
+    // D2H: maximal runs of segments that are adjacent on both sides
+    const std::vector<int>& idx = groups[g];
+    size_t k = 0;
+    while (k < idx.size()) {
+      size_t e = k + 1;
+      while (e < idx.size() && idx[e] == idx[e - 1] + 1) ++e;
+      const int i0 = idx[k];
+      int64_t n = 0;
+      for (size_t q = k; q < e; ++q) n += lens[idx[q]];
+      CK(cudaMemcpyAsync(h_out + (size_t)NS * h_off[i0], d_out + (size_t)NS * d_off[i0], (size_t)n * NS * sizeof(float),
+                         cudaMemcpyDeviceToHost, gs));
+      k = e;
+    }
+    return 0;
+  };
+  std::vector<int> rc(S, 0);
+  std::vector<std::string> err(S);
+  std::vector<std::thread> workers;
+  for (int g = 1; g < S; ++g)
+    workers.emplace_back([&, g]() {
+      rc[g] = run_group(g, m->aux_st[g]);
+      if (rc[g]) err[g] = g_err;
+    });
+  rc[0] = run_group(0, st);
+  if (rc[0]) err[0] = g_err;
+  for (auto& w : workers) w.join();
+  for (int g = 1; g < S; ++g) {
+    CK(cudaEventRecord(m->ev_join[g], m->aux_st[g]));
+    CK(cudaStreamWaitEvent(st, m->ev_join[g], 0));
+  }
+  CK(cudaEventRecord(m->hin_ev, st));
   for (int g = 0; g < S; ++g)
     if (rc[g]) return fail("%s", err[g].c_str());
   return 0;

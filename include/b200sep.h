@@ -133,6 +133,26 @@ int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* 
 #define B200SEP_PIT_OVERLAP3 0 /* scripts/osd/overlap3_core.py:66-117                         */
 #define B200SEP_PIT_EVALSRC 1  /* scripts/osd/evaluate_with_sources.py:334-441                */
 
+/*
+ * Number of concurrent sub-batches b200sep_separate_batch[_host] will cut this batch into (segments are independent;
+ * a large batch runs as tile-balanced sub-batches on separate streams so that the persistent kernels of one fill the
+ * SMs the other has drained; 1 while profiling / debugging hooks are on; B200SEP_SPLIT=<n> overrides).  -1 on error.
+ */
+int b200sep_split_count(const b200sep_model* m, const int32_t* lens, int32_t n_seg);
+
+/*
+ * Host boundary of the same forward: replaces Separator.separate (src/osd/separation.py:66-89: numpy in ->
+ * `.to(device)` -> model -> `.cpu().numpy()`), batched.  `h_segs[i]` points to `lens[i]` fp32 samples in ANY host
+ * memory; `h_out` (page-locked memory recommended) receives, for segment i and source s, `lens[i]` samples at
+ * `h_out + n_src * sum(lens[0..i-1]) + s * lens[i]`.  The call gathers the segments into the library's pinned
+ * staging, and queues H2D copy, forward and D2H copy of each concurrent sub-batch on its own stream; it returns when
+ * everything is QUEUED -- synchronise `stream` before reading `h_out`.  `d_ws`: 256-byte aligned device scratch of
+ * at least b200sep_host_workspace_bytes() bytes (forward scratch + packed device input / output).
+ */
+size_t b200sep_host_workspace_bytes(const b200sep_model* m, const int32_t* lens, int32_t n_seg);
+int b200sep_separate_batch_host(b200sep_model* m, const float* const* h_segs, const int32_t* lens,
+                                int32_t n_seg, float* h_out, void* d_ws, size_t ws_bytes, void* stream);
+
 /* doubles of device scratch needed by b200sep_pit_sisdr_batch */
 size_t b200sep_pit_workspace_bytes(const int32_t* lens, int32_t n_seg);
 
