@@ -28,6 +28,8 @@ EXPORTS = [
     "b200sep_debug_layout", "b200sep_profile_enable", "b200sep_profile_read",
     "b200sep_debug_abort_flag", "b200sep_pipeline", "b200sep_debug_timeline",
     "b200sep_host_workspace_bytes", "b200sep_separate_batch_host", "b200sep_split_count",
+    "b200sep_resample_out_lens", "b200sep_resample_batch", "b200sep_frame_rms_out_lens",
+    "b200sep_frame_rms_batch", "b200sep_gt_overlap_mask_batch",
 ]
 
 
@@ -85,6 +87,16 @@ def lib() -> C.CDLL:
         L.b200sep_workspace_bytes.argtypes = [vp, i32p, i32]
         L.b200sep_separate_batch.restype = C.c_int
         L.b200sep_separate_batch.argtypes = [vp, vp, i64p, i32p, i32, vp, vp, C.c_size_t, vp]
+        L.b200sep_resample_out_lens.restype = C.c_int
+        L.b200sep_resample_out_lens.argtypes = [i32p, i32, i32, i32, i32, i32p]
+        L.b200sep_resample_batch.restype = C.c_int
+        L.b200sep_resample_batch.argtypes = [vp, i32p, i32, i32, i32, i32, vp, vp]
+        L.b200sep_frame_rms_out_lens.restype = C.c_int
+        L.b200sep_frame_rms_out_lens.argtypes = [i32p, i32, i32, i32, i32p]
+        L.b200sep_frame_rms_batch.restype = C.c_int
+        L.b200sep_frame_rms_batch.argtypes = [vp, i32p, i32, i32, i32, vp, vp]
+        L.b200sep_gt_overlap_mask_batch.restype = C.c_int
+        L.b200sep_gt_overlap_mask_batch.argtypes = [vp, vp, i32p, i32, C.c_float, vp, vp]
         L.b200sep_split_count.restype = C.c_int
         L.b200sep_split_count.argtypes = [vp, i32p, i32]
         L.b200sep_host_workspace_bytes.restype = C.c_size_t

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -26,6 +27,7 @@
 #include "fused_block.cuh"
 #include "tail_kernel.cuh"
 #include "pit.cuh"
+#include "aux_kernels.cuh"
 
 using namespace b200sep;
 
@@ -1317,6 +1319,209 @@ int b200sep_pit_sisdr_batch(const float* d_refs, const float* d_ests, const floa
   pit_finalize_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(partial, a.len, n_seg, max_chunks, K, N, variant, d_pair,
                                                          d_sisdr, d_sisdri, d_perm);
   CK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- aux ops
+// Ragged-batch tables of the auxiliary kernels: pinned staging slot + a device mirror of the same size, recycled
+// through an 8-deep ring (a slot is reused once the copy / kernels recorded on its event have completed).
+struct AuxSlot {
+  void* host = nullptr;
+  void* dev = nullptr;
+  size_t cap = 0;
+  cudaEvent_t ev = nullptr;
+};
+static AuxSlot g_aux[8];
+static int g_aux_next = 0;
+static std::mutex g_aux_mu;
+static int aux_acquire(size_t bytes, AuxSlot** out) {
+  AuxSlot& s = g_aux[g_aux_next];
+  g_aux_next = (g_aux_next + 1) % 8;
+  if (!s.ev) CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+  else CK(cudaEventSynchronize(s.ev));
+  if (s.cap < bytes) {
+    if (s.host) CK(cudaFreeHost(s.host));
+    if (s.dev) CK(cudaFree(s.dev));
+    s.host = s.dev = nullptr;
+    s.cap = 0;
+    const size_t cap = align_up(bytes * 2, 4096);
+    CK(cudaHostAlloc(&s.host, cap, cudaHostAllocDefault));
+    CK(cudaMalloc(&s.dev, cap));
+    s.cap = cap;
+  }
+  *out = &s;
+  return 0;
+}
+// Packs (in_len, out_len) into tightly packed offsets and uploads the four tables; fills `io` with device pointers.
+static int aux_upload_io(const int32_t* in_len, const int32_t* out_len, int n, cudaStream_t st, RaggedIO* io, AuxSlot** slot_out) {
+  const size_t b64 = align_up((size_t)n * 8, 256), b32 = align_up((size_t)n * 4, 256);
+  AuxSlot* slot = nullptr;
+  if (aux_acquire(2 * b64 + 2 * b32, &slot)) return 1;
+  uint8_t* h = static_cast<uint8_t*>(slot->host);
+  int64_t* h_io = reinterpret_cast<int64_t*>(h);
+  int64_t* h_oo = reinterpret_cast<int64_t*>(h + b64);
+  int32_t* h_il = reinterpret_cast<int32_t*>(h + 2 * b64);
+  int32_t* h_ol = reinterpret_cast<int32_t*>(h + 2 * b64 + b32);
+  int64_t ri = 0, ro = 0;
+  for (int i = 0; i < n; ++i) {
+    h_io[i] = ri; h_oo[i] = ro; h_il[i] = in_len[i]; h_ol[i] = out_len[i];
+    ri += in_len[i]; ro += out_len[i];
+  }
+  CK(cudaMemcpyAsync(slot->dev, h, 2 * b64 + 2 * b32, cudaMemcpyHostToDevice, st));
+  uint8_t* d = static_cast<uint8_t*>(slot->dev);
+  io->in_off = reinterpret_cast<const int64_t*>(d);
+  io->out_off = reinterpret_cast<const int64_t*>(d + b64);
+  io->in_len = reinterpret_cast<const int32_t*>(d + 2 * b64);
+  io->out_len = reinterpret_cast<const int32_t*>(d + 2 * b64 + b32);
+  *slot_out = slot;
+  return 0;
+}
+
+static int gcd_i(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
+
+// torchaudio _get_sinc_resample_kernel (sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99) evaluated in fp32 in
+// the same operation order (functional.resample passes the waveform's dtype): bank [new][2 width + orig].
+struct SincBank {
+  float* dev = nullptr;
+  int orig = 0, neu = 0, width = 0, kw = 0;
+};
+static std::map<std::pair<int, int>, SincBank> g_sinc;
+static int sinc_bank(int sr_in, int sr_out, SincBank* out) {
+  const auto key = std::make_pair(sr_in, sr_out);
+  auto it = g_sinc.find(key);
+  if (it != g_sinc.end()) { *out = it->second; return 0; }
+  const int g = gcd_i(sr_in, sr_out);
+  const int orig = sr_in / g, neu = sr_out / g;
+  const int lpw = 6;
+  const double base_freq = (double)std::min(orig, neu) * 0.99;  // Python float arithmetic
+  const int width = (int)std::ceil((double)lpw * (double)orig / base_freq);
+  const int kw = 2 * width + orig;
+  if ((long long)neu * kw > (1ll << 24)) return fail("resample %d -> %d: filter bank too large", sr_in, sr_out);
+  std::vector<float> bank((size_t)neu * kw);
+  const float bf = (float)base_freq, pi_over = (float)(M_PI / lpw / 2.0), pif = (float)M_PI, scale = (float)(base_freq / orig);
+  for (int p = 0; p < neu; ++p)
+    for (int k = 0; k < kw; ++k) {
+      const float idx = (float)(k - width) / (float)orig;
+      float t = (float)(-p) / (float)neu + idx;
+      t *= bf;
+      t = std::min(std::max(t, (float)-lpw), (float)lpw);
+      const float c = std::cos(t * pif / (float)lpw / 2.0f);
+      (void)pi_over;
+      const float window = c * c;
+      t *= pif;
+      const float kern = (t == 0.f) ? 1.0f : std::sin(t) / t;
+      bank[(size_t)p * kw + k] = kern * (window * scale);
+    }
+  SincBank b;
+  b.orig = orig; b.neu = neu; b.width = width; b.kw = kw;
+  CK(cudaMalloc(reinterpret_cast<void**>(&b.dev), bank.size() * sizeof(float)));
+  CK(cudaMemcpy(b.dev, bank.data(), bank.size() * sizeof(float), cudaMemcpyHostToDevice));
+  g_sinc[key] = b;
+  *out = b;
+  return 0;
+}
+
+int b200sep_resample_out_lens(const int32_t* lens, int32_t n_seg, int32_t sr_in, int32_t sr_out, int32_t method,
+                              int32_t* out_lens) {
+  if (!lens || !out_lens || n_seg <= 0) return fail("null / empty argument");
+  if (sr_in <= 0 || sr_out <= 0) return fail("sample rates must be positive");
+  if (method != B200SEP_RESAMPLE_LINEAR && method != B200SEP_RESAMPLE_SINC) return fail("bad resample method");
+  const int g = gcd_i(sr_in, sr_out);
+  for (int i = 0; i < n_seg; ++i) {
+    const int n = lens[i];
+    if (n < 0) return fail("negative length");
+    int o = n;
+    if (sr_in != sr_out && n > 1) {
+      if (method == B200SEP_RESAMPLE_LINEAR) {
+        // separation.py:98: int(round(len * sample_rate / sr)) (round-half-even on the correctly rounded quotient)
+        const double q = (double)((long long)n * sr_out) / (double)sr_in;
+        const long long t = (long long)std::nearbyint(q);
+        o = (t <= 1) ? n : (int)t;  // :99-100: tgt_n <= 1 -> unchanged
+      } else {
+        o = (int)std::ceil((double)((long long)(sr_out / g) * n) / (double)(sr_in / g));
+      }
+    }
+    out_lens[i] = o;
+  }
+  return 0;
+}
+
+int b200sep_resample_batch(const float* d_in, const int32_t* lens, int32_t n_seg, int32_t sr_in, int32_t sr_out,
+                           int32_t method, float* d_out, void* stream) {
+  if (!d_in || !d_out || !lens) return fail("null argument");
+  std::vector<int32_t> ol(std::max(n_seg, 1));
+  if (b200sep_resample_out_lens(lens, n_seg, sr_in, sr_out, method, ol.data())) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lock(g_aux_mu);
+  RaggedIO io;
+  AuxSlot* slot = nullptr;
+  if (aux_upload_io(lens, ol.data(), n_seg, st, &io, &slot)) return 1;
+  int max_out = 1;
+  bool any_change = false;
+  for (int i = 0; i < n_seg; ++i) { max_out = std::max(max_out, ol[i]); any_change |= (ol[i] != lens[i]); }
+  const dim3 grid(std::min((max_out + 255) / 256, 1024), n_seg);
+  if (method == B200SEP_RESAMPLE_LINEAR || sr_in == sr_out || !any_change) {
+    // (a pass-through signal has n_out == n_in: positions are the integers, the kernel copies)
+    resample_linear_kernel<<<grid, 256, 0, st>>>(d_in, d_out, io);
+  } else {
+    SincBank b;
+    if (sinc_bank(sr_in, sr_out, &b)) return 1;
+    // signals of <= 1 sample pass through unchanged (overlap3_core.py:139): out_len == in_len there and the sinc
+    // kernel would scale them, so they are routed through the copy path of the linear kernel first
+    bool tiny = false;
+    for (int i = 0; i < n_seg; ++i) tiny |= (lens[i] <= 1);
+    if (tiny) return fail("sinc resample of signals with <= 1 sample is a pass-through; filter them on the host");
+    SincArgs a{b.dev, b.orig, b.neu, b.width, b.kw};
+    const size_t smem = ((size_t)b.neu * b.kw * 4 <= 48 * 1024) ? (size_t)b.neu * b.kw * 4 : 0;
+    resample_sinc_kernel<<<grid, 256, smem, st>>>(d_in, d_out, io, a);
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(slot->ev, st));
+  return 0;
+}
+
+int b200sep_frame_rms_out_lens(const int32_t* lens, int32_t n_seg, int32_t win_s, int32_t hop_s, int32_t* out_lens) {
+  if (!lens || !out_lens || n_seg <= 0) return fail("null / empty argument");
+  if (win_s <= 0) return fail("win too small");  // evaluate_with_sources.py:185-186
+  if (hop_s <= 0) return fail("hop too small");  // :187-188
+  for (int i = 0; i < n_seg; ++i) {
+    if (lens[i] < 0) return fail("negative length");
+    const int stop = std::max(lens[i] - win_s + 1, 1);  // range(0, max(len - win_s + 1, 1), hop_s)
+    out_lens[i] = (stop + hop_s - 1) / hop_s;
+  }
+  return 0;
+}
+
+int b200sep_frame_rms_batch(const float* d_wav, const int32_t* lens, int32_t n_seg, int32_t win_s, int32_t hop_s,
+                            float* d_rms, void* stream) {
+  if (!d_wav || !d_rms || !lens) return fail("null argument");
+  std::vector<int32_t> ol(std::max(n_seg, 1));
+  if (b200sep_frame_rms_out_lens(lens, n_seg, win_s, hop_s, ol.data())) return 1;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lock(g_aux_mu);
+  RaggedIO io;
+  AuxSlot* slot = nullptr;
+  if (aux_upload_io(lens, ol.data(), n_seg, st, &io, &slot)) return 1;
+  int max_fr = 1;
+  for (int i = 0; i < n_seg; ++i) max_fr = std::max(max_fr, ol[i]);
+  const dim3 grid(std::min((max_fr + 7) / 8, 2048), n_seg);
+  frame_rms_kernel<<<grid, 256, 0, st>>>(d_wav, d_rms, io, RmsArgs{win_s, hop_s});
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(slot->ev, st));
+  return 0;
+}
+
+int b200sep_gt_overlap_mask_batch(const float* d_rms1, const float* d_rms2, const int32_t* n_frames, int32_t n_seg,
+                                  float thr_ratio, uint8_t* d_mask, void* stream) {
+  if (!d_rms1 || !d_rms2 || !n_frames || !d_mask || n_seg <= 0) return fail("null / empty argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  std::lock_guard<std::mutex> lock(g_aux_mu);
+  RaggedIO io;
+  AuxSlot* slot = nullptr;
+  if (aux_upload_io(n_frames, n_frames, n_seg, st, &io, &slot)) return 1;
+  gt_overlap_mask_kernel<<<n_seg, 256, 0, st>>>(d_rms1, d_rms2, io.in_off, io.in_len, thr_ratio, d_mask);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(slot->ev, st));
   return 0;
 }
 

@@ -5,9 +5,15 @@
 * ``sep_metrics``    -- the ``sep_*`` keys of ``metrics.json`` (``overlap3_core.py:911-925``), which
                         ``/root/reference/batch_eval.py:65-84`` averages across runs
 * ``sep_detail_row`` -- one ``overlap_sep_details.csv`` row (``overlap3_core.py:732-742``)
+* ``write_sep_details_csv`` -- the file itself, header included
+                        (``/root/reference/scripts/osd/offline_overlap_3src.py:209-228``)
+* ``merge_metrics``  -- ``metrics.update(...)`` of the ``sep_*`` keys into a metrics.json dict
+                        (``overlap3_core.py:911-925``), written with the reference's json.dump settings
 """
 from __future__ import annotations
 
+import csv
+import json
 from typing import Any, Dict, List, Optional, Sequence
 
 import numpy as np
@@ -35,3 +41,31 @@ def sep_detail_row(mix_path: str, s: float, e: float, K: int, best: float, sdri:
                    idx_sel: Sequence[int]) -> List[Any]:
     return [mix_path, f"{s:.3f}", f"{e:.3f}", K, f"{best:.4f}", f"{sdri:.4f}",
             ";".join(str(int(i)) for i in idx_sel)]
+
+
+SEP_DETAILS_HEADER = ["wav", "start", "end", "k_refs", "sisdr", "sisdri", "selected_pred_indices"]
+
+
+def write_sep_details_csv(path: str, rows: Sequence[Sequence[Any]]) -> None:
+    """offline_overlap_3src.py:209-228: utf-8, ``newline=""``, header row, then ``sep_details_rows`` verbatim."""
+    with open(path, "w", newline="", encoding="utf-8") as fh:
+        w = csv.writer(fh)
+        w.writerow(SEP_DETAILS_HEADER)
+        for row in rows:
+            w.writerow(row)
+
+
+def merge_metrics(metrics: Dict[str, Any], sisdr: Sequence[float], sisdri: Sequence[float],
+                  time_sep_sec: Optional[float] = None) -> Dict[str, Any]:
+    """Adds the ``sep_*`` keys (and ``time_sep_sec`` rounded to 3 dp, ``overlap3_core.py:903``) to a metrics dict."""
+    out = dict(metrics)
+    if time_sep_sec is not None:
+        out["time_sep_sec"] = round(float(time_sep_sec), 3)
+    out.update(sep_metrics(sisdr, sisdri))
+    return out
+
+
+def write_metrics_json(path: str, metrics: Dict[str, Any]) -> None:
+    """offline_overlap_3src.py writes metrics.json with ``ensure_ascii=False, indent=2``."""
+    with open(path, "w", encoding="utf-8") as f:
+        json.dump(metrics, f, ensure_ascii=False, indent=2)

@@ -149,6 +149,33 @@ class SeparationEngine:
         return [float(buf[i]) for i in range(min(n.value, 256))]
 
     # ------------------------------------------------------------------ host boundary
+    def separate_batch_resampled(self, chunks: Sequence[np.ndarray], sr_in: int, sr_out: int) -> List[List[np.ndarray]]:
+        """float32 chunks at ``sr_in`` -> device linear resample to ``sr_out`` (``Separator._ensure_sr`` semantics,
+        ``separation.py:91-103``) -> forward -> host.  Output arrays have the RESAMPLED length, as in the reference."""
+        from . import aux
+        torch = self._torch
+        dev = torch.device("cuda", self.device)
+        S = self.n_src
+        lens_in = [int(c.shape[0]) for c in chunks]
+        with self._lock, torch.cuda.device(dev):
+            flat = torch.from_numpy(np.concatenate([np.ascontiguousarray(c) for c in chunks])).pin_memory()
+            d_raw = flat.to(dev, non_blocking=True)
+            d_mix, lens = aux.resample_device(d_raw, lens_in, sr_in, sr_out, "linear")
+            d_out = self.separate_device(d_mix, lens)
+            total = int(sum(lens))
+            pinned_out, hout = self._acquire_pinned_out(total * S)
+            pinned_out[:total * S].copy_(d_out[:total * S], non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            if nat.abort_flag():
+                raise RuntimeError("b200sep: a device-side pipeline wait timed out; results are invalid")
+        res: List[List[np.ndarray]] = []
+        o = 0
+        for n in lens:
+            seg = hout[o * S:(o + n) * S].reshape(S, n)
+            res.append([seg[s] for s in range(S)])
+            o += n
+        return res
+
     def _acquire_pinned_out(self, n_floats: int):
         """A page-locked output buffer nobody holds views of any more (CPython reference counts of the base
         ndarray), else a new one.  The results handed to the caller are numpy VIEWS of it, so a buffer returns to the
@@ -281,9 +308,15 @@ class Separator:
         return [out[i] for i in range(self.n_src)]
 
     def separate_batch(self, chunks: Sequence[np.ndarray], sr: int) -> List[List[np.ndarray]]:
-        """All overlap segments of one (or many) mixtures in a single forward."""
+        """All overlap segments of one (or many) mixtures in a single forward.  When ``sr`` differs from
+        ``sample_rate`` and the chunks are float32, ``_ensure_sr``'s linear interpolation runs on the device
+        (bit-identical to the NumPy path, see ``b200sep.aux``) between the H2D copy and the encoder."""
         if self._model is None:
             raise RuntimeError("Separator model is not initialized.")
+        chunks = list(chunks)
+        if sr != self.sample_rate and len(chunks) > 0 and all(
+                isinstance(c, np.ndarray) and c.dtype == np.float32 and c.ndim == 1 for c in chunks):
+            return self._model.separate_batch_resampled(chunks, int(sr), int(self.sample_rate))
         return self._model.separate_batch([self._ensure_sr(c, sr) for c in chunks])
 
     @property

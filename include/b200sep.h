@@ -179,6 +179,39 @@ int b200sep_pit_sisdr_batch(const float* d_refs, const float* d_ests, const floa
                             double* d_sisdr, double* d_sisdri, int32_t* d_perm, void* d_ws,
                             size_t ws_bytes, void* stream);
 
+/* ---- either side of the separation path: resampling and GT overlap masks ------------ */
+#define B200SEP_RESAMPLE_LINEAR 0 /* Separator._ensure_sr, src/osd/separation.py:91-103 (np.interp, fp64 -> fp32)     */
+#define B200SEP_RESAMPLE_SINC 1   /* torchaudio.functional.resample defaults: scripts/osd/overlap3_core.py:136-143,    */
+                                  /* scripts/osd/evaluate_with_sources.py:163-178                                      */
+/*
+ * Output lengths of a resample of `lens[i]` samples from sr_in to sr_out.  LINEAR: int(round(len * sr_out / sr_in))
+ * with the reference's pass-through rules (same rate, len <= 1 or target <= 1 -> unchanged, separation.py:92-100);
+ * SINC: ceil(new * len / orig) on the gcd-reduced rates (len <= 1 -> unchanged, overlap3_core.py:139).
+ */
+int b200sep_resample_out_lens(const int32_t* lens, int32_t n_seg, int32_t sr_in, int32_t sr_out, int32_t method,
+                              int32_t* out_lens);
+/*
+ * Resamples a tightly packed ragged batch of fp32 signals on the device (`d_in`: signal i at sum(lens[0..i-1]);
+ * `d_out`: signal i at sum(out_lens[0..i-1])).  LINEAR replays np.interp operation by operation in fp64 and is
+ * bit-identical to the reference for fp32 inputs; SINC applies the same polyphase windowed-sinc filter bank as
+ * torchaudio (fp32, agreement to fp32 rounding).
+ */
+int b200sep_resample_batch(const float* d_in, const int32_t* lens, int32_t n_seg, int32_t sr_in, int32_t sr_out,
+                           int32_t method, float* d_out, void* stream);
+/*
+ * frame_rms (scripts/osd/evaluate_with_sources.py:181-197), batched: frames of win_s samples every hop_s samples,
+ * rms = sqrt(mean(frame^2) + 1e-12); signal i yields len(range(0, max(len - win_s + 1, 1), hop_s)) values, packed.
+ */
+int b200sep_frame_rms_out_lens(const int32_t* lens, int32_t n_seg, int32_t win_s, int32_t hop_s, int32_t* out_lens);
+int b200sep_frame_rms_batch(const float* d_wav, const int32_t* lens, int32_t n_seg, int32_t win_s, int32_t hop_s,
+                            float* d_rms, void* stream);
+/*
+ * build_gt_overlap_mask (scripts/osd/evaluate_with_sources.py:226-241), batched over pairs of RMS tracks with the
+ * same packed layout: peak = max(max(rms1), max(rms2), 1e-9); mask = (rms1 > peak * thr) & (rms2 > peak * thr).
+ */
+int b200sep_gt_overlap_mask_batch(const float* d_rms1, const float* d_rms2, const int32_t* n_frames, int32_t n_seg,
+                                  float thr_ratio, uint8_t* d_mask, void* stream);
+
 /*
  * Development/validation hook: raw GEMM  C[M,N] = A * B^T  through the same tcgen05/TMA
  * kernel the model uses (A given row-major [M,K] fp32 on device, B [N,K] fp32 on device,
