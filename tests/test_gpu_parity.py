@@ -360,3 +360,31 @@ def test_fused_and_unfused_pipelines_agree(b200, model3, monkeypatch):
         for fused in ("1", "0"):
             assert min_sisdr(ref, np.stack(outs[fused][i])) >= GATE_FP16_DB
         assert min_sisdr(np.stack(outs["0"][i]), np.stack(outs["1"][i])) >= 50.0
+
+
+def test_config5_streaming_chunked_60s_mixture(b200, model3):
+    """BASELINE.json configs[4]: a 60 s mixture cut as the streaming path does (chunk = int(8000 p / 1024) * 1024
+    samples, streaming_overlap_3src.py:89-91; p = 2.0 -> 15360, p = 5.0 -> 39936), every chunk an independent
+    segment, plus the whole-chunk separation of streaming_overlap3_core.py:186 -- here the full 60 s signal as ONE
+    segment (59 999 frames = 469 m-tiles normalised together)."""
+    from b200sep import synth
+    sd, args, ref_model = model3
+    sep = b200.Separator(backend="b200", device="cuda:0", sample_rate=8000, n_src=3, state_dict=sd, model_args=args)
+    mix, _ = synth.make_mixture(4242, 60 * 8000, 3)
+    chunks = []
+    for p in (2.0, 5.0):
+        n = synth.streaming_chunk_samples(p)
+        chunks += [mix[o:o + n] for o in range(0, len(mix) - n + 1, n)]
+    tail = mix[(len(mix) // 15360) * 15360:]  # the ragged last read of the stream
+    chunks.append(tail)
+    chunks.append(mix)
+    outs = sep.separate_batch(chunks, 8000)
+    assert len(outs) == len(chunks) == 31 + 12 + 2
+    check = [0, 17, 30, 31, 42, 43, 44]
+    for i in check:
+        ref = oracle_separate(ref_model, chunks[i])
+        assert outs[i][0].shape == chunks[i].shape
+        assert min_sisdr(ref, np.stack(outs[i])) >= GATE_FP16_DB, i
+    # a chunk's result does not depend on what else is in the batch (bit-identical)
+    solo = sep.separate(chunks[17], 8000)
+    assert all(np.array_equal(a, b) for a, b in zip(solo, outs[17]))
