@@ -367,7 +367,7 @@ static int compute_layout(const b200sep_config& c, bool half, bool fused, const 
   lo->o_tables = take(lo->tables_bytes);
   lo->o_enc = take(rows * C_ENC * es);
   lo->o_x = take(rows * C_BN * 4);
-  lo->o_xa = (half && !fused) ? take(rows * C_BN * es) : lo->o_x;
+  lo->o_xa = (half && (!fused || B200SEP_X16)) ? take(rows * C_BN * es) : lo->o_x;  // fp16 operand shadow / fp16 stream
   lo->o_skip = take(fused ? 0 : rows * C_SKIP * 4);
   lo->o_skipa = take(rows * C_SKIP * es);
   lo->o_h1 = take(rows * C_HID * es);
@@ -596,7 +596,9 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
 
   // 2. bottleneck: x = Wb . gLN(tf_rep) + bb
   {
-    EpiBottleneck<T> e{p0, 2, m->bn_rs, m->bn_cb, x, xa_or_null};
+    // (fused path with B200SEP_X16: the fp16 copy is the residual stream the TCN blocks update)
+    const bool x16 = kHalf && fused_mode && B200SEP_X16;
+    EpiBottleneck<T> e{p0, 2, m->bn_rs, m->bn_cb, x16 ? nullptr : x, x16 ? xa : xa_or_null};
     if (run_gemm<T, 128, C_ENC>(m, enc, &tm_enc, reinterpret_cast<const T*>(m->bn_w), &m->tm_bn, nt, C_BN, e, tb, st))
       return 1;
   }
@@ -621,6 +623,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
         if (b.dilation > 128) return fail("fused path supports dilations up to 128 (got %d)", b.dilation);
         fb::ApplyParams ap{};
         ap.x = x;
+        ap.x16 = reinterpret_cast<__half*>(xa);
         if (i > 0) {
           ap.g = gbuf;
           ap.part2 = p2 + (size_t)(i - 1) * lo.part2_stride;

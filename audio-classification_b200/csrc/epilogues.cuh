@@ -87,8 +87,10 @@ struct EpiBottleneck {
       const float2 o1 = fma2(make_float2(acc[4 * q + 2], acc[4 * q + 3]), rstd2, t1);
       out[4 * q + 0] = o0.x; out[4 * q + 1] = o0.y; out[4 * q + 2] = o1.x; out[4 * q + 3] = o1.y;
     }
+    if (x != nullptr) {  // (nullptr: the fused pipeline keeps the residual stream in fp16 only)
 #pragma unroll
-    for (int j = 0; j < W; ++j) x[idx0 + (size_t)j * TILE_M] = out[j];
+      for (int j = 0; j < W; ++j) x[idx0 + (size_t)j * TILE_M] = out[j];
+    }
     if (xa != nullptr) {
 #pragma unroll
       for (int j = 0; j < W; ++j) xa[idx0 + (size_t)j * TILE_M] = from_f32<T>(out[j]);

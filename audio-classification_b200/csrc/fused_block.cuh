@@ -790,12 +790,17 @@ struct KbCfg {
   static_assert(SMEM_BYTES <= 232448, "K_B shared memory over the 227 KiB limit");
 };
 
+#ifndef B200SEP_X16
+#define B200SEP_X16 1  // residual stream x stored in fp16 between blocks (the update itself is fp32 in registers): K_B moves
+                       // 1792 instead of 2304 B/frame; isolated cost 75 -> 69 dB on the oracle, measured on the whole path
+#endif
 struct ApplyParams {
   const __half* g;      // [nt][128][128] raw residual-conv output of the previous block (nullptr: block 0)
   const float2* part2;  // [nt] gLN2 partials of the previous block
   const float* rs;      // [>=128] rowsum(W_res . gamma2) of the previous block
   const float* cb;      // [>=128] W_res * beta2 + b_res
-  float* x;             // [nt][128][128] fp32 residual stream (updated in place)
+  float* x;             // [nt][128][128] fp32 residual stream (updated in place)            (B200SEP_X16 == 0)
+  __half* x16;          // [nt][128][128] fp16 residual stream (updated in place)            (B200SEP_X16 == 1)
 };
 
 template <bool A01>
@@ -1133,11 +1138,19 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
 #ifndef B200SEP_EXP_KB_NO_L2PF
       if (pt == 0 && w + (int)gridDim.x < n_tiles) {  // next tile's x / G_res -> L2 while this tile is processed
         const size_t nidx = tt_index(w + gridDim.x, C_BN, 0, 0);
+#if B200SEP_X16
+        l2_prefetch_bulk(ap.x16 + nidx, TILE_M * C_BN * 2);
+#else
         l2_prefetch_bulk(ap.x + nidx, TILE_M * C_BN * 4);
+#endif
         if (has_g) l2_prefetch_bulk(ap.g + nidx, TILE_M * C_BN * 2);
       }
 #endif
+#if B200SEP_X16
+      __half* __restrict__ xt = ap.x16 + tt_index(w, C_BN, 0, f0);
+#else
       float* __restrict__ xt = ap.x + tt_index(w, C_BN, 0, f0);
+#endif
       const __half* __restrict__ gt = has_g ? ap.g + tt_index(w, C_BN, 0, f0) : nullptr;
       // all global loads of the tile are issued before the (possibly blocking) operand-buffer wait
       constexpr int PASSES = C_BN / ROWS;
@@ -1146,12 +1159,19 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
       static_assert(PASSES % RND == 0, "prologue rounds");
 #pragma unroll 1
       for (int p0 = 0; p0 < PASSES; p0 += RND) {
+#if B200SEP_X16
+        uint4 xh[RND];
+#else
         float4 xa[RND], xb[RND];
+#endif
         uint4 gr[RND];
 #pragma unroll
         for (int j = 0; j < RND; ++j) {
           const size_t off = (size_t)((p0 + j) * ROWS + crow) * TILE_M;
-#ifndef B200SEP_EXP_NO_PRO_IO
+#if B200SEP_X16
+          xh[j] = *reinterpret_cast<const uint4*>(xt + off);
+          if (has_g) gr[j] = ldg_v4(gt + off);
+#elif !defined(B200SEP_EXP_NO_PRO_IO)
           xa[j] = *reinterpret_cast<const float4*>(xt + off);
           xb[j] = *reinterpret_cast<const float4*>(xt + off + 4);
           if (has_g) gr[j] = ldg_v4(gt + off);
@@ -1168,7 +1188,19 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
         for (int j = 0; j < RND; ++j) {
           const int c = (p0 + j) * ROWS + crow;
           const size_t off = (size_t)c * TILE_M;
+#if B200SEP_X16
+          float xv[8];
+          {
+            const uint32_t xw[4] = {xh[j].x, xh[j].y, xh[j].z, xh[j].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __half22float2(u32_as_h2(xw[i]));
+              xv[2 * i] = f.x; xv[2 * i + 1] = f.y;
+            }
+          }
+#else
           float xv[8] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w, xb[j].x, xb[j].y, xb[j].z, xb[j].w};
+#endif
           if (has_g) {
             const float kr = fmaf(nmr, __ldg(ap.rs + c), __ldg(ap.cb + c));
             const uint32_t gw[4] = {gr[j].x, gr[j].y, gr[j].z, gr[j].w};
@@ -1179,12 +1211,21 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
               const float2 nx = fma2(dr, vm[i >> 1], make_float2(xv[i], xv[i + 1]));
               xv[i] = nx.x; xv[i + 1] = nx.y;
             }
-#ifndef B200SEP_EXP_NO_PRO_IO
+#if B200SEP_X16
+            const uint4 pk = pack8(xv);  // the rounded stream IS the GEMM operand: one rounding, stored twice
+            *reinterpret_cast<uint4*>(xt + off) = pk;
+            st_shared_v4(xn + (uint32_t)((c >> 6) * 16384) + a_chunk_off(c & 63, f0), pk);
+            continue;
+#elif !defined(B200SEP_EXP_NO_PRO_IO)
             *reinterpret_cast<float4*>(xt + off) = make_float4(xv[0], xv[1], xv[2], xv[3]);
             *reinterpret_cast<float4*>(xt + off + 4) = make_float4(xv[4], xv[5], xv[6], xv[7]);
 #endif
           }
+#if B200SEP_X16
+          st_shared_v4(xn + (uint32_t)((c >> 6) * 16384) + a_chunk_off(c & 63, f0), xh[j]);  // block 0: x as stored
+#else
           st_shared_v4(xn + (uint32_t)((c >> 6) * 16384) + a_chunk_off(c & 63, f0), pack8(xv));
+#endif
         }
       }
       fence_proxy_async();
