@@ -98,6 +98,9 @@ __device__ __forceinline__ void tile_partial_reduce(float2* red, int* cnt, int n
     }
   }
 }
+#ifndef B200SEP_KA_REVERSE
+#define B200SEP_KA_REVERSE 1
+#endif
 #ifndef B200SEP_KA_CLUSTER
 #define B200SEP_KA_CLUSTER 0  // 1: K_A runs as 2-CTA clusters, each CTA multicasts half of every weight stage (measured slower)
 #endif
@@ -399,7 +402,13 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
 #if B200SEP_KA_CLUSTER
     const int wr = (pair + it * n_pairs) * 2 + crank;
 #else
+#if B200SEP_KA_REVERSE
+    // K_B walks the m-tiles upwards, K_A downwards: K_A starts on the h1 tiles K_B wrote LAST (still in the 126 MB
+    // L2) and finishes on the tiles the next K_B reads FIRST (their G_res lines are the freshest)
+    const int wr = n_tiles - 1 - (pair + it * n_pairs);
+#else
     const int wr = pair + it * n_pairs;
+#endif
 #endif
     valid = wr < n_tiles;
     return valid ? wr : n_tiles - 1;
@@ -770,7 +779,13 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
 struct KbCfg {
   static constexpr int W_BYTES = C_HID * C_BN * 2;      // 128 KiB: [2 k-blocks][512 rows][64 k]
   static constexpr int XN_BYTES = TILE_M * C_BN * 2;    // 32 KiB: [2 k-blocks][64 k][128 m]
-  static constexpr int EPI_WARPS = 8, PRO_WARPS = 8;  // EPI_WARPS / 4 epilogue warps per TMEM lane quadrant
+#ifndef B200SEP_KB_PRO_WARPS
+#define B200SEP_KB_PRO_WARPS 8
+#endif
+#ifndef B200SEP_KB_PRO_RND
+#define B200SEP_KB_PRO_RND 4
+#endif
+  static constexpr int EPI_WARPS = 8, PRO_WARPS = B200SEP_KB_PRO_WARPS;  // EPI_WARPS / 4 epilogue warps per TMEM lane quadrant
   static constexpr int THREADS = (EPI_WARPS + 1 + PRO_WARPS) * 32;  // 544
   static constexpr int TMEM_COLS = 512;                 // 4 chunks of 128 output channels
 #ifndef B200SEP_KB_TMA_STORE
@@ -1155,7 +1170,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
       // all global loads of the tile are issued before the (possibly blocking) operand-buffer wait
       constexpr int PASSES = C_BN / ROWS;
       uint32_t xn = 0;
-      constexpr int RND = 4;  // passes per round (global loads in flight per thread: 3 x RND vectors)
+      constexpr int RND = B200SEP_KB_PRO_RND;  // passes per round (global loads in flight per thread: 3 x RND vectors)
       static_assert(PASSES % RND == 0, "prologue rounds");
 #pragma unroll 1
       for (int p0 = 0; p0 < PASSES; p0 += RND) {

@@ -1,0 +1,4 @@
+cd $GRAFT_REPO_ROOT
+timeout 100 python tests/gpu_diag.py e2e 2>&1 | grep "fp16 \|FAILED\|rror" | head
+B200SEP_SPLIT=1 timeout 100 python tests/variant_time.py 2>&1 | tail -1 | cut -c1-200
+for i in 1 2; do timeout 100 python tests/split_time.py 2>&1 | tail -1; done
