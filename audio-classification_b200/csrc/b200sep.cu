@@ -483,7 +483,7 @@ static int launch_dw_rs(const b200sep_model* m, const KaArgs& a, const Tables& t
     configured = true;
   }
   // 2-CTA clusters (each CTA multicasts half of every weight stage to its peer): even grid, one pair per SM pair
-#if B200SEP_KA_CLUSTER
+#if B200SEP_KA_CL
   const int n_pairs = std::min((tb.n_tiles + 1) / 2, m->n_sm / 2);
   const int grid = 2 * n_pairs;
 #else
@@ -496,7 +496,7 @@ static int launch_dw_rs(const b200sep_model* m, const KaArgs& a, const Tables& t
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = B200SEP_KA_CLUSTER ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = B200SEP_KA_CL ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
@@ -643,7 +643,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
         int hk = 0;  // halo box: 8 frames for d < 8, else d frames
         while ((8 << hk) < b.dilation) ++hk;
         // stash layout [tile][block][128][128]
-        KaArgs ka{B200SEP_KA_CLUSTER ? &b.tm_rs_half : &b.tm_rs, &tm_hc, &tm_hh[hk], gbuf, stash + (size_t)i * (C_SKIP * TILE_M),
+        KaArgs ka{B200SEP_KA_CL ? &b.tm_rs_half : &b.tm_rs, &tm_hc, &tm_hh[hk], gbuf, stash + (size_t)i * (C_SKIP * TILE_M),
                   (size_t)m->n_layers * C_SKIP * TILE_M, p1,
                   p2 + (size_t)i * lo.part2_stride, fb::DwTab{b.dw_t0, b.dw_t1, b.dw_cb, b.a2, b.dilation}};
         const bool a01 = b.a2 >= 0.f && b.a2 <= 1.f;

@@ -104,6 +104,11 @@ __device__ __forceinline__ void tile_partial_reduce(float2* red, int* cnt, int n
 #ifndef B200SEP_KA_CLUSTER
 #define B200SEP_KA_CLUSTER 0  // 1: K_A runs as 2-CTA clusters, each CTA multicasts half of every weight stage (measured slower)
 #endif
+#ifndef B200SEP_KA_PAIR
+#define B200SEP_KA_PAIR 0  // 1: K_A as CTA pairs issuing tcgen05.mma.cta_group::2 (M = 256 over two SMs): every SM stages and
+                           // feeds only HALF of each weight k-block (the other half comes from its peer's shared memory)
+#endif
+#define B200SEP_KA_CL (B200SEP_KA_CLUSTER || B200SEP_KA_PAIR)  // launched as 2-CTA clusters, tiles visited in pairs
 // ---- 2-CTA cluster helpers (K_A: each CTA TMA-multicasts half of every weight stage to both CTAs) ----------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -129,6 +134,76 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"(mask)
                : "memory");
+}
+
+// ---- cta_group::2 (CTA pair) helpers ---------------------------------------------------------------------------
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// arrive on an mbarrier anywhere in the cluster (release at cluster scope: the waiter may sit in the peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(20000)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait whose arrivals may come from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster_b(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+  for (uint32_t i = 0; i < (1u << 18); ++i) {
+    if (mbar_try_cluster(bar, parity)) return;
+    if ((i & 31u) == 31u && *reinterpret_cast<volatile int*>(&g_abort) != 0) return;
+  }
+  *reinterpret_cast<volatile int*>(&g_abort) = 1;
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A (256 x K: 128 rows from each CTA's smem) * B (N x K: N/2 rows from each CTA's smem)
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit of the pair's MMAs: one arrival on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+// TMA tile load into THIS CTA's shared memory whose complete_tx lands on an mbarrier of the pair (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* desc, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+// kind::f16 instruction descriptor of the pair MMA: as make_idesc, M = 256
+__host__ __device__ constexpr uint32_t make_idesc_pair(int bn) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(bn >> 3) << 17) |
+         ((uint32_t)(256 >> 4) << 24);
 }
 
 // TMA tile store shared -> global (bulk async group of the issuing thread)
@@ -250,14 +325,21 @@ struct KaCfg {
   // when the MMA that read it has completed, and its L2 -> shared-memory latency (~1.7 k cycles) is three times
   // the MMA time of a k-block (512 cycles); with 2 stages that latency, not the work, paced the kernel.
   static constexpr int A_STAGE = TILE_M * 64 * 2;    // 16 KiB
-  static constexpr int B_STAGE = BN * 64 * 2;        // 32 / 16 KiB
+  static constexpr int B_STAGE = BN * 64 * 2 / (B200SEP_KA_PAIR ? 2 : 1);  // 32 / 16 KiB (pair: this CTA's N/2 rows)
   static constexpr int B_MAX_STAGES = 4;
   static constexpr int TAB_BYTES = C_HID * (16 + 16 + 4);  // 18 KiB
   static constexpr int EPI_WARPS = 4, PROD_WARPS = 16;
   static constexpr int THREADS = (EPI_WARPS + 3 + PROD_WARPS) * 32;  // 736
   static constexpr int TMEM_COLS = 2 * BN;
+#ifndef B200SEP_KA_APG
+#define B200SEP_KA_APG (B200SEP_KA_PAIR ? 2 : 1)
+#endif
+  // A stages per producer group: with 2 the producers of a group write k-block n + 1 while the MMA of k-block n (and, in
+  // pair mode, the cross-SM arrive / commit round trip) is still in flight
+  static constexpr int A_PG = B200SEP_KA_APG;
+  static_assert(A_PG == 1 || A_PG == 2, "A stages per group");
   static constexpr int OFF_A = 0;
-  static constexpr int OFF_TAB = OFF_A + 2 * A_STAGE;
+  static constexpr int OFF_TAB = OFF_A + 2 * A_PG * A_STAGE;
   static constexpr int OFF_TI = OFF_TAB + TAB_BYTES;
   static constexpr int OFF_RED = OFF_TI + TI_CACHE * 32;
   static constexpr int OFF_CNT = OFF_RED + 2 * PROD_WARPS * 8;
@@ -369,10 +451,10 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   float2* s_red = reinterpret_cast<float2*>(smem_gen + Cfg::OFF_RED);  // [2][16]
   int* s_cnt = reinterpret_cast<int*>(smem_gen + Cfg::OFF_CNT);          // [2]
   const uint32_t bar0 = smem_base + Cfg::OFF_BAR;
-  auto raw_full = [&](int s) { return bar0 + 8u * s; };          // [2]  TMA -> producers (stage = group)
-  auto raw_empty = [&](int s) { return bar0 + 8u * (2 + s); };     // [2]
-  auto a_full = [&](int s) { return bar0 + 8u * (4 + s); };        // [2]  producers -> MMA (stage = group)
-  auto a_empty = [&](int s) { return bar0 + 8u * (6 + s); };       // [2]
+  auto raw_full = [&](int s) { return bar0 + 8u * (30 + s); };     // [2 or 4]  TMA -> producers (stage s belongs to group s & 1)
+  auto raw_empty = [&](int s) { return bar0 + 8u * (34 + s); };    // [2 or 4]
+  auto a_full = [&](int s) { return bar0 + 8u * (22 + s); };       // [2 * A_PG]  producers -> MMA (stage = group * A_PG + n % A_PG)
+  auto a_empty = [&](int s) { return bar0 + 8u * (26 + s); };      // [2 * A_PG]
   auto b_full = [&](int s) { return bar0 + 8u * (8 + s); };        // [4]  TMA (weights) -> MMA
   auto b_empty = [&](int s) { return bar0 + 8u * (12 + s); };      // [4]
   auto tfull_bar = [&](int s) { return bar0 + 8u * (16 + s); };
@@ -389,7 +471,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   // 2-CTA clusters: the pair (2p, 2p+1) visits the tile pairs p, p + n_pairs, ...; rank r takes tile 2*pair_tile + r.
   // Both CTAs of a pair make the same number of visits (each visit consumes 8 weight stages that the two CTAs load
   // for each other); with an odd tile count the last visit of rank 1 re-processes the last tile without writing.
-#if B200SEP_KA_CLUSTER
+#if B200SEP_KA_CL
   const int crank = (int)cluster_ctarank();
   const int n_pairs = (int)(gridDim.x >> 1), pair = (int)(blockIdx.x >> 1);
   const int n_pair_tiles = (n_tiles + 1) >> 1;
@@ -399,8 +481,12 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
 #endif
   const int n_visits = (pair < n_pair_tiles) ? (n_pair_tiles - pair + n_pairs - 1) / n_pairs : 0;
   auto tile_at = [&](int it, bool& valid) {
-#if B200SEP_KA_CLUSTER
+#if B200SEP_KA_CL
+#if B200SEP_KA_REVERSE
+    const int wr = (n_pair_tiles - 1 - (pair + it * n_pairs)) * 2 + crank;
+#else
     const int wr = (pair + it * n_pairs) * 2 + crank;
+#endif
 #else
 #if B200SEP_KA_REVERSE
     // K_B walks the m-tiles upwards, K_A downwards: K_A starts on the h1 tiles K_B wrote LAST (still in the 126 MB
@@ -417,9 +503,16 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   const int hw = (D > 0) ? 8 : d;  // halo width in frames (multiple of 8, <= 128)
   const uint32_t halo_bytes = (uint32_t)(64 * hw * 2);
   const uint32_t raw_stage_bytes = (16384u + 2u * halo_bytes + 1023u) & ~1023u;
-  // two raw stages (one per producer group: every stage and its mbarriers belong to ONE group, so a parity wait is
-  // never more than one phase ahead), the rest of the shared memory is the weight ring
-  const uint32_t off_b = (uint32_t)Cfg::OFF_RAW + 2u * raw_stage_bytes;
+  // raw ring: k-block kb lives in stage kb % raw_stages; with an EVEN ring every stage and its mbarriers belong to ONE
+  // producer group (kb & 1), so a parity wait is never more than one phase ahead.  Four stages (two per group: the next
+  // k-block's L2 -> shared-memory latency, ~2.3 k cycles, hides behind the current one's arithmetic) when they fit next to
+  // two weight stages, else two; the rest of the shared memory is the weight ring.
+#ifndef B200SEP_KA_RAW_MAX
+#define B200SEP_KA_RAW_MAX 4
+#endif
+  const int raw_stages = (B200SEP_KA_RAW_MAX >= 4 && (uint32_t)Cfg::OFF_RAW + 4u * raw_stage_bytes + 2u * (uint32_t)Cfg::B_STAGE <=
+                                                        (uint32_t)Cfg::SMEM_USABLE) ? 4 : 2;
+  const uint32_t off_b = (uint32_t)Cfg::OFF_RAW + (uint32_t)raw_stages * raw_stage_bytes;
   const int b_stages = min((int)(((uint32_t)Cfg::SMEM_USABLE - off_b) / (uint32_t)Cfg::B_STAGE), Cfg::B_MAX_STAGES);
   auto stage_b = [&](int s) { return smem_base + off_b + (uint32_t)(s * Cfg::B_STAGE); };
   auto raw_st = [&](int s) { return smem_base + (uint32_t)Cfg::OFF_RAW + (uint32_t)s * raw_stage_bytes; };
@@ -437,29 +530,39 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
   if (warp == 4 && lane == 0) { tma_prefetch_desc(&tm_hc); tma_prefetch_desc(&tm_hh); }
   if (warp == 5 && lane == 0) tma_prefetch_desc(&tm_b);
+  if (B200SEP_KA_PAIR) cluster_sync_all();  // both CTAs of the pair are resident before the pair-wide TMEM allocation
   if (warp == 6) {
     if (lane == 0) {
-      for (int s = 0; s < 2; ++s) {
+      for (int s = 0; s < 4; ++s) {
         mbar_init(raw_full(s), 1);
         mbar_init(raw_empty(s), Cfg::PROD_WARPS * 16);
-        mbar_init(a_full(s), Cfg::PROD_WARPS * 16);
-        mbar_init(a_empty(s), 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        // pair mode: the producers / epilogue threads of BOTH CTAs arrive on the leader's a_full / tempty
         mbar_init(tfull_bar(s), 1);
-        mbar_init(tempty_bar(s), 32 * Cfg::EPI_WARPS);
+        mbar_init(tempty_bar(s), B200SEP_KA_PAIR ? 2 * Cfg::EPI_WARPS : 32 * Cfg::EPI_WARPS);
+      }
+      for (int s = 0; s < 2 * Cfg::A_PG; ++s) {
+        mbar_init(a_full(s), B200SEP_KA_PAIR ? Cfg::PROD_WARPS : Cfg::PROD_WARPS * 16);  // pair: one arrival per warp
+        mbar_init(a_empty(s), 1);
       }
       for (int s = 0; s < Cfg::B_MAX_STAGES; ++s) {
         mbar_init(b_full(s), 1);
-        mbar_init(b_empty(s), B200SEP_KA_CLUSTER ? 2 : 1);  // cluster: this CTA's and the peer's MMA both release a (multicast-filled) weight stage
+        mbar_init(b_empty(s), B200SEP_KA_CLUSTER ? 2 : 1);  // (pair mode: ONE multicast commit of the leader)  // cluster: this CTA's and the peer's MMA both release a (multicast-filled) weight stage
       }
       mbar_init(done_bar, 1);
       fence_barrier_init();
     }
     __syncwarp();
+#if B200SEP_KA_PAIR
+    tmem_alloc_pair(tmem_ptr_smem, Cfg::TMEM_COLS);  // issued by one warp of EACH CTA of the pair
+#else
     tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+#endif
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (B200SEP_KA_CLUSTER) cluster_sync_all();  // both CTAs' mbarriers are initialised before either multicasts into the other
+  if (B200SEP_KA_CL) cluster_sync_all();  // both CTAs' mbarriers are initialised before either signals the other
   tcgen05_fence_after();
   pdl_wait();
   uint32_t tmem_base;
@@ -503,7 +606,12 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
 #endif
       }
       tcgen05_fence_before();
+#if B200SEP_KA_PAIR
+      __syncwarp();  // one (remote) arrival per warp: the leader's MMA thread waits for both CTAs' epilogues
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(as), 0));
+#else
       mbar_arrive(tempty_bar(as));
+#endif
       if (threadIdx.x == 0) tl_stamp(it, 81);
     }
   } else if (warp == 4) {
@@ -525,7 +633,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
           tl_stamp(it, 88 + kb);
 #ifdef B200SEP_EXP_KA_NO_RAW_TMA  // timing experiment: no activation traffic into shared memory
           mbar_arrive(raw_full(stage));
-          if (++stage == 2) { stage = 0; phase ^= 1u; }
+          if (++stage == raw_stages) { stage = 0; phase ^= 1u; }
           continue;
 #endif
           mbar_expect_tx(raw_full(stage), bytes);
@@ -535,7 +643,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
           // start of the next; rows outside the tensor are zero-filled by the TMA unit
           tma_load_2d(dst + 16384u, &tm_hh, raw_full(stage), TILE_M - hw, (w - 1) * C_HID + kb * 64);
           tma_load_2d(dst + 16384u + halo_bytes, &tm_hh, raw_full(stage), 0, (w + 1) * C_HID + kb * 64);
-          if (++stage == 2) { stage = 0; phase ^= 1u; }
+          if (++stage == raw_stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -551,8 +659,16 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
 #ifndef B200SEP_EXP_KA_NO_B_TMA
           // the whole stage lands here (own half + the peer's half); this CTA loads rows [crank * BN/2, +BN/2) of the
           // k-block and multicasts them to the same offset of both CTAs
+#if B200SEP_KA_PAIR
+          // each CTA stages ITS N/2 rows of the k-block; both transfers complete on the leader's b_full, which expects
+          // the bytes of both halves
+          if (crank == 0) mbar_expect_tx(b_full(stage), 2 * Cfg::B_STAGE);
+          tma_load_2d_pair(stage_b(stage), &tm_b, mapa_rank(b_full(stage), 0), kb * 64, crank * (BN / 2));
+#else
           mbar_expect_tx(b_full(stage), Cfg::B_STAGE);
-#if B200SEP_KA_CLUSTER
+#endif
+#if B200SEP_KA_PAIR
+#elif B200SEP_KA_CLUSTER
           tma_load_2d_mc(stage_b(stage) + (uint32_t)(crank * (Cfg::B_STAGE / 2)), &tm_b, b_full(stage), kb * 64,
                          crank * (BN / 2), (uint16_t)0x3);
 #else
@@ -568,6 +684,48 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
     __syncwarp();
   } else if (warp == 6) {
     // ================================ MMA issuer ==================================================
+#if B200SEP_KA_PAIR
+    // CTA pair: ONLY the leader (cluster rank 0) issues; one tcgen05.mma.cta_group::2 covers both CTAs' m-tiles
+    // (M = 256: 128 A rows from each CTA's A stage) against the k-block's weights (N/2 rows from each CTA's B stage)
+    // and accumulates into both CTAs' tensor memory.  Commits are multicast: both CTAs' producers / weight loaders /
+    // epilogues wait on their LOCAL a_empty / b_empty / tfull barriers.
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = make_idesc_pair(BN);
+      int bs = 0;
+      uint32_t bphase = 0;
+      for (int it = 0; it < n_visits; ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait_cluster_b(tempty_bar(as), aphase ^ 1u);  // both CTAs' epilogues have drained this accumulator
+        tcgen05_fence_after();
+        tl_stamp(it, 64);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < 8; ++kb) {
+          const int nseq = it * 4 + (kb >> 1);               // k-blocks this group has produced before this one
+          const int g = (kb & 1) * Cfg::A_PG + (nseq & (Cfg::A_PG - 1));
+          const uint32_t gphase = (uint32_t)(nseq / Cfg::A_PG) & 1u;
+          mbar_wait_cluster_b(a_full(g), gphase);          // both CTAs' producer groups have written their A stage
+          mbar_wait_b(b_full(bs), bphase);                 // both halves of the weight k-block have landed
+          tcgen05_fence_after();
+          tl_stamp(it, 65 + kb);
+          const uint32_t sa = stage_a(g), sb = stage_b(bs);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint64_t da = make_smem_desc(sa + j * 2048u, 8192u, 1024u);
+            const uint64_t db = make_smem_desc(sb + j * 32u, 16u, 1024u);
+            umma_f16_pair(tmem_d, da, db, idesc, (uint32_t)((kb | j) != 0));
+          }
+          umma_commit_pair(a_empty(g), (uint16_t)0x3);
+          umma_commit_pair(b_empty(bs), (uint16_t)0x3);
+          if (kb == 7) umma_commit_pair(tfull_bar(as), (uint16_t)0x3);
+          if (++bs == b_stages) { bs = 0; bphase ^= 1u; }
+        }
+      }
+      umma_commit_pair(done_bar, (uint16_t)0x1);  // every asynchronous arrive has landed before the pair tears down
+      mbar_wait_b(done_bar, 0);
+    }
+    __syncwarp();
+#else
     if (lane == 0) {
 #ifndef B200SEP_EXP_KA_HALF_N
       constexpr uint32_t idesc = make_idesc(BN);
@@ -575,7 +733,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       constexpr uint32_t idesc = make_idesc(BN / 2);
 #endif
       int bs = 0;
-      uint32_t bphase = 0, gphase = 0;  // gphase: phase of the (per-group) A stages, flips every 2 k-blocks
+      uint32_t bphase = 0;
       for (int it = 0; it < n_visits; ++it) {
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
@@ -584,7 +742,9 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         tl_stamp(it, 64);
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         for (int kb = 0; kb < 8; ++kb) {
-          const int g = kb & 1;
+          const int nseq = it * 4 + (kb >> 1);  // k-blocks this group has produced before this one
+          const int g = (kb & 1) * Cfg::A_PG + (nseq & (Cfg::A_PG - 1));
+          const uint32_t gphase = (uint32_t)(nseq / Cfg::A_PG) & 1u;
           mbar_wait_b(a_full(g), gphase);
           mbar_wait_b(b_full(bs), bphase);
           tcgen05_fence_after();
@@ -604,7 +764,6 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
 #endif
           if (kb == 7) umma_commit(tfull_bar(as));
           if (++bs == b_stages) { bs = 0; bphase ^= 1u; }
-          if (g == 1) gphase ^= 1u;
         }
       }
       // the last ab_empty arrivals have no waiter: make sure every asynchronous arrive has landed before exit
@@ -612,6 +771,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       mbar_wait_b(done_bar, 0);
     }
     __syncwarp();
+#endif
   } else {
     // ================================ depthwise producers =========================================
     // Two groups of 8 warps; group g produces the k-blocks kb = g, g+2, ... (and owns A/B stage g), so
@@ -636,15 +796,12 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
     const uint32_t l_base = l_off + (uint32_t)row0 * l_pitch, r_base = r_off + (uint32_t)row0 * r_pitch;
     const uint32_t c_step = 16u * c_pitch, l_step = 16u * l_pitch, r_step = 16u * r_pitch;
     const uint32_t a_off0 = a_chunk_off(row0, lane16 * 8);  // (row & 7) is the same for every step; step j = + 2048 j
-    const uint32_t sa = stage_a(grp) + a_off0;
-    const uint32_t my_ab_full = a_full(grp), my_ab_empty = a_empty(grp);
+    int nseq = 0;  // k-blocks produced by this group so far -> A stage / phase
     const __half2 alpha_h2 = __float2half2_rn(alpha);
     const bool tl_on = (gw == 0 && lane == 0);
     const int tl_base = grp ? 100 : 40;  // timeline slots: group 0 40.., group 1 100..
 
-    const int rs_ = grp;  // raw stage of this group
-    uint32_t rphase = 0;
-    uint32_t aphase = 0;
+    const int rpg = raw_stages >> 1;  // raw stages per group
     float nmean = 0.f, nrstd = 0.f;  // statistics of the NEXT tile's segment (computed mid-tile)
     if (n_visits > 0) {
       bool v_;
@@ -684,6 +841,17 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       }
 #pragma unroll 1
       for (int kb = grp; kb < 8; kb += 2) {
+        const int a_idx = grp * Cfg::A_PG + (nseq & (Cfg::A_PG - 1));
+        const uint32_t aphase = (uint32_t)(nseq / Cfg::A_PG) & 1u;
+        const uint32_t sa = stage_a(a_idx) + a_off0;
+#if B200SEP_KA_PAIR
+        const uint32_t my_ab_full = mapa_rank(a_full(a_idx), 0);  // the LEADER's barrier (cluster address)
+#else
+        const uint32_t my_ab_full = a_full(a_idx);
+#endif
+        const uint32_t my_ab_empty = a_empty(a_idx);
+        const int rs_ = grp + 2 * (nseq & (rpg - 1));             // raw stage of this k-block (= kb % raw_stages)
+        const uint32_t rphase = (uint32_t)(nseq / rpg) & 1u;
         mbar_wait_b(raw_full(rs_), rphase);
         if (tl_on) tl_stamp(it, tl_base + 3 * (kb >> 1));
         const uint32_t raw = raw_st(rs_);
@@ -747,11 +915,15 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
           }
         }
         fence_proxy_async();
+#if B200SEP_KA_PAIR
+        __syncwarp();  // every lane has fenced its A-stage writes; lane 0 arrives (release.cluster is cumulative)
+        if (lane == 0) mbar_arrive_cluster(my_ab_full);
+#else
         mbar_arrive(my_ab_full);
+#endif
         mbar_arrive(raw_empty(rs_));
         if (tl_on) tl_stamp(it, tl_base + 3 * (kb >> 1) + 2);
-        rphase ^= 1u;
-        aphase ^= 1u;
+        ++nseq;
         // statistics of the next tile's segment, off the tile-boundary critical path
         if (kb == 4 + grp && has_next) seg_stats_pre(part1, tn, pre, nmean, nrstd);
       }
@@ -766,10 +938,14 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
 
   tcgen05_fence_before();
   __syncthreads();
-  if (B200SEP_KA_CLUSTER) cluster_sync_all();  // the peer may multicast into / arrive on this CTA's shared memory until it is done too
+  if (B200SEP_KA_CL) cluster_sync_all();  // the peer may multicast into / arrive on this CTA's shared memory until it is done too
   if (warp == 6) {
     tcgen05_fence_after();
+#if B200SEP_KA_PAIR
+    tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+#else
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+#endif
   }
 }
 
