@@ -952,6 +952,12 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
 // =================================================================================================
 // K_B: apply previous block's G_res (x += res) + in-conv GEMM -> h1
 // =================================================================================================
+#ifndef B200SEP_KB_TMA_STORE
+#define B200SEP_KB_TMA_STORE 0  // (lane = frame orientation only) 1: h1 via 2-byte st.shared staging + TMA stores: slower
+#endif
+#ifndef B200SEP_KB_TRANSPOSED
+#define B200SEP_KB_TRANSPOSED 1  // in-conv GEMM as D[channel][frame]: epilogue thread = channel, 16-byte staging stores
+#endif
 struct KbCfg {
   static constexpr int W_BYTES = C_HID * C_BN * 2;      // 128 KiB: [2 k-blocks][512 rows][64 k]
   static constexpr int XN_BYTES = TILE_M * C_BN * 2;    // 32 KiB: [2 k-blocks][64 k][128 m]
@@ -961,15 +967,13 @@ struct KbCfg {
 #ifndef B200SEP_KB_PRO_RND
 #define B200SEP_KB_PRO_RND 4
 #endif
-  static constexpr int EPI_WARPS = 8, PRO_WARPS = B200SEP_KB_PRO_WARPS;  // EPI_WARPS / 4 epilogue warps per TMEM lane quadrant
+#ifndef B200SEP_KB_EPI16
+#define B200SEP_KB_EPI16 0  // 1: transposed epilogue on 16 warps (4 per TMEM lane quadrant, 32 frames each) instead of 8
+#endif
+  static constexpr int EPI_WARPS = (B200SEP_KB_TRANSPOSED && B200SEP_KB_EPI16) ? 16 : 8;  // EPI_WARPS / 4 per TMEM lane quadrant
+  static constexpr int PRO_WARPS = B200SEP_KB_PRO_WARPS;
   static constexpr int THREADS = (EPI_WARPS + 1 + PRO_WARPS) * 32;  // 544
   static constexpr int TMEM_COLS = 512;                 // 4 chunks of 128 output channels
-#ifndef B200SEP_KB_TMA_STORE
-#define B200SEP_KB_TMA_STORE 0  // (lane = frame orientation only) 1: h1 via 2-byte st.shared staging + TMA stores: slower
-#endif
-#ifndef B200SEP_KB_TRANSPOSED
-#define B200SEP_KB_TRANSPOSED 1  // in-conv GEMM as D[channel][frame]: epilogue thread = channel, 16-byte staging stores
-#endif
   static constexpr int ST_BYTES = (B200SEP_KB_TMA_STORE || B200SEP_KB_TRANSPOSED) ? TILE_M * 128 * 2 : 0;  // h1 staging
   static constexpr int OFF_XN = W_BYTES;
   static constexpr int OFF_ST = OFF_XN + 2 * XN_BYTES;
@@ -1055,7 +1059,81 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
-#if B200SEP_KB_TRANSPOSED
+#if B200SEP_KB_TRANSPOSED && B200SEP_KB_EPI16
+  if (warp < MMA_WARP) {
+    // ================================ epilogue: bias + PReLU -> h1, gLN1 partials ==================
+    // D[channel][frame]: TMEM lane = output channel of the 128-channel chunk, column = frame.  16 warps: warp =
+    // (lane quadrant, 32-frame quarter of the m-tile); per chunk a thread owns 32 consecutive frames of one channel (one
+    // tcgen05.ld): the bias is a per-lane constant, eight frames pack into one 16-byte st.shared (swizzled like a TMA
+    // box, conflict-free), and h1 leaves the SM as 64 x 64 TMA tile stores.  Four warps per scheduler hide the
+    // TMEM-load / shared-memory latencies that two could not (the traffic-free skeleton of the 8-warp version took
+    // 43 of the kernel's 60 us).
+    static_assert(Cfg::EPI_WARPS == 16, "epilogue mapping: four warps per TMEM lane quadrant");
+    const int ew = warp, quad = ew & 3, part = ew >> 2;   // part = 32-frame quarter of the m-tile
+    const int half = part >> 1, hh = part & 1;
+    const int cl = quad * 32 + lane;                       // channel inside the chunk
+    const int kb64 = cl >> 6, row = cl & 63;
+    const int grp = kb64 * 2 + half;                       // staging box = (64-channel block, frame half): 4 warps
+    const uint32_t st_box = smem_base + (uint32_t)(Cfg::OFF_ST + kb64 * 16384 + half * 8192);
+    const uint32_t st_row = st_box + (uint32_t)(row * 128);
+    const bool issuer = ((quad & 1) == 0 && hh == 0 && lane == 0);  // one thread per box issues its TMA store
+    const float alpha = epi.alpha;
+    const int f0 = part * 32;                              // first frame of this warp's piece inside the m-tile
+    int it = 0;
+    for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
+      const TileInfo ti = ti_get(s_ti, tb, it, w);
+      const int nvalid = ti.F - ti.t0;                     // frames >= nvalid lie beyond the segment end
+      const bool full = nvalid >= TILE_M;
+      float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+      const uint32_t ph = (uint32_t)it & 1u;
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        float v[32];
+        mbar_wait_b(tfull_bar(q), ph);
+        tcgen05_fence_after();
+        if (threadIdx.x == 0) tl_stamp(it, 16 + q);
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(q * 128 + part * 32), v);
+        const float bch = __ldg(epi.bias + q * 128 + cl);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        mbar_arrive(tempty_bar(q));  // the warp's part of chunk q is in registers: the MMA may overwrite it
+        const float2 b2 = make_float2(bch, bch);
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float2 u = add2(make_float2(v[j], v[j + 1]), b2);
+          u = prelu2<A01>(u, alpha);
+          pk[j >> 1] = h2_as_u32(__floats2half2_rn(u.x, u.y));
+          if (!full) {  // statistics exclude frames beyond the segment end
+            if (f0 + j >= nvalid) u.x = 0.f;
+            if (f0 + j + 1 >= nvalid) u.y = 0.f;
+          }
+          s2 = add2(s2, u);
+          q2 = fma2(u, u, q2);
+        }
+        // the previous chunk's TMA store must have finished READING this staging box before it is rewritten
+        if (issuer) bulk_wait_read0();
+        named_bar_sync(1 + grp, 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          st_shared_v4(st_row + (uint32_t)((((hh * 4 + k) ^ (row & 7))) << 4),
+                       make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
+        fence_proxy_async();
+        named_bar_sync(1 + grp, 128);
+#ifndef B200SEP_EXP_KB_NO_H1_STORE
+        if (issuer) {
+          tma_store_2d(&tm_h1, st_box, half * 64, w * C_HID + q * 128 + kb64 * 64);
+          bulk_commit();
+        }
+#endif
+        if (threadIdx.x == 0) tl_stamp(it, 20 + q);
+      }
+      const float s = warp_sum(s2.x + s2.y), qq = warp_sum(q2.x + q2.y);
+      tile_partial_reduce(s_red + (it & 1) * Cfg::EPI_WARPS, s_cnt + (it & 1), Cfg::EPI_WARPS, ew, s, qq,
+                          epi.part_out + w);
+    }
+    if (issuer) bulk_wait0();  // all h1 tile stores complete before the CTA exits
+#elif B200SEP_KB_TRANSPOSED
   if (warp < MMA_WARP) {
     // ================================ epilogue: bias + PReLU -> h1, gLN1 partials ==================
     // D[channel][frame]: TMEM lane = output channel of the 128-channel chunk, column = frame.  A thread owns 32
@@ -1112,6 +1190,11 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
         const float2 b2 = make_float2(bch, bch);
         const int f0 = half * 64 + hh * 32;  // first frame of the piece inside the m-tile
         uint32_t pk[16];
+#ifdef B200SEP_EXP_KB_NO_MATH  // timing experiment: no epilogue arithmetic
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = __float_as_uint(v[pi & 1][j]) ^ __float_as_uint(v[pi & 1][j + 16]);
+        s2.x += b2.x;
+#else
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float2 u = add2(make_float2(v[pi & 1][j], v[pi & 1][j + 1]), b2);
@@ -1124,17 +1207,24 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
           s2 = add2(s2, u);
           q2 = fma2(u, u, q2);
         }
+#endif
+#ifdef B200SEP_EXP_KB_NO_STS  // timing experiment: no staging stores
+        if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u && pk[15] == 1u) st_shared_v4(st_row, make_uint4(pk[1], pk[2], pk[3], pk[4]));
+#else
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           st_shared_v4(st_row + (uint32_t)((((hh * 4 + k) ^ (row & 7))) << 4),
                        make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
+#endif
         if (hh == 1) {
           fence_proxy_async();
           named_bar_sync(1 + grp, 64);
+#ifndef B200SEP_EXP_KB_NO_H1_STORE  // (timing experiment when defined: h1 never leaves the SM)
           if (issuer) {
             tma_store_2d(&tm_h1, st_box, half * 64, w * C_HID + q * 128 + kb64 * 64);
             bulk_commit();
           }
+#endif
           if (threadIdx.x == 0) tl_stamp(it, 20 + q);
         }
         bch = bnext;
@@ -1359,7 +1449,9 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < RND; ++j) {
           const size_t off = (size_t)((p0 + j) * ROWS + crow) * TILE_M;
-#if B200SEP_X16
+#if B200SEP_X16 && defined(B200SEP_EXP_NO_PRO_IO)  // timing experiment: no prologue global traffic
+          xh[j] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, (uint32_t)off); gr[j] = xh[j];
+#elif B200SEP_X16
           xh[j] = *reinterpret_cast<const uint4*>(xt + off);
           if (has_g) gr[j] = ldg_v4(gt + off);
 #elif !defined(B200SEP_EXP_NO_PRO_IO)
@@ -1404,7 +1496,9 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
             }
 #if B200SEP_X16
             const uint4 pk = pack8(xv);  // the rounded stream IS the GEMM operand: one rounding, stored twice
+#ifndef B200SEP_EXP_NO_PRO_IO
             *reinterpret_cast<uint4*>(xt + off) = pk;
+#endif
             st_shared_v4(xn + (uint32_t)((c >> 6) * 16384) + a_chunk_off(c & 63, f0), pk);
             continue;
 #elif !defined(B200SEP_EXP_NO_PRO_IO)
