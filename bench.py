@@ -316,10 +316,10 @@ def main():
             "in_conv_gemm": ("tensor", 2 * frames * 128 * 512),
             "dwconv": ("hbm", 2 * 512 * frames * es),
             "res_skip_gemm": ("tensor", 2 * frames * 512 * 256),
-            # fused block kernels: HBM bytes per frame = G_res 256 + x r/w 1024 + h1 1024 (K_B); h1 1024 +
-            # G_res 256 + skip stash 256 (K_A); their GEMM FLOPs are reported beside as tensor_tflops;
+            # fused block kernels: HBM bytes per frame = G_res 256 + x r/w 512 (fp16 residual stream) + h1 1024
+            # (K_B); h1 1024 + G_res 256 + skip stash 256 (K_A); their GEMM FLOPs are reported beside as tensor_tflops;
             # skip merge: one 256 B stash slot per block read once + the fp16 mask operand
-            "apply_in_gemm": ("hbm", 2304 * frames),
+            "apply_in_gemm": ("hbm", 1792 * frames),
             "dw_rs_gemm": ("hbm", 1536 * frames),
             "final_skip": ("hbm", (256 * n_layers + 256) * frames),
             "mask_gemm": ("tensor", 2 * frames * 128 * 512 * N_SRC),
