@@ -15,6 +15,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <tuple>
 #include <type_traits>
 #include <vector>
 
@@ -188,6 +189,19 @@ struct b200sep_model {
   // concurrent sub-batches (b200sep_separate_batch): auxiliary streams and fork / join events
   cudaStream_t aux_st[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  // CUDA graphs of the launch sequence for small batches (one per (n_seg, n_tiles, buffer addresses)): a single short
+  // segment is launch-bound (52 launches, ~7 us of host time each), the reference's per-segment separate() loop lives there
+  struct GraphKey {
+    int n_seg, n_tiles;
+    const void *mix, *out, *ws;
+    bool operator<(const GraphKey& o) const {
+      return std::tie(n_seg, n_tiles, mix, out, ws) < std::tie(o.n_seg, o.n_tiles, o.mix, o.out, o.ws);
+    }
+  };
+  cudaStream_t own_st = nullptr;  // stands in for the legacy default stream (StreamHop)
+  cudaEvent_t own_ev = nullptr;
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  long long graph_hits = 0, graph_misses = 0;  // a caller that passes fresh buffers every call never hits: give up then
   float* hin = nullptr;  // pinned input staging of b200sep_separate_batch_host
   size_t hin_cap = 0;    // floats
   cudaEvent_t hin_ev = nullptr;
@@ -832,6 +846,9 @@ void b200sep_model_destroy(b200sep_model* m) {
     if (m->ev_join[g]) cudaEventDestroy(m->ev_join[g]);
   }
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
+  if (m->own_st) cudaStreamDestroy(m->own_st);
+  if (m->own_ev) cudaEventDestroy(m->own_ev);
   if (m->hin_ev) cudaEventDestroy(m->hin_ev);
   if (m->hin) cudaFreeHost(m->hin);
   delete m;
@@ -1054,19 +1071,93 @@ static int run_sub(b200sep_model* m, const float* d_mix, const int64_t* offsets,
   tb.n_tiles = lo.n_tiles;
 
   const bool l16 = (m->cfg.kernel_size == 16);
-  if (m->half)
-    return l16 ? forward<__half, 16>(m, lo, tb, d_mix, d_out, ws, st) : forward<__half, 32>(m, lo, tb, d_mix, d_out, ws, st);
-  return l16 ? forward<float, 16>(m, lo, tb, d_mix, d_out, ws, st) : forward<float, 32>(m, lo, tb, d_mix, d_out, ws, st);
+  auto run_forward = [&]() -> int {
+    if (m->half)
+      return l16 ? forward<__half, 16>(m, lo, tb, d_mix, d_out, ws, st) : forward<__half, 32>(m, lo, tb, d_mix, d_out, ws, st);
+    return l16 ? forward<float, 16>(m, lo, tb, d_mix, d_out, ws, st) : forward<float, 32>(m, lo, tb, d_mix, d_out, ws, st);
+  };
+  // Small batches (at most one m-tile per SM) replay a captured graph of the launch sequence: every kernel argument is
+  // a function of (n_seg, n_tiles, buffer addresses) -- the per-call data (segment lengths, offsets) lives in the layout
+  // tables uploaded above, outside the graph.
+  static const bool graphs_on = [] { const char* e = getenv("B200SEP_GRAPH"); return !(e && atoi(e) == 0); }();
+  const bool use_graph = graphs_on && st != nullptr && !m->prof_on && m->debug_stop_after == 0 && lo.n_tiles <= m->n_sm &&
+                         getenv("B200SEP_SYNC_DEBUG") == nullptr;
+  if (!use_graph || (m->graph_misses > 64 && m->graph_hits < m->graph_misses)) return run_forward();
+  const b200sep_model::GraphKey key{n_seg, lo.n_tiles, d_mix, d_out, ws};
+  auto it = m->graphs.find(key);
+  if (it != m->graphs.end()) ++m->graph_hits;
+  else {
+    ++m->graph_misses;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_forward();
+    const std::string keep = g_err;
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc != 0 || e != cudaSuccess || g == nullptr) {
+      if (g) cudaGraphDestroy(g);
+      (void)cudaGetLastError();
+      if (rc != 0) return fail("%s", keep.c_str());
+      return fail("graph capture of the launch sequence failed: %s", cudaGetErrorString(e));
+    }
+    cudaGraphExec_t ex = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+    if (m->graphs.size() >= 256) {  // bounded cache: drop everything rather than track recency
+      for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
+      m->graphs.clear();
+    }
+    it = m->graphs.emplace(key, ex).first;
+  }
+  CK(cudaGraphLaunch(it->second, st));
+  return 0;
 }
+
+// A caller on the legacy default stream (NULL) is moved onto a stream of the model for the duration of the call,
+// ordered after / before the default stream by events: stream capture (the graphs of run_sub) is not possible on the
+// legacy stream.
+struct StreamHop {
+  b200sep_model* m;
+  cudaStream_t user, st;
+  int enter() {
+    st = user;
+    if (user != nullptr) return 0;
+    if (!m->own_st) CK(cudaStreamCreateWithFlags(&m->own_st, cudaStreamNonBlocking));
+    if (!m->own_ev) CK(cudaEventCreateWithFlags(&m->own_ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(m->own_ev, user));
+    CK(cudaStreamWaitEvent(m->own_st, m->own_ev, 0));
+    st = m->own_st;
+    return 0;
+  }
+  int leave() {
+    if (user != nullptr) return 0;
+    CK(cudaEventRecord(m->own_ev, m->own_st));
+    CK(cudaStreamWaitEvent(user, m->own_ev, 0));
+    return 0;
+  }
+};
+
+static int separate_batch_locked(b200sep_model* m, const float* d_mix, const int64_t* offsets, const int32_t* lens,
+                                 int32_t n_seg, float* d_out, void* d_ws, size_t ws_bytes, cudaStream_t st);
 
 int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* offsets, const int32_t* lens,
                            int32_t n_seg, float* d_out, void* d_ws, size_t ws_bytes, void* stream) {
   if (!m || !d_mix || !lens || !d_out || !d_ws) return fail("null argument");
   if ((reinterpret_cast<uintptr_t>(d_ws) & 255u) != 0) return fail("d_ws must be 256-byte aligned");
   if (n_seg <= 0) return fail("empty batch");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   std::lock_guard<std::mutex> lock(m->mu);
   CK(cudaSetDevice(m->device));
+  StreamHop hop{m, reinterpret_cast<cudaStream_t>(stream), nullptr};
+  if (hop.enter()) return 1;
+  const int rc = separate_batch_locked(m, d_mix, offsets, lens, n_seg, d_out, d_ws, ws_bytes, hop.st);
+  const std::string keep = g_err;
+  if (hop.leave()) return 1;
+  if (rc) return fail("%s", keep.c_str());
+  return 0;
+}
+
+static int separate_batch_locked(b200sep_model* m, const float* d_mix, const int64_t* offsets, const int32_t* lens,
+                                 int32_t n_seg, float* d_out, void* d_ws, size_t ws_bytes, cudaStream_t st) {
   std::vector<std::vector<int>> groups;
   if (plan_split(m, lens, n_seg, &groups)) return 1;
   const int S = (int)groups.size();
@@ -1148,14 +1239,27 @@ size_t b200sep_host_workspace_bytes(const b200sep_model* m, const int32_t* lens,
   return align_up(fw, 1024) + host_extra_bytes(m, lens, n_seg, nullptr, nullptr);
 }
 
+static int separate_batch_host_locked(b200sep_model* m, const float* const* h_segs, const int32_t* lens, int32_t n_seg,
+                                      float* h_out, void* d_ws, size_t ws_bytes, cudaStream_t st);
+
 int b200sep_separate_batch_host(b200sep_model* m, const float* const* h_segs, const int32_t* lens, int32_t n_seg,
                                 float* h_out, void* d_ws, size_t ws_bytes, void* stream) {
   if (!m || !h_segs || !lens || !h_out || !d_ws) return fail("null argument");
   if ((reinterpret_cast<uintptr_t>(d_ws) & 255u) != 0) return fail("d_ws must be 256-byte aligned");
   if (n_seg <= 0) return fail("empty batch");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   std::lock_guard<std::mutex> lock(m->mu);
   CK(cudaSetDevice(m->device));
+  StreamHop hop{m, reinterpret_cast<cudaStream_t>(stream), nullptr};
+  if (hop.enter()) return 1;
+  const int rc = separate_batch_host_locked(m, h_segs, lens, n_seg, h_out, d_ws, ws_bytes, hop.st);
+  const std::string keep = g_err;
+  if (hop.leave()) return 1;
+  if (rc) return fail("%s", keep.c_str());
+  return 0;
+}
+
+static int separate_batch_host_locked(b200sep_model* m, const float* const* h_segs, const int32_t* lens, int32_t n_seg,
+                                      float* h_out, void* d_ws, size_t ws_bytes, cudaStream_t st) {
   std::vector<std::vector<int>> groups;
   if (plan_split(m, lens, n_seg, &groups)) return 1;
   const int S = (int)groups.size(), NS = m->cfg.n_src;

@@ -388,3 +388,25 @@ def test_config5_streaming_chunked_60s_mixture(b200, model3):
     # a chunk's result does not depend on what else is in the batch (bit-identical)
     solo = sep.separate(chunks[17], 8000)
     assert all(np.array_equal(a, b) for a, b in zip(solo, outs[17]))
+
+
+def test_graph_replay_of_small_batches_is_bit_identical_to_the_batched_run(b200, model3):
+    """Small batches replay a captured CUDA graph of the launch sequence keyed by (n_seg, n_tiles, buffers): the same
+    graph serves segments of different lengths (the lengths live in the layout tables, outside the graph), on the
+    legacy default stream as well as on a side stream, and gives what the big two-sub-batch run gives."""
+    from b200sep import synth
+    sd, args, _ = model3
+    sep = b200.Separator(backend="b200", device="cuda:0", sample_rate=8000, n_src=3, state_dict=sd, model_args=args)
+    lens = [8000, 8001, 7990, 8100, 1600, 1607, 31990, 32000, 8000]   # several lengths per tile count
+    mixes = [synth.make_mixture(600 + i, n, 3)[0] for i, n in enumerate(lens)]
+    big = [synth.make_mixture(700 + i, 32000, 3)[0] for i in range(20)]  # pushes the batched run past 3 x 148 tiles
+    ref = sep.separate_batch(mixes + big, 8000)
+    for rep in range(2):
+        for m, r in zip(mixes, ref):
+            out = sep.separate(m, 8000)                       # legacy default stream -> the model's own stream
+            assert all(np.array_equal(a, b) for a, b in zip(out, r))
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for m, r in zip(mixes, ref):
+            out = sep.separate(m, 8000)
+            assert all(np.array_equal(a, b) for a, b in zip(out, r))
