@@ -138,7 +138,8 @@ def check(rc: int, what: str) -> None:
 
 
 def abort_flag(reset: bool = True) -> int:
-    """1 when a bounded device-side wait of the fused kernels ran out (synchronises the device)."""
+    """Device flags (synchronises the device): bit 0 = a bounded device-side wait of the fused kernels ran out,
+    bit 1 = the last forward wrote non-finite output samples."""
     v = C.c_int32(0)
     check(lib().b200sep_debug_abort_flag(C.byref(v), 1 if reset else 0), "abort flag")
     return int(v.value)

@@ -29,7 +29,7 @@
 
 namespace b200sep {
 
-__device__ int g_abort = 0;  // set when a bounded wait ran out (read by b200sep_debug_abort_flag)
+__device__ int g_abort = 0;  // bit 0: a bounded wait ran out; bit 1: non-finite output samples (read by b200sep_debug_abort_flag)
 
 // Optional in-kernel timeline (b200sep_debug_timeline): clock64 stamps per (CTA, tile visit, slot).
 constexpr int TL_TILES = 8, TL_SLOTS = 128;
@@ -61,9 +61,9 @@ __device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity) {
 #pragma unroll 1
   for (uint32_t i = 0; i < (1u << 18); ++i) {
     if (mbar_try(bar, parity)) return;
-    if ((i & 31u) == 31u && *reinterpret_cast<volatile int*>(&g_abort) != 0) return;
+    if ((i & 31u) == 31u && (*reinterpret_cast<volatile int*>(&g_abort) & 1) != 0) return;
   }
-  *reinterpret_cast<volatile int*>(&g_abort) = 1;
+  atomicOr(&g_abort, 1);
 }
 // L2 prefetch of a contiguous global range (bytes % 16 == 0) / of a TMA box
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
@@ -165,9 +165,9 @@ __device__ __forceinline__ void mbar_wait_cluster_b(uint32_t bar, uint32_t parit
 #pragma unroll 1
   for (uint32_t i = 0; i < (1u << 18); ++i) {
     if (mbar_try_cluster(bar, parity)) return;
-    if ((i & 31u) == 31u && *reinterpret_cast<volatile int*>(&g_abort) != 0) return;
+    if ((i & 31u) == 31u && (*reinterpret_cast<volatile int*>(&g_abort) & 1) != 0) return;
   }
-  *reinterpret_cast<volatile int*>(&g_abort) = 1;
+  atomicOr(&g_abort, 1);
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");

@@ -310,6 +310,9 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               if (hh < TILE_M && f_hi < F) { val += s_ola[hh][l]; any = true; }
               if (hh >= 1 && f_lo < F) { val += s_ola[hh - 1][S + l]; any = true; }
               if (!any) continue;
+              // inf / NaN samples (fp16 overflow of an activation, or non-finite input): flagged for the host, which
+              // warns and points at precision="fp32"; the values are still written, as the reference would
+              if (!(fabsf(val) <= 3.0e38f)) atomicOr(&g_abort, 2);
               const size_t idx = (size_t)(t0 + hh) * S + l;
               if (hh == 0 || hh == TILE_M) atomicAdd(o + idx, val);
               else o[idx] = val;

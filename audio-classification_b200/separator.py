@@ -17,6 +17,7 @@ import ctypes as C
 import os
 import sys
 import threading
+import warnings
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence
 
@@ -26,6 +27,15 @@ from . import _native as nat
 from . import weights as W
 
 BACKEND_NAME = "b200"
+
+
+def _check_device_flags(v: int) -> None:
+    """bit 0: a bounded device-side pipeline wait ran out (results invalid); bit 1: non-finite output samples."""
+    if v & 1:
+        raise RuntimeError("b200sep: a device-side pipeline wait timed out; results are invalid")
+    if v & 2:
+        warnings.warn("b200sep: the separated output contains non-finite samples (fp16 overflow of an activation, or "
+                      "non-finite input); precision='fp32' avoids the former", RuntimeWarning, stacklevel=3)
 
 
 class SeparationEngine:
@@ -166,8 +176,7 @@ class SeparationEngine:
             pinned_out, hout = self._acquire_pinned_out(total * S)
             pinned_out[:total * S].copy_(d_out[:total * S], non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
-            if nat.abort_flag():
-                raise RuntimeError("b200sep: a device-side pipeline wait timed out; results are invalid")
+            _check_device_flags(nat.abort_flag())
         res: List[List[np.ndarray]] = []
         o = 0
         for n in lens:
@@ -231,8 +240,7 @@ class SeparationEngine:
                     self._handle, ptrs, arr, len(lens), C.c_void_p(pinned_out.data_ptr()), C.c_void_p(ws_ptr),
                     C.c_size_t(ws_bytes), C.c_void_p(stream.cuda_stream)), "b200sep_separate_batch_host")
                 stream.synchronize()
-                if nat.abort_flag():
-                    raise RuntimeError("b200sep: a device-side pipeline wait timed out; results are invalid")
+                _check_device_flags(nat.abort_flag())
         res: List[List[np.ndarray]] = []
         o = 0
         for n in lens:

@@ -410,3 +410,24 @@ def test_graph_replay_of_small_batches_is_bit_identical_to_the_batched_run(b200,
         for m, r in zip(mixes, ref):
             out = sep.separate(m, 8000)
             assert all(np.array_equal(a, b) for a, b in zip(out, r))
+
+
+def test_non_finite_output_is_flagged_not_silent(b200, model3):
+    """fp16 overflow of an activation (or a non-finite input sample) ends in inf / NaN output samples: the decoder's
+    overlap-add flags them on the device and the host wrapper warns and names the fp32 escape hatch; the arrays are
+    still returned (the reference would return NaNs without a word)."""
+    import warnings
+    from b200sep import synth
+    sd, args, _ = model3
+    sep = b200.Separator(backend="b200", device="cuda:0", sample_rate=8000, n_src=3, state_dict=sd, model_args=args)
+    mix = synth.make_mixture(800, 8000, 3)[0].copy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        sep.separate(mix, 8000)  # clean input: no warning
+    mix[4000] = np.inf
+    with pytest.warns(RuntimeWarning, match="non-finite"):
+        out = sep.separate(mix, 8000)
+    assert len(out) == 3 and not np.isfinite(np.stack(out)).all()
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        sep.separate(mix[:3000], 8000)  # the flag is cleared once reported
