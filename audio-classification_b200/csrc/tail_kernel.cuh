@@ -236,7 +236,11 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         for (int h = 0; h < 2; ++h) {  // two halves of 32 filters: keeps the live register set small
           float e[32];
 #pragma unroll
+#ifdef B200SEP_EXP_TAIL_NO_ENC  // timing experiment: no encoder-output loads
+          for (int j = 0; j < 32; ++j) e[j] = 0.5f + (float)j;
+#else
           for (int j = 0; j < 32; ++j) e[j] = __half2float(ep[(size_t)(h * 32 + j) * TILE_M]);
+#endif
           if (h == 0) {
             tmem_ld_wait();
             tcgen05_fence_before();
@@ -251,8 +255,12 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             if (p.act == 0) {
               // sigmoid(v) = 0.5 * tanh(0.5 v) + 0.5 (one MUFU op per element)
               float t0_, t1_;
+#ifdef B200SEP_EXP_TAIL_NO_TANH  // timing experiment: no MUFU
+              t0_ = 0.5f * a0; t1_ = 0.5f * a1;
+#else
               asm("tanh.approx.f32 %0, %1;" : "=f"(t0_) : "f"(0.5f * a0));
               asm("tanh.approx.f32 %0, %1;" : "=f"(t1_) : "f"(0.5f * a1));
+#endif
               m0 = fmaf(t0_, 0.5f, 0.5f) * e[j];
               m1 = fmaf(t1_, 0.5f, 0.5f) * e[j + 1];
             } else {

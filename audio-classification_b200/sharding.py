@@ -11,7 +11,7 @@ from typing import Callable, List, Sequence, Tuple
 
 import numpy as np
 
-__all__ = ["lpt_partition", "bucket_by_length", "gather_records", "frames_of"]
+__all__ = ["lpt_partition", "bucket_by_length", "gather_records", "frames_of", "evaluate_sharded"]
 
 
 def frames_of(n_samples: int, kernel_size: int = 16, stride: int = 8) -> int:
@@ -90,3 +90,37 @@ def gather_records(local_ids: Sequence[int], local_records: np.ndarray, n_total:
             g = g[:k].cpu().numpy()
             out[g[:, 0].astype(np.int64)] = g[:, 1:]
     return out
+
+
+def evaluate_sharded(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.ndarray]], sr: int,
+                     separate_batch: Callable, pit_batch: Callable, max_samples: int = 4 << 20,
+                     kernel_size: int = 16, stride: int = 8, variant: str = "overlap3", device=None):
+    """Separation + PIT SI-SDR / SI-SDRi of a list of independent segments across the ranks of the initialised
+    ``torch.distributed`` group (or this process alone): LPT partition on frame counts, length-bucketed batches per
+    rank, ``separate_batch(chunks, sr)`` and ``pit_batch(mixes, refs, preds, variant)`` per batch, then ONE
+    ``all_gather`` of the per-segment records ``(sisdr, sisdri, perm...)``.  Every rank returns the full table:
+    ``(sisdr[n], sisdri[n], perm[n, K], seconds_spent_separating_on_this_rank)``.  No waveform leaves its rank.
+
+    This is the evaluation loop of ``/root/reference/scripts/osd/overlap3_core.py:689-744`` (separate, score, collect
+    ``sep_sisdr_list`` / ``sep_sisdri_list``) over segments that are already cut, for BASELINE.json configs[3] / [4]."""
+    import time
+    import torch.distributed as dist
+    n = len(mixes)
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank() if world > 1 else 0
+    lens = [int(np.asarray(m).shape[-1]) for m in mixes]
+    K = len(refs[0]) if n else 0
+    mine = lpt_partition([frames_of(v, kernel_size, stride) for v in lens], world)[rank] if n else []
+    rec = np.full((len(mine), 2 + K), np.nan)
+    pos = {seg: k for k, seg in enumerate(mine)}
+    t_sep = 0.0
+    for batch in bucket_by_length(mine, lens, max_samples):
+        t0 = time.time()
+        outs = separate_batch([mixes[i] for i in batch], sr)
+        t_sep += time.time() - t0
+        res = pit_batch([mixes[i] for i in batch], [refs[i] for i in batch], outs, variant)
+        for k, i in enumerate(batch):
+            rec[pos[i], 0], rec[pos[i], 1] = res.sisdr[k], res.sisdri[k]
+            rec[pos[i], 2:] = np.asarray(res.perm[k][:K], dtype=np.float64)
+    table = gather_records(mine, rec, n, device=device)
+    return table[:, 0], table[:, 1], table[:, 2:].astype(np.int64), t_sep
