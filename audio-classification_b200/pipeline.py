@@ -66,12 +66,15 @@ class OverlapBatchDriver:
     ``pit`` is ``b200sep.pit_sisdr_batch`` unless another callable with that signature is injected."""
 
     def __init__(self, sep, min_overlap_dur: float = 0.4, eval_separation: bool = False,
-                 pit: Optional[Callable] = None, max_batch_samples: int = 64 * 1024 * 1024):
+                 pit: Optional[Callable] = None, max_batch_samples: int = 64 * 1024 * 1024, fused_eval: bool = False):
         self.sep = sep
         self.min_overlap_dur = float(min_overlap_dur)
         self.eval_separation = bool(eval_separation)
         self._pit = pit
         self.max_batch_samples = int(max_batch_samples)
+        # fused_eval: segments whose references cover them completely are separated AND scored in one device-resident
+        # call (``SeparationEngine.separate_and_score``); ``time_sep`` then includes the PIT kernel
+        self.fused_eval = bool(fused_eval) and eval_separation and pit is None and hasattr(sep, "engine")
 
     # ---- selection rules of the reference loop -------------------------------------------------
     def plan(self, jobs: Sequence[MixtureJob]):
@@ -112,7 +115,36 @@ class OverlapBatchDriver:
         by_sr: Dict[int, List[SepRecord]] = {}
         for r in overlap:
             by_sr.setdefault(int(jobs[r.job].sr), []).append(r)
+        fused_done = set()
         for sr, recs in by_sr.items():
+            if self.fused_eval and sr == getattr(self.sep, "sample_rate", sr):
+                # references present, K in {2, 3}, every reference slice as long as the chunk -> one fused call per K
+                per_k: Dict[int, List[Tuple[SepRecord, List[np.ndarray]]]] = {}
+                for r in recs:
+                    refs_full = jobs[r.job].refs
+                    if not refs_full or r.chunk.shape[0] == 0 or r.chunk.dtype != np.float32:
+                        continue
+                    K = 3 if len(refs_full) >= 3 else len(refs_full)
+                    if K not in (2, 3) or K > int(getattr(self.sep, "n_src", K)):
+                        continue
+                    s_i, e_i = int(r.s * sr), int(r.e * sr)
+                    refs = [np.asarray(x)[s_i:e_i] for x in list(refs_full)[:K]]
+                    if all(x.shape[0] == r.chunk.shape[0] for x in refs):
+                        per_k.setdefault(K, []).append((r, refs))
+                for K, items in per_k.items():
+                    for batch in self._batches([r for r, _ in items]):
+                        lookup = {id(r): refs for r, refs in items}
+                        t0 = time.time()
+                        res, wav = self.sep.engine.separate_and_score([r.chunk for r in batch],
+                                                                      [lookup[id(r)] for r in batch], "overlap3")
+                        time_sep += time.time() - t0
+                        for k, r in enumerate(batch):
+                            r.branches = list(wav[k])
+                            fused_done.add(id(r))
+                            best, sdri = float(res.sisdr[k]), float(res.sisdri[k])
+                            if not (np.isnan(best) or np.isnan(sdri)):
+                                r.sisdr, r.sisdri, r.perm = best, sdri, [int(v) for v in res.perm[k][:K]]
+                recs = [r for r in recs if id(r) not in fused_done]
             for batch in self._batches(recs):
                 t0 = time.time()
                 outs = self.sep.separate_batch([r.chunk for r in batch], sr)
@@ -131,7 +163,7 @@ class OverlapBatchDriver:
             groups: Dict[Tuple[int, int], List[Tuple[SepRecord, List[np.ndarray]]]] = {}
             for r in overlap:
                 refs_full = jobs[r.job].refs
-                if not refs_full:
+                if not refs_full or id(r) in fused_done:
                     continue
                 K = 3 if len(refs_full) >= 3 else len(refs_full)            # :709
                 if K not in (2, 3) or len(r.branches) < K:                   # :710-713 (raises -> row skipped)

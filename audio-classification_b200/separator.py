@@ -185,6 +185,62 @@ class SeparationEngine:
             o += n
         return res
 
+    def separate_and_score(self, chunks: Sequence[np.ndarray], refs: Sequence[Sequence[np.ndarray]],
+                           variant: str = "overlap3", return_waveforms: bool = True):
+        """``--eval-separation`` without the host round trip: mixtures and references go to the device once, the
+        forward writes its estimates in exactly the ragged layout the PIT kernel reads
+        (``[seg][n_src][len]``, include/b200sep.h), the PIT kernel scores them in place, and only the per-segment
+        records (and, if wanted, the waveforms) come back.  Every reference must have its mixture's length (the call
+        site cuts both with the same indices, ``scripts/osd/overlap3_core.py:606-607, 716-722``); ragged cases go
+        through ``pit_sisdr_batch``.  Returns ``(PitResult, waveforms or None)``."""
+        from .pit import PitResult, pit_sisdr_device
+        torch = self._torch
+        n = len(chunks)
+        if n == 0:
+            z = np.zeros(0)
+            return PitResult(z, z, np.zeros((0, 0), np.int32), np.zeros(0, bool), np.zeros((0, 3, 4))), []
+        S = self.n_src
+        K = len(refs[0])
+        segs = [np.ascontiguousarray(np.asarray(c).reshape(-1), dtype=np.float32) for c in chunks]
+        lens = [int(a.shape[0]) for a in segs]
+        if K not in (2, 3) or K > S or any(len(r) != K for r in refs) or any(
+                int(np.asarray(a).shape[-1]) != ln for r, ln in zip(refs, lens) for a in r):
+            raise ValueError("separate_and_score needs K in {2, 3} references per segment, each of its mixture's length")
+        total = int(sum(lens))
+        dev = torch.device("cuda", self.device)
+        with self._lock, torch.cuda.device(dev):
+            h_in = torch.empty(total * (1 + K), dtype=torch.float32, pin_memory=True)
+            hv = h_in.numpy()
+            o = 0
+            for a in segs:
+                hv[o:o + a.shape[0]] = a
+                o += a.shape[0]
+            for r, ln in zip(refs, lens):           # [seg][K][len], the PIT kernel's reference layout
+                for a in r:
+                    hv[o:o + ln] = np.asarray(a, dtype=np.float32).reshape(-1)
+                    o += ln
+            d_in = h_in.to(dev, non_blocking=True)
+            d_mix, d_refs = d_in[:total], d_in[total:]
+            d_out = self.separate_device(d_mix, lens)
+            pair, sisdr, sisdri, perm = pit_sisdr_device(d_refs, d_out, d_mix, lens, K, S, variant)
+            hout = None
+            if return_waveforms:
+                pinned_out, hout = self._acquire_pinned_out(total * S)
+                pinned_out[:total * S].copy_(d_out[:total * S], non_blocking=True)
+            pair, sisdr, sisdri, perm = pair.cpu().numpy(), sisdr.cpu().numpy(), sisdri.cpu().numpy(), perm.cpu().numpy()
+            torch.cuda.current_stream(dev).synchronize()
+            _check_device_flags(nat.abort_flag())
+        res = PitResult(sisdr, sisdri, perm[:, :K].astype(np.int32), perm[:, 3].astype(bool), pair)
+        if not return_waveforms:
+            return res, None
+        wav: List[List[np.ndarray]] = []
+        o = 0
+        for ln in lens:
+            seg = hout[o * S:(o + ln) * S].reshape(S, ln)
+            wav.append([seg[s] for s in range(S)])
+            o += ln
+        return res, wav
+
     def _acquire_pinned_out(self, n_floats: int):
         """A page-locked output buffer nobody holds views of any more (CPython reference counts of the base
         ndarray), else a new one.  The results handed to the caller are numpy VIEWS of it, so a buffer returns to the

@@ -94,11 +94,14 @@ def gather_records(local_ids: Sequence[int], local_records: np.ndarray, n_total:
 
 def evaluate_sharded(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.ndarray]], sr: int,
                      separate_batch: Callable, pit_batch: Callable, max_samples: int = 4 << 20,
-                     kernel_size: int = 16, stride: int = 8, variant: str = "overlap3", device=None):
+                     kernel_size: int = 16, stride: int = 8, variant: str = "overlap3", device=None,
+                     separate_and_score: Callable = None):
     """Separation + PIT SI-SDR / SI-SDRi of a list of independent segments across the ranks of the initialised
     ``torch.distributed`` group (or this process alone): LPT partition on frame counts, length-bucketed batches per
     rank, ``separate_batch(chunks, sr)`` and ``pit_batch(mixes, refs, preds, variant)`` per batch, then ONE
-    ``all_gather`` of the per-segment records ``(sisdr, sisdri, perm...)``.  Every rank returns the full table:
+    ``all_gather`` of the per-segment records ``(sisdr, sisdri, perm...)``.  With ``separate_and_score`` (the engine's
+    device-resident ``separate_and_score(chunks, refs, variant, return_waveforms=False)``) the estimates never leave the
+    GPU between the forward and the PIT kernel.  Every rank returns the full table:
     ``(sisdr[n], sisdri[n], perm[n, K], seconds_spent_separating_on_this_rank)``.  No waveform leaves its rank.
 
     This is the evaluation loop of ``/root/reference/scripts/osd/overlap3_core.py:689-744`` (separate, score, collect
@@ -116,9 +119,13 @@ def evaluate_sharded(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.nda
     t_sep = 0.0
     for batch in bucket_by_length(mine, lens, max_samples):
         t0 = time.time()
-        outs = separate_batch([mixes[i] for i in batch], sr)
-        t_sep += time.time() - t0
-        res = pit_batch([mixes[i] for i in batch], [refs[i] for i in batch], outs, variant)
+        if separate_and_score is not None:
+            res, _ = separate_and_score([mixes[i] for i in batch], [refs[i] for i in batch], variant, False)
+            t_sep += time.time() - t0
+        else:
+            outs = separate_batch([mixes[i] for i in batch], sr)
+            t_sep += time.time() - t0
+            res = pit_batch([mixes[i] for i in batch], [refs[i] for i in batch], outs, variant)
         for k, i in enumerate(batch):
             rec[pos[i], 0], rec[pos[i], 1] = res.sisdr[k], res.sisdri[k]
             rec[pos[i], 2:] = np.asarray(res.perm[k][:K], dtype=np.float64)

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 import b200sep
 from b200sep import metrics, sharding, synth, weights
 
-n_seg = int(sys.argv[1]) if len(sys.argv) > 1 else 600
+n_seg = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 600
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
@@ -33,7 +33,9 @@ if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
 t0 = time.time()
-sisdr, sisdri, perm, t_sep = sharding.evaluate_sharded(mixes, srcs, 8000, sep.separate_batch, pit, max_samples=1 << 20)
+fused = sep.engine.separate_and_score if "--two-step" not in sys.argv else None
+sisdr, sisdri, perm, t_sep = sharding.evaluate_sharded(mixes, srcs, 8000, sep.separate_batch, pit, max_samples=1 << 20,
+                                                       separate_and_score=fused)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
@@ -49,7 +51,7 @@ if rank == 0:
         best, sdri, idx = pr.compute_sdr_improvement_pit_k_o3(mixes[i], srcs[i], list(est))
         worst = max(worst, abs(sdri - sisdri[i])); same &= (list(perm[i]) == idx)
     audio = sum(len(m) for m in mixes) / 8000.0
-    line = {"segments": len(mixes), "world": world, "audio_s": round(audio, 1), "sweep_s": round(dt, 3),
+    line = {"segments": len(mixes), "world": world, "device_resident_pit": fused is not None, "audio_s": round(audio, 1), "sweep_s": round(dt, 3),
             "audio_s_per_s_incl_host_pit_and_gather": round(audio / dt, 1), "rank0_time_sep_sec": round(t_sep, 3),
             "max_abs_dSISDRi_vs_oracle_on_sample_dB": round(worst, 4), "perm_identical_on_sample": bool(same)}
     line.update(metrics.sep_metrics(list(sisdr), list(sisdri)))

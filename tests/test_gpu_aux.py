@@ -145,3 +145,36 @@ def test_batched_driver_end_to_end_matches_per_segment_reference_flow(b200):
             k += 1
     m = res.sep_metrics()
     assert m["sep_eval_segments"] == 4 and m["sep_sisdri_mean"] is not None
+    # the fused (device-resident) evaluation gives the same rows
+    res_f = OverlapBatchDriver(sep, min_overlap_dur=0.4, eval_separation=True, fused_eval=True).run(jobs)
+    assert [r[:4] + [r[6]] for r in res_f.sep_details_rows] == [r[:4] + [r[6]] for r in res.sep_details_rows]
+    assert np.allclose(res_f.sep_sisdri_list, res.sep_sisdri_list, atol=1e-6)
+    for a, b in zip(res_f.overlap, res.overlap):
+        assert all(np.array_equal(x, y) for x, y in zip(a.branches, b.branches))
+
+
+def test_separate_and_score_on_device_equals_the_two_step_path(b200):
+    """--eval-separation with estimates and references resident on the device == separate_batch + pit_sisdr_batch."""
+    import time
+    from b200sep import synth, weights
+    sd, args = weights.random_state_dict(3, 0)
+    sep = b200.Separator(backend="b200", device="cuda:0", sample_rate=8000, n_src=3, state_dict=sd, model_args=args)
+    mixes, srcs = synth.make_batch(40, seed=11, n_src=3, lo_s=0.4, hi_s=4.0, with_sources=True)
+    outs = sep.separate_batch(mixes, 8000)
+    two = b200.pit_sisdr_batch(mixes, srcs, outs, "overlap3")
+    one, wav = sep.engine.separate_and_score(mixes, srcs, "overlap3")
+    assert np.array_equal(one.perm, two.perm)
+    np.testing.assert_allclose(one.sisdr, two.sisdr, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(one.sisdri, two.sisdri, rtol=0, atol=1e-9)
+    for a, b in zip(wav, outs):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    # K = 2 references against 3 estimates, records only
+    r2, none = sep.engine.separate_and_score(mixes[:7], [s[:2] for s in srcs[:7]], "overlap3", return_waveforms=False)
+    t2 = b200.pit_sisdr_batch(mixes[:7], [s[:2] for s in srcs[:7]], outs[:7], "overlap3")
+    assert none is None and np.array_equal(r2.perm, t2.perm)
+    np.testing.assert_allclose(r2.sisdri, t2.sisdri, rtol=0, atol=1e-9)
+    with pytest.raises(ValueError):
+        sep.engine.separate_and_score(mixes[:2], [[s[0][:-1], s[1], s[2]] for s in srcs[:2]])
+    t0 = time.perf_counter(); sep.engine.separate_and_score(mixes, srcs, "overlap3", return_waveforms=False); t1 = time.perf_counter()
+    outs = sep.separate_batch(mixes, 8000); b200.pit_sisdr_batch(mixes, srcs, outs, "overlap3"); t2_ = time.perf_counter()
+    print(f"separate_and_score {1e3 * (t1 - t0):.2f} ms vs two-step {1e3 * (t2_ - t1):.2f} ms for 40 segments")
