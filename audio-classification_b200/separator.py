@@ -65,6 +65,9 @@ class SeparationEngine:
         # default wave size: env override, else whole batch in one wave
         self.wave_frames = int(os.environ.get("B200SEP_WAVE_FRAMES", "0")) or None
         self._lock = threading.Lock()
+        # largest batch (in samples) sent through one forward; larger inputs are cut into consecutive sub-batches
+        # (4 Mi samples = 524 s of 8 kHz audio ~ 4.9 GB of scratch)
+        self.max_batch_samples = int(os.environ.get("B200SEP_MAX_BATCH_SAMPLES", str(4 << 20)))
         self._out_pool = []   # page-locked output buffers: (tensor, base ndarray)
         self._ws_host = None  # cached device scratch of the host entry point (grown on demand)
         self._pinned_out = None
@@ -278,6 +281,21 @@ class SeparationEngine:
         segs = [np.ascontiguousarray(np.asarray(c).reshape(-1), dtype=np.float32) for c in chunks]
         lens = [int(a.shape[0]) for a in segs]
         total = int(sum(lens))
+        if total > self.max_batch_samples and len(segs) > 1:
+            # bound the device scratch (~9.3 KB per encoder frame): consecutive sub-batches of at most
+            # max_batch_samples samples, each a full forward; results keep the caller's order
+            res_all: List[List[np.ndarray]] = []
+            cur: List[np.ndarray] = []
+            acc = 0
+            for a in segs:
+                if cur and acc + a.shape[0] > self.max_batch_samples:
+                    res_all += self.separate_batch(cur)
+                    cur, acc = [], 0
+                cur.append(a)
+                acc += a.shape[0]
+            if cur:
+                res_all += self.separate_batch(cur)
+            return res_all
         arr = nat.i32_array(lens)
         ptrs = (C.c_void_p * len(segs))(*[a.ctypes.data for a in segs])
         with self._lock:

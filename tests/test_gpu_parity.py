@@ -431,3 +431,17 @@ def test_non_finite_output_is_flagged_not_silent(b200, model3):
     with warnings.catch_warnings():
         warnings.simplefilter("error")
         sep.separate(mix[:3000], 8000)  # the flag is cleared once reported
+
+
+def test_oversized_batches_are_cut_into_sub_batches(b200, model3):
+    """A batch beyond max_batch_samples runs as consecutive forwards (bounded scratch) with identical results."""
+    from b200sep import synth
+    sd, args, _ = model3
+    sep = b200.Separator(backend="b200", device="cuda:0", sample_rate=8000, n_src=3, state_dict=sd, model_args=args)
+    mixes = synth.make_batch(24, seed=21, n_src=3, lo_s=0.3, hi_s=2.0)
+    whole = sep.separate_batch(mixes, 8000)
+    sep.engine.max_batch_samples = 30000   # forces ~10 sub-batches, some of a single segment
+    cut = sep.separate_batch(mixes, 8000)
+    assert len(cut) == len(whole) == 24
+    for a, b, m in zip(cut, whole, mixes):
+        assert a[0].shape == m.shape and all(np.array_equal(x, y) for x, y in zip(a, b))
