@@ -1083,6 +1083,13 @@ static int run_sub(b200sep_model* m, const float* d_mix, const int64_t* offsets,
   const bool use_graph = graphs_on && st != nullptr && !m->prof_on && m->debug_stop_after == 0 && lo.n_tiles <= m->n_sm &&
                          getenv("B200SEP_SYNC_DEBUG") == nullptr;
   if (!use_graph || (m->graph_misses > 64 && m->graph_hits < m->graph_misses)) return run_forward();
+  {  // a caller that is itself capturing this stream gets the plain launch sequence recorded into ITS graph
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      (void)cudaGetLastError();
+      return run_forward();
+    }
+  }
   const b200sep_model::GraphKey key{n_seg, lo.n_tiles, d_mix, d_out, ws};
   auto it = m->graphs.find(key);
   if (it != m->graphs.end()) ++m->graph_hits;
