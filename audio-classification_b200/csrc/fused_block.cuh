@@ -967,8 +967,9 @@ struct KbCfg {
 #ifndef B200SEP_KB_PRO_RND
 #define B200SEP_KB_PRO_RND 4
 #endif
-#ifndef B200SEP_KB_DIRECT_STORE
-#define B200SEP_KB_DIRECT_STORE 0  // 1: the transposed epilogue writes h1 with 16-byte global stores instead of staging + TMA
+#ifndef B200SEP_KB_DIRECT_MASK
+#define B200SEP_KB_DIRECT_MASK 0  // bit q set: chunk q of the transposed epilogue writes h1 with 16-byte global stores (LSU)
+                                  // instead of staging + TMA (shared memory); 0xF = all direct (89 us), 0 = all staged (60 us)
 #endif
 #ifndef B200SEP_KB_EPI16
 #define B200SEP_KB_EPI16 0  // 1: transposed epilogue on 16 warps (4 per TMEM lane quadrant, 32 frames each) instead of 8
@@ -1185,13 +1186,12 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qn * 128 + half * 64 + ((pi + 1) & 1) * 32),
                     v[(pi + 1) & 1]);
         }
-#if !B200SEP_KB_DIRECT_STORE
-        if (hh == 0) {
-          // the previous chunk's TMA store must have finished READING this staging box before it is rewritten
+        const bool direct = ((B200SEP_KB_DIRECT_MASK >> q) & 1) != 0;  // compile-time per unrolled piece
+        if (hh == 0 && !direct) {
+          // the previous staged chunk's TMA store must have finished READING this staging box before it is rewritten
           if (issuer) bulk_wait_read0();
           named_bar_sync(1 + grp, 64);
         }
-#endif
         const float2 b2 = make_float2(bch, bch);
         const int f0 = half * 64 + hh * 32;  // first frame of the piece inside the m-tile
         uint32_t pk[16];
@@ -1215,23 +1215,19 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
 #endif
 #ifdef B200SEP_EXP_KB_NO_STS  // timing experiment: no staging stores
         if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u && pk[15] == 1u) st_shared_v4(st_row, make_uint4(pk[1], pk[2], pk[3], pk[4]));
-#elif B200SEP_KB_DIRECT_STORE
-        {  // 32 consecutive frames of this thread's channel = 64 contiguous bytes of h1: four 16-byte global stores
+#else
+        if (direct) {  // 32 consecutive frames of this thread's channel = 64 contiguous bytes of h1: four 16-byte global stores
           uint4* __restrict__ gp = reinterpret_cast<uint4*>(epi.h1 + tt_index(w, C_HID, q * 128 + cl, f0));
 #pragma unroll
           for (int k = 0; k < 4; ++k) gp[k] = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
-        }
-#else
+        } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          st_shared_v4(st_row + (uint32_t)((((hh * 4 + k) ^ (row & 7))) << 4),
-                       make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
+          for (int k = 0; k < 4; ++k)
+            st_shared_v4(st_row + (uint32_t)((((hh * 4 + k) ^ (row & 7))) << 4),
+                         make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
+        }
 #endif
-#if B200SEP_KB_DIRECT_STORE
-        if (false) {
-#else
-        if (hh == 1) {
-#endif
+        if (hh == 1 && !direct) {
           fence_proxy_async();
           named_bar_sync(1 + grp, 64);
 #ifndef B200SEP_EXP_KB_NO_H1_STORE  // (timing experiment when defined: h1 never leaves the SM)
