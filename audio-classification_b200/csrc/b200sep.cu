@@ -605,7 +605,16 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
   const int slots1 = (kHalf && m->use_tc) ? C_HID / 256 : C_HID / 128;  // partial slots the in-conv GEMM writes
 
   // 1. encoder (+ bottleneck-gLN partials)
-  CK(launch_k(encoder_kernel<T, L>, dim3(nt, 2), dim3(256), 0, st, d_mix, (const float*)m->enc_w, enc, p0, tb));
+  if constexpr (L == 16) {
+    // B200SEP_ENCODER_V2=1: four frames per thread with packed FFMA2 (bandwidth_kernels.cuh) -- half the instructions and a
+    // quarter of the shared-memory wavefronts per output, but measured SLOWER (102 vs 94 us: 88 registers, 37 KB of
+    // shared memory per CTA, and FFMA2 issues at half rate), so the one-frame-per-thread kernel stays the default
+    static const bool enc_v1 = getenv("B200SEP_ENCODER_V2") == nullptr;
+    if (!enc_v1) CK(launch_k(encoder4_kernel<T>, dim3(nt, 2), dim3(256), 0, st, d_mix, (const float*)m->enc_w, enc, p0, tb));
+    else CK(launch_k(encoder_kernel<T, L>, dim3(nt, 2), dim3(256), 0, st, d_mix, (const float*)m->enc_w, enc, p0, tb));
+  } else {
+    CK(launch_k(encoder_kernel<T, L>, dim3(nt, 2), dim3(256), 0, st, d_mix, (const float*)m->enc_w, enc, p0, tb));
+  }
   if (stop()) return sync_failed ? 1 : 0;
 
   // 2. bottleneck: x = Wb . gLN(tf_rep) + bb

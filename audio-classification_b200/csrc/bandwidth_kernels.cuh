@@ -411,6 +411,98 @@ template <> struct Ld2<float> {
   __device__ __forceinline__ static float2 ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
 };
 
+// Encoder, second version (L = 16): a thread owns FOUR consecutive frames and walks 32 filters; the taps of a filter are
+// read once per thread as (w, w) pairs (one 16-byte shared-memory load = two taps) and applied to two frame pairs with
+// packed FFMA2 -- a quarter of the shared-memory wavefronts and half of the FMA instructions per output of the
+// one-frame-per-thread kernel above (which was L1-bound at 83 %).  Same tap order per output, so results are identical.
+// grid = (n_tiles, 2): a CTA = 128 frames x 256 filters, warp w -> filters [32 w, 32 w + 32), lane -> frames 4 lane .. + 3.
+template <typename T> __device__ __forceinline__ void enc_store4(T* p, float a, float b, float c, float d);
+template <> __device__ __forceinline__ void enc_store4<float>(float* p, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void enc_store4<__half>(__half* p, float a, float b, float c, float d) {
+  const __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+template <typename T>
+__global__ void __launch_bounds__(256) encoder4_kernel(const float* __restrict__ mix,
+                                                       const float* __restrict__ w_enc,  // [512][16]
+                                                       T* __restrict__ encT,             // [nt][512][128]
+                                                       float2* __restrict__ part,        // [nt][2]
+                                                       Tables tb) {
+  constexpr int L = 16, S = 8, CH_PER_CTA = 256;
+  pdl_enter();
+  __shared__ float4 s_w2[CH_PER_CTA * L / 2];               // (w_l, w_l, w_{l+1}, w_{l+1}): 32 KiB
+  __shared__ float4 s_x4[(TILE_M * S + S) / 4 + 2];
+  __shared__ float s_red[16];
+  float* s_x = reinterpret_cast<float*>(s_x4);
+  const int m_tile = blockIdx.x, chalf = blockIdx.y, tid = threadIdx.x;
+  const TileInfo ti = load_tile_info(tb.tile_info + m_tile);
+  const int seg = ti.seg, t0 = ti.t0, F = ti.F;
+  const int T_len = tb.seg_len[seg];
+  const float* x = mix + tb.seg_in_off[seg];
+  const float2* wg = reinterpret_cast<const float2*>(w_enc + (size_t)chalf * CH_PER_CTA * L);
+  for (int i = tid; i < CH_PER_CTA * L / 2; i += 256) {
+    const float2 w = __ldg(wg + i);
+    s_w2[i] = make_float4(w.x, w.x, w.y, w.y);
+  }
+  const int s0 = t0 * S;
+  for (int i = tid; i < TILE_M * S + S; i += 256) {
+    const int gi = s0 + i;
+    s_x[i] = (gi < T_len) ? x[gi] : 0.f;
+  }
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int f0 = 4 * lane;
+  // samples of the four frames: 40 consecutive floats; pairs (frame 0, frame 1) and (frame 2, frame 3) per tap
+  float xv[40];
+#pragma unroll
+  for (int q = 0; q < 10; ++q) {
+    const float4 v = s_x4[(f0 * S) / 4 + q];
+    xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
+  }
+  float2 p01[L], p23[L];
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    p01[l] = make_float2(xv[l], xv[S + l]);
+    p23[l] = make_float2(xv[2 * S + l], xv[3 * S + l]);
+  }
+  const float2 vm01 = make_float2((t0 + f0) < F ? 1.f : 0.f, (t0 + f0 + 1) < F ? 1.f : 0.f);
+  const float2 vm23 = make_float2((t0 + f0 + 2) < F ? 1.f : 0.f, (t0 + f0 + 3) < F ? 1.f : 0.f);
+  float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+  const int c_base = warp * 32;
+  T* dst = encT + tt_index(m_tile, C_ENC, chalf * CH_PER_CTA + c_base, f0);
+#pragma unroll 2
+  for (int j = 0; j < 32; ++j) {
+    const float4* w4 = s_w2 + (c_base + j) * (L / 2);
+    float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < L / 2; ++q) {
+      const float4 w = w4[q];
+      a01 = fma2(make_float2(w.x, w.y), p01[2 * q], a01);
+      a23 = fma2(make_float2(w.x, w.y), p23[2 * q], a23);
+      a01 = fma2(make_float2(w.z, w.w), p01[2 * q + 1], a01);
+      a23 = fma2(make_float2(w.z, w.w), p23[2 * q + 1], a23);
+    }
+    a01 = mul2(a01, vm01);
+    a23 = mul2(a23, vm23);
+    enc_store4<T>(dst + (size_t)j * TILE_M, a01.x, a01.y, a23.x, a23.y);
+    s2 = add2(s2, add2(a01, a23));
+    q2 = fma2(a01, a01, q2);
+    q2 = fma2(a23, a23, q2);
+  }
+  const float s_acc = warp_sum(s2.x + s2.y), q_acc = warp_sum(q2.x + q2.y);
+  if (lane == 0) { s_red[warp] = s_acc; s_red[8 + warp] = q_acc; }
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { s += s_red[w]; q += s_red[8 + w]; }
+    part[(size_t)m_tile * 2 + chalf] = make_float2(s, q);
+  }
+}
+
 template <typename T, int L>
 __global__ void __launch_bounds__(256) decoder_kernel(const T* __restrict__ masked,  // [nt][S*512][128]
                                                       const float* __restrict__ w_dec,  // [512][L]
