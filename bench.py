@@ -46,7 +46,8 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML polled from a thread of this process every
+    ~2 ms (nvidia_ml_py), with `nvidia-smi -lms` as the fallback when NVML cannot be imported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -55,8 +56,50 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.handle = None
+        self.samples = []      # (sm_mhz, reasons bitmask)
+        self.sm_max = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may remap indices: go through the UUID of the CUDA device when torch exposes it
+            self.handle = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+            except Exception:
+                self.handle = None
+            if self.handle is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                phys = int(ids[gpu_index]) if len(ids) > gpu_index and ids[gpu_index].isdigit() else gpu_index
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(
+                    n, "nvmlDeviceGetCurrentClocksEventReasons") else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((sm, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE,
@@ -70,6 +113,19 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            if self._thread is not None:
+                self._thread.join(timeout=1.0)
+            n = self.nvml
+            names = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            sm = [s for s, _ in self.samples]
+            reasons = sorted(k for k, bit in names.items() if any(r & bit for _, r in self.samples))
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -91,7 +147,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def make_workload(rank: int, n_seg: int):
