@@ -39,6 +39,24 @@ __device__ __forceinline__ void tl_stamp(int it, int slot) {
   if (tl != nullptr && it < TL_TILES) tl[((size_t)blockIdx.x * TL_TILES + it) * TL_SLOTS + slot] = clock64();
 }
 
+// wall-clock (globaltimer, ns) stamp of a CTA's entry / exit (row 7 of the CTA's timeline block); only in builds with
+// -DB200SEP_TL_NS=1 (tests/cta_lifetimes.py)
+#ifndef B200SEP_TL_NS
+#define B200SEP_TL_NS 0
+#endif
+__device__ __forceinline__ void tl_stamp_ns(int slot) {
+#if B200SEP_TL_NS
+  long long* tl = c_timeline;
+  if (tl != nullptr && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tl[((size_t)blockIdx.x * TL_TILES + 7) * TL_SLOTS + slot] = (long long)t;
+  }
+#else
+  (void)slot;
+#endif
+}
+
 namespace fb {
 using namespace tc;
 
@@ -465,6 +483,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   // PDL: everything up to the prologue barrier touches only constants (weights, tap tables, per-call layout
   // tables), so it may overlap the previous kernel's tail; activations are read after pdl_wait().
   pdl_launch_dependents();
+  tl_stamp_ns(124);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n_tiles = tb.n_tiles;
@@ -939,6 +958,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   tcgen05_fence_before();
   __syncthreads();
   if (B200SEP_KA_CL) cluster_sync_all();  // the peer may multicast into / arrive on this CTA's shared memory until it is done too
+  tl_stamp_ns(125);
   if (warp == 6) {
     tcgen05_fence_after();
 #if B200SEP_KA_PAIR
@@ -1025,6 +1045,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
   const uint32_t done_bar = bar0 + 8u * 14;  // final tcgen05.commit: no async mbarrier arrive may outlive the CTA
 
   pdl_launch_dependents();  // PDL: the prologue below (barriers, TMEM, resident W_in, layout tables) reads constants only
+  tl_stamp_ns(120);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n_tiles = tb.n_tiles;
@@ -1532,6 +1553,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
 
   tcgen05_fence_before();
   __syncthreads();
+  tl_stamp_ns(121);
   if (warp == MMA_WARP) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
