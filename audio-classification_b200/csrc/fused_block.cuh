@@ -116,6 +116,9 @@ __device__ __forceinline__ void tile_partial_reduce(float2* red, int* cnt, int n
     }
   }
 }
+#ifndef B200SEP_KA_SHFL_TAPS
+#define B200SEP_KA_SHFL_TAPS 0  // 1: d < 8: neighbour-vector words through warp shuffles instead of shared-memory reads (measured: neutral)
+#endif
 #ifndef B200SEP_KA_REVERSE
 #define B200SEP_KA_REVERSE 1
 #endif
@@ -879,10 +882,33 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
 #pragma unroll
           for (int jj = 0; jj < 4; jj += 2) {
             // both steps' vectors and table entries first (independent shared-memory loads in flight) ...
-            const uint4 vc0 = ld_shared_v4(raw + c_base + jj * c_step), va0 = ld_shared_v4(raw + l_base + jj * l_step);
-            const uint4 vb0 = ld_shared_v4(raw + r_base + jj * r_step);
-            const uint4 vc1 = ld_shared_v4(raw + c_base + (jj + 1) * c_step), va1 = ld_shared_v4(raw + l_base + (jj + 1) * l_step);
-            const uint4 vb1 = ld_shared_v4(raw + r_base + (jj + 1) * r_step);
+            const uint4 vc0 = ld_shared_v4(raw + c_base + jj * c_step);
+            const uint4 vc1 = ld_shared_v4(raw + c_base + (jj + 1) * c_step);
+            uint4 va0, vb0, va1, vb1;
+            if (D > 0 && B200SEP_KA_SHFL_TAPS) {
+              // d < 8: the taps reach D frames into the NEIGHBOURING 8-frame vectors, which the adjacent lanes have just
+              // loaded as their centre vectors: one or two words per side come over the warp shuffle network instead
+              // of two more 16-byte shared-memory reads per output vector (K_A is shared-memory-bandwidth bound); only the
+              // first / last lane of a 16-lane channel row reads its neighbour from the halo
+              va0.z = __shfl_up_sync(0xffffffffu, vc0.z, 1);   va0.w = __shfl_up_sync(0xffffffffu, vc0.w, 1);
+              vb0.x = __shfl_down_sync(0xffffffffu, vc0.x, 1); vb0.y = __shfl_down_sync(0xffffffffu, vc0.y, 1);
+              va1.z = __shfl_up_sync(0xffffffffu, vc1.z, 1);   va1.w = __shfl_up_sync(0xffffffffu, vc1.w, 1);
+              vb1.x = __shfl_down_sync(0xffffffffu, vc1.x, 1); vb1.y = __shfl_down_sync(0xffffffffu, vc1.y, 1);
+              va0.x = va0.y = vb0.z = vb0.w = va1.x = va1.y = vb1.z = vb1.w = 0u;
+              if (lane16 == 0) {
+                va0 = ld_shared_v4(raw + l_base + jj * l_step);
+                va1 = ld_shared_v4(raw + l_base + (jj + 1) * l_step);
+              }
+              if (lane16 == 15) {
+                vb0 = ld_shared_v4(raw + r_base + jj * r_step);
+                vb1 = ld_shared_v4(raw + r_base + (jj + 1) * r_step);
+              }
+            } else {
+              va0 = ld_shared_v4(raw + l_base + jj * l_step);
+              vb0 = ld_shared_v4(raw + r_base + jj * r_step);
+              va1 = ld_shared_v4(raw + l_base + (jj + 1) * l_step);
+              vb1 = ld_shared_v4(raw + r_base + (jj + 1) * r_step);
+            }
             const float4 ta = s_t0[ch0 + jj * 16], tb_ = s_t0[ch0 + jj * 16 + 16];
             const float cba = s_cb[ch0 + jj * 16], cbb = s_cb[ch0 + jj * 16 + 16];
             // ... then the arithmetic; the (single) A stage of this group is only needed for the stores, so the
