@@ -29,6 +29,15 @@ from . import weights as W
 BACKEND_NAME = "b200"
 
 
+def _data_ptr(a: np.ndarray) -> int:
+    """Address of a contiguous ndarray's data (twice as fast as ``a.ctypes.data``, which builds a helper object per
+    call; 64 segments per batch make that visible in the end-to-end time)."""
+    try:
+        return C.addressof(C.c_char.from_buffer(a))
+    except (TypeError, ValueError):  # read-only or empty buffers
+        return a.ctypes.data
+
+
 def _check_device_flags(v: int) -> None:
     """bit 0: a bounded device-side pipeline wait ran out (results invalid); bit 1: non-finite output samples."""
     if v & 1:
@@ -278,8 +287,10 @@ class SeparationEngine:
         # the kernels of the other).  The OUTPUT pinned buffer is allocated per call (torch's caching host allocator
         # makes that cheap) and handed to the caller as numpy views, so the 4 * S * T bytes of results are never
         # copied a second time on the host.
-        segs = [np.ascontiguousarray(np.asarray(c).reshape(-1), dtype=np.float32) for c in chunks]
-        lens = [int(a.shape[0]) for a in segs]
+        # (float32, 1-D, contiguous chunks -- what the pipeline passes -- are used in place; anything else is converted)
+        segs = [c if (type(c) is np.ndarray and c.dtype == np.float32 and c.ndim == 1 and c.flags.c_contiguous)
+                else np.ascontiguousarray(np.asarray(c).reshape(-1), dtype=np.float32) for c in chunks]
+        lens = [a.shape[0] for a in segs]
         total = int(sum(lens))
         if total > self.max_batch_samples and len(segs) > 1:
             # bound the device scratch (~9.3 KB per encoder frame): consecutive sub-batches of at most
@@ -297,7 +308,7 @@ class SeparationEngine:
                 res_all += self.separate_batch(cur)
             return res_all
         arr = nat.i32_array(lens)
-        ptrs = (C.c_void_p * len(segs))(*[a.ctypes.data for a in segs])
+        ptrs = (C.c_void_p * len(segs))(*[_data_ptr(a) for a in segs])
         with self._lock:
             need = int(nat.lib().b200sep_host_workspace_bytes(self._handle, arr, len(lens)))
             if need == 0:
