@@ -977,11 +977,16 @@ static int plan_split(const b200sep_model* m, const int32_t* lens, int n_seg, st
   std::vector<int> order(n_seg);
   for (int i = 0; i < n_seg; ++i) order[i] = i;
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return nt[a] > nt[b]; });
+  // target shares: equal, unless B200SEP_SPLIT_RATIO=<share of group 0> (experiments: a smaller first group finishes
+  // earlier, so its device -> host copy overlaps the other group's last kernels)
+  static const double ratio0 = [] { const char* e = getenv("B200SEP_SPLIT_RATIO"); return e ? atof(e) : 0.0; }();
+  std::vector<double> share(S, 1.0 / S);
+  if (S == 2 && ratio0 > 0.05 && ratio0 < 0.95) { share[0] = ratio0; share[1] = 1.0 - ratio0; }
   std::vector<long long> load(S, 0);
   for (int i : order) {
     int best = 0;
     for (int g = 1; g < S; ++g)
-      if (load[g] < load[best]) best = g;
+      if ((double)load[g] / share[g] < (double)load[best] / share[best]) best = g;
     (*groups)[best].push_back(i);
     load[best] += nt[i];
   }
