@@ -676,7 +676,9 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
         if (stop()) return sync_failed ? 1 : 0;
       }
       if (m->n_layers > fb::MAX_LAYERS) return fail("fused path supports up to %d TCN blocks", fb::MAX_LAYERS);
-      CK(launch_k(fb::skip_merge_kernel, dim3(nt), dim3(256), 0, st, (const __half*)stash,
+      static const int merge_split = [] { const char* e = getenv("B200SEP_MERGE_SPLIT"); const int v = e ? atoi(e) : 2;
+                                          return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 2; }();
+      CK(launch_k(fb::skip_merge_kernel, dim3(nt, merge_split), dim3(256), 0, st, (const __half*)stash,
                   (const float2*)p2, lo.part2_stride, (const float*)m->skip_rs, (const float*)m->skip_cb, skipa,
                   m->alpha_mask, m->n_layers, tb));
       if (stop()) return sync_failed ? 1 : 0;

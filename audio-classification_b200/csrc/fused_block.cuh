@@ -1618,7 +1618,10 @@ __global__ void __launch_bounds__(256) skip_merge_kernel(const __half* __restric
   const int lane16 = threadIdx.x & 15, crow = threadIdx.x >> 4;
   const int f0 = lane16 * 8;
 #pragma unroll 1
-  for (int ps = 0; ps < 8; ++ps) {
+  // grid = (n_tiles, SKIP_MERGE_SPLIT): a CTA covers 128 / SKIP_MERGE_SPLIT channel rows of its m-tile, so that the launch
+  // is many short CTAs (1050 whole-tile CTAs on 148 x 5 resident slots were 1.4 waves: the second wave ran at 42 %)
+  const int ps_per = 8 / (int)gridDim.y;
+  for (int ps = (int)blockIdx.y * ps_per; ps < ((int)blockIdx.y + 1) * ps_per; ++ps) {
     const int c = ps * 16 + crow;
     const size_t idx = tt_index(w, C_SKIP, c, f0);
     // stash layout [tile][block][128][128]: the n_layers slots of an m-tile are contiguous
