@@ -26,7 +26,7 @@ EXPORTS = [
     "b200sep_workspace_bytes", "b200sep_separate_batch", "b200sep_pit_workspace_bytes",
     "b200sep_pit_sisdr_batch", "b200sep_debug_gemm", "b200sep_debug_set_stop",
     "b200sep_debug_layout", "b200sep_profile_enable", "b200sep_profile_read",
-    "b200sep_debug_abort_flag", "b200sep_pipeline", "b200sep_debug_timeline",
+    "b200sep_pipeline", "b200sep_debug_timeline",
     "b200sep_host_workspace_bytes", "b200sep_separate_batch_host", "b200sep_split_count",
     "b200sep_resample_out_lens", "b200sep_resample_batch", "b200sep_frame_rms_out_lens",
     "b200sep_frame_rms_batch", "b200sep_gt_overlap_mask_batch",
@@ -51,7 +51,7 @@ class Weights(C.Structure):
         ("norm1_beta", _FPP), ("dw_weight", _FPP), ("dw_bias", _FPP), ("prelu2", _FPP),
         ("norm2_gamma", _FPP), ("norm2_beta", _FPP), ("res_weight", _FPP), ("res_bias", _FPP),
         ("skip_weight", _FPP), ("skip_bias", _FPP),
-        ("mask_prelu", _FP), ("mask_weight", _FP), ("mask_bias", _FP),
+        ("mask_prelu", _FP), ("mask_weight", _FP), ("mask_bias", _FP), ("gln_eps", _FP),
     ]
 
 
@@ -86,7 +86,7 @@ def lib() -> C.CDLL:
         L.b200sep_workspace_bytes.restype = C.c_size_t
         L.b200sep_workspace_bytes.argtypes = [vp, i32p, i32]
         L.b200sep_separate_batch.restype = C.c_int
-        L.b200sep_separate_batch.argtypes = [vp, vp, i64p, i32p, i32, vp, vp, C.c_size_t, vp]
+        L.b200sep_separate_batch.argtypes = [vp, vp, i64p, i32p, i32, vp, vp, C.c_size_t, vp, vp]
         L.b200sep_resample_out_lens.restype = C.c_int
         L.b200sep_resample_out_lens.argtypes = [i32p, i32, i32, i32, i32, i32p]
         L.b200sep_resample_batch.restype = C.c_int
@@ -102,7 +102,7 @@ def lib() -> C.CDLL:
         L.b200sep_host_workspace_bytes.restype = C.c_size_t
         L.b200sep_host_workspace_bytes.argtypes = [vp, i32p, i32]
         L.b200sep_separate_batch_host.restype = C.c_int
-        L.b200sep_separate_batch_host.argtypes = [vp, C.POINTER(vp), i32p, i32, vp, vp, C.c_size_t, vp]
+        L.b200sep_separate_batch_host.argtypes = [vp, C.POINTER(vp), i32p, i32, vp, vp, C.c_size_t, vp, vp]
         L.b200sep_pit_workspace_bytes.restype = C.c_size_t
         L.b200sep_pit_workspace_bytes.argtypes = [i32p, i32]
         L.b200sep_pit_sisdr_batch.restype = C.c_int
@@ -118,8 +118,6 @@ def lib() -> C.CDLL:
         L.b200sep_profile_enable.argtypes = [vp, C.c_int]
         L.b200sep_profile_read.restype = C.c_int
         L.b200sep_profile_read.argtypes = [vp, C.POINTER(C.c_float), i32, i32p]
-        L.b200sep_debug_abort_flag.restype = C.c_int
-        L.b200sep_debug_abort_flag.argtypes = [i32p, i32]
         L.b200sep_debug_timeline.restype = C.c_int
         L.b200sep_debug_timeline.argtypes = [vp]
         L.b200sep_pipeline.restype = C.c_int
@@ -137,12 +135,9 @@ def check(rc: int, what: str) -> None:
         raise RuntimeError(f"{what}: {last_error()}")
 
 
-def abort_flag(reset: bool = True) -> int:
-    """Device flags (synchronises the device): bit 0 = a bounded device-side wait of the fused kernels ran out,
-    bit 1 = the last forward wrote non-finite output samples."""
-    v = C.c_int32(0)
-    check(lib().b200sep_debug_abort_flag(C.byref(v), 1 if reset else 0), "abort flag")
-    return int(v.value)
+MAX_SPLIT = 4          # B200SEP_MAX_SPLIT: h_flags words per call
+FLAG_WAIT_TIMEOUT = 1  # B200SEP_FLAG_WAIT_TIMEOUT
+FLAG_NONFINITE = 2     # B200SEP_FLAG_NONFINITE
 
 
 def i32_array(vals):

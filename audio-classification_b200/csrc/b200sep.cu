@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -54,6 +55,19 @@ static int fail(const char* fmt, ...) {
   } while (0)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Function attributes (opt-in shared-memory size) are per DEVICE: one flag per (kernel instantiation, device).
+constexpr int kMaxDev = 64;
+struct DevOnce {
+  std::atomic<uint64_t> mask{0};
+  bool need(int dev) const { return dev < 0 || dev >= kMaxDev || ((mask.load(std::memory_order_acquire) >> dev) & 1ull) == 0; }
+  void done(int dev) { if (dev >= 0 && dev < kMaxDev) mask.fetch_or(1ull << dev, std::memory_order_release); }
+};
+static int current_device_index() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDev) return 0;
+  return d;
+}
 
 // ------------------------------------------------------------------------------------------------
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
@@ -157,6 +171,7 @@ struct BlockW {
   float *rs = nullptr, *cb = nullptr;
   int dilation = 1;
   int n_out = 256;
+  float eps1 = GLN_EPS, eps2 = GLN_EPS;  // eps of gLN1 / gLN2 of this block (b200sep_weights.gln_eps)
   CUtensorMap tm_in, tm_rs, tm_rs_half;
   float4 *dw_t0 = nullptr, *dw_t1 = nullptr;  // folded depthwise tap tables (fused_block.cuh DwTab)
   float* dw_cb = nullptr;
@@ -182,6 +197,8 @@ struct b200sep_model {
   float alpha_mask = 0.25f;
   CUtensorMap tm_bn, tm_mask;
   float *skip_rs = nullptr, *skip_cb = nullptr;  // [n_layers][128] skip halves of rs / cb (skip_merge_kernel)
+  float* skip_eps = nullptr;                     // [n_layers] eps of every block's gLN2 (skip_merge_kernel)
+  float eps_bn = GLN_EPS;                        // eps of the bottleneck gLN
   Staging staging;
   std::mutex mu;
   int debug_stop_after = 0;  // 0 = run everything; k = stop after k-th launch (tests)
@@ -201,6 +218,7 @@ struct b200sep_model {
   cudaStream_t own_st = nullptr;  // stands in for the legacy default stream (StreamHop)
   cudaEvent_t own_ev = nullptr;
   std::map<GraphKey, cudaGraphExec_t> graphs;
+  std::mutex graph_mu;
   long long graph_hits = 0, graph_misses = 0;  // a caller that passes fresh buffers every call never hits: give up then
   float* hin = nullptr;  // pinned input staging of b200sep_separate_batch_host
   size_t hin_cap = 0;    // floats
@@ -210,7 +228,7 @@ struct b200sep_model {
   int prof_n = 0;
 };
 
-static Staging g_pit_staging;
+static Staging g_pit_staging[kMaxDev];  // per device (events and pinned slots belong to a device context)
 static std::mutex g_pit_mu;
 
 template <typename T> static T host_cvt(float v);
@@ -278,11 +296,19 @@ static int build_weights(b200sep_model* m, const b200sep_weights* w) {
                          &m->bn_rs, &m->bn_cb))
     return 1;
   m->blocks.resize(m->n_layers);
-  std::vector<float> skip_rs, skip_cb;
+  std::vector<float> skip_rs, skip_cb, skip_eps;
+  auto eps_at = [&](int k) -> float {
+    const float e = w->gln_eps ? w->gln_eps[k] : GLN_EPS;
+    return e;
+  };
+  m->eps_bn = eps_at(0);
   for (int i = 0; i < m->n_layers; ++i) {
     BlockW& b = m->blocks[i];
     const bool last = (i == m->n_layers - 1);
     b.dilation = 1 << (i % c.n_blocks);
+    b.eps1 = eps_at(1 + 2 * i);
+    b.eps2 = eps_at(2 + 2 * i);
+    skip_eps.push_back(b.eps2);
     if (upload_cvt<T>(m, w->in_weight[i], (size_t)C_HID * C_BN, &b.w_in)) return 1;
     if (dev_upload(m, w->in_bias[i], C_HID * 4, reinterpret_cast<void**>(&b.b_in))) return 1;
     b.a1 = w->prelu1[i][0];
@@ -325,6 +351,7 @@ static int build_weights(b200sep_model* m, const b200sep_weights* w) {
   }
   if (dev_upload_f(m, skip_rs, &m->skip_rs)) return 1;
   if (dev_upload_f(m, skip_cb, &m->skip_cb)) return 1;
+  if (dev_upload_f(m, skip_eps, &m->skip_eps)) return 1;
   {  // decoder filterbank as a K-major fp16 B operand: [L][512]
     std::vector<__half> wd((size_t)L * C_ENC);
     for (int n = 0; n < C_ENC; ++n)
@@ -347,7 +374,7 @@ struct Layout {
   size_t o_tables, o_enc, o_x, o_xa, o_skip, o_skipa, o_h1, o_h2, o_g, o_stash, o_masked, o_p0, o_p1, o_p2, total;
   size_t stash_stride = 0, part2_stride = 0;  // elements per block slot
   // offsets inside the table block
-  size_t t_info, t_in_off, t_out_off, t_inv, t_len, t_frames, t_tile0, t_ntiles, t_tile_seg;
+  size_t t_info, t_in_off, t_out_off, t_inv, t_len, t_frames, t_tile0, t_ntiles, t_tile_seg, t_flags;
 };
 
 static int compute_layout(const b200sep_config& c, bool half, bool fused, const int32_t* lens, int n_seg, Layout* lo) {
@@ -373,6 +400,7 @@ static int compute_layout(const b200sep_config& c, bool half, bool fused, const 
   lo->t_tile0 = t; t += align_up((size_t)n_seg * 4, 16);
   lo->t_ntiles = t; t += align_up((size_t)n_seg * 4, 16);
   lo->t_tile_seg = t; t += align_up((size_t)tiles * 4, 16);
+  lo->t_flags = t; t += 16;  // device flag word of the call (the zero-filled staging image clears it)
   lo->tables_bytes = t;
   const size_t es = half ? 2 : 4;  // activation element size
   const size_t rows = (size_t)tiles * TILE_M;
@@ -442,11 +470,7 @@ static int launch_tc(const b200sep_model* m, const CUtensorMap& ta, const CUtens
                      const Epi& epi, const Tables& tb, cudaStream_t st, uint32_t a_lbo = 8192, uint32_t a_sbo = 1024) {
   using Cfg = tc::TcConfig<BN, K>;
   auto kern = tc::gemm_tc_kernel<BN, K, Epi>;
-  static bool configured = false;  // per template instantiation
-  if (!configured) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  { static DevOnce once; if (once.need(m->device)) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); once.done(m->device); } }
   const int n_ntiles = N / BN;
   const int total = n_mtiles * n_ntiles;
   const int grid = std::min(total, m->n_sm);
@@ -491,11 +515,7 @@ template <int BN, int D, bool A01>
 static int launch_dw_rs(const b200sep_model* m, const KaArgs& a, const Tables& tb, cudaStream_t st) {
   using Cfg = fb::KaCfg<BN>;
   auto kern = fb::dw_rs_kernel<BN, D, A01>;
-  static bool configured = false;  // per template instantiation
-  if (!configured) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  { static DevOnce once; if (once.need(m->device)) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); once.done(m->device); } }
   // 2-CTA clusters (each CTA multicasts half of every weight stage to its peer): even grid, one pair per SM pair
 #if B200SEP_KA_CL
   const int n_pairs = std::min((tb.n_tiles + 1) / 2, m->n_sm / 2);
@@ -533,11 +553,7 @@ static int launch_apply_in(const b200sep_model* m, const CUtensorMap& tmw, const
                            const EpiIn<__half, A01>& epi, const Tables& tb, cudaStream_t st) {
   using Cfg = fb::KbCfg;
   auto kern = fb::apply_in_kernel<A01>;
-  static bool configured = false;  // per template instantiation
-  if (!configured) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  { static DevOnce once; if (once.need(m->device)) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); once.done(m->device); } }
   const int grid = std::min(tb.n_tiles, m->n_sm);
   CK(launch_k(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tmw, tmh1, ap, epi, tb));
   return 0;
@@ -621,7 +637,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
   {
     // (fused path with B200SEP_X16: the fp16 copy is the residual stream the TCN blocks update)
     const bool x16 = kHalf && fused_mode && B200SEP_X16;
-    EpiBottleneck<T> e{p0, 2, m->bn_rs, m->bn_cb, x16 ? nullptr : x, x16 ? xa : xa_or_null};
+    EpiBottleneck<T> e{p0, 2, m->bn_rs, m->bn_cb, x16 ? nullptr : x, x16 ? xa : xa_or_null, m->eps_bn};
     if (run_gemm<T, 128, C_ENC>(m, enc, &tm_enc, reinterpret_cast<const T*>(m->bn_w), &m->tm_bn, nt, C_BN, e, tb, st))
       return 1;
   }
@@ -652,6 +668,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
           ap.part2 = p2 + (size_t)(i - 1) * lo.part2_stride;
           ap.rs = m->blocks[i - 1].rs;
           ap.cb = m->blocks[i - 1].cb;
+          ap.eps2 = m->blocks[i - 1].eps2;
         }
         int rc;
         if (b.a1 >= 0.f && b.a1 <= 1.f) {
@@ -668,7 +685,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
         // stash layout [tile][block][128][128]
         KaArgs ka{B200SEP_KA_CL ? &b.tm_rs_half : &b.tm_rs, &tm_hc, &tm_hh[hk], gbuf, stash + (size_t)i * (C_SKIP * TILE_M),
                   (size_t)m->n_layers * C_SKIP * TILE_M, p1,
-                  p2 + (size_t)i * lo.part2_stride, fb::DwTab{b.dw_t0, b.dw_t1, b.dw_cb, b.a2, b.dilation}};
+                  p2 + (size_t)i * lo.part2_stride, fb::DwTab{b.dw_t0, b.dw_t1, b.dw_cb, b.a2, b.dilation, b.eps1}};
         const bool a01 = b.a2 >= 0.f && b.a2 <= 1.f;
         if (!last) rc = a01 ? launch_dw_rs_d<256, true>(m, ka, tb, st) : launch_dw_rs_d<256, false>(m, ka, tb, st);
         else rc = a01 ? launch_dw_rs_d<128, true>(m, ka, tb, st) : launch_dw_rs_d<128, false>(m, ka, tb, st);
@@ -679,7 +696,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
       static const int merge_split = [] { const char* e = getenv("B200SEP_MERGE_SPLIT"); const int v = e ? atoi(e) : 2;
                                           return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 2; }();
       CK(launch_k(fb::skip_merge_kernel, dim3(nt, merge_split), dim3(256), 0, st, (const __half*)stash,
-                  (const float2*)p2, lo.part2_stride, (const float*)m->skip_rs, (const float*)m->skip_cb, skipa,
+                  (const float2*)p2, lo.part2_stride, (const float*)m->skip_rs, (const float*)m->skip_cb, (const float*)m->skip_eps, skipa,
                   m->alpha_mask, m->n_layers, tb));
       if (stop()) return sync_failed ? 1 : 0;
       fused_done = true;
@@ -701,7 +718,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
     }
     if (stop()) return sync_failed ? 1 : 0;
     {
-      DwParams p{b.g1, b.be1, b.wd, b.bd, b.a2, b.dilation};
+      DwParams p{b.g1, b.be1, b.wd, b.bd, b.a2, b.dilation, b.eps1};
       const dim3 g(DW_SLOTS, nt);
       const bool a01 = b.a2 >= 0.f && b.a2 <= 1.f;
 #define DW_LAUNCH(D_)                                                                         \
@@ -718,7 +735,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
     if (stop()) return sync_failed ? 1 : 0;
     {
       EpiResSkip<T> e{p2, DW_SLOTS, b.rs, b.cb, x, xa_or_null, skip, skipa, m->alpha_mask, last ? 0 : 1, first ? 1 : 0,
-                      last ? 1 : 0};
+                      last ? 1 : 0, b.eps2};
       int rc;
       if (!last)
         rc = run_gemm<T, 256, C_HID>(m, h2, &tm_h2, reinterpret_cast<const T*>(b.w_rs), &b.tm_rs, nt, 2 * C_BN, e, tb, st);
@@ -734,11 +751,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
     if (fused_mode && m->fused_tail) {
       using Cfg = tail::TailCfg<L>;
       auto kern = tail::mask_dec_kernel<L>;
-      static bool configured = false;  // per template instantiation
-      if (!configured) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-      }
+          { static DevOnce once; if (once.need(m->device)) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); once.done(m->device); } }
       tail::TailParams tp{m->mask_b, enc, d_out, c.n_src, c.mask_act};
       CK(launch_k(kern, dim3(std::min(nt, m->n_sm)), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tm_skipa, m->tm_mask128,
                   m->tm_wd, tp, tb));
@@ -767,11 +780,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
   {
     constexpr int kSmem = decoder_smem_bytes<L>();
     auto kern = decoder_kernel<T, L>;
-    static bool configured = false;  // per template instantiation
-    if (!configured) {
-      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-      configured = true;
-    }
+      { static DevOnce once; if (once.need(m->device)) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem)); once.done(m->device); } }
     CK(launch_k(kern, dim3(nt, c.n_src), dim3(256), kSmem, st, (const T*)masked, (const float*)m->dec_w, d_out, c.n_src, tb));
   }
   prof_mark();
@@ -871,20 +880,6 @@ int b200sep_debug_set_stop(b200sep_model* m, int stop_after) {
   return 0;
 }
 
-// 1 when a bounded device-side wait of the fused kernels ran out (a protocol bug; results are invalid).
-// Synchronises the device.  `reset` != 0 clears the flag afterwards.
-int b200sep_debug_abort_flag(int32_t* out, int32_t reset) {
-  if (!out) return fail("null argument");
-  int v = 0;
-  CK(cudaMemcpyFromSymbol(&v, b200sep::g_abort, sizeof(int)));
-  *out = v;
-  if (reset && v) {
-    const int z = 0;
-    CK(cudaMemcpyToSymbol(b200sep::g_abort, &z, sizeof(int)));
-  }
-  return 0;
-}
-
 // Registers (or, with nullptr, removes) a device buffer of 148 * 8 * 128 int64 the fused kernels stamp with
 // clock64 values per (CTA, tile visit, slot) -- see tl_stamp in fused_block.cuh.  Debug only.
 int b200sep_debug_timeline(void* d_buf) {
@@ -948,7 +943,7 @@ static int split_env() {
   }
   return v;
 }
-static constexpr int MAX_SPLIT = 4;
+static constexpr int MAX_SPLIT = B200SEP_MAX_SPLIT;
 // Deterministic LPT partition of the segments into tile-balanced groups (original order kept inside a group).
 static int plan_split(const b200sep_model* m, const int32_t* lens, int n_seg, std::vector<std::vector<int>>* groups) {
   long long tiles = 0;
@@ -1028,8 +1023,11 @@ int b200sep_split_count(const b200sep_model* m, const int32_t* lens, int32_t n_s
 
 // One forward over the segments (offsets[i], lens[i]) on stream `st`, workspace `ws`.  The caller has zero-filled the
 // output span.  Error text is left in this thread's g_err.
+static int run_sub_launch(b200sep_model* m, const Layout& lo, const Tables& tb, const float* d_mix, float* d_out, uint8_t* ws,
+                          int n_seg, cudaStream_t st);
+
 static int run_sub(b200sep_model* m, const float* d_mix, const int64_t* offsets, const int32_t* lens, int n_seg,
-                   float* d_out, uint8_t* ws, cudaStream_t st) {
+                   float* d_out, uint8_t* ws, cudaStream_t st, int32_t* h_flag) {
   Layout lo;
   if (compute_layout(m->cfg, m->half, m->half && m->use_tc && m->fused, lens, n_seg, &lo)) return 1;
   CK(cudaSetDevice(m->device));
@@ -1083,9 +1081,18 @@ static int run_sub(b200sep_model* m, const float* d_mix, const int64_t* offsets,
   tb.seg_tile0 = reinterpret_cast<const int32_t*>(t + lo.t_tile0);
   tb.seg_ntiles = reinterpret_cast<const int32_t*>(t + lo.t_ntiles);
   tb.tile_seg = reinterpret_cast<const int32_t*>(t + lo.t_tile_seg);
+  tb.flags = reinterpret_cast<int*>(t + lo.t_flags);
   tb.n_seg = n_seg;
   tb.n_tiles = lo.n_tiles;
 
+  if (run_sub_launch(m, lo, tb, d_mix, d_out, ws, n_seg, st)) return 1;
+  // the call's device flags -> the caller's (pinned) host word, readable once the stream has been synchronised
+  if (h_flag) CK(cudaMemcpyAsync(h_flag, tb.flags, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+static int run_sub_launch(b200sep_model* m, const Layout& lo, const Tables& tb, const float* d_mix, float* d_out, uint8_t* ws,
+                          int n_seg, cudaStream_t st) {
   const bool l16 = (m->cfg.kernel_size == 16);
   auto run_forward = [&]() -> int {
     if (m->half)
@@ -1106,6 +1113,7 @@ static int run_sub(b200sep_model* m, const float* d_mix, const int64_t* offsets,
       return run_forward();
     }
   }
+  std::lock_guard<std::mutex> glock(m->graph_mu);  // sub-batch worker threads share the cache
   const b200sep_model::GraphKey key{n_seg, lo.n_tiles, d_mix, d_out, ws};
   auto it = m->graphs.find(key);
   if (it != m->graphs.end()) ++m->graph_hits;
@@ -1161,10 +1169,11 @@ struct StreamHop {
 };
 
 static int separate_batch_locked(b200sep_model* m, const float* d_mix, const int64_t* offsets, const int32_t* lens,
-                                 int32_t n_seg, float* d_out, void* d_ws, size_t ws_bytes, cudaStream_t st);
+                                 int32_t n_seg, float* d_out, void* d_ws, size_t ws_bytes, cudaStream_t st,
+                                 int32_t* h_flags);
 
 int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* offsets, const int32_t* lens,
-                           int32_t n_seg, float* d_out, void* d_ws, size_t ws_bytes, void* stream) {
+                           int32_t n_seg, float* d_out, void* d_ws, size_t ws_bytes, void* stream, int32_t* h_flags) {
   if (!m || !d_mix || !lens || !d_out || !d_ws) return fail("null argument");
   if ((reinterpret_cast<uintptr_t>(d_ws) & 255u) != 0) return fail("d_ws must be 256-byte aligned");
   if (n_seg <= 0) return fail("empty batch");
@@ -1172,7 +1181,8 @@ int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* 
   CK(cudaSetDevice(m->device));
   StreamHop hop{m, reinterpret_cast<cudaStream_t>(stream), nullptr};
   if (hop.enter()) return 1;
-  const int rc = separate_batch_locked(m, d_mix, offsets, lens, n_seg, d_out, d_ws, ws_bytes, hop.st);
+  if (h_flags) for (int g = 0; g < B200SEP_MAX_SPLIT; ++g) h_flags[g] = 0;
+  const int rc = separate_batch_locked(m, d_mix, offsets, lens, n_seg, d_out, d_ws, ws_bytes, hop.st, h_flags);
   const std::string keep = g_err;
   if (hop.leave()) return 1;
   if (rc) return fail("%s", keep.c_str());
@@ -1180,7 +1190,8 @@ int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* 
 }
 
 static int separate_batch_locked(b200sep_model* m, const float* d_mix, const int64_t* offsets, const int32_t* lens,
-                                 int32_t n_seg, float* d_out, void* d_ws, size_t ws_bytes, cudaStream_t st) {
+                                 int32_t n_seg, float* d_out, void* d_ws, size_t ws_bytes, cudaStream_t st,
+                                 int32_t* h_flags) {
   std::vector<std::vector<int>> groups;
   if (plan_split(m, lens, n_seg, &groups)) return 1;
   const int S = (int)groups.size();
@@ -1212,7 +1223,7 @@ static int separate_batch_locked(b200sep_model* m, const float* d_mix, const int
   uint8_t* ws = static_cast<uint8_t*>(d_ws);
   // zero-fill the output span (overlap-add boundary hops accumulate atomically; pad_x_to_y tail)
   CK(cudaMemsetAsync(d_out + out_lo, 0, (size_t)(out_hi - out_lo) * sizeof(float), st));
-  if (S == 1) return run_sub(m, d_mix, g_off[0].data(), g_len[0].data(), n_seg, d_out, ws, st);
+  if (S == 1) return run_sub(m, d_mix, g_off[0].data(), g_len[0].data(), n_seg, d_out, ws, st, h_flags);
 
   // fork: sub-batch 0 on the caller's stream, the others on the model's auxiliary streams, launches issued by one
   // host thread per sub-batch so that the streams fill at the same pace
@@ -1228,11 +1239,12 @@ static int separate_batch_locked(b200sep_model* m, const float* d_mix, const int
   for (int g = 1; g < S; ++g) {
     CK(cudaStreamWaitEvent(m->aux_st[g], m->ev_fork, 0));
     workers.emplace_back([&, g]() {
-      rc[g] = run_sub(m, d_mix, g_off[g].data(), g_len[g].data(), (int)g_len[g].size(), d_out, ws + g_ws[g], m->aux_st[g]);
+      rc[g] = run_sub(m, d_mix, g_off[g].data(), g_len[g].data(), (int)g_len[g].size(), d_out, ws + g_ws[g], m->aux_st[g],
+                      h_flags ? h_flags + g : nullptr);
       if (rc[g]) err[g] = g_err;
     });
   }
-  rc[0] = run_sub(m, d_mix, g_off[0].data(), g_len[0].data(), (int)g_len[0].size(), d_out, ws + g_ws[0], st);
+  rc[0] = run_sub(m, d_mix, g_off[0].data(), g_len[0].data(), (int)g_len[0].size(), d_out, ws + g_ws[0], st, h_flags);
   if (rc[0]) err[0] = g_err;
   for (auto& w : workers) w.join();
   // join (also on failure: the caller's stream must not run ahead of work already queued on the auxiliary streams)
@@ -1263,10 +1275,10 @@ size_t b200sep_host_workspace_bytes(const b200sep_model* m, const int32_t* lens,
 }
 
 static int separate_batch_host_locked(b200sep_model* m, const float* const* h_segs, const int32_t* lens, int32_t n_seg,
-                                      float* h_out, void* d_ws, size_t ws_bytes, cudaStream_t st);
+                                      float* h_out, void* d_ws, size_t ws_bytes, cudaStream_t st, int32_t* h_flags);
 
 int b200sep_separate_batch_host(b200sep_model* m, const float* const* h_segs, const int32_t* lens, int32_t n_seg,
-                                float* h_out, void* d_ws, size_t ws_bytes, void* stream) {
+                                float* h_out, void* d_ws, size_t ws_bytes, void* stream, int32_t* h_flags) {
   if (!m || !h_segs || !lens || !h_out || !d_ws) return fail("null argument");
   if ((reinterpret_cast<uintptr_t>(d_ws) & 255u) != 0) return fail("d_ws must be 256-byte aligned");
   if (n_seg <= 0) return fail("empty batch");
@@ -1274,7 +1286,8 @@ int b200sep_separate_batch_host(b200sep_model* m, const float* const* h_segs, co
   CK(cudaSetDevice(m->device));
   StreamHop hop{m, reinterpret_cast<cudaStream_t>(stream), nullptr};
   if (hop.enter()) return 1;
-  const int rc = separate_batch_host_locked(m, h_segs, lens, n_seg, h_out, d_ws, ws_bytes, hop.st);
+  if (h_flags) for (int g = 0; g < B200SEP_MAX_SPLIT; ++g) h_flags[g] = 0;
+  const int rc = separate_batch_host_locked(m, h_segs, lens, n_seg, h_out, d_ws, ws_bytes, hop.st, h_flags);
   const std::string keep = g_err;
   if (hop.leave()) return 1;
   if (rc) return fail("%s", keep.c_str());
@@ -1282,7 +1295,7 @@ int b200sep_separate_batch_host(b200sep_model* m, const float* const* h_segs, co
 }
 
 static int separate_batch_host_locked(b200sep_model* m, const float* const* h_segs, const int32_t* lens, int32_t n_seg,
-                                      float* h_out, void* d_ws, size_t ws_bytes, cudaStream_t st) {
+                                      float* h_out, void* d_ws, size_t ws_bytes, cudaStream_t st, int32_t* h_flags) {
   std::vector<std::vector<int>> groups;
   if (plan_split(m, lens, n_seg, &groups)) return 1;
   const int S = (int)groups.size(), NS = m->cfg.n_src;
@@ -1347,7 +1360,9 @@ static int separate_batch_host_locked(b200sep_model* m, const float* const* h_se
     for (int i : groups[g]) memcpy(m->hin + d_off[i], h_segs[i], (size_t)lens[i] * sizeof(float));
     CK(cudaMemcpyAsync(d_mix + g_begin[g], m->hin + g_begin[g], (size_t)(g_end[g] - g_begin[g]) * sizeof(float),
                        cudaMemcpyHostToDevice, gs));
-    if (run_sub(m, d_mix, g_off[g].data(), g_len[g].data(), (int)g_len[g].size(), d_out, ws + g_ws[g], gs)) return 1;
+    if (run_sub(m, d_mix, g_off[g].data(), g_len[g].data(), (int)g_len[g].size(), d_out, ws + g_ws[g], gs,
+                h_flags ? h_flags + g : nullptr))
+      return 1;
     // D2H: maximal runs of segments that are adjacent on both sides
     const std::vector<int>& idx = groups[g];
     size_t k = 0;
@@ -1424,7 +1439,7 @@ int b200sep_pit_sisdr_batch(const float* d_refs, const float* d_ests, const floa
 
   const size_t off_bytes = align_up((size_t)n_seg * 8, 256), len_bytes = align_up((size_t)n_seg * 4, 256);
   StagingSlot* slot = nullptr;
-  if (g_pit_staging.acquire(off_bytes + len_bytes, &slot)) return 1;
+  if (g_pit_staging[current_device_index()].acquire(off_bytes + len_bytes, &slot)) return 1;
   uint8_t* h = static_cast<uint8_t*>(slot->host);
   int64_t* h_off = reinterpret_cast<int64_t*>(h);
   int32_t* h_len = reinterpret_cast<int32_t*>(h + off_bytes);
@@ -1461,12 +1476,13 @@ struct AuxSlot {
   size_t cap = 0;
   cudaEvent_t ev = nullptr;
 };
-static AuxSlot g_aux[8];
-static int g_aux_next = 0;
+static AuxSlot g_aux[kMaxDev][8];  // per device: the device mirror and the event live on one device
+static int g_aux_next[kMaxDev] = {0};
 static std::mutex g_aux_mu;
 static int aux_acquire(size_t bytes, AuxSlot** out) {
-  AuxSlot& s = g_aux[g_aux_next];
-  g_aux_next = (g_aux_next + 1) % 8;
+  const int dev = current_device_index();
+  AuxSlot& s = g_aux[dev][g_aux_next[dev]];
+  g_aux_next[dev] = (g_aux_next[dev] + 1) % 8;
   if (!s.ev) CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
   else CK(cudaEventSynchronize(s.ev));
   if (s.cap < bytes) {
@@ -1515,9 +1531,9 @@ struct SincBank {
   float* dev = nullptr;
   int orig = 0, neu = 0, width = 0, kw = 0;
 };
-static std::map<std::pair<int, int>, SincBank> g_sinc;
+static std::map<std::tuple<int, int, int>, SincBank> g_sinc;  // (device, sr_in, sr_out) -> filter bank on that device
 static int sinc_bank(int sr_in, int sr_out, SincBank* out) {
-  const auto key = std::make_pair(sr_in, sr_out);
+  const auto key = std::make_tuple(current_device_index(), sr_in, sr_out);
   auto it = g_sinc.find(key);
   if (it != g_sinc.end()) { *out = it->second; return 0; }
   const int g = gcd_i(sr_in, sr_out);
@@ -1668,6 +1684,7 @@ int b200sep_debug_gemm(const float* d_a, const float* d_b, float* d_c, int32_t M
   CK(cudaGetDeviceProperties(&prop, dev));
   if (prop.major != 10) return fail("sm_100 device required");
   b200sep_model fake;
+  fake.device = dev;
   fake.n_sm = prop.multiProcessorCount;
   const int nt = M / 128;
   __half *a16 = nullptr, *b16 = nullptr;

@@ -112,6 +112,7 @@ struct DwParams {
   const float* bias;    // [512]
   float alpha2;         // PReLU slope after the depthwise conv
   int dilation;
+  float eps1;           // eps of gLN1
 };
 
 #ifndef B200SEP_DW_CH
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(256, B200SEP_DW_MINB) dwconv_kernel(const T* _
 
   // every warp reduces the (tiny) partial list itself: identical results, no extra barrier
   float mean, rstd;
-  warp_seg_stats(part1, tile0, ntiles, slots1, ti.inv_count, mean, rstd);
+  warp_seg_stats(part1, tile0, ntiles, slots1, ti.inv_count, p.eps1, mean, rstd);
   for (int i = tid; i < DW_CH; i += 256) {
     const int c = cg * DW_CH + i;
     const float a = p.gamma1[c] * rstd;

@@ -22,7 +22,7 @@ constexpr int C_ENC = 512;   // n_filters (N)
 constexpr int C_BN = 128;    // bn_chan (B)
 constexpr int C_HID = 512;   // hid_chan (H)
 constexpr int C_SKIP = 128;  // skip_chan (Sc)
-constexpr float GLN_EPS = 1e-8f;
+constexpr float GLN_EPS = 1e-8f;  // asteroid GlobLN default; the per-gLN value actually used comes from the model (b200sep_weights.gln_eps)
 static_assert(C_ENC == C_HID, "one inverse element count per segment serves every gLN (all normalise 512 channels)");
 
 // Everything a kernel needs to know about an m-tile, in one 32-byte record (one load, no dependent
@@ -59,6 +59,7 @@ struct Tables {
   const int32_t* seg_ntiles;   // [n_seg] ceil(F_i / 128)
   const int32_t* tile_seg;     // [n_tiles] m-tile -> segment
   const double* seg_inv_count; // [n_seg] 1 / (512 * F_i): every gLN here normalises 512 channels
+  int* flags;                  // device flag word of THIS call (zeroed with the tables): bit 0 wait timeout, bit 1 non-finite output
   int32_t n_seg;
   int32_t n_tiles;
 };
@@ -118,8 +119,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 // inv_count = 1 / (C * F_i) (host-computed).  var = E[x^2] - mean^2 in fp64 (biased, like asteroid
 // GlobLN); the final reciprocal square root is taken in fp32 (rsqrtf + one Newton step).
 __device__ __forceinline__ void warp_seg_stats(const float2* __restrict__ part, int tile0,
-                                               int ntiles, int slots, double inv_count, float& mean,
-                                               float& rstd) {
+                                               int ntiles, int slots, double inv_count, float eps,
+                                               float& mean, float& rstd) {
   const int lane = threadIdx.x & 31;
   const int n = ntiles * slots;
   const float2* p = part + (size_t)tile0 * slots;
@@ -135,7 +136,7 @@ __device__ __forceinline__ void warp_seg_stats(const float2* __restrict__ part, 
   double var = fma(-m, m, q * inv_count);
   if (var < 0.0) var = 0.0;
   mean = (float)m;
-  const float ve = (float)var + GLN_EPS;
+  const float ve = (float)var + eps;
   float y = rsqrtf(ve);
   y = y * (1.5f - 0.5f * ve * y * y);  // Newton step: ~0.5 ulp
   rstd = y;

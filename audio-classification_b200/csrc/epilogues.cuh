@@ -59,12 +59,13 @@ struct EpiBottleneck {
   const float* rs; const float* cb;  // [128]
   float* x;                          // [nt][128][128] fp32
   T* xa;                             // [nt][128][128] operand copy, or nullptr when T == float
+  float eps;                         // eps of the bottleneck gLN
   static constexpr bool kStats = false;
 
   __device__ __forceinline__ void tile_begin(EpiState& st, int m_tile, const Tables& tb) const {
     int seg, tile0, ntiles;
     epi_tile_ctx(st, m_tile, tb, seg, tile0, ntiles);
-    warp_seg_stats(part_in, tile0, ntiles, slots_in, st.inv_count, st.mean, st.rstd);
+    warp_seg_stats(part_in, tile0, ntiles, slots_in, st.inv_count, eps, st.mean, st.rstd);
   }
   template <int W>
   __device__ __forceinline__ void prefetch(int, int, int, float (&)[W]) const {}
@@ -167,12 +168,13 @@ struct EpiResSkip {
   T* skipa;     // PReLU(skip) in operand precision, written by the last block only
   float alpha_mask;
   int has_res, first, last;
+  float eps;    // eps of this block's gLN2
   static constexpr bool kStats = false;
 
   __device__ __forceinline__ void tile_begin(EpiState& st, int m_tile, const Tables& tb) const {
     int seg, tile0, ntiles;
     epi_tile_ctx(st, m_tile, tb, seg, tile0, ntiles);
-    warp_seg_stats(part_in, tile0, ntiles, slots_in, st.inv_count, st.mean, st.rstd);
+    warp_seg_stats(part_in, tile0, ntiles, slots_in, st.inv_count, eps, st.mean, st.rstd);
   }
   // old x / skip values: independent loads, consecutive lanes (frames) hit consecutive addresses
   template <int W>

@@ -19,7 +19,7 @@
 // HBM bytes per frame and block: K_A 1024 (h1) + 512 (G); K_B 256 (G_res) + 1024 (x r/w) + 1024 (h1);
 // + 256 per block read once by the skip merge = 4.1 KB vs 6.6 KB for the three unfused kernels.
 //
-// Every mbarrier wait is bounded (g_abort): a protocol bug degrades into wrong numbers plus an error
+// Every mbarrier wait is bounded (Tables::flags): a protocol bug degrades into wrong numbers plus an error
 // flag the host reads, never into a hung GPU.
 #pragma once
 #include "bandwidth_kernels.cuh"
@@ -29,7 +29,10 @@
 
 namespace b200sep {
 
-__device__ int g_abort = 0;  // bit 0: a bounded wait ran out; bit 1: non-finite output samples (read by b200sep_debug_abort_flag)
+// Device flags of ONE forward call live in the call's table block (Tables::flags, zeroed by the table upload):
+// bit 0: a bounded wait ran out; bit 1: non-finite output samples.  The host gets them through the `h_flags` argument
+// of b200sep_separate_batch[_host].
+constexpr int FLAG_WAIT_TIMEOUT = 1, FLAG_NONFINITE = 2;
 
 // Optional in-kernel timeline (b200sep_debug_timeline): clock64 stamps per (CTA, tile visit, slot).
 constexpr int TL_TILES = 8, TL_SLOTS = 128;
@@ -75,13 +78,13 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: ~seconds in the worst case, then flags the abort and lets the caller run on (all
 // addresses stay in bounds; the host reports the failure).
-__device__ __forceinline__ void mbar_wait_b(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_b(int* flags, uint32_t bar, uint32_t parity) {
 #pragma unroll 1
   for (uint32_t i = 0; i < (1u << 18); ++i) {
     if (mbar_try(bar, parity)) return;
-    if ((i & 31u) == 31u && (*reinterpret_cast<volatile int*>(&g_abort) & 1) != 0) return;
+    if ((i & 31u) == 31u && (*reinterpret_cast<volatile int*>(flags) & FLAG_WAIT_TIMEOUT) != 0) return;
   }
-  atomicOr(&g_abort, 1);
+  atomicOr(flags, FLAG_WAIT_TIMEOUT);
 }
 // L2 prefetch of a contiguous global range (bytes % 16 == 0) / of a TMA box
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
@@ -182,13 +185,13 @@ __device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity) 
   return ok != 0;
 }
 // bounded wait whose arrivals may come from the peer CTA
-__device__ __forceinline__ void mbar_wait_cluster_b(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_cluster_b(int* flags, uint32_t bar, uint32_t parity) {
 #pragma unroll 1
   for (uint32_t i = 0; i < (1u << 18); ++i) {
     if (mbar_try_cluster(bar, parity)) return;
-    if ((i & 31u) == 31u && (*reinterpret_cast<volatile int*>(&g_abort) & 1) != 0) return;
+    if ((i & 31u) == 31u && (*reinterpret_cast<volatile int*>(flags) & FLAG_WAIT_TIMEOUT) != 0) return;
   }
-  atomicOr(&g_abort, 1);
+  atomicOr(flags, FLAG_WAIT_TIMEOUT);
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -294,7 +297,7 @@ __device__ __forceinline__ TileInfo ti_get(const TileInfo* s_ti, const Tables& t
 // Segment gLN statistics from single-slot per-tile partials; `pre` is this lane's (pre-fetched) first
 // element part[tile0 + lane] (zeros when lane >= ntiles).  Same arithmetic as warp_seg_stats.
 __device__ __forceinline__ void seg_stats_pre(const float2* __restrict__ part, const TileInfo& ti, float2 pre,
-                                              float& mean, float& rstd) {
+                                              float eps, float& mean, float& rstd) {
   const int lane = threadIdx.x & 31;
   double s = (double)pre.x, q = (double)pre.y;
   for (int i = lane + 32; i < ti.ntiles; i += 32) {
@@ -308,7 +311,7 @@ __device__ __forceinline__ void seg_stats_pre(const float2* __restrict__ part, c
   double var = fma(-m, m, q * ti.inv_count);
   if (var < 0.0) var = 0.0;
   mean = (float)m;
-  const float ve = (float)var + GLN_EPS;
+  const float ve = (float)var + eps;
   float y = rsqrtf(ve);
   y = y * (1.5f - 0.5f * ve * y * y);
   rstd = y;
@@ -334,6 +337,7 @@ struct DwTab {
   const float* cb;   // [512]
   float alpha2;      // PReLU slope after the depthwise conv
   int dilation;
+  float eps1;        // eps of gLN1 (shared_block.2)
 };
 
 template <int BN>
@@ -600,7 +604,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       const int w = tile_at(it, valid);
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait_b(tfull_bar(as), aphase);
+      mbar_wait_b(tb.flags, tfull_bar(as), aphase);
       tcgen05_fence_after();
       if (threadIdx.x == 0) tl_stamp(it, 80);
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
@@ -651,7 +655,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
 #ifndef B200SEP_EXP_KA_NO_L2PF
           if (nvalid) l2_prefetch_tma_2d(&tm_hc, 0, wn * C_HID + kb * 64);
 #endif
-          mbar_wait_b(raw_empty(stage), phase ^ 1u);
+          mbar_wait_b(tb.flags, raw_empty(stage), phase ^ 1u);
           tl_stamp(it, 88 + kb);
 #ifdef B200SEP_EXP_KA_NO_RAW_TMA  // timing experiment: no activation traffic into shared memory
           mbar_arrive(raw_full(stage));
@@ -677,7 +681,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       uint32_t phase = 0;
       for (int it = 0; it < n_visits; ++it) {
         for (int kb = 0; kb < 8; ++kb) {
-          mbar_wait_b(b_empty(stage), phase ^ 1u);  // BOTH CTAs' MMAs are done with this stage
+          mbar_wait_b(tb.flags, b_empty(stage), phase ^ 1u);  // BOTH CTAs' MMAs are done with this stage
 #ifndef B200SEP_EXP_KA_NO_B_TMA
           // the whole stage lands here (own half + the peer's half); this CTA loads rows [crank * BN/2, +BN/2) of the
           // k-block and multicasts them to the same offset of both CTAs
@@ -718,7 +722,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       for (int it = 0; it < n_visits; ++it) {
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait_cluster_b(tempty_bar(as), aphase ^ 1u);  // both CTAs' epilogues have drained this accumulator
+        mbar_wait_cluster_b(tb.flags, tempty_bar(as), aphase ^ 1u);  // both CTAs' epilogues have drained this accumulator
         tcgen05_fence_after();
         tl_stamp(it, 64);
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
@@ -726,8 +730,8 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
           const int nseq = it * 4 + (kb >> 1);               // k-blocks this group has produced before this one
           const int g = (kb & 1) * Cfg::A_PG + (nseq & (Cfg::A_PG - 1));
           const uint32_t gphase = (uint32_t)(nseq / Cfg::A_PG) & 1u;
-          mbar_wait_cluster_b(a_full(g), gphase);          // both CTAs' producer groups have written their A stage
-          mbar_wait_b(b_full(bs), bphase);                 // both halves of the weight k-block have landed
+          mbar_wait_cluster_b(tb.flags, a_full(g), gphase);          // both CTAs' producer groups have written their A stage
+          mbar_wait_b(tb.flags, b_full(bs), bphase);                 // both halves of the weight k-block have landed
           tcgen05_fence_after();
           tl_stamp(it, 65 + kb);
           const uint32_t sa = stage_a(g), sb = stage_b(bs);
@@ -744,7 +748,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         }
       }
       umma_commit_pair(done_bar, (uint16_t)0x1);  // every asynchronous arrive has landed before the pair tears down
-      mbar_wait_b(done_bar, 0);
+      mbar_wait_b(tb.flags, done_bar, 0);
     }
     __syncwarp();
 #else
@@ -759,7 +763,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       for (int it = 0; it < n_visits; ++it) {
         const int as = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait_b(tempty_bar(as), aphase ^ 1u);
+        mbar_wait_b(tb.flags, tempty_bar(as), aphase ^ 1u);
         tcgen05_fence_after();
         tl_stamp(it, 64);
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
@@ -767,8 +771,8 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
           const int nseq = it * 4 + (kb >> 1);  // k-blocks this group has produced before this one
           const int g = (kb & 1) * Cfg::A_PG + (nseq & (Cfg::A_PG - 1));
           const uint32_t gphase = (uint32_t)(nseq / Cfg::A_PG) & 1u;
-          mbar_wait_b(a_full(g), gphase);
-          mbar_wait_b(b_full(bs), bphase);
+          mbar_wait_b(tb.flags, a_full(g), gphase);
+          mbar_wait_b(tb.flags, b_full(bs), bphase);
           tcgen05_fence_after();
           tl_stamp(it, 65 + kb);
           const uint32_t sa = stage_a(g), sb = stage_b(bs);
@@ -790,7 +794,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       }
       // the last ab_empty arrivals have no waiter: make sure every asynchronous arrive has landed before exit
       umma_commit(done_bar);
-      mbar_wait_b(done_bar, 0);
+      mbar_wait_b(tb.flags, done_bar, 0);
     }
     __syncwarp();
 #endif
@@ -828,7 +832,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
     if (n_visits > 0) {
       bool v_;
       const TileInfo t0i = ti_get(s_ti, tb, 0, tile_at(0, v_));
-      seg_stats_pre(part1, t0i, part_prefetch(part1, t0i), nmean, nrstd);
+      seg_stats_pre(part1, t0i, part_prefetch(part1, t0i), p.eps1, nmean, nrstd);
     }
     for (int it = 0; it < n_visits; ++it) {
       bool valid;
@@ -874,7 +878,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         const uint32_t my_ab_empty = a_empty(a_idx);
         const int rs_ = grp + 2 * (nseq & (rpg - 1));             // raw stage of this k-block (= kb % raw_stages)
         const uint32_t rphase = (uint32_t)(nseq / rpg) & 1u;
-        mbar_wait_b(raw_full(rs_), rphase);
+        mbar_wait_b(tb.flags, raw_full(rs_), rphase);
         if (tl_on) tl_stamp(it, tl_base + 3 * (kb >> 1));
         const uint32_t raw = raw_st(rs_);
         const int ch0 = kb * 64 + row0;
@@ -922,7 +926,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
             const uint4 o1 = dw_step_h2<D, A01>(vc1, va1, vb1, tb_, cbb, rstd, rm, alpha_h2, s2, q2);
 #endif
             if (jj == 0) {
-              mbar_wait_b(my_ab_empty, aphase ^ 1u);
+              mbar_wait_b(tb.flags, my_ab_empty, aphase ^ 1u);
               if (tl_on) tl_stamp(it, tl_base + 3 * (kb >> 1) + 1);
             }
             st_shared_v4(sa + jj * 2048u, o0);
@@ -955,7 +959,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
               s2 = add2(s2, u);
               q2 = fma2(u, u, q2);
             }
-            if (j == 0) mbar_wait_b(my_ab_empty, aphase ^ 1u);
+            if (j == 0) mbar_wait_b(tb.flags, my_ab_empty, aphase ^ 1u);
             st_shared_v4(sa + j * 2048u, pack8(o));
           }
         }
@@ -970,7 +974,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         if (tl_on) tl_stamp(it, tl_base + 3 * (kb >> 1) + 2);
         ++nseq;
         // statistics of the next tile's segment, off the tile-boundary critical path
-        if (kb == 4 + grp && has_next) seg_stats_pre(part1, tn, pre, nmean, nrstd);
+        if (kb == 4 + grp && has_next) seg_stats_pre(part1, tn, pre, p.eps1, nmean, nrstd);
       }
       // gLN2 partial of this m-tile: fixed-order block reduction -> one slot per tile
       const float s_acc = warp_sum(s2.x + s2.y);
@@ -1046,6 +1050,7 @@ struct ApplyParams {
   const float* cb;      // [>=128] W_res * beta2 + b_res
   float* x;             // [nt][128][128] fp32 residual stream (updated in place)            (B200SEP_X16 == 0)
   __half* x16;          // [nt][128][128] fp16 residual stream (updated in place)            (B200SEP_X16 == 1)
+  float eps2;           // eps of the previous block's gLN2 (shared_block.5)
 };
 
 template <bool A01>
@@ -1140,7 +1145,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         float v[32];
-        mbar_wait_b(tfull_bar(q), ph);
+        mbar_wait_b(tb.flags, tfull_bar(q), ph);
         tcgen05_fence_after();
         if (threadIdx.x == 0) tl_stamp(it, 16 + q);
         tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(q * 128 + part * 32), v);
@@ -1208,7 +1213,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
       float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
       const uint32_t ph = (uint32_t)it & 1u;
       float v[2][32];
-      mbar_wait_b(tfull_bar(0), ph);
+      mbar_wait_b(tb.flags, tfull_bar(0), ph);
       tcgen05_fence_after();
       if (threadIdx.x == 0) tl_stamp(it, 16);
       tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64), v[0]);
@@ -1225,7 +1230,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
         if (pi + 1 < 8) {
           const int qn = (pi + 1) >> 1;
           if (((pi + 1) & 1) == 0) {
-            mbar_wait_b(tfull_bar(qn), ph);
+            mbar_wait_b(tb.flags, tfull_bar(qn), ph);
             tcgen05_fence_after();
             if (threadIdx.x == 0) tl_stamp(it, 16 + qn);
             bnext = __ldg(epi.bias + qn * 128 + cl);
@@ -1319,7 +1324,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
       // 8 pieces of 32 columns per m-tile (4 chunks x 2); the tcgen05.ld of piece i+1 is in flight while piece i
       // is processed (TMEM drains at ~64 B/cycle/SM: loads and arithmetic must overlap inside a warp)
       float v[2][32];
-      mbar_wait_b(tfull_bar(0), ph);
+      mbar_wait_b(tb.flags, tfull_bar(0), ph);
       tcgen05_fence_after();
       if (threadIdx.x == 0) tl_stamp(it, 16);
       tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64), v[0]);
@@ -1334,7 +1339,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
         if (pi + 1 < 8) {
           const int qn = (pi + 1) >> 1;
           if (((pi + 1) & 1) == 0) {
-            mbar_wait_b(tfull_bar(qn), ph);
+            mbar_wait_b(tb.flags, tfull_bar(qn), ph);
             tcgen05_fence_after();
             if (threadIdx.x == 0) tl_stamp(it, 16 + qn);
           }
@@ -1412,16 +1417,16 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
 #else
       constexpr uint32_t idesc = make_idesc(128);
 #endif
-      mbar_wait_b(w_bar, 0);
+      mbar_wait_b(tb.flags, w_bar, 0);
       int it = 0;
       for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
         const int b = it & 1;
-        mbar_wait_b(xn_full(b), (uint32_t)(it >> 1) & 1u);
+        mbar_wait_b(tb.flags, xn_full(b), (uint32_t)(it >> 1) & 1u);
         tcgen05_fence_after();
         tl_stamp(it, 8);
         const uint32_t sa = smem_xn(b);
         for (int q = 0; q < 4; ++q) {
-          mbar_wait_b(tempty_bar(q), ((uint32_t)it & 1u) ^ 1u);
+          mbar_wait_b(tb.flags, tempty_bar(q), ((uint32_t)it & 1u) ^ 1u);
           tcgen05_fence_after();
           tl_stamp(it, 9 + q);
           const uint32_t tmem_d = tmem_base + (uint32_t)(q * 128);
@@ -1443,7 +1448,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
         umma_commit(xn_empty(b));
       }
       umma_commit(done_bar);  // the last xn_empty arrivals have no waiter
-      mbar_wait_b(done_bar, 0);
+      mbar_wait_b(tb.flags, done_bar, 0);
     }
     __syncwarp();
   } else {
@@ -1461,7 +1466,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
       const TileInfo ti = ti_get(s_ti, tb, it, w);
       float mean = 0.f, rstd = 0.f;
       if (has_g) {
-        seg_stats_pre(ap.part2, ti, pre, mean, rstd);
+        seg_stats_pre(ap.part2, ti, pre, ap.eps2, mean, rstd);
         if (w + (int)gridDim.x < n_tiles) pre = part_prefetch(ap.part2, ti_get(s_ti, tb, it + 1, w + gridDim.x));
       }
       float2 vm[4];
@@ -1521,7 +1526,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
 #endif
         }
         if (p0 == 0) {
-          mbar_wait_b(xn_empty(b), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+          mbar_wait_b(tb.flags, xn_empty(b), ((uint32_t)(it >> 1) & 1u) ^ 1u);
           xn = smem_xn(b);
           if (pt == 0) tl_stamp(it, 1);
         }
@@ -1595,7 +1600,7 @@ constexpr int MAX_LAYERS = 64;
 __global__ void __launch_bounds__(256) skip_merge_kernel(const __half* __restrict__ stash,
                                                          const float2* __restrict__ part2, size_t part_stride,
                                                          const float* __restrict__ rs, const float* __restrict__ cb,
-                                                         __half* __restrict__ skipa, float alpha_mask, int n_layers,
+                                                         const float* __restrict__ eps2, __half* __restrict__ skipa, float alpha_mask, int n_layers,
                                                          Tables tb) {
   __shared__ float2 s_stat[MAX_LAYERS];    // (rstd, -mean*rstd) per block
   __shared__ uint16_t s_rstd_h[MAX_LAYERS];  // rstd rounded to fp16: multiplier of the mixed-precision FMA
@@ -1605,7 +1610,7 @@ __global__ void __launch_bounds__(256) skip_merge_kernel(const __half* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int b = warp; b < n_layers; b += 8) {
     float mean, rstd;
-    warp_seg_stats(part2 + (size_t)b * part_stride, ti.tile0, ti.ntiles, 1, ti.inv_count, mean, rstd);
+    warp_seg_stats(part2 + (size_t)b * part_stride, ti.tile0, ti.ntiles, 1, ti.inv_count, __ldg(eps2 + b), mean, rstd);
     if (lane == 0) {
       // the constant term uses the SAME rounded rstd, so sum_b rstd_b * (G_b - mean_b * rs_b) stays consistent
       const __half rh = __float2half_rn(rstd);

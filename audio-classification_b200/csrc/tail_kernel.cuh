@@ -147,14 +147,14 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       uint32_t bphase = 0;
       int it = 0;
       for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
-        mbar_wait_b(a_empty, ((uint32_t)it & 1u) ^ 1u);
+        mbar_wait_b(tb.flags, a_empty, ((uint32_t)it & 1u) ^ 1u);
         mbar_expect_tx(a_full, Cfg::A_BYTES);
         for (int kb = 0; kb < 2; ++kb) {
           tma_load_2d(smem_a + (uint32_t)(kb * 16384), &tm_a, a_full, 0, w * C_SKIP + kb * 64);
           tma_load_2d(smem_a + (uint32_t)(kb * 16384 + 8192), &tm_a, a_full, 64, w * C_SKIP + kb * 64);
         }
         for (int c = 0; c < n_chunks; ++c) {
-          mbar_wait_b(b_empty(bs), bphase ^ 1u);
+          mbar_wait_b(tb.flags, b_empty(bs), bphase ^ 1u);
           mbar_expect_tx(b_full(bs), Cfg::B_STAGE);
           tma_load_2d(smem_b(bs), &tm_b, b_full(bs), 0, c * 128);
           tma_load_2d(smem_b(bs) + 16384u, &tm_b, b_full(bs), 64, c * 128);
@@ -168,15 +168,15 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     if (lane == 0) {
       constexpr uint32_t idesc_mask = make_idesc(128);     // A MN-major (tile-transposed skip operand)
       constexpr uint32_t idesc_dec = make_idesc_kk(L);     // A K-major (masked chunk written by the epilogue)
-      mbar_wait_b(wd_bar, 0);
+      mbar_wait_b(tb.flags, wd_bar, 0);
       int bs = 0;
       uint32_t bphase = 0;
       int n_acc = 0, n_st = 0, n_dec = 0;  // running counters -> stage / phase
       auto issue_mask = [&](int c) {
         (void)c;
         const int as = n_acc & 1;
-        mbar_wait_b(acc_empty(as), (((uint32_t)n_acc >> 1) & 1u) ^ 1u);
-        mbar_wait_b(b_full(bs), bphase);
+        mbar_wait_b(tb.flags, acc_empty(as), (((uint32_t)n_acc >> 1) & 1u) ^ 1u);
+        mbar_wait_b(tb.flags, b_full(bs), bphase);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * 128);
 #pragma unroll
@@ -195,15 +195,15 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       };
       int it = 0;
       for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
-        mbar_wait_b(a_full, (uint32_t)it & 1u);
+        mbar_wait_b(tb.flags, a_full, (uint32_t)it & 1u);
         issue_mask(0);
         for (int c = 0; c < n_chunks; ++c) {
           if (c + 1 < n_chunks) issue_mask(c + 1);  // keeps the tensor core busy while chunk c is in its epilogue
           else umma_commit(a_empty);                // all mask MMAs of this m-tile issued: operand reusable when done
           const int src = c >> 2, cc = c & 3;
           const int ss = n_st & 1;
-          if (cc == 0) mbar_wait_b(dec_empty, ((uint32_t)n_dec & 1u) ^ 1u);  // overlap-add drained the accumulator
-          mbar_wait_b(st_full(ss), ((uint32_t)n_st >> 1) & 1u);
+          if (cc == 0) mbar_wait_b(tb.flags, dec_empty, ((uint32_t)n_dec & 1u) ^ 1u);  // overlap-add drained the accumulator
+          mbar_wait_b(tb.flags, st_full(ss), ((uint32_t)n_st >> 1) & 1u);
           tcgen05_fence_after();
           const uint32_t tmem_dec = tmem_base + (uint32_t)(Cfg::DEC_COL0 + (src & 1) * L);
 #pragma unroll
@@ -221,7 +221,7 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
       }
       umma_commit(done_bar);  // the last b_empty / st_empty / a_empty arrivals have no waiter
-      mbar_wait_b(done_bar, 0);
+      mbar_wait_b(tb.flags, done_bar, 0);
     }
     __syncwarp();
 #if B200SEP_TAIL_EPI16
@@ -249,7 +249,7 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         __half eh[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) eh[j] = ep[(size_t)j * TILE_M];
-        mbar_wait_b(acc_full(as), ((uint32_t)n_acc >> 1) & 1u);
+        mbar_wait_b(tb.flags, acc_full(as), ((uint32_t)n_acc >> 1) & 1u);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 128 + part * 32);
         uint32_t pk[16];
@@ -285,7 +285,7 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
         }
         // masked quarter -> K-major SWIZZLE_128B operand: k-block = half, row = frame, 8 filters per 16-byte chunk
-        mbar_wait_b(st_empty(ss), (((uint32_t)n_st >> 1) & 1u) ^ 1u);
+        mbar_wait_b(tb.flags, st_empty(ss), (((uint32_t)n_st >> 1) & 1u) ^ 1u);
         const uint32_t row_base = smem_st(ss) + (uint32_t)(half * 16384 + r * 128);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -298,7 +298,7 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         if (cc == 3) {
           // ---- decoder output of source `src`: taps -> overlap-add -> global (4 warps, one per lane quadrant)
           if (part == 0) {
-            mbar_wait_b(dec_full, (uint32_t)n_dec & 1u);
+            mbar_wait_b(tb.flags, dec_full, (uint32_t)n_dec & 1u);
             tcgen05_fence_after();
             float taps[32];
             const uint32_t daddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::DEC_COL0 + (src & 1) * L);
@@ -328,7 +328,7 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               if (hh < TILE_M && f_hi < F) { val += s_ola[hh][l]; any = true; }
               if (hh >= 1 && f_lo < F) { val += s_ola[hh - 1][S + l]; any = true; }
               if (!any) continue;
-              if (!(fabsf(val) <= 3.0e38f)) atomicOr(&g_abort, 2);  // inf / NaN samples: flagged for the host
+              if (!(fabsf(val) <= 3.0e38f)) atomicOr(tb.flags, 2);  // inf / NaN samples: flagged for the host
               const size_t idx = (size_t)(t0 + hh) * S + l;
               if (hh == 0 || hh == TILE_M) atomicAdd(o + idx, val);
               else o[idx] = val;
@@ -357,7 +357,7 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const int ch0 = cc * 128 + half * 64;           // first filter of this warp's 64 columns
         const __half* __restrict__ ep = p.enc + tt_index(w, C_ENC, ch0, r);
         const float* __restrict__ bp = p.bias + src * C_ENC + ch0;
-        mbar_wait_b(acc_full(as), ((uint32_t)n_acc >> 1) & 1u);
+        mbar_wait_b(tb.flags, acc_full(as), ((uint32_t)n_acc >> 1) & 1u);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 128 + half * 64);
         float v[2][32];
@@ -405,7 +405,7 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
         }
         // masked chunk -> K-major SWIZZLE_128B operand: k-block = half, row = frame, 8 filters per 16-byte chunk
-        mbar_wait_b(st_empty(ss), (((uint32_t)n_st >> 1) & 1u) ^ 1u);
+        mbar_wait_b(tb.flags, st_empty(ss), (((uint32_t)n_st >> 1) & 1u) ^ 1u);
         const uint32_t row_base = smem_st(ss) + (uint32_t)(half * 16384 + r * 128);
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -417,7 +417,7 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         if (cc == 3) {
           // ---- decoder output of source `src`: taps -> overlap-add -> global (4 warps, one per lane quadrant)
           if (half == 0) {
-            mbar_wait_b(dec_full, (uint32_t)n_dec & 1u);
+            mbar_wait_b(tb.flags, dec_full, (uint32_t)n_dec & 1u);
             tcgen05_fence_after();
             float taps[32];
             const uint32_t daddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::DEC_COL0 + (src & 1) * L);
@@ -452,7 +452,7 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               if (!any) continue;
               // inf / NaN samples (fp16 overflow of an activation, or non-finite input): flagged for the host, which
               // warns and points at precision="fp32"; the values are still written, as the reference would
-              if (!(fabsf(val) <= 3.0e38f)) atomicOr(&g_abort, 2);
+              if (!(fabsf(val) <= 3.0e38f)) atomicOr(tb.flags, 2);
               const size_t idx = (size_t)(t0 + hh) * S + l;
               if (hh == 0 || hh == TILE_M) atomicAdd(o + idx, val);
               else o[idx] = val;

@@ -15,9 +15,9 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-import sys
 import threading
 import warnings
+import weakref
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Sequence
 
@@ -38,13 +38,61 @@ def _data_ptr(a: np.ndarray) -> int:
         return a.ctypes.data
 
 
-def _check_device_flags(v: int) -> None:
-    """bit 0: a bounded device-side pipeline wait ran out (results invalid); bit 1: non-finite output samples."""
-    if v & 1:
-        raise RuntimeError("b200sep: a device-side pipeline wait timed out; results are invalid")
-    if v & 2:
-        warnings.warn("b200sep: the separated output contains non-finite samples (fp16 overflow of an activation, or "
-                      "non-finite input); precision='fp32' avoids the former", RuntimeWarning, stacklevel=3)
+class _FlagSlots:
+    """Page-locked int32 words the native calls copy their per-call device flags into (``h_flags`` of
+    ``b200sep_separate_batch[_host]``): one slot of ``MAX_SPLIT`` words per call, handed out round-robin.  A slot is only
+    read after the stream it was queued on has been synchronised."""
+
+    def __init__(self, torch, n_slots: int = 64):
+        self._t = torch.zeros(n_slots * nat.MAX_SPLIT, dtype=torch.int32).pin_memory()
+        self._np = self._t.numpy()
+        self._n = n_slots
+        self._next = 0
+        self._lock = threading.Lock()
+
+    def take(self) -> int:
+        with self._lock:
+            i = self._next
+            self._next = (i + 1) % self._n
+        return i
+
+    def ptr(self, i: int) -> int:
+        return self._t.data_ptr() + 4 * nat.MAX_SPLIT * i
+
+    def read(self, i: int) -> int:
+        return int(np.bitwise_or.reduce(self._np[i * nat.MAX_SPLIT:(i + 1) * nat.MAX_SPLIT]))
+
+
+class _PinnedPool:
+    """Page-locked host buffers for results.  A lease is a fresh ndarray over the buffer; the arrays handed to the
+    caller are views of it, so the buffer returns to the pool when the last of them is garbage-collected (a
+    ``weakref.finalize`` on the lease -- no interpreter-specific reference counting).  At most ``max_idle`` idle
+    buffers are kept; the rest are freed."""
+
+    def __init__(self, torch, max_idle: int = 4):
+        self._torch = torch
+        self._idle = []
+        self._max_idle = max_idle
+        self._lock = threading.Lock()
+
+    def _release(self, t) -> None:
+        with self._lock:
+            self._idle.append(t)
+            if len(self._idle) > self._max_idle:
+                self._idle.sort(key=lambda x: x.numel())
+                del self._idle[0]
+
+    def lease(self, n_floats: int):
+        n_floats = max(int(n_floats), 1)
+        with self._lock:
+            fit = [k for k, t in enumerate(self._idle) if t.numel() >= n_floats]
+            t = self._idle.pop(min(fit, key=lambda k: self._idle[k].numel())) if fit else None
+        if t is None:
+            t = self._torch.empty(max(n_floats, 1 << 16), dtype=self._torch.float32, pin_memory=True)
+        buf = (C.c_float * n_floats).from_address(t.data_ptr())
+        arr = np.frombuffer(buf, dtype=np.float32)
+        weakref.finalize(arr, self._release, t)
+        return t, arr
 
 
 class SeparationEngine:
@@ -65,6 +113,9 @@ class SeparationEngine:
         self.stride = int(model_args["stride"])
         self.precision = precision
         packed = W.PackedWeights(state_dict, model_args)
+        self.conditioning = packed.conditioning  # power-of-two exponents of the range conditioning (weights.py) or None
+        self._state_dict, self._fallback = state_dict, None
+        self.fallback_reruns = 0
         cfg = packed.config(precision)
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -77,7 +128,11 @@ class SeparationEngine:
         # largest batch (in samples) sent through one forward; larger inputs are cut into consecutive sub-batches
         # (4 Mi samples = 524 s of 8 kHz audio ~ 4.9 GB of scratch)
         self.max_batch_samples = int(os.environ.get("B200SEP_MAX_BATCH_SAMPLES", str(4 << 20)))
-        self._out_pool = []   # page-locked output buffers: (tensor, base ndarray)
+        self._pool = _PinnedPool(torch)  # page-locked output buffers
+        self._pinned_in = None           # page-locked input staging of separate_and_score (grown on demand)
+        self.small_result_bytes = int(os.environ.get("B200SEP_SMALL_RESULT_BYTES", str(1 << 20)))
+        self._flags = _FlagSlots(torch)
+        self._tls = threading.local()  # flag slots of separate_device calls this thread has not checked yet
         self._ws_host = None  # cached device scratch of the host entry point (grown on demand)
         self._pinned_out = None
 
@@ -85,6 +140,47 @@ class SeparationEngine:
         h, self._handle = self._handle, None
         if h:
             nat.lib().b200sep_model_destroy(h)
+        fb, self._fallback = self._fallback, None
+        if fb is not None:
+            fb.close()
+
+    # ------------------------------------------------------------------ device flags / fp32 fallback
+    def _flags_fatal(self, v: int) -> None:
+        if v & nat.FLAG_WAIT_TIMEOUT:
+            raise RuntimeError("b200sep: a device-side pipeline wait timed out; results are invalid")
+
+    def _fallback_engine(self) -> "SeparationEngine":
+        """fp32 twin of this engine (CUDA-core GEMMs, fp32 storage: >= 100 dB vs the oracle), built on first use: the
+        re-run target when the fp16 pipeline reports non-finite output samples."""
+        if self._fallback is None:
+            self._fallback = SeparationEngine(self._state_dict, self.model_args, self.device, "fp32")
+        return self._fallback
+
+    def _needs_rerun(self, v: int) -> bool:
+        """True when the call must be repeated on the fp32 twin (non-finite output of a half-precision pipeline)."""
+        self._flags_fatal(v)
+        if not (v & nat.FLAG_NONFINITE):
+            return False
+        if self.precision == "fp32" or os.environ.get("B200SEP_FP32_FALLBACK", "1") == "0":
+            warnings.warn("b200sep: the separated output contains non-finite samples (non-finite input?)",
+                          RuntimeWarning, stacklevel=4)
+            return False
+        self.fallback_reruns += 1
+        warnings.warn("b200sep: an activation left the fp16 range (non-finite output samples); the batch was re-run on "
+                      "the fp32 pipeline", RuntimeWarning, stacklevel=4)
+        return True
+
+    def check(self) -> int:
+        """For ``separate_device`` callers: call after synchronising the stream(s) the calls of THIS thread were queued
+        on.  Returns the OR of their device flags; raises on a pipeline timeout.  (The host-level entry points check --
+        and re-run in fp32 when needed -- by themselves.)"""
+        pend = getattr(self._tls, "pending", [])
+        self._tls.pending = []
+        v = 0
+        for i in pend:
+            v |= self._flags.read(i)
+        self._flags_fatal(v)
+        return v
 
     def __del__(self):  # pragma: no cover
         try:
@@ -146,15 +242,22 @@ class SeparationEngine:
         elif out.numel() < total * self.n_src or out.dtype != torch.float32:
             raise RuntimeError("out buffer too small")
         stream = torch.cuda.current_stream(dev).cuda_stream
+        pend = getattr(self._tls, "pending", None)
+        if pend is None:
+            pend = self._tls.pending = []
         with torch.cuda.device(dev):
             off = 0
             for w in waves:
                 wl = lens[w.start:w.stop]
                 arr = nat.i32_array(wl)
+                slot = self._flags.take()
                 nat.check(nat.lib().b200sep_separate_batch(
                     self._handle, C.c_void_p(d_mix.data_ptr() + 4 * off), None, arr, len(wl),
                     C.c_void_p(out.data_ptr() + 4 * off * self.n_src), C.c_void_p(ws_ptr), C.c_size_t(ws_bytes),
-                    C.c_void_p(stream)), "b200sep_separate_batch")
+                    C.c_void_p(stream), C.c_void_p(self._flags.ptr(slot))), "b200sep_separate_batch")
+                pend.append(slot)
+                if len(pend) > 32:
+                    del pend[0]
                 off += sum(wl)
         # keep the workspace alive until the stream has consumed it
         workspace.record_stream(torch.cuda.current_stream(dev))
@@ -188,14 +291,10 @@ class SeparationEngine:
             pinned_out, hout = self._acquire_pinned_out(total * S)
             pinned_out[:total * S].copy_(d_out[:total * S], non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
-            _check_device_flags(nat.abort_flag())
-        res: List[List[np.ndarray]] = []
-        o = 0
-        for n in lens:
-            seg = hout[o * S:(o + n) * S].reshape(S, n)
-            res.append([seg[s] for s in range(S)])
-            o += n
-        return res
+            rerun = self._needs_rerun(self.check())
+        if rerun:
+            return self._fallback_engine().separate_batch_resampled(chunks, sr_in, sr_out)
+        return self._results(hout, lens)
 
     def separate_and_score(self, chunks: Sequence[np.ndarray], refs: Sequence[Sequence[np.ndarray]],
                            variant: str = "overlap3", return_waveforms: bool = True):
@@ -221,7 +320,9 @@ class SeparationEngine:
         total = int(sum(lens))
         dev = torch.device("cuda", self.device)
         with self._lock, torch.cuda.device(dev):
-            h_in = torch.empty(total * (1 + K), dtype=torch.float32, pin_memory=True)
+            if self._pinned_in is None or self._pinned_in.numel() < total * (1 + K):
+                self._pinned_in = torch.empty(max(2 * total * (1 + K), 1 << 16), dtype=torch.float32, pin_memory=True)
+            h_in = self._pinned_in[:total * (1 + K)]  # reusable: every call ends with a stream synchronise under the lock
             hv = h_in.numpy()
             o = 0
             for a in segs:
@@ -241,37 +342,34 @@ class SeparationEngine:
                 pinned_out[:total * S].copy_(d_out[:total * S], non_blocking=True)
             pair, sisdr, sisdri, perm = pair.cpu().numpy(), sisdr.cpu().numpy(), sisdri.cpu().numpy(), perm.cpu().numpy()
             torch.cuda.current_stream(dev).synchronize()
-            _check_device_flags(nat.abort_flag())
+            rerun = self._needs_rerun(self.check())
+        if rerun:
+            return self._fallback_engine().separate_and_score(chunks, refs, variant, return_waveforms)
         res = PitResult(sisdr, sisdri, perm[:, :K].astype(np.int32), perm[:, 3].astype(bool), pair)
         if not return_waveforms:
             return res, None
-        wav: List[List[np.ndarray]] = []
-        o = 0
-        for ln in lens:
-            seg = hout[o * S:(o + ln) * S].reshape(S, ln)
-            wav.append([seg[s] for s in range(S)])
-            o += ln
-        return res, wav
+        return res, self._results(hout, lens)
 
     def _acquire_pinned_out(self, n_floats: int):
-        """A page-locked output buffer nobody holds views of any more (CPython reference counts of the base
-        ndarray), else a new one.  The results handed to the caller are numpy VIEWS of it, so a buffer returns to the
-        pool exactly when the caller drops its last result array; cudaHostAlloc (~10 ms for a 13 MB batch) stays off
-        the steady-state path."""
-        torch = self._torch
-        best = None
-        for ent in self._out_pool:
-            # references: the pool entry, the loop variable's tuple item, getrefcount's argument
-            if ent[1].size >= n_floats and sys.getrefcount(ent[1]) <= 2:
-                if best is None or ent[1].size < best[1].size:
-                    best = ent
-        if best is None:
-            t = torch.empty(max(n_floats, 1 << 16), dtype=torch.float32, pin_memory=True)
-            best = (t, t.numpy())
-            self._out_pool.append(best)
-            if len(self._out_pool) > 8:  # drop the oldest idle buffers
-                self._out_pool = [e for e in self._out_pool if sys.getrefcount(e[1]) > 2][-8:] + [best]
-        return best
+        """``(pinned tensor, float32 ndarray over it)`` leased from the engine's pool (``_PinnedPool``)."""
+        return self._pool.lease(n_floats)
+
+    def _results(self, hout: np.ndarray, lens: Sequence[int]) -> List[List[np.ndarray]]:
+        """Per-segment lists of ``n_src`` arrays.  Large batches are handed out as VIEWS of the page-locked buffer
+        (no second host copy of 4 * S * T bytes; the buffer returns to the pool when the caller drops the last view);
+        small results are copied into ordinary arrays so that a caller who keeps them (the streaming SV / ASR pipeline
+        does) does not pin page-locked memory."""
+        S = self.n_src
+        copy_out = hout.size * 4 <= self.small_result_bytes
+        res: List[List[np.ndarray]] = []
+        o = 0
+        for n in lens:
+            seg = hout[o * S:(o + n) * S].reshape(S, n)
+            if copy_out:
+                seg = seg.copy()
+            res.append([seg[s] for s in range(S)])
+            o += n
+        return res
 
     def separate_batch(self, chunks: Sequence[np.ndarray]) -> List[List[np.ndarray]]:
         """numpy in -> numpy out through pinned staging: one H2D copy, one forward, one D2H copy."""
@@ -321,18 +419,16 @@ class SeparationEngine:
                 ws_ptr = (self._ws_host.data_ptr() + 255) // 256 * 256
                 ws_bytes = self._ws_host.numel() - (ws_ptr - self._ws_host.data_ptr())
                 stream = torch.cuda.current_stream(dev)
+                slot = self._flags.take()
                 nat.check(nat.lib().b200sep_separate_batch_host(
                     self._handle, ptrs, arr, len(lens), C.c_void_p(pinned_out.data_ptr()), C.c_void_p(ws_ptr),
-                    C.c_size_t(ws_bytes), C.c_void_p(stream.cuda_stream)), "b200sep_separate_batch_host")
+                    C.c_size_t(ws_bytes), C.c_void_p(stream.cuda_stream), C.c_void_p(self._flags.ptr(slot))),
+                    "b200sep_separate_batch_host")
                 stream.synchronize()
-                _check_device_flags(nat.abort_flag())
-        res: List[List[np.ndarray]] = []
-        o = 0
-        for n in lens:
-            seg = hout[o * S:(o + n) * S].reshape(S, n)
-            res.append([seg[s] for s in range(S)])
-            o += n
-        return res
+                rerun = self._needs_rerun(self._flags.read(slot))
+        if rerun:
+            return self._fallback_engine().separate_batch(segs)
+        return self._results(hout, lens)
 
 
 @dataclass

@@ -95,7 +95,7 @@ def gather_records(local_ids: Sequence[int], local_records: np.ndarray, n_total:
 def evaluate_sharded(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.ndarray]], sr: int,
                      separate_batch: Callable, pit_batch: Callable, max_samples: int = 4 << 20,
                      kernel_size: int = 16, stride: int = 8, variant: str = "overlap3", device=None,
-                     separate_and_score: Callable = None):
+                     separate_and_score: Callable = None, lens: Sequence[int] = None, n_refs: int = None):
     """Separation + PIT SI-SDR / SI-SDRi of a list of independent segments across the ranks of the initialised
     ``torch.distributed`` group (or this process alone): LPT partition on frame counts, length-bucketed batches per
     rank, ``separate_batch(chunks, sr)`` and ``pit_batch(mixes, refs, preds, variant)`` per batch, then ONE
@@ -104,15 +104,21 @@ def evaluate_sharded(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.nda
     GPU between the forward and the PIT kernel.  Every rank returns the full table:
     ``(sisdr[n], sisdri[n], perm[n, K], seconds_spent_separating_on_this_rank)``.  No waveform leaves its rank.
 
+    ``mixes`` / ``refs`` may be sequences over ALL segments, or -- so that a rank only ever materialises its own shard --
+    mappings ``{global index: array(s)}`` holding at least this rank's LPT shard, with ``lens`` (samples of every segment
+    of the sweep, in global order) and ``n_refs`` given explicitly.
+
     This is the evaluation loop of ``/root/reference/scripts/osd/overlap3_core.py:689-744`` (separate, score, collect
     ``sep_sisdr_list`` / ``sep_sisdri_list``) over segments that are already cut, for BASELINE.json configs[3] / [4]."""
     import time
     import torch.distributed as dist
-    n = len(mixes)
     world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
     rank = dist.get_rank() if world > 1 else 0
-    lens = [int(np.asarray(m).shape[-1]) for m in mixes]
-    K = len(refs[0]) if n else 0
+    if lens is None:
+        lens = [int(np.asarray(m).shape[-1]) for m in mixes]
+    lens = [int(v) for v in lens]
+    n = len(lens)
+    K = int(n_refs) if n_refs is not None else (len(refs[0]) if n else 0)
     mine = lpt_partition([frames_of(v, kernel_size, stride) for v in lens], world)[rank] if n else []
     rec = np.full((len(mine), 2 + K), np.nan)
     pos = {seg: k for k, seg in enumerate(mine)}

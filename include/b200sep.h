@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define B200SEP_VERSION 100 /* 0.1.0 */
+#define B200SEP_VERSION 200 /* 0.2.0 */
 
 /* mask activation of TDConvNet (asteroid mask_act) */
 #define B200SEP_MASK_SIGMOID 0
@@ -92,6 +92,14 @@ typedef struct b200sep_weights {
   const float* mask_prelu;      /* masker.mask_net.0.weight           (1)     */
   const float* mask_weight;     /* masker.mask_net.1.weight           (S*N,Sc,1) */
   const float* mask_bias;       /* masker.mask_net.1.bias             (S*N)   */
+  /*
+   * eps of every GlobLN (asteroid masknn/norms.py: 1e-8), in model order: [0] masker.bottleneck.0, then for block i
+   * [1 + 2 i] shared_block.2 and [2 + 2 i] shared_block.5.  NULL = 1e-8 everywhere.  Not a checkpoint tensor: the
+   * host-side range conditioning (weights.condition_state_dict) rescales the tensors feeding a gLN by 2^p -- which
+   * the norm removes again -- and passes eps * 4^p here so that the conditioned model computes EXACTLY the function
+   * of the original one while its pre-norm activations sit in the fp16 range.
+   */
+  const float* gln_eps;         /* (1 + 2 * n_blocks * n_repeats) or NULL */
 } b200sep_weights;
 
 typedef struct b200sep_model b200sep_model; /* opaque: device weights, TMA descriptors */
@@ -124,10 +132,18 @@ size_t b200sep_workspace_bytes(const b200sep_model* m, const int32_t* lens, int3
  * batched over independent segments: ConvTasNet forward of every segment, each normalised
  * (gLN) over its own frames exactly as a batch-1 call would be.  Bytes of d_out between
  * segments (when offsets leave gaps) are zero-filled.  `d_ws` must be 256-byte aligned.
+ *
+ * `h_flags` (NULL, or B200SEP_MAX_SPLIT int32 words of page-locked HOST memory owned by this call until `stream` has
+ * been synchronised): the call's device flags, one word per concurrent sub-batch, copied back at the end of the
+ * stream work -- OR them together.  Flags are per CALL (they live in the call's table block inside `d_ws`): nothing is
+ * shared between engines, threads or calls and nothing is sticky.
  */
+#define B200SEP_MAX_SPLIT 4
+#define B200SEP_FLAG_WAIT_TIMEOUT 1 /* a bounded device-side pipeline wait ran out: results invalid (protocol bug)    */
+#define B200SEP_FLAG_NONFINITE 2    /* the separated output holds inf / NaN samples (fp16 range exceeded or bad input) */
 int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* offsets,
                            const int32_t* lens, int32_t n_seg, float* d_out, void* d_ws,
-                           size_t ws_bytes, void* stream);
+                           size_t ws_bytes, void* stream, int32_t* h_flags);
 
 /* PIT enumeration / tie-break order to reproduce */
 #define B200SEP_PIT_OVERLAP3 0 /* scripts/osd/overlap3_core.py:66-117                         */
@@ -151,7 +167,8 @@ int b200sep_split_count(const b200sep_model* m, const int32_t* lens, int32_t n_s
  */
 size_t b200sep_host_workspace_bytes(const b200sep_model* m, const int32_t* lens, int32_t n_seg);
 int b200sep_separate_batch_host(b200sep_model* m, const float* const* h_segs, const int32_t* lens,
-                                int32_t n_seg, float* h_out, void* d_ws, size_t ws_bytes, void* stream);
+                                int32_t n_seg, float* h_out, void* d_ws, size_t ws_bytes, void* stream,
+                                int32_t* h_flags);
 
 /* doubles of device scratch needed by b200sep_pit_sisdr_batch */
 size_t b200sep_pit_workspace_bytes(const int32_t* lens, int32_t n_seg);
@@ -235,10 +252,6 @@ int b200sep_profile_read(b200sep_model* m, float* ms_out, int32_t cap, int32_t* 
  * out[0..10] = enc, x, xa, skip, skipa, h1, h2, masked, n_tiles, total, g. */
 int b200sep_debug_set_stop(b200sep_model* m, int stop_after);
 int b200sep_debug_layout(const b200sep_model* m, const int32_t* lens, int32_t n_seg, uint64_t* out);
-
-/* 1 when a bounded device-side wait of the fused kernels ran out (protocol bug: results invalid);
- * synchronises the device; `reset` != 0 clears the flag. */
-int b200sep_debug_abort_flag(int32_t* out, int32_t reset);
 
 /* Debug: register (nullptr: remove) a device buffer of n_sm * 8 * 128 int64 that the fused kernels stamp
  * with clock64 values per (CTA, tile visit, slot); used by tests/timeline.py to see the pipeline. */

@@ -24,7 +24,7 @@ def test_library_builds_and_exports_every_declared_symbol(built_lib):
     for name in declared:
         assert hasattr(built_lib, name), f"{name} declared in include/b200sep.h but not exported"
     assert sorted(nat.EXPORTS) == declared
-    assert built_lib.b200sep_version() == 100
+    assert built_lib.b200sep_version() == 200
 
 
 def test_library_is_sm100a_with_blackwell_instructions(built_lib):
@@ -113,8 +113,9 @@ def test_packed_weights_point_at_contiguous_fp32_copies():
     from b200sep import weights
     sd, args = weights.random_state_dict(3, 2, n_blocks=2, n_repeats=2)
     sd["masker.bottleneck.1.weight"] = sd["masker.bottleneck.1.weight"].double()   # any float dtype accepted
-    pk = weights.PackedWeights(sd, args)
+    pk = weights.PackedWeights(sd, args, condition=False)
     w = pk.struct
+    assert not w.gln_eps or np.allclose(np.ctypeslib.as_array(w.gln_eps, (9,)), 1e-8)
     assert np.ctypeslib.as_array(w.enc_filters, (512 * 16,))[5] == pytest.approx(float(sd["encoder.filterbank._filters"].reshape(-1)[5]))
     assert np.ctypeslib.as_array(w.res_bias[3], (128,))[7] == pytest.approx(float(sd["masker.TCN.3.res_conv.bias"][7]))
     cfg = pk.config("fp32")

@@ -27,18 +27,17 @@ for rep in range(4):
     ws_bytes = eng._ws_host.numel() - (ws_ptr - eng._ws_host.data_ptr())
     stream = torch.cuda.current_stream(dev)
     nat.check(nat.lib().b200sep_separate_batch_host(eng._handle, ptrs, arr, len(lens), C.c_void_p(pinned_out.data_ptr()),
-                                                    C.c_void_p(ws_ptr), C.c_size_t(ws_bytes), C.c_void_p(stream.cuda_stream)), "x")
+                                                    C.c_void_p(ws_ptr), C.c_size_t(ws_bytes), C.c_void_p(stream.cuda_stream), None), "x")
     t4 = time.perf_counter()
     stream.synchronize()
     t5 = time.perf_counter()
-    nat.abort_flag()
     t6 = time.perf_counter()
     hout = pinned_out.numpy(); res = []; o = 0
     for n in lens:
         seg = hout[o * S:(o + n) * S].reshape(S, n); res.append([seg[s] for s in range(S)]); o += n
     t7 = time.perf_counter()
     print(f"prep {1e3*(t1-t0):.2f} wsbytes {1e3*(t2-t1):.2f} pinned_alloc {1e3*(t3-t2):.2f} c_call {1e3*(t4-t3):.2f} "
-          f"sync {1e3*(t5-t4):.2f} abort_flag {1e3*(t6-t5):.2f} views {1e3*(t7-t6):.2f} total {1e3*(t7-t0):.2f} ms", flush=True)
+          f"sync {1e3*(t5-t4):.2f} views {1e3*(t7-t6):.2f} total {1e3*(t7-t0):.2f} ms", flush=True)
     if rep % 2 == 0:
         del res, hout, pinned_out
 t0 = time.perf_counter()

@@ -30,4 +30,4 @@ for _ in range(3):
     for k, v in classify_launches(eng.profile_read(), 24, pipeline).items():
         acc[k].extend(v)
 print(os.path.basename(os.environ.get("B200SEP_LIB", "default")), f"{min(ts):.3f} ms",
-      " ".join(f"{k}={1e3*sum(v)/len(v):.1f}" for k, v in acc.items() if v), "abort=", nat.abort_flag(), flush=True)
+      " ".join(f"{k}={1e3*sum(v)/len(v):.1f}" for k, v in acc.items() if v), flush=True)
