@@ -29,7 +29,7 @@ EXPORTS = [
     "b200sep_pipeline", "b200sep_debug_timeline",
     "b200sep_host_workspace_bytes", "b200sep_separate_batch_host", "b200sep_split_count",
     "b200sep_resample_out_lens", "b200sep_resample_batch", "b200sep_frame_rms_out_lens",
-    "b200sep_frame_rms_batch", "b200sep_gt_overlap_mask_batch",
+    "b200sep_frame_rms_batch", "b200sep_gt_overlap_mask_batch", "b200sep_debug_ts_probe",
 ]
 
 
@@ -107,9 +107,11 @@ def lib() -> C.CDLL:
         L.b200sep_pit_workspace_bytes.argtypes = [i32p, i32]
         L.b200sep_pit_sisdr_batch.restype = C.c_int
         L.b200sep_pit_sisdr_batch.argtypes = [vp, vp, vp, i64p, i32p, i32, i32, i32, i32, vp, vp,
-                                              vp, vp, vp, C.c_size_t, vp]
+                                              vp, vp, vp, vp, C.c_size_t, vp]
         L.b200sep_debug_gemm.restype = C.c_int
         L.b200sep_debug_gemm.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
+        L.b200sep_debug_ts_probe.restype = C.c_int
+        L.b200sep_debug_ts_probe.argtypes = [vp, vp, vp, i32, vp]
         L.b200sep_debug_set_stop.restype = C.c_int
         L.b200sep_debug_set_stop.argtypes = [vp, C.c_int]
         L.b200sep_debug_layout.restype = C.c_int
@@ -138,6 +140,7 @@ def check(rc: int, what: str) -> None:
 MAX_SPLIT = 4          # B200SEP_MAX_SPLIT: h_flags words per call
 FLAG_WAIT_TIMEOUT = 1  # B200SEP_FLAG_WAIT_TIMEOUT
 FLAG_NONFINITE = 2     # B200SEP_FLAG_NONFINITE
+FLAG_EPS_DOMINATED = 4  # B200SEP_FLAG_EPS_DOMINATED
 
 
 def i32_array(vals):

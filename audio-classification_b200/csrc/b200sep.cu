@@ -27,6 +27,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "fused_block.cuh"
+#include "pair_common.cuh"
 #include "tail_kernel.cuh"
 #include "pit.cuh"
 #include "aux_kernels.cuh"
@@ -1407,7 +1408,7 @@ static int pit_geometry(const int32_t* lens, int n_seg, int* chunk, int* max_chu
     if (lens[i] < 0) return fail("negative length");
     max_len = std::max(max_len, lens[i]);
   }
-  int ch = 8192;
+  int ch = 4096;
   while ((max_len + ch - 1) / ch > 64) ch *= 2;
   *chunk = ch;
   *max_chunks = std::max(1, (max_len + ch - 1) / ch);
@@ -1423,8 +1424,8 @@ size_t b200sep_pit_workspace_bytes(const int32_t* lens, int32_t n_seg) {
 
 int b200sep_pit_sisdr_batch(const float* d_refs, const float* d_ests, const float* d_mix, const int64_t* offsets,
                             const int32_t* lens, int32_t n_seg, int32_t K, int32_t N, int32_t variant, double* d_pair,
-                            double* d_sisdr, double* d_sisdri, int32_t* d_perm, void* d_ws, size_t ws_bytes,
-                            void* stream) {
+                            double* d_sisdr, double* d_sisdri, int32_t* d_perm, double* d_gap, void* d_ws,
+                            size_t ws_bytes, void* stream) {
   if (!d_refs || !d_ests || !d_mix || !lens || !d_pair || !d_sisdr || !d_sisdri || !d_perm || !d_ws)
     return fail("null argument");
   if (!(K == 2 || K == 3) || N < K || N > 3) return fail("PIT supports K in {2,3}, K <= N <= 3 (got K=%d N=%d)", K, N);
@@ -1462,7 +1463,7 @@ int b200sep_pit_sisdr_batch(const float* d_refs, const float* d_ests, const floa
   else pit_moments_kernel<3, 3><<<grid, 256, 0, st>>>(a, partial);
   CK(cudaGetLastError());
   pit_finalize_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(partial, a.len, n_seg, max_chunks, K, N, variant, d_pair,
-                                                         d_sisdr, d_sisdri, d_perm);
+                                                         d_sisdr, d_sisdri, d_perm, d_gap);
   CK(cudaGetLastError());
   return 0;
 }
@@ -1720,6 +1721,41 @@ int b200sep_debug_gemm(const float* d_a, const float* d_b, float* d_c, int32_t M
   cudaFree(b16);
   if (rc) return rc;
   if (se != cudaSuccess) return fail("debug gemm execution failed: %s", cudaGetErrorString(se));
+  return 0;
+}
+
+// Validation hook of the tensor-memory-A / CTA-pair MMA the K_A pair kernel is built on (pair_common.cuh):
+// out[c][f] = sum_k W[c][k] * H[f][k], K = 64; W [256][64], H [256][64], out [256][256] fp32 device arrays (operands
+// rounded to fp16).  pair = 0: one CTA, the top-left 128 x 128 block; pair = 1: a CTA pair, everything.
+int b200sep_debug_ts_probe(const float* d_w, const float* d_h, float* d_out, int32_t pair, void* stream) {
+  if (!d_w || !d_h || !d_out) return fail("null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  __half *w16 = nullptr, *h16 = nullptr;
+  CK(cudaMalloc(&w16, 256 * 64 * 2));
+  CK(cudaMalloc(&h16, 256 * 64 * 2));
+  convert_kernel<__half><<<64, 256, 0, st>>>(d_w, w16, (size_t)256 * 64);
+  to_tile_transposed_kernel<__half><<<64, 256, 0, st>>>(d_h, h16, 256, 64);
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(d_out, 0, 256 * 256 * 4, st));
+  const size_t smem = 16384 + 64 + 1024;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(pair ? 2 : 1);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le;
+  if (pair) le = cudaLaunchKernelEx(&cfg, pr2::ts_probe_kernel<1>, (const __half*)w16, (const __half*)h16, d_out);
+  else le = cudaLaunchKernelEx(&cfg, pr2::ts_probe_kernel<0>, (const __half*)w16, (const __half*)h16, d_out);
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(w16);
+  cudaFree(h16);
+  if (le != cudaSuccess) return fail("ts probe launch failed: %s", cudaGetErrorString(le));
+  if (se != cudaSuccess) return fail("ts probe execution failed: %s", cudaGetErrorString(se));
   return 0;
 }
 

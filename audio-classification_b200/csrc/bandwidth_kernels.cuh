@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(256, B200SEP_DW_MINB) dwconv_kernel(const T* _
 
   // every warp reduces the (tiny) partial list itself: identical results, no extra barrier
   float mean, rstd;
-  warp_seg_stats(part1, tile0, ntiles, slots1, ti.inv_count, p.eps1, mean, rstd);
+  warp_seg_stats(part1, tile0, ntiles, slots1, ti.inv_count, p.eps1, mean, rstd, tb.flags);
   for (int i = tid; i < DW_CH; i += 256) {
     const int c = cg * DW_CH + i;
     const float a = p.gamma1[c] * rstd;

@@ -112,6 +112,21 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// A gLN whose input variance is far below its eps divides by ~sqrt(eps) instead of the signal's own scale: the
+// normalised signal becomes a small ripple on the bias terms of the following layers, which fp16 activation storage
+// cannot carry (measured: 5 dB at var / eps = 1e-4).  The half-precision pipelines report it (flag bit 2,
+// B200SEP_FLAG_EPS_DOMINATED) and the host re-runs the batch on the fp32 pipeline.
+//
+// The same place catches fp16 OVERFLOW anywhere upstream: an inf / NaN in a stored activation makes the next gLN's
+// variance non-finite (flag bit 1).  The check at the output alone is not enough -- the sigmoid mask maps +-inf
+// scores to a clean 0 / 1, so an overflowed network can emit finite garbage (measured with weights scaled by 1e6).
+constexpr float EPS_DOMINATED_RATIO = 1.0f / 16.0f;
+__device__ __forceinline__ void flag_eps_dominated(int* flags, float var, float eps) {
+  if (flags == nullptr || (threadIdx.x & 31) != 0) return;
+  if (!(var <= 3.0e38f)) atomicOr(flags, 2);
+  else if (var < eps * EPS_DOMINATED_RATIO) atomicOr(flags, 4);
+}
+
 // gLN statistics of one segment from the per-tile partial sums a producer kernel left behind.
 // part[(tile0 + i) * slots + s] = (sum, sum of squares) over the valid frames of that slot.
 // Must be called by all 32 lanes of a warp; every lane (and every warp that repeats the call)
@@ -120,7 +135,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // GlobLN); the final reciprocal square root is taken in fp32 (rsqrtf + one Newton step).
 __device__ __forceinline__ void warp_seg_stats(const float2* __restrict__ part, int tile0,
                                                int ntiles, int slots, double inv_count, float eps,
-                                               float& mean, float& rstd) {
+                                               float& mean, float& rstd, int* flags = nullptr) {
   const int lane = threadIdx.x & 31;
   const int n = ntiles * slots;
   const float2* p = part + (size_t)tile0 * slots;
@@ -140,6 +155,7 @@ __device__ __forceinline__ void warp_seg_stats(const float2* __restrict__ part, 
   float y = rsqrtf(ve);
   y = y * (1.5f - 0.5f * ve * y * y);  // Newton step: ~0.5 ulp
   rstd = y;
+  flag_eps_dominated(flags, (float)var, eps);
 }
 
 }  // namespace b200sep

@@ -65,7 +65,7 @@ struct EpiBottleneck {
   __device__ __forceinline__ void tile_begin(EpiState& st, int m_tile, const Tables& tb) const {
     int seg, tile0, ntiles;
     epi_tile_ctx(st, m_tile, tb, seg, tile0, ntiles);
-    warp_seg_stats(part_in, tile0, ntiles, slots_in, st.inv_count, eps, st.mean, st.rstd);
+    warp_seg_stats(part_in, tile0, ntiles, slots_in, st.inv_count, eps, st.mean, st.rstd, tb.flags);
   }
   template <int W>
   __device__ __forceinline__ void prefetch(int, int, int, float (&)[W]) const {}
@@ -174,7 +174,7 @@ struct EpiResSkip {
   __device__ __forceinline__ void tile_begin(EpiState& st, int m_tile, const Tables& tb) const {
     int seg, tile0, ntiles;
     epi_tile_ctx(st, m_tile, tb, seg, tile0, ntiles);
-    warp_seg_stats(part_in, tile0, ntiles, slots_in, st.inv_count, eps, st.mean, st.rstd);
+    warp_seg_stats(part_in, tile0, ntiles, slots_in, st.inv_count, eps, st.mean, st.rstd, tb.flags);
   }
   // old x / skip values: independent loads, consecutive lanes (frames) hit consecutive addresses
   template <int W>

@@ -32,7 +32,7 @@ namespace b200sep {
 // Device flags of ONE forward call live in the call's table block (Tables::flags, zeroed by the table upload):
 // bit 0: a bounded wait ran out; bit 1: non-finite output samples.  The host gets them through the `h_flags` argument
 // of b200sep_separate_batch[_host].
-constexpr int FLAG_WAIT_TIMEOUT = 1, FLAG_NONFINITE = 2;
+constexpr int FLAG_WAIT_TIMEOUT = 1, FLAG_NONFINITE = 2;  // (bit 2, eps-dominated gLN: common.cuh flag_eps_dominated)
 
 // Optional in-kernel timeline (b200sep_debug_timeline): clock64 stamps per (CTA, tile visit, slot).
 constexpr int TL_TILES = 8, TL_SLOTS = 128;
@@ -82,9 +82,9 @@ __device__ __forceinline__ void mbar_wait_b(int* flags, uint32_t bar, uint32_t p
 #pragma unroll 1
   for (uint32_t i = 0; i < (1u << 18); ++i) {
     if (mbar_try(bar, parity)) return;
-    if ((i & 31u) == 31u && (*reinterpret_cast<volatile int*>(flags) & FLAG_WAIT_TIMEOUT) != 0) return;
+    if ((i & 31u) == 31u && flags != nullptr && (*reinterpret_cast<volatile int*>(flags) & FLAG_WAIT_TIMEOUT) != 0) return;
   }
-  atomicOr(flags, FLAG_WAIT_TIMEOUT);
+  if (flags != nullptr) atomicOr(flags, FLAG_WAIT_TIMEOUT);
 }
 // L2 prefetch of a contiguous global range (bytes % 16 == 0) / of a TMA box
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
@@ -189,9 +189,9 @@ __device__ __forceinline__ void mbar_wait_cluster_b(int* flags, uint32_t bar, ui
 #pragma unroll 1
   for (uint32_t i = 0; i < (1u << 18); ++i) {
     if (mbar_try_cluster(bar, parity)) return;
-    if ((i & 31u) == 31u && (*reinterpret_cast<volatile int*>(flags) & FLAG_WAIT_TIMEOUT) != 0) return;
+    if ((i & 31u) == 31u && flags != nullptr && (*reinterpret_cast<volatile int*>(flags) & FLAG_WAIT_TIMEOUT) != 0) return;
   }
-  atomicOr(flags, FLAG_WAIT_TIMEOUT);
+  if (flags != nullptr) atomicOr(flags, FLAG_WAIT_TIMEOUT);
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -297,7 +297,7 @@ __device__ __forceinline__ TileInfo ti_get(const TileInfo* s_ti, const Tables& t
 // Segment gLN statistics from single-slot per-tile partials; `pre` is this lane's (pre-fetched) first
 // element part[tile0 + lane] (zeros when lane >= ntiles).  Same arithmetic as warp_seg_stats.
 __device__ __forceinline__ void seg_stats_pre(const float2* __restrict__ part, const TileInfo& ti, float2 pre,
-                                              float eps, float& mean, float& rstd) {
+                                              float eps, float& mean, float& rstd, int* flags = nullptr) {
   const int lane = threadIdx.x & 31;
   double s = (double)pre.x, q = (double)pre.y;
   for (int i = lane + 32; i < ti.ntiles; i += 32) {
@@ -315,6 +315,7 @@ __device__ __forceinline__ void seg_stats_pre(const float2* __restrict__ part, c
   float y = rsqrtf(ve);
   y = y * (1.5f - 0.5f * ve * y * y);
   rstd = y;
+  flag_eps_dominated(flags, (float)var, eps);
 }
 __device__ __forceinline__ float2 part_prefetch(const float2* __restrict__ part, const TileInfo& ti) {
   const int lane = threadIdx.x & 31;
@@ -832,7 +833,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
     if (n_visits > 0) {
       bool v_;
       const TileInfo t0i = ti_get(s_ti, tb, 0, tile_at(0, v_));
-      seg_stats_pre(part1, t0i, part_prefetch(part1, t0i), p.eps1, nmean, nrstd);
+      seg_stats_pre(part1, t0i, part_prefetch(part1, t0i), p.eps1, nmean, nrstd, tb.flags);
     }
     for (int it = 0; it < n_visits; ++it) {
       bool valid;
@@ -974,7 +975,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         if (tl_on) tl_stamp(it, tl_base + 3 * (kb >> 1) + 2);
         ++nseq;
         // statistics of the next tile's segment, off the tile-boundary critical path
-        if (kb == 4 + grp && has_next) seg_stats_pre(part1, tn, pre, p.eps1, nmean, nrstd);
+        if (kb == 4 + grp && has_next) seg_stats_pre(part1, tn, pre, p.eps1, nmean, nrstd, tb.flags);
       }
       // gLN2 partial of this m-tile: fixed-order block reduction -> one slot per tile
       const float s_acc = warp_sum(s2.x + s2.y);
@@ -1466,7 +1467,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
       const TileInfo ti = ti_get(s_ti, tb, it, w);
       float mean = 0.f, rstd = 0.f;
       if (has_g) {
-        seg_stats_pre(ap.part2, ti, pre, ap.eps2, mean, rstd);
+        seg_stats_pre(ap.part2, ti, pre, ap.eps2, mean, rstd, tb.flags);
         if (w + (int)gridDim.x < n_tiles) pre = part_prefetch(ap.part2, ti_get(s_ti, tb, it + 1, w + gridDim.x));
       }
       float2 vm[4];
@@ -1610,7 +1611,7 @@ __global__ void __launch_bounds__(256) skip_merge_kernel(const __half* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int b = warp; b < n_layers; b += 8) {
     float mean, rstd;
-    warp_seg_stats(part2 + (size_t)b * part_stride, ti.tile0, ti.ntiles, 1, ti.inv_count, __ldg(eps2 + b), mean, rstd);
+    warp_seg_stats(part2 + (size_t)b * part_stride, ti.tile0, ti.ntiles, 1, ti.inv_count, __ldg(eps2 + b), mean, rstd, tb.flags);
     if (lane == 0) {
       // the constant term uses the SAME rounded rstd, so sum_b rstd_b * (G_b - mean_b * rs_b) stays consistent
       const __half rh = __float2half_rn(rstd);

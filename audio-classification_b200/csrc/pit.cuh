@@ -49,13 +49,31 @@ __global__ void __launch_bounds__(256) pit_moments_kernel(PitArgs a, double* __r
   double acc[PIT_NACC];
 #pragma unroll
   for (int i = 0; i < PIT_NACC; ++i) acc[i] = 0.0;
-  for (int t = beg + threadIdx.x; t < end; t += 256) {
+  // U samples per thread and trip: all (K + N + 1) * U loads are issued before the first fp64 FMA consumes one (the
+  // kernel is a pure stream: memory-level parallelism, not arithmetic, sets its rate); the accumulation order of a
+  // thread is unchanged (t ascending), so results are bit-identical to the one-sample-per-trip loop
+  constexpr int U = 4;
+  for (int t0 = beg + threadIdx.x; t0 < end; t0 += 256 * U) {
+    float rl[U][3], el[U][3], ml[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 + u * 256;
+      const bool ok = t < end;
+#pragma unroll
+      for (int i = 0; i < K; ++i) rl[u][i] = ok ? __ldg(r + (size_t)i * T + t) : 0.f;
+#pragma unroll
+      for (int j = 0; j < N; ++j) el[u][j] = ok ? __ldg(e + (size_t)j * T + t) : 0.f;
+      ml[u] = ok ? __ldg(m + t) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+    if (t0 + u * 256 >= end) break;
     double rv[3] = {0, 0, 0}, ev[3] = {0, 0, 0};
 #pragma unroll
-    for (int i = 0; i < K; ++i) rv[i] = (double)__ldg(r + (size_t)i * T + t);
+    for (int i = 0; i < K; ++i) rv[i] = (double)rl[u][i];
 #pragma unroll
-    for (int j = 0; j < N; ++j) ev[j] = (double)__ldg(e + (size_t)j * T + t);
-    const double mv = (double)__ldg(m + t);
+    for (int j = 0; j < N; ++j) ev[j] = (double)el[u][j];
+    const double mv = (double)ml[u];
     acc[PA_M] += mv;
     acc[PA_MM] = fma(mv, mv, acc[PA_MM]);
 #pragma unroll
@@ -70,6 +88,7 @@ __global__ void __launch_bounds__(256) pit_moments_kernel(PitArgs a, double* __r
     for (int j = 0; j < N; ++j) {
       acc[PA_E + j] += ev[j];
       acc[PA_EE + j] = fma(ev[j], ev[j], acc[PA_EE + j]);
+    }
     }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,7 +121,8 @@ __device__ __forceinline__ double si_sdr_from_moments(double Srr, double See, do
 __global__ void pit_finalize_kernel(const double* __restrict__ partial, const int32_t* __restrict__ len,
                                     int n_seg, int max_chunks, int K, int N, int variant,
                                     double* __restrict__ pair, double* __restrict__ sisdr,
-                                    double* __restrict__ sisdri, int32_t* __restrict__ perm_out) {
+                                    double* __restrict__ sisdri, int32_t* __restrict__ perm_out,
+                                    double* __restrict__ gap_out) {
   const int seg = blockIdx.x * blockDim.x + threadIdx.x;
   if (seg >= n_seg) return;
   double a[PIT_NACC];
@@ -141,6 +161,9 @@ __global__ void pit_finalize_kernel(const double* __restrict__ partial, const in
   }
 
   double best = -1e9;
+  // top-2 gap: best minus the second-best mean over the DISTINCT assignments (how far the choice is from flipping)
+  double cand[6];
+  int n_cand = 0;
   int bi[3] = {-1, -1, -1};
   int swapped = 0;
   bool found = false;
@@ -167,6 +190,7 @@ __global__ void pit_finalize_kernel(const double* __restrict__ partial, const in
         }
         if (!valid) continue;
         const double mean_sdr = s / (double)K;
+        if (n_cand < 6) cand[n_cand++] = mean_sdr;
         if (mean_sdr > best) {
           best = mean_sdr;
           found = true;
@@ -185,6 +209,7 @@ __global__ void pit_finalize_kernel(const double* __restrict__ partial, const in
         const double s21 = 0.5 * (M[0][k] + M[1][j]);
         double cur;
         int sw;
+        if (!isnan(s12) && n_cand < 6) cand[n_cand++] = s12;  // (j, k) unswapped; its swap is pair (k, j)'s unswapped
         if (s12 >= s21) { cur = s12; sw = 0; } else { cur = s21; sw = 1; }
         if (cur > best) { best = cur; bi[0] = j; bi[1] = k; swapped = sw; found = true; }
       }
@@ -192,8 +217,17 @@ __global__ void pit_finalize_kernel(const double* __restrict__ partial, const in
     // evaluate_with_sources.py:418-427 -- permutations(cols, 3), perm[i] = estimate for ref i
     for (int pi = 0; pi < 6; ++pi) {
       const double cur = (M[0][perms3[pi][0]] + M[1][perms3[pi][1]] + M[2][perms3[pi][2]]) / 3.0;
+      if (!isnan(cur) && n_cand < 6) cand[n_cand++] = cur;
       if (cur > best) { best = cur; found = true; for (int i = 0; i < 3; ++i) bi[i] = perms3[pi][i]; }
     }
+  }
+  if (gap_out != nullptr) {
+    double b1 = -INFINITY, b2 = -INFINITY;
+    for (int c = 0; c < n_cand; ++c) {
+      if (cand[c] > b1) { b2 = b1; b1 = cand[c]; }
+      else if (cand[c] > b2) b2 = cand[c];
+    }
+    gap_out[seg] = (found && n_cand > 1) ? b1 - b2 : ((found && n_cand == 1) ? INFINITY : nan(""));
   }
   if (!found || isnan(base)) {
     sisdr[seg] = nan("");

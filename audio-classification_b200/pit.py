@@ -28,13 +28,14 @@ class PitResult:
     perm: np.ndarray     # [n_seg, K] int32: estimate index assigned to reference i (-1 when undefined)
     swapped: np.ndarray  # [n_seg] bool, K=2 "evalsrc" variant only
     pair: np.ndarray     # [n_seg, 3, 4] float64: pair[i][j] = SI-SDR(ref_i, est_j); [:, :, 3] = vs mixture
+    gap: np.ndarray = None  # [n_seg] float64: best - second-best mean SI-SDR over the distinct assignments (dB)
 
 
 def pit_sisdr_device(d_refs, d_ests, d_mix, lens: Sequence[int], K: int, N: int,
                      variant: str = "overlap3"):
     """Device-resident entry: all tensors 1-D float32 CUDA, ragged layout of include/b200sep.h
     (segment i, source k at ``K*off_i + k*len_i``).  Returns CUDA tensors
-    ``(pair [n,3,4] f64, sisdr [n] f64, sisdri [n] f64, perm [n,4] i32)``; asynchronous."""
+    ``(pair [n,3,4] f64, sisdr [n] f64, sisdri [n] f64, perm [n,4] i32, gap [n] f64)``; asynchronous."""
     import torch
     if variant not in nat.PIT_VARIANTS:
         raise ValueError(f"unknown PIT variant {variant!r}")
@@ -56,15 +57,16 @@ def pit_sisdr_device(d_refs, d_ests, d_mix, lens: Sequence[int], K: int, N: int,
     sisdr = torch.empty(n, dtype=torch.float64, device=dev)
     sisdri = torch.empty(n, dtype=torch.float64, device=dev)
     perm = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    gap = torch.empty(n, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
     with torch.cuda.device(dev):
         nat.check(nat.lib().b200sep_pit_sisdr_batch(
             C.c_void_p(d_refs.data_ptr()), C.c_void_p(d_ests.data_ptr()), C.c_void_p(d_mix.data_ptr()),
             None, arr, n, int(K), int(N), nat.PIT_VARIANTS[variant], C.c_void_p(pair.data_ptr()),
             C.c_void_p(sisdr.data_ptr()), C.c_void_p(sisdri.data_ptr()), C.c_void_p(perm.data_ptr()),
-            C.c_void_p(ws_ptr), C.c_size_t(need), C.c_void_p(stream)), "b200sep_pit_sisdr_batch")
+            C.c_void_p(gap.data_ptr()), C.c_void_p(ws_ptr), C.c_size_t(need), C.c_void_p(stream)), "b200sep_pit_sisdr_batch")
     ws.record_stream(torch.cuda.current_stream(dev))
-    return pair, sisdr, sisdri, perm
+    return pair, sisdr, sisdri, perm, gap
 
 
 def _pack(list_of_lists: Sequence[Sequence[np.ndarray]], lens: Sequence[int], width: int) -> np.ndarray:
@@ -164,15 +166,18 @@ def pit_sisdr_batch(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.ndar
         d_mix = torch.from_numpy(h_mix).to(dev)
         d_ref = torch.from_numpy(h_ref).to(dev)
         d_est = torch.from_numpy(h_est).to(dev)
-        pair, sisdr, sisdri, perm = pit_sisdr_device(d_ref, d_est, d_mix, lens, K, N, variant)
-        pair, sisdr, sisdri, perm = pair.cpu().numpy(), sisdr.cpu().numpy(), sisdri.cpu().numpy(), perm.cpu().numpy()
+        pair, sisdr, sisdri, perm, gap = pit_sisdr_device(d_ref, d_est, d_mix, lens, K, N, variant)
+        pair, sisdr, sisdri, perm, gap = (pair.cpu().numpy(), sisdr.cpu().numpy(), sisdri.cpu().numpy(), perm.cpu().numpy(),
+                                          gap.cpu().numpy())
     o_pair = np.full((n, 3, 4), np.nan)
     o_sisdr, o_sisdri = np.full(n, np.nan), np.full(n, np.nan)
     o_perm, o_sw = np.full((n, K), -1, np.int32), np.zeros(n, bool)
+    o_gap = np.full(n, np.nan)
     for j, (i, _ln) in enumerate(jobs):
         if i not in ragged:
             o_pair[i], o_sisdr[i], o_sisdri[i] = pair[j], sisdr[j], sisdri[j]
             o_perm[i], o_sw[i] = perm[j, :K], bool(perm[j, 3])
+            o_gap[i] = gap[j]
     for i, info in ragged.items():
         M = np.full((3, 4), np.nan)
         for a in range(K):
@@ -181,7 +186,7 @@ def pit_sisdr_batch(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.ndar
             M[a, 3] = pair[info["jobs"][min(info["lr"][a], info["lm"])], a, 3]
         best, sdri, idx, sw = _select_host(M[:, :3], M[:, 3], K, N, variant)
         o_pair[i], o_sisdr[i], o_sisdri[i], o_perm[i], o_sw[i] = M, best, sdri, idx, sw
-    return PitResult(o_sisdr, o_sisdri, o_perm, o_sw, o_pair)
+    return PitResult(o_sisdr, o_sisdri, o_perm, o_sw, o_pair, o_gap)
 
 
 # ---- reference-shaped single-segment wrappers ---------------------------------------------------

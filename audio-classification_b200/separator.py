@@ -159,15 +159,20 @@ class SeparationEngine:
     def _needs_rerun(self, v: int) -> bool:
         """True when the call must be repeated on the fp32 twin (non-finite output of a half-precision pipeline)."""
         self._flags_fatal(v)
-        if not (v & nat.FLAG_NONFINITE):
+        if self.precision == "fp32":
+            if v & nat.FLAG_NONFINITE:
+                warnings.warn("b200sep: the separated output contains non-finite samples (non-finite input?)",
+                              RuntimeWarning, stacklevel=4)
             return False
-        if self.precision == "fp32" or os.environ.get("B200SEP_FP32_FALLBACK", "1") == "0":
-            warnings.warn("b200sep: the separated output contains non-finite samples (non-finite input?)",
-                          RuntimeWarning, stacklevel=4)
+        if not (v & (nat.FLAG_NONFINITE | nat.FLAG_EPS_DOMINATED)):
+            return False
+        why = ("an activation left the fp16 range (non-finite output samples)" if v & nat.FLAG_NONFINITE else
+               "a GlobLN saw a variance far below its eps (signal reduced to a ripple on the biases: beyond fp16 storage)")
+        if os.environ.get("B200SEP_FP32_FALLBACK", "1") == "0":
+            warnings.warn(f"b200sep: {why}; results may be inaccurate (fp32 fallback disabled)", RuntimeWarning, stacklevel=4)
             return False
         self.fallback_reruns += 1
-        warnings.warn("b200sep: an activation left the fp16 range (non-finite output samples); the batch was re-run on "
-                      "the fp32 pipeline", RuntimeWarning, stacklevel=4)
+        warnings.warn(f"b200sep: {why}; the batch was re-run on the fp32 pipeline", RuntimeWarning, stacklevel=4)
         return True
 
     def check(self) -> int:
@@ -335,17 +340,18 @@ class SeparationEngine:
             d_in = h_in.to(dev, non_blocking=True)
             d_mix, d_refs = d_in[:total], d_in[total:]
             d_out = self.separate_device(d_mix, lens)
-            pair, sisdr, sisdri, perm = pit_sisdr_device(d_refs, d_out, d_mix, lens, K, S, variant)
+            pair, sisdr, sisdri, perm, gap = pit_sisdr_device(d_refs, d_out, d_mix, lens, K, S, variant)
             hout = None
             if return_waveforms:
                 pinned_out, hout = self._acquire_pinned_out(total * S)
                 pinned_out[:total * S].copy_(d_out[:total * S], non_blocking=True)
-            pair, sisdr, sisdri, perm = pair.cpu().numpy(), sisdr.cpu().numpy(), sisdri.cpu().numpy(), perm.cpu().numpy()
+            pair, sisdr, sisdri, perm, gap = (pair.cpu().numpy(), sisdr.cpu().numpy(), sisdri.cpu().numpy(),
+                                              perm.cpu().numpy(), gap.cpu().numpy())
             torch.cuda.current_stream(dev).synchronize()
             rerun = self._needs_rerun(self.check())
         if rerun:
             return self._fallback_engine().separate_and_score(chunks, refs, variant, return_waveforms)
-        res = PitResult(sisdr, sisdri, perm[:, :K].astype(np.int32), perm[:, 3].astype(bool), pair)
+        res = PitResult(sisdr, sisdri, perm[:, :K].astype(np.int32), perm[:, 3].astype(bool), pair, gap)
         if not return_waveforms:
             return res, None
         return res, self._results(hout, lens)

@@ -141,6 +141,7 @@ size_t b200sep_workspace_bytes(const b200sep_model* m, const int32_t* lens, int3
 #define B200SEP_MAX_SPLIT 4
 #define B200SEP_FLAG_WAIT_TIMEOUT 1 /* a bounded device-side pipeline wait ran out: results invalid (protocol bug)    */
 #define B200SEP_FLAG_NONFINITE 2    /* the separated output holds inf / NaN samples (fp16 range exceeded or bad input) */
+#define B200SEP_FLAG_EPS_DOMINATED 4 /* a gLN saw var < eps / 16: the signal is a ripple on the biases, beyond fp16 storage */
 int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* offsets,
                            const int32_t* lens, int32_t n_seg, float* d_out, void* d_ws,
                            size_t ws_bytes, void* stream, int32_t* h_flags);
@@ -189,11 +190,15 @@ size_t b200sep_pit_workspace_bytes(const int32_t* lens, int32_t n_seg);
  *   d_sisdri[n_seg] fp64       : best - mean_i SI-SDR(ref_i, mix)
  *   d_perm  [n_seg][4] int32   : perm[i] = estimate index assigned to reference i (i<K);
  *                                perm[3] = "swapped" flag of the K=2 EVALSRC variant, else 0
+ *   d_gap   [n_seg] fp64 or NULL: best minus second-best mean SI-SDR over the distinct assignments (dB; +inf when
+ *                                there is only one): the margin by which the permutation choice is decided -- the
+ *                                kernel's fp64 moments differ from the reference's fp32 reductions by up to ~2e-3 dB,
+ *                                so "identical permutation" is only defined where the gap exceeds that
  */
 int b200sep_pit_sisdr_batch(const float* d_refs, const float* d_ests, const float* d_mix,
                             const int64_t* offsets, const int32_t* lens, int32_t n_seg,
                             int32_t K, int32_t N, int32_t variant, double* d_pair,
-                            double* d_sisdr, double* d_sisdri, int32_t* d_perm, void* d_ws,
+                            double* d_sisdr, double* d_sisdri, int32_t* d_perm, double* d_gap, void* d_ws,
                             size_t ws_bytes, void* stream);
 
 /* ---- either side of the separation path: resampling and GT overlap masks ------------ */
@@ -237,6 +242,13 @@ int b200sep_gt_overlap_mask_batch(const float* d_rms1, const float* d_rms2, cons
  */
 int b200sep_debug_gemm(const float* d_a, const float* d_b, float* d_c, int32_t M, int32_t N,
                        int32_t K, int32_t bn, int32_t use_tc, void* stream);
+
+/*
+ * Validation hook of the MMA form the block kernel K_A uses: A operand resident in tensor memory, B from the shared
+ * memory of one CTA (pair = 0: M = N = 128) or of a CTA pair (pair = 1: tcgen05 cta_group::2, M = N = 256).
+ * out[c][f] = sum_k W[c][k] * H[f][k], K = 64; W [256][64], H [256][64], out [256][256] fp32 DEVICE arrays.
+ */
+int b200sep_debug_ts_probe(const float* d_w, const float* d_h, float* d_out, int32_t pair, void* stream);
 
 /*
  * Per-launch timing for the roofline report (bench.py): when enabled, b200sep_separate_batch

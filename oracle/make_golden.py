@@ -4,6 +4,8 @@
   pit_golden.npz        -- outputs of the REFERENCE's own PIT functions (imported unmodified from
                            /root/reference/scripts/osd/{overlap3_core,evaluate_with_sources}.py)
                            on seeded inputs: pins oracle/pit_restated.py and the CUDA PIT kernel.
+  pit_golden_ties.npz   -- the same functions on exact ties and near-ties (duplicated estimates / references, all
+                           scores equal, 1e-7-relative differences) + the top-2 gap of the reference's pair matrix.
   separator_golden.npz  -- output of the REFERENCE's own Separator wrapper
                            (/root/reference/src/osd/separation.py, unmodified) driving the restated
                            Asteroid model through the oracle shim on seeded mixtures and the seeded
@@ -102,6 +104,79 @@ def make_pit_golden():
     print("wrote pit_golden.npz with", len(cases), "cases")
 
 
+def pit_tie_cases():
+    """Exact ties and near-ties: duplicated estimates, duplicated references, all-equal scores,
+    estimates / references that differ by 1e-7 .. 1e-6 relative."""
+    rng = np.random.default_rng(20261018)
+    n = 2400
+
+    def sig(scale=0.05):
+        return (rng.standard_normal(n) * scale).astype(np.float32)
+
+    def noisy(x, a):
+        return (x + a * float(np.std(x)) * rng.standard_normal(n).astype(np.float32)).astype(np.float32)
+
+    cases = []
+    r = [sig(), sig(), sig()]
+    e0 = noisy(r[0], 0.2)
+    cases.append((3, 3, [r[0], r[1], r[2]], [e0, e0.copy(), noisy(r[2], 0.2)]))                  # t0 duplicated estimates
+    cases.append((3, 3, [r[0], r[0].copy(), r[2]], [noisy(r[0], 0.3), noisy(r[0], 0.1), noisy(r[2], 0.2)]))  # t1 dup refs
+    cases.append((3, 3, [r[0], r[1], r[2]], [e0, e0.copy(), e0.copy()]))                          # t2 all estimates equal
+    cases.append((3, 3, [r[1], r[1].copy(), r[1].copy()], [e0, e0.copy(), e0.copy()]))            # t3 every score equal
+    cases.append((3, 3, [r[0], r[1], r[2]], [e0, (e0 + np.float32(1e-7) * sig(1.0)).astype(np.float32), noisy(r[2], 0.2)]))  # t4 near tie
+    cases.append((2, 2, [r[0], r[1]], [e0, e0.copy()]))                                            # t5 K=2 duplicated estimates
+    cases.append((2, 3, [r[0], r[1]], [noisy(r[1], 0.2), e0, e0.copy()]))                          # t6 K=2, N=3, duplicates
+    cases.append((3, 3, [r[0], (r[0] * np.float32(1.0 + 1e-6)).astype(np.float32), r[2]],
+                  [noisy(r[0], 0.25), noisy(r[0], 0.25), noisy(r[2], 0.2)]))                       # t7 near-duplicate refs
+    out = []
+    for K, N, refs, preds in cases:
+        out.append((K, N, np.sum(refs, axis=0).astype(np.float32), refs, preds))
+    return out
+
+
+def _top2_gap(pair, K, N):
+    """best - second-best mean SI-SDR over the DISTINCT assignments the reference enumerates (python floats)."""
+    import itertools
+    vals = {}
+    for cols in itertools.combinations(range(N), K):
+        for perm in itertools.permutations(range(K)):
+            s = 0.0
+            for r_ in range(K):
+                s += float(pair[perm[r_]][cols[r_]])
+            vals[tuple(cols[perm.index(i)] for i in range(K))] = s / float(K)
+    v = sorted(vals.values(), reverse=True)
+    return v[0] - v[1] if len(v) > 1 else float("inf")
+
+
+def make_pit_tie_golden():
+    o3, ews = shim.import_reference_pit()
+    out = {}
+    cases = pit_tie_cases()
+    out["n_cases"] = np.int64(len(cases))
+    for ci, (K, N, mix, refs, preds) in enumerate(cases):
+        out[f"c{ci}_KN"] = np.array([K, N], np.int64)
+        out[f"c{ci}_mix"] = mix
+        for k, r in enumerate(refs):
+            out[f"c{ci}_ref{k}"] = r
+        for j, p in enumerate(preds):
+            out[f"c{ci}_pred{j}"] = p
+        pair = np.array([[o3._si_sdr(r, p) for p in preds] for r in refs], np.float64)
+        best, sdri, idx = o3._compute_sdr_improvement_pit_k(mix, refs, preds)
+        out[f"c{ci}_o3_pair"] = pair
+        out[f"c{ci}_o3_res"] = np.array([best, sdri], np.float64)
+        out[f"c{ci}_o3_idx"] = np.array(idx, np.int64)
+        out[f"c{ci}_o3_gap"] = np.float64(_top2_gap(pair, K, N))
+        if K == 2:
+            best, sdri, idx, sw = ews.compute_sdr_improvement_pit(mix, refs[0], refs[1], preds)
+            out[f"c{ci}_ews_swapped"] = np.int64(bool(sw))
+        else:
+            best, sdri, idx = ews.compute_sdr_improvement_pit_k(mix, refs, preds)
+        out[f"c{ci}_ews_res"] = np.array([best, sdri], np.float64)
+        out[f"c{ci}_ews_idx"] = np.array(idx, np.int64)
+    np.savez_compressed(os.path.join(OUT, "pit_golden_ties.npz"), **out)
+    print("wrote pit_golden_ties.npz with", len(cases), "cases")
+
+
 def make_separator_golden():
     from b200sep import synth, weights
     RefSeparator = shim.import_reference_separator()
@@ -138,5 +213,7 @@ if __name__ == "__main__":
     if not shim.reference_available():
         raise SystemExit("/root/reference not present: golden vectors can only be generated in the build container")
     os.makedirs(OUT, exist_ok=True)
-    make_pit_golden()
-    make_separator_golden()
+    if "--ties-only" not in sys.argv:   # (the round-1 fixtures stay byte-identical unless regenerated on purpose)
+        make_pit_golden()
+        make_separator_golden()
+    make_pit_tie_golden()

@@ -40,6 +40,28 @@ def test_restatement_matches_reference_golden_bit_exact(golden_dir):
     assert n == 18
 
 
+def test_restatement_matches_reference_on_ties_bit_exact(golden_dir):
+    """Tie-breaking (enumeration order, strict `>`, the K=2 `>=` swap rule) pinned on the reference's own outputs for
+    duplicated estimates / references, all-equal scores and 1e-7-relative near-ties (oracle/make_golden.py)."""
+    g = np.load(os.path.join(golden_dir, "pit_golden_ties.npz"))
+    assert int(g["n_cases"]) == 8
+    for ci in range(int(g["n_cases"])):
+        K, N = [int(v) for v in g[f"c{ci}_KN"]]
+        mix = g[f"c{ci}_mix"]
+        refs = [g[f"c{ci}_ref{k}"] for k in range(K)]
+        preds = [g[f"c{ci}_pred{j}"] for j in range(N)]
+        pair = np.array([[pr.si_sdr_o3(r, p) for p in preds] for r in refs])
+        assert np.array_equal(pair, g[f"c{ci}_o3_pair"]), ci
+        best, sdri, idx = pr.compute_sdr_improvement_pit_k_o3(mix, refs, preds)
+        assert np.array_equal(np.array([best, sdri]), g[f"c{ci}_o3_res"]) and list(idx) == list(g[f"c{ci}_o3_idx"]), ci
+        if K == 2:
+            best, sdri, idx, sw = pr.compute_sdr_improvement_pit_ews(mix, refs[0], refs[1], preds)
+            assert int(bool(sw)) == int(g[f"c{ci}_ews_swapped"]), ci
+        else:
+            best, sdri, idx = pr.compute_sdr_improvement_pit_k_ews(mix, refs, preds)
+        assert np.array_equal(np.array([best, sdri]), g[f"c{ci}_ews_res"]) and list(idx) == list(g[f"c{ci}_ews_idx"]), ci
+
+
 def test_assigned_index_semantics():
     # SURVEY.md 8(a) a10 probe: preds = refs[[2,0,1]] + noise  =>  [1, 2, 0]
     rng = np.random.default_rng(0)
