@@ -28,6 +28,7 @@
 #include "gemm_tc.cuh"
 #include "fused_block.cuh"
 #include "pair_common.cuh"
+#include "fused_pair.cuh"
 #include "tail_kernel.cuh"
 #include "pit.cuh"
 #include "aux_kernels.cuh"
@@ -169,11 +170,12 @@ struct BlockW {
   float *g1 = nullptr, *be1 = nullptr, *wd = nullptr, *bd = nullptr;  // [512],[512],[512][3],[512]
   float a2 = 0.25f;
   void* w_rs = nullptr;  // [256][512] T ([128][512] for the last block): (W . gamma2)
+  void* w_rs_pair = nullptr;  // [256][512] fp16 for the pair kernel: w_rs, or (last block) [128 zero rows | skip rows]
   float *rs = nullptr, *cb = nullptr;
   int dilation = 1;
   int n_out = 256;
   float eps1 = GLN_EPS, eps2 = GLN_EPS;  // eps of gLN1 / gLN2 of this block (b200sep_weights.gln_eps)
-  CUtensorMap tm_in, tm_rs, tm_rs_half;
+  CUtensorMap tm_in, tm_rs;
   float4 *dw_t0 = nullptr, *dw_t1 = nullptr;  // folded depthwise tap tables (fused_block.cuh DwTab)
   float* dw_cb = nullptr;
 };
@@ -186,6 +188,7 @@ struct b200sep_model {
   bool half = true, use_tc = true;
   bool fused = true;  // fp16 tensor-core mode: two fused kernels per TCN block (fused_block.cuh)
   bool fused_tail = true;  // ... and mask GEMM + mask application + decoder in one kernel (tail_kernel.cuh)
+  bool ka_pair = false;    // K_A as a CTA pair with the [res | skip] weights resident in tensor memory (fused_pair.cuh)
   void* dec_w16 = nullptr;  // [L][512] fp16 decoder filterbank (B operand of the decoder MMA)
   CUtensorMap tm_mask128, tm_wd;
   std::vector<void*> allocs;
@@ -205,8 +208,9 @@ struct b200sep_model {
   int debug_stop_after = 0;  // 0 = run everything; k = stop after k-th launch (tests)
   // optional per-launch CUDA-event timing (bench.py roofline pass)
   // concurrent sub-batches (b200sep_separate_batch): auxiliary streams and fork / join events
-  cudaStream_t aux_st[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  // (two sets: calls of the host entry point alternate between them, see hin below)
+  cudaStream_t aux_st2[2][4] = {};
+  cudaEvent_t ev_fork2[2] = {}, ev_join2[2][4] = {};
   // CUDA graphs of the launch sequence for small batches (one per (n_seg, n_tiles, buffer addresses)): a single short
   // segment is launch-bound (52 launches, ~7 us of host time each), the reference's per-segment separate() loop lives there
   struct GraphKey {
@@ -221,9 +225,13 @@ struct b200sep_model {
   std::map<GraphKey, cudaGraphExec_t> graphs;
   std::mutex graph_mu;
   long long graph_hits = 0, graph_misses = 0;  // a caller that passes fresh buffers every call never hits: give up then
-  float* hin = nullptr;  // pinned input staging of b200sep_separate_batch_host
-  size_t hin_cap = 0;    // floats
-  cudaEvent_t hin_ev = nullptr;
+  // pinned input staging of b200sep_separate_batch_host: two slots used alternately, so that a caller may queue the
+  // next call (on another stream, with another workspace) while the previous one is still copying / computing
+  static constexpr int kHin = 2;
+  float* hin[kHin] = {nullptr, nullptr};
+  size_t hin_cap[kHin] = {0, 0};  // floats
+  cudaEvent_t hin_ev[kHin] = {nullptr, nullptr};
+  int hin_next = 0;
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;
   int prof_n = 0;
@@ -349,6 +357,17 @@ static int build_weights(b200sep_model* m, const b200sep_weights* w) {
       skip_rs.insert(skip_rs.end(), h_rs.begin(), h_rs.end());
       skip_cb.insert(skip_cb.end(), h_cb.begin(), h_cb.end());
     }
+    b.w_rs_pair = b.w_rs;
+    if (last && std::is_same<T, __half>::value) {
+      // the pair kernel always runs M = 256: rank 0's (dead) residual rows are zeros, rank 1 holds the skip rows
+      void* padded = nullptr;
+      CK(cudaMalloc(&padded, (size_t)2 * C_BN * C_HID * 2));
+      m->allocs.push_back(padded);
+      CK(cudaMemset(padded, 0, (size_t)C_BN * C_HID * 2));
+      CK(cudaMemcpy(static_cast<uint8_t*>(padded) + (size_t)C_BN * C_HID * 2, b.w_rs, (size_t)C_SKIP * C_HID * 2,
+                    cudaMemcpyDeviceToDevice));
+      b.w_rs_pair = padded;
+    }
   }
   if (dev_upload_f(m, skip_rs, &m->skip_rs)) return 1;
   if (dev_upload_f(m, skip_cb, &m->skip_cb)) return 1;
@@ -410,7 +429,7 @@ static int compute_layout(const b200sep_config& c, bool half, bool fused, const 
   lo->o_tables = take(lo->tables_bytes);
   lo->o_enc = take(rows * C_ENC * es);
   lo->o_x = take(rows * C_BN * 4);
-  lo->o_xa = (half && (!fused || B200SEP_X16)) ? take(rows * C_BN * es) : lo->o_x;  // fp16 operand shadow / fp16 stream
+  lo->o_xa = half ? take(rows * C_BN * es) : lo->o_x;  // fp16 operand shadow (unfused) / fp16 residual stream (fused)
   lo->o_skip = take(fused ? 0 : rows * C_SKIP * 4);
   lo->o_skipa = take(rows * C_SKIP * es);
   lo->o_h1 = take(rows * C_HID * es);
@@ -517,13 +536,7 @@ static int launch_dw_rs(const b200sep_model* m, const KaArgs& a, const Tables& t
   using Cfg = fb::KaCfg<BN>;
   auto kern = fb::dw_rs_kernel<BN, D, A01>;
   { static DevOnce once; if (once.need(m->device)) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); once.done(m->device); } }
-  // 2-CTA clusters (each CTA multicasts half of every weight stage to its peer): even grid, one pair per SM pair
-#if B200SEP_KA_CL
-  const int n_pairs = std::min((tb.n_tiles + 1) / 2, m->n_sm / 2);
-  const int grid = 2 * n_pairs;
-#else
   const int grid = std::min(tb.n_tiles, m->n_sm);
-#endif
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(Cfg::THREADS);
@@ -531,7 +544,7 @@ static int launch_dw_rs(const b200sep_model* m, const KaArgs& a, const Tables& t
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = B200SEP_KA_CL ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
@@ -547,6 +560,48 @@ static int launch_dw_rs_d(const b200sep_model* m, const KaArgs& a, const Tables&
     case 2: return launch_dw_rs<BN, 2, A01>(m, a, tb, st);
     case 4: return launch_dw_rs<BN, 4, A01>(m, a, tb, st);
     default: return launch_dw_rs<BN, 0, A01>(m, a, tb, st);
+  }
+}
+struct KpArgs {
+  const CUtensorMap* tm_hc;
+  const CUtensorMap* tm_hh;
+  const CUtensorMap* tm_res;
+  const CUtensorMap* tm_skip;
+  const __half* w256;
+  int res_dead, skip_row0, skip_tile_rows;
+  const float2* p1;
+  float2* p2;
+  fb::DwTab tab;
+};
+template <int D, bool A01>
+static int launch_dw_rs_pair(const b200sep_model* m, const KpArgs& a, const Tables& tb, cudaStream_t st) {
+  using Cfg = pr2::KpCfg;
+  auto kern = pr2::dw_rs_pair_kernel<D, A01>;
+  { static DevOnce once; if (once.need(m->device)) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); once.done(m->device); } }
+  const int n_pairs = std::max(1, std::min((tb.n_tiles + 1) / 2, m->n_sm / 2));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * n_pairs);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  CK(cudaLaunchKernelEx(&cfg, kern, *a.tm_hc, *a.tm_hh, *a.tm_res, *a.tm_skip, a.w256, a.res_dead, a.skip_row0,
+                        a.skip_tile_rows, a.p1, a.p2, a.tab, tb));
+  return 0;
+}
+template <bool A01>
+static int launch_dw_rs_pair_d(const b200sep_model* m, const KpArgs& a, const Tables& tb, cudaStream_t st) {
+  switch (a.tab.dilation) {
+    case 1: return launch_dw_rs_pair<1, A01>(m, a, tb, st);
+    case 2: return launch_dw_rs_pair<2, A01>(m, a, tb, st);
+    case 4: return launch_dw_rs_pair<4, A01>(m, a, tb, st);
+    default: return launch_dw_rs_pair<0, A01>(m, a, tb, st);
   }
 }
 template <bool A01>
@@ -636,8 +691,8 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
 
   // 2. bottleneck: x = Wb . gLN(tf_rep) + bb
   {
-    // (fused path with B200SEP_X16: the fp16 copy is the residual stream the TCN blocks update)
-    const bool x16 = kHalf && fused_mode && B200SEP_X16;
+    // (fused path: the fp16 copy IS the residual stream the TCN blocks update)
+    const bool x16 = kHalf && fused_mode;
     EpiBottleneck<T> e{p0, 2, m->bn_rs, m->bn_cb, x16 ? nullptr : x, x16 ? xa : xa_or_null, m->eps_bn};
     if (run_gemm<T, 128, C_ENC>(m, enc, &tm_enc, reinterpret_cast<const T*>(m->bn_w), &m->tm_bn, nt, C_BN, e, tb, st))
       return 1;
@@ -654,6 +709,12 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
       CUtensorMap tm_hc, tm_hh[5];  // raw h1 views: centre box and halo boxes of 8..128 frames
       CUtensorMap tm_h1s;  // swizzled 64 x 64 store boxes of h1 (K_B epilogue)
       if (make_tmap_act(&tm_h1s, h1, nt, C_HID)) return 1;
+      // K_A as a CTA pair with tensor-memory-resident weights (fused_pair.cuh; model created under B200SEP_KA=pair): raw
+      // G_res / skip-stash store boxes.  Default: the one-CTA kernel (86 vs 92 us per launch on the configs[1] batch)
+      const bool ka_pair = m->ka_pair;
+      CUtensorMap tm_gres, tm_stash;
+      if (make_tmap_act(&tm_gres, gbuf, nt, C_BN)) return 1;
+      if (make_tmap_2d(&tm_stash, stash, TILE_M, (uint64_t)nt * m->n_layers * C_SKIP, TILE_M * 2, 64, 64)) return 1;
       if (make_tmap_act_raw(&tm_hc, h1, nt, C_HID, TILE_M)) return 1;
       for (int k = 0; k < 5; ++k)
         if (make_tmap_act_raw(&tm_hh[k], h1, nt, C_HID, 8 << k)) return 1;
@@ -684,11 +745,16 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
         int hk = 0;  // halo box: 8 frames for d < 8, else d frames
         while ((8 << hk) < b.dilation) ++hk;
         // stash layout [tile][block][128][128]
-        KaArgs ka{B200SEP_KA_CL ? &b.tm_rs_half : &b.tm_rs, &tm_hc, &tm_hh[hk], gbuf, stash + (size_t)i * (C_SKIP * TILE_M),
+        KaArgs ka{&b.tm_rs, &tm_hc, &tm_hh[hk], gbuf, stash + (size_t)i * (C_SKIP * TILE_M),
                   (size_t)m->n_layers * C_SKIP * TILE_M, p1,
                   p2 + (size_t)i * lo.part2_stride, fb::DwTab{b.dw_t0, b.dw_t1, b.dw_cb, b.a2, b.dilation, b.eps1}};
         const bool a01 = b.a2 >= 0.f && b.a2 <= 1.f;
-        if (!last) rc = a01 ? launch_dw_rs_d<256, true>(m, ka, tb, st) : launch_dw_rs_d<256, false>(m, ka, tb, st);
+        if (ka_pair) {
+          KpArgs kp{&tm_hc, &tm_hh[hk], &tm_gres, &tm_stash, reinterpret_cast<const __half*>(b.w_rs_pair), last ? 1 : 0,
+                    i * C_SKIP, m->n_layers * C_SKIP, p1, p2 + (size_t)i * lo.part2_stride,
+                    fb::DwTab{b.dw_t0, b.dw_t1, b.dw_cb, b.a2, b.dilation, b.eps1}};
+          rc = a01 ? launch_dw_rs_pair_d<true>(m, kp, tb, st) : launch_dw_rs_pair_d<false>(m, kp, tb, st);
+        } else if (!last) rc = a01 ? launch_dw_rs_d<256, true>(m, ka, tb, st) : launch_dw_rs_d<256, false>(m, ka, tb, st);
         else rc = a01 ? launch_dw_rs_d<128, true>(m, ka, tb, st) : launch_dw_rs_d<128, false>(m, ka, tb, st);
         if (rc) return 1;
         if (stop()) return sync_failed ? 1 : 0;
@@ -832,6 +898,7 @@ int b200sep_model_create(const b200sep_config* cfg, const b200sep_weights* w, in
   m->use_tc = (c.precision == B200SEP_PREC_FP16_TC);
   if (const char* f = getenv("B200SEP_FUSED")) m->fused = atoi(f) != 0;
   if (const char* f = getenv("B200SEP_FUSED_TAIL")) m->fused_tail = atoi(f) != 0;
+  if (const char* f = getenv("B200SEP_KA")) m->ka_pair = strcmp(f, "pair") == 0;
   const char* dbg = getenv("B200SEP_DEBUG_STOP_AFTER");
   if (dbg) m->debug_stop_after = atoi(dbg);
   int rc = m->half ? build_weights<__half>(m, w) : build_weights<float>(m, w);
@@ -841,7 +908,6 @@ int b200sep_model_create(const b200sep_config* cfg, const b200sep_weights* w, in
       BlockW& b = m->blocks[i];
       rc = make_tmap_w(&b.tm_in, b.w_in, C_HID, C_BN, 256);
       if (!rc) rc = make_tmap_w(&b.tm_rs, b.w_rs, b.n_out, C_HID, b.n_out == 256 ? 256 : 128);
-      if (!rc) rc = make_tmap_w(&b.tm_rs_half, b.w_rs, b.n_out, C_HID, b.n_out / 2);  // K_A: per-CTA half of a stage
     }
     if (!rc) rc = make_tmap_w(&m->tm_mask, m->mask_w, c.n_src * C_ENC, C_SKIP, 256);
     if (!rc) rc = make_tmap_w(&m->tm_mask128, m->mask_w, c.n_src * C_ENC, C_SKIP, 128);
@@ -862,16 +928,20 @@ void b200sep_model_destroy(b200sep_model* m) {
   cudaSetDevice(m->device);
   for (void* p : m->allocs) cudaFree(p);
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
-  for (int g = 0; g < 4; ++g) {
-    if (m->aux_st[g]) cudaStreamDestroy(m->aux_st[g]);
-    if (m->ev_join[g]) cudaEventDestroy(m->ev_join[g]);
+  for (int k = 0; k < 2; ++k) {
+    for (int g = 0; g < 4; ++g) {
+      if (m->aux_st2[k][g]) cudaStreamDestroy(m->aux_st2[k][g]);
+      if (m->ev_join2[k][g]) cudaEventDestroy(m->ev_join2[k][g]);
+    }
+    if (m->ev_fork2[k]) cudaEventDestroy(m->ev_fork2[k]);
   }
-  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
   if (m->own_st) cudaStreamDestroy(m->own_st);
   if (m->own_ev) cudaEventDestroy(m->own_ev);
-  if (m->hin_ev) cudaEventDestroy(m->hin_ev);
-  if (m->hin) cudaFreeHost(m->hin);
+  for (int k = 0; k < b200sep_model::kHin; ++k) {
+    if (m->hin_ev[k]) cudaEventDestroy(m->hin_ev[k]);
+    if (m->hin[k]) cudaFreeHost(m->hin[k]);
+  }
   delete m;
 }
 
@@ -1193,6 +1263,9 @@ int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* 
 static int separate_batch_locked(b200sep_model* m, const float* d_mix, const int64_t* offsets, const int32_t* lens,
                                  int32_t n_seg, float* d_out, void* d_ws, size_t ws_bytes, cudaStream_t st,
                                  int32_t* h_flags) {
+  cudaStream_t* aux_st = m->aux_st2[0];
+  cudaEvent_t* ev_join = m->ev_join2[0];
+  cudaEvent_t& ev_fork = m->ev_fork2[0];
   std::vector<std::vector<int>> groups;
   if (plan_split(m, lens, n_seg, &groups)) return 1;
   const int S = (int)groups.size();
@@ -1228,19 +1301,19 @@ static int separate_batch_locked(b200sep_model* m, const float* d_mix, const int
 
   // fork: sub-batch 0 on the caller's stream, the others on the model's auxiliary streams, launches issued by one
   // host thread per sub-batch so that the streams fill at the same pace
-  if (!m->ev_fork) CK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+  if (!ev_fork) CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
   for (int g = 1; g < S; ++g) {
-    if (!m->aux_st[g]) CK(cudaStreamCreateWithFlags(&m->aux_st[g], cudaStreamNonBlocking));
-    if (!m->ev_join[g]) CK(cudaEventCreateWithFlags(&m->ev_join[g], cudaEventDisableTiming));
+    if (!aux_st[g]) CK(cudaStreamCreateWithFlags(&aux_st[g], cudaStreamNonBlocking));
+    if (!ev_join[g]) CK(cudaEventCreateWithFlags(&ev_join[g], cudaEventDisableTiming));
   }
-  CK(cudaEventRecord(m->ev_fork, st));
+  CK(cudaEventRecord(ev_fork, st));
   std::vector<int> rc(S, 0);
   std::vector<std::string> err(S);
   std::vector<std::thread> workers;
   for (int g = 1; g < S; ++g) {
-    CK(cudaStreamWaitEvent(m->aux_st[g], m->ev_fork, 0));
+    CK(cudaStreamWaitEvent(aux_st[g], ev_fork, 0));
     workers.emplace_back([&, g]() {
-      rc[g] = run_sub(m, d_mix, g_off[g].data(), g_len[g].data(), (int)g_len[g].size(), d_out, ws + g_ws[g], m->aux_st[g],
+      rc[g] = run_sub(m, d_mix, g_off[g].data(), g_len[g].data(), (int)g_len[g].size(), d_out, ws + g_ws[g], aux_st[g],
                       h_flags ? h_flags + g : nullptr);
       if (rc[g]) err[g] = g_err;
     });
@@ -1250,8 +1323,8 @@ static int separate_batch_locked(b200sep_model* m, const float* d_mix, const int
   for (auto& w : workers) w.join();
   // join (also on failure: the caller's stream must not run ahead of work already queued on the auxiliary streams)
   for (int g = 1; g < S; ++g) {
-    CK(cudaEventRecord(m->ev_join[g], m->aux_st[g]));
-    CK(cudaStreamWaitEvent(st, m->ev_join[g], 0));
+    CK(cudaEventRecord(ev_join[g], aux_st[g]));
+    CK(cudaStreamWaitEvent(st, ev_join[g], 0));
   }
   for (int g = 0; g < S; ++g)
     if (rc[g]) return fail("%s", err[g].c_str());
@@ -1334,32 +1407,38 @@ static int separate_batch_host_locked(b200sep_model* m, const float* const* h_se
   float* d_out = reinterpret_cast<float*>(ws + fw_need + o_out);
 
   // pinned input staging (grown on demand); its previous H2D copies must have completed before it is rewritten
-  if (m->hin_cap < (size_t)total) {
-    if (m->hin_ev) CK(cudaEventSynchronize(m->hin_ev));
-    if (m->hin) CK(cudaFreeHost(m->hin));
-    m->hin = nullptr; m->hin_cap = 0;
+  const int hs = m->hin_next;
+  m->hin_next = (hs + 1) % b200sep_model::kHin;
+  if (m->hin_cap[hs] < (size_t)total) {
+    if (m->hin_ev[hs]) CK(cudaEventSynchronize(m->hin_ev[hs]));
+    if (m->hin[hs]) CK(cudaFreeHost(m->hin[hs]));
+    m->hin[hs] = nullptr; m->hin_cap[hs] = 0;
     const size_t cap = std::max<size_t>((size_t)total * 2, 1 << 16);
-    CK(cudaHostAlloc(reinterpret_cast<void**>(&m->hin), cap * sizeof(float), cudaHostAllocDefault));
-    m->hin_cap = cap;
+    CK(cudaHostAlloc(reinterpret_cast<void**>(&m->hin[hs]), cap * sizeof(float), cudaHostAllocDefault));
+    m->hin_cap[hs] = cap;
   }
-  if (!m->hin_ev) CK(cudaEventCreateWithFlags(&m->hin_ev, cudaEventDisableTiming));
-  else CK(cudaEventSynchronize(m->hin_ev));
+  if (!m->hin_ev[hs]) CK(cudaEventCreateWithFlags(&m->hin_ev[hs], cudaEventDisableTiming));
+  else CK(cudaEventSynchronize(m->hin_ev[hs]));  // the call that used this slot two calls ago has copied its input
+  float* const hin = m->hin[hs];
+  cudaStream_t* aux_st = m->aux_st2[hs];
+  cudaEvent_t* ev_join = m->ev_join2[hs];
+  cudaEvent_t& ev_fork = m->ev_fork2[hs];
 
   CK(cudaMemsetAsync(d_out, 0, (size_t)total * NS * sizeof(float), st));
-  if (!m->ev_fork) CK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+  if (!ev_fork) CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
   for (int g = 1; g < S; ++g) {
-    if (!m->aux_st[g]) CK(cudaStreamCreateWithFlags(&m->aux_st[g], cudaStreamNonBlocking));
-    if (!m->ev_join[g]) CK(cudaEventCreateWithFlags(&m->ev_join[g], cudaEventDisableTiming));
+    if (!aux_st[g]) CK(cudaStreamCreateWithFlags(&aux_st[g], cudaStreamNonBlocking));
+    if (!ev_join[g]) CK(cudaEventCreateWithFlags(&ev_join[g], cudaEventDisableTiming));
   }
-  CK(cudaEventRecord(m->ev_fork, st));
-  for (int g = 1; g < S; ++g) CK(cudaStreamWaitEvent(m->aux_st[g], m->ev_fork, 0));
+  CK(cudaEventRecord(ev_fork, st));
+  for (int g = 1; g < S; ++g) CK(cudaStreamWaitEvent(aux_st[g], ev_fork, 0));
 
   // per group: gather -> H2D -> forward -> D2H, everything of a group on its own stream and host thread, so the
   // gather / copies of one group overlap the kernels of the other
   auto run_group = [&](int g, cudaStream_t gs) -> int {
     CK(cudaSetDevice(m->device));
-    for (int i : groups[g]) memcpy(m->hin + d_off[i], h_segs[i], (size_t)lens[i] * sizeof(float));
-    CK(cudaMemcpyAsync(d_mix + g_begin[g], m->hin + g_begin[g], (size_t)(g_end[g] - g_begin[g]) * sizeof(float),
+    for (int i : groups[g]) memcpy(hin + d_off[i], h_segs[i], (size_t)lens[i] * sizeof(float));
+    CK(cudaMemcpyAsync(d_mix + g_begin[g], hin + g_begin[g], (size_t)(g_end[g] - g_begin[g]) * sizeof(float),
                        cudaMemcpyHostToDevice, gs));
     if (run_sub(m, d_mix, g_off[g].data(), g_len[g].data(), (int)g_len[g].size(), d_out, ws + g_ws[g], gs,
                 h_flags ? h_flags + g : nullptr))
@@ -1384,17 +1463,17 @@ static int separate_batch_host_locked(b200sep_model* m, const float* const* h_se
   std::vector<std::thread> workers;
   for (int g = 1; g < S; ++g)
     workers.emplace_back([&, g]() {
-      rc[g] = run_group(g, m->aux_st[g]);
+      rc[g] = run_group(g, aux_st[g]);
       if (rc[g]) err[g] = g_err;
     });
   rc[0] = run_group(0, st);
   if (rc[0]) err[0] = g_err;
   for (auto& w : workers) w.join();
   for (int g = 1; g < S; ++g) {
-    CK(cudaEventRecord(m->ev_join[g], m->aux_st[g]));
-    CK(cudaStreamWaitEvent(st, m->ev_join[g], 0));
+    CK(cudaEventRecord(ev_join[g], aux_st[g]));
+    CK(cudaStreamWaitEvent(st, ev_join[g], 0));
   }
-  CK(cudaEventRecord(m->hin_ev, st));
+  CK(cudaEventRecord(m->hin_ev[hs], st));
   for (int g = 0; g < S; ++g)
     if (rc[g]) return fail("%s", err[g].c_str());
   return 0;
@@ -1408,8 +1487,11 @@ static int pit_geometry(const int32_t* lens, int n_seg, int* chunk, int* max_chu
     if (lens[i] < 0) return fail("negative length");
     max_len = std::max(max_len, lens[i]);
   }
+  // chunk = samples per CTA of the moments kernel: small for small batches (parallelism), large for big sweeps (the
+  // 26-value fp64 block reduction at the end of a CTA costs as much as streaming ~10 k samples)
   int ch = 4096;
   while ((max_len + ch - 1) / ch > 64) ch *= 2;
+  while ((long long)n_seg * ((max_len + ch - 1) / ch) > 4096 && ch < 65536 && ch < max_len) ch *= 2;
   *chunk = ch;
   *max_chunks = std::max(1, (max_len + ch - 1) / ch);
   return 0;

@@ -133,19 +133,13 @@ struct EpiIn {
       float2 v1 = add2(make_float2(acc[4 * q + 2], acc[4 * q + 3]), make_float2(b4.z, b4.w));
       v0 = prelu2<A01>(v0, alpha);
       v1 = prelu2<A01>(v1, alpha);
-#ifndef B200SEP_EXP_NO_H1_STORE
       dst[(size_t)(4 * q + 0) * TILE_M] = from_f32<T>(v0.x);
       dst[(size_t)(4 * q + 1) * TILE_M] = from_f32<T>(v0.y);
       dst[(size_t)(4 * q + 2) * TILE_M] = from_f32<T>(v1.x);
       dst[(size_t)(4 * q + 3) * TILE_M] = from_f32<T>(v1.y);
-#else
-      if (v0.x == 123.456f) dst[0] = from_f32<T>(v0.y + v1.x + v1.y);
-#endif
-#ifndef B200SEP_EXP_NO_STATS
       const float2 m0 = mul2(v0, vm2), m1 = mul2(v1, vm2);
       s2 = add2(s2, add2(m0, m1));
       q2 = fma2(m0, v0, fma2(m1, v1, q2));
-#endif
     }
     st.s += s2.x + s2.y;
     st.q += q2.x + q2.y;

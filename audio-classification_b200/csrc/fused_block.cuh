@@ -42,23 +42,6 @@ __device__ __forceinline__ void tl_stamp(int it, int slot) {
   if (tl != nullptr && it < TL_TILES) tl[((size_t)blockIdx.x * TL_TILES + it) * TL_SLOTS + slot] = clock64();
 }
 
-// wall-clock (globaltimer, ns) stamp of a CTA's entry / exit (row 7 of the CTA's timeline block); only in builds with
-// -DB200SEP_TL_NS=1 (tests/cta_lifetimes.py)
-#ifndef B200SEP_TL_NS
-#define B200SEP_TL_NS 0
-#endif
-__device__ __forceinline__ void tl_stamp_ns(int slot) {
-#if B200SEP_TL_NS
-  long long* tl = c_timeline;
-  if (tl != nullptr && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    tl[((size_t)blockIdx.x * TL_TILES + 7) * TL_SLOTS + slot] = (long long)t;
-  }
-#else
-  (void)slot;
-#endif
-}
 
 namespace fb {
 using namespace tc;
@@ -119,21 +102,7 @@ __device__ __forceinline__ void tile_partial_reduce(float2* red, int* cnt, int n
     }
   }
 }
-#ifndef B200SEP_KA_SHFL_TAPS
-#define B200SEP_KA_SHFL_TAPS 0  // 1: d < 8: neighbour-vector words through warp shuffles instead of shared-memory reads (measured: neutral)
-#endif
-#ifndef B200SEP_KA_REVERSE
-#define B200SEP_KA_REVERSE 1
-#endif
-#ifndef B200SEP_KA_CLUSTER
-#define B200SEP_KA_CLUSTER 0  // 1: K_A runs as 2-CTA clusters, each CTA multicasts half of every weight stage (measured slower)
-#endif
-#ifndef B200SEP_KA_PAIR
-#define B200SEP_KA_PAIR 0  // 1: K_A as CTA pairs issuing tcgen05.mma.cta_group::2 (M = 256 over two SMs): every SM stages and
-                           // feeds only HALF of each weight k-block (the other half comes from its peer's shared memory)
-#endif
-#define B200SEP_KA_CL (B200SEP_KA_CLUSTER || B200SEP_KA_PAIR)  // launched as 2-CTA clusters, tiles visited in pairs
-// ---- 2-CTA cluster helpers (K_A: each CTA TMA-multicasts half of every weight stage to both CTAs) ----------------
+// ---- 2-CTA cluster helpers (used by the CTA-pair K_A, fused_pair.cuh) --------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -143,23 +112,6 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// TMA tile load delivered to the same shared-memory offset of every CTA in `mask`; each destination CTA's mbarrier at
-// the given offset receives the complete_tx
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const void* desc, uint32_t bar, int c0, int c1,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
-      "[%2], %5;" ::"r"(smem_dst),
-      "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-// tcgen05.commit whose mbarrier arrive lands on the barrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(mask)
-               : "memory");
-}
-
 // ---- cta_group::2 (CTA pair) helpers ---------------------------------------------------------------------------
 // shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
@@ -167,31 +119,12 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-// arrive on an mbarrier anywhere in the cluster (release at cluster scope: the waiter may sit in the peer CTA)
+// arrive on an mbarrier anywhere in the cluster.  Default semantics (release at CTA scope), as CUTLASS's
+// ClusterBarrier::arrive(cta_id) does: the data the peer's tensor core reads afterwards was made visible to the async
+// proxy by the writers' fence.proxy.async.  (`.release.cluster` here compiles to MEMBAR.ALL.GPU + CGAERRBAR in front of
+// every arrive -- measured: the CTA-pair kernel ran 105 instead of 92 us with it.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(20000)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait whose arrivals may come from the peer CTA
-__device__ __forceinline__ void mbar_wait_cluster_b(int* flags, uint32_t bar, uint32_t parity) {
-#pragma unroll 1
-  for (uint32_t i = 0; i < (1u << 18); ++i) {
-    if (mbar_try_cluster(bar, parity)) return;
-    if ((i & 31u) == 31u && flags != nullptr && (*reinterpret_cast<volatile int*>(flags) & FLAG_WAIT_TIMEOUT) != 0) return;
-  }
-  if (flags != nullptr) atomicOr(flags, FLAG_WAIT_TIMEOUT);
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -200,36 +133,12 @@ __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncol
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem of both CTAs] (+)= A (256 x K: 128 rows from each CTA's smem) * B (N x K: N/2 rows from each CTA's smem)
-__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                              uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // commit of the pair's MMAs: one arrival on the barrier at this offset in every CTA of `mask`
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"(mask)
                : "memory");
 }
-// TMA tile load into THIS CTA's shared memory whose complete_tx lands on an mbarrier of the pair (cluster address)
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* desc, uint32_t bar_cluster, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_cluster), "r"(c0), "r"(c1)
-      : "memory");
-}
-// kind::f16 instruction descriptor of the pair MMA: as make_idesc, M = 256
-__host__ __device__ constexpr uint32_t make_idesc_pair(int bn) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(bn >> 3) << 17) |
-         ((uint32_t)(256 >> 4) << 24);
-}
-
 // TMA tile store shared -> global (bulk async group of the issuing thread)
 __device__ __forceinline__ void tma_store_2d(const void* desc, uint32_t smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -351,18 +260,15 @@ struct KaCfg {
   // when the MMA that read it has completed, and its L2 -> shared-memory latency (~1.7 k cycles) is three times
   // the MMA time of a k-block (512 cycles); with 2 stages that latency, not the work, paced the kernel.
   static constexpr int A_STAGE = TILE_M * 64 * 2;    // 16 KiB
-  static constexpr int B_STAGE = BN * 64 * 2 / (B200SEP_KA_PAIR ? 2 : 1);  // 32 / 16 KiB (pair: this CTA's N/2 rows)
+  static constexpr int B_STAGE = BN * 64 * 2;  // 32 KiB
   static constexpr int B_MAX_STAGES = 4;
   static constexpr int TAB_BYTES = C_HID * (16 + 16 + 4);  // 18 KiB
   static constexpr int EPI_WARPS = 4, PROD_WARPS = 16;
   static constexpr int THREADS = (EPI_WARPS + 3 + PROD_WARPS) * 32;  // 736
   static constexpr int TMEM_COLS = 2 * BN;
-#ifndef B200SEP_KA_APG
-#define B200SEP_KA_APG (B200SEP_KA_PAIR ? 2 : 1)
-#endif
   // A stages per producer group: with 2 the producers of a group write k-block n + 1 while the MMA of k-block n (and, in
   // pair mode, the cross-SM arrive / commit round trip) is still in flight
-  static constexpr int A_PG = B200SEP_KA_APG;
+  static constexpr int A_PG = 1;
   static_assert(A_PG == 1 || A_PG == 2, "A stages per group");
   static constexpr int OFF_A = 0;
   static constexpr int OFF_TAB = OFF_A + 2 * A_PG * A_STAGE;
@@ -413,7 +319,7 @@ __device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_c
 template <int D, bool A01>
 __device__ __forceinline__ uint4 dw_step_h2(const uint4 vc, const uint4 va, const uint4 vb, const float4 t0,
                                             const float cb, const float rstd, const float rm, const __half2 alpha2,
-                                            float2& s2, float2& q2) {
+                                            __half2& sh, __half2& qh) {
   const uint32_t c[4] = {vc.x, vc.y, vc.z, vc.w};
   const uint32_t pv[4] = {va.x, va.y, va.z, va.w};
   const uint32_t nv[4] = {vb.x, vb.y, vb.z, vb.w};
@@ -435,13 +341,8 @@ __device__ __forceinline__ uint4 dw_step_h2(const uint4 vc, const uint4 va, cons
     l[0] = pv[2]; l[1] = pv[3]; l[2] = c[0]; l[3] = c[1];
     r[0] = c[2]; r[1] = c[3]; r[2] = nv[0]; r[3] = nv[1];
   }
-#ifndef B200SEP_EXP_NO_COEF_CVT
   const __half2 w0 = __float2half2_rn(t0.x * rstd), w1 = __float2half2_rn(t0.y * rstd);
   const __half2 w2 = __float2half2_rn(t0.z * rstd), cw = __float2half2_rn(fmaf(-t0.w, rm, cb));
-#else  // timing experiment only (wrong numbers): no XU-pipe conversions on the step path
-  const __half2 w0 = u32_as_h2(__float_as_uint(t0.x * rstd) & 0x3c003c00u), w1 = u32_as_h2(__float_as_uint(t0.y * rstd) & 0x3c003c00u);
-  const __half2 w2 = u32_as_h2(__float_as_uint(t0.z * rstd) & 0x3c003c00u), cw = u32_as_h2(__float_as_uint(fmaf(-t0.w, rm, cb)) & 0x3c003c00u);
-#endif
   uint32_t o[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -449,14 +350,24 @@ __device__ __forceinline__ uint4 dw_step_h2(const uint4 vc, const uint4 va, cons
     if (A01) u = __hmax2(u, __hmul2(u, alpha2));
     else u = __hadd2(__hmax2(u, __float2half2_rn(0.f)), __hmul2(alpha2, __hmin2(u, __float2half2_rn(0.f))));
     o[i] = h2_as_u32(u);
-    // gLN2 statistics of the ROUNDED outputs, fp32 accumulation, straight from the packed halves
-    const uint16_t lo = (uint16_t)(o[i] & 0xffffu), hi = (uint16_t)(o[i] >> 16);
-    s2.x = fma_f32_f16(lo, (uint16_t)0x3c00u, s2.x);  // + lo * 1.0
-    s2.y = fma_f32_f16(hi, (uint16_t)0x3c00u, s2.y);
-    q2.x = fma_f32_f16(lo, lo, q2.x);
-    q2.y = fma_f32_f16(hi, hi, q2.y);
+    // gLN2 statistics of the ROUNDED outputs: first level in packed halves (two instructions per pair instead of four
+    // scalar mixed-precision FMAs -- the producers are bound by the FMA pipe); the caller folds (sh, qh) into its fp32
+    // accumulators after at most 8 values per half lane (dw_stats_flush), so the fp16 partial sums stay short
+    sh = __hadd2(sh, u);
+    qh = __hfma2(u, u, qh);
   }
   return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// fp16 partial statistics of (at most) two producer steps -> the thread's fp32 accumulators
+__device__ __forceinline__ void dw_stats_flush(__half2& sh, __half2& qh, float2& s2, float2& q2) {
+  const uint32_t su = h2_as_u32(sh), qu = h2_as_u32(qh);
+  s2.x = fma_f32_f16((uint16_t)(su & 0xffffu), (uint16_t)0x3c00u, s2.x);  // + lo * 1.0
+  s2.y = fma_f32_f16((uint16_t)(su >> 16), (uint16_t)0x3c00u, s2.y);
+  q2.x = fma_f32_f16((uint16_t)(qu & 0xffffu), (uint16_t)0x3c00u, q2.x);
+  q2.y = fma_f32_f16((uint16_t)(qu >> 16), (uint16_t)0x3c00u, q2.y);
+  sh = __float2half2_rn(0.f);
+  qh = __float2half2_rn(0.f);
 }
 
 template <int BN, int D, bool A01>
@@ -491,38 +402,19 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   // PDL: everything up to the prologue barrier touches only constants (weights, tap tables, per-call layout
   // tables), so it may overlap the previous kernel's tail; activations are read after pdl_wait().
   pdl_launch_dependents();
-  tl_stamp_ns(124);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n_tiles = tb.n_tiles;
   // 2-CTA clusters: the pair (2p, 2p+1) visits the tile pairs p, p + n_pairs, ...; rank r takes tile 2*pair_tile + r.
   // Both CTAs of a pair make the same number of visits (each visit consumes 8 weight stages that the two CTAs load
   // for each other); with an odd tile count the last visit of rank 1 re-processes the last tile without writing.
-#if B200SEP_KA_CL
-  const int crank = (int)cluster_ctarank();
-  const int n_pairs = (int)(gridDim.x >> 1), pair = (int)(blockIdx.x >> 1);
-  const int n_pair_tiles = (n_tiles + 1) >> 1;
-#else  // plain grid: "pair" = CTA, one tile per visit
   const int n_pairs = (int)gridDim.x, pair = (int)blockIdx.x;
   const int n_pair_tiles = n_tiles;
-#endif
   const int n_visits = (pair < n_pair_tiles) ? (n_pair_tiles - pair + n_pairs - 1) / n_pairs : 0;
   auto tile_at = [&](int it, bool& valid) {
-#if B200SEP_KA_CL
-#if B200SEP_KA_REVERSE
-    const int wr = (n_pair_tiles - 1 - (pair + it * n_pairs)) * 2 + crank;
-#else
-    const int wr = (pair + it * n_pairs) * 2 + crank;
-#endif
-#else
-#if B200SEP_KA_REVERSE
     // K_B walks the m-tiles upwards, K_A downwards: K_A starts on the h1 tiles K_B wrote LAST (still in the 126 MB
     // L2) and finishes on the tiles the next K_B reads FIRST (their G_res lines are the freshest)
     const int wr = n_tiles - 1 - (pair + it * n_pairs);
-#else
-    const int wr = pair + it * n_pairs;
-#endif
-#endif
     valid = wr < n_tiles;
     return valid ? wr : n_tiles - 1;
   };
@@ -534,10 +426,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   // producer group (kb & 1), so a parity wait is never more than one phase ahead.  Four stages (two per group: the next
   // k-block's L2 -> shared-memory latency, ~2.3 k cycles, hides behind the current one's arithmetic) when they fit next to
   // two weight stages, else two; the rest of the shared memory is the weight ring.
-#ifndef B200SEP_KA_RAW_MAX
-#define B200SEP_KA_RAW_MAX 4
-#endif
-  const int raw_stages = (B200SEP_KA_RAW_MAX >= 4 && (uint32_t)Cfg::OFF_RAW + 4u * raw_stage_bytes + 2u * (uint32_t)Cfg::B_STAGE <=
+  const int raw_stages = ((uint32_t)Cfg::OFF_RAW + 4u * raw_stage_bytes + 2u * (uint32_t)Cfg::B_STAGE <=
                                                         (uint32_t)Cfg::SMEM_USABLE) ? 4 : 2;
   const uint32_t off_b = (uint32_t)Cfg::OFF_RAW + (uint32_t)raw_stages * raw_stage_bytes;
   const int b_stages = min((int)(((uint32_t)Cfg::SMEM_USABLE - off_b) / (uint32_t)Cfg::B_STAGE), Cfg::B_MAX_STAGES);
@@ -557,7 +446,6 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
   if (warp == 4 && lane == 0) { tma_prefetch_desc(&tm_hc); tma_prefetch_desc(&tm_hh); }
   if (warp == 5 && lane == 0) tma_prefetch_desc(&tm_b);
-  if (B200SEP_KA_PAIR) cluster_sync_all();  // both CTAs of the pair are resident before the pair-wide TMEM allocation
   if (warp == 6) {
     if (lane == 0) {
       for (int s = 0; s < 4; ++s) {
@@ -567,29 +455,24 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       for (int s = 0; s < 2; ++s) {
         // pair mode: the producers / epilogue threads of BOTH CTAs arrive on the leader's a_full / tempty
         mbar_init(tfull_bar(s), 1);
-        mbar_init(tempty_bar(s), B200SEP_KA_PAIR ? 2 * Cfg::EPI_WARPS : 32 * Cfg::EPI_WARPS);
+        mbar_init(tempty_bar(s), 32 * Cfg::EPI_WARPS);
       }
       for (int s = 0; s < 2 * Cfg::A_PG; ++s) {
-        mbar_init(a_full(s), B200SEP_KA_PAIR ? Cfg::PROD_WARPS : Cfg::PROD_WARPS * 16);  // pair: one arrival per warp
+        mbar_init(a_full(s), Cfg::PROD_WARPS * 16);
         mbar_init(a_empty(s), 1);
       }
       for (int s = 0; s < Cfg::B_MAX_STAGES; ++s) {
         mbar_init(b_full(s), 1);
-        mbar_init(b_empty(s), B200SEP_KA_CLUSTER ? 2 : 1);  // (pair mode: ONE multicast commit of the leader)  // cluster: this CTA's and the peer's MMA both release a (multicast-filled) weight stage
+        mbar_init(b_empty(s), 1);
       }
       mbar_init(done_bar, 1);
       fence_barrier_init();
     }
     __syncwarp();
-#if B200SEP_KA_PAIR
-    tmem_alloc_pair(tmem_ptr_smem, Cfg::TMEM_COLS);  // issued by one warp of EACH CTA of the pair
-#else
     tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
-#endif
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (B200SEP_KA_CL) cluster_sync_all();  // both CTAs' mbarriers are initialised before either signals the other
   tcgen05_fence_after();
   pdl_wait();
   uint32_t tmem_base;
@@ -620,9 +503,6 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         // BN == 256: columns 0-127 = residual conv, 128-255 = skip conv; BN == 128 (last block): skip only
         __half* __restrict__ dst = (BN == 256 && c < 4) ? d_res + (size_t)(c * 32) * TILE_M
                                                         : d_skip + (size_t)((BN == 256 ? c - 4 : c) * 32) * TILE_M;
-#ifdef B200SEP_EXP_KA_NO_EPI_STORE  // timing experiment: drain TMEM only
-        if (v[c & 1][0] == 123.456f) dst[0] = __float2half(v[c & 1][31]);
-#else
         if (valid)
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {  // one packed conversion per two channels
@@ -630,15 +510,9 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
           dst[(size_t)j * TILE_M] = __low2half(h);
           dst[(size_t)(j + 1) * TILE_M] = __high2half(h);
         }
-#endif
       }
       tcgen05_fence_before();
-#if B200SEP_KA_PAIR
-      __syncwarp();  // one (remote) arrival per warp: the leader's MMA thread waits for both CTAs' epilogues
-      if (lane == 0) mbar_arrive_cluster(mapa_rank(tempty_bar(as), 0));
-#else
       mbar_arrive(tempty_bar(as));
-#endif
       if (threadIdx.x == 0) tl_stamp(it, 81);
     }
   } else if (warp == 4) {
@@ -653,16 +527,9 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         const int wn = (it + 1 < n_visits) ? tile_at(it + 1, nvalid) : 0;
         for (int kb = 0; kb < 8; ++kb) {
           // pull the same k-block of the NEXT tile this CTA visits into L2 (a whole tile ahead of its use)
-#ifndef B200SEP_EXP_KA_NO_L2PF
           if (nvalid) l2_prefetch_tma_2d(&tm_hc, 0, wn * C_HID + kb * 64);
-#endif
           mbar_wait_b(tb.flags, raw_empty(stage), phase ^ 1u);
           tl_stamp(it, 88 + kb);
-#ifdef B200SEP_EXP_KA_NO_RAW_TMA  // timing experiment: no activation traffic into shared memory
-          mbar_arrive(raw_full(stage));
-          if (++stage == raw_stages) { stage = 0; phase ^= 1u; }
-          continue;
-#endif
           mbar_expect_tx(raw_full(stage), bytes);
           const uint32_t dst = raw_st(stage);
           tma_load_2d(dst, &tm_hc, raw_full(stage), 0, w * C_HID + kb * 64);
@@ -683,27 +550,10 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       for (int it = 0; it < n_visits; ++it) {
         for (int kb = 0; kb < 8; ++kb) {
           mbar_wait_b(tb.flags, b_empty(stage), phase ^ 1u);  // BOTH CTAs' MMAs are done with this stage
-#ifndef B200SEP_EXP_KA_NO_B_TMA
           // the whole stage lands here (own half + the peer's half); this CTA loads rows [crank * BN/2, +BN/2) of the
           // k-block and multicasts them to the same offset of both CTAs
-#if B200SEP_KA_PAIR
-          // each CTA stages ITS N/2 rows of the k-block; both transfers complete on the leader's b_full, which expects
-          // the bytes of both halves
-          if (crank == 0) mbar_expect_tx(b_full(stage), 2 * Cfg::B_STAGE);
-          tma_load_2d_pair(stage_b(stage), &tm_b, mapa_rank(b_full(stage), 0), kb * 64, crank * (BN / 2));
-#else
           mbar_expect_tx(b_full(stage), Cfg::B_STAGE);
-#endif
-#if B200SEP_KA_PAIR
-#elif B200SEP_KA_CLUSTER
-          tma_load_2d_mc(stage_b(stage) + (uint32_t)(crank * (Cfg::B_STAGE / 2)), &tm_b, b_full(stage), kb * 64,
-                         crank * (BN / 2), (uint16_t)0x3);
-#else
           tma_load_2d(stage_b(stage), &tm_b, b_full(stage), kb * 64, 0);
-#endif
-#else  // timing experiment: no weight traffic into shared memory
-          mbar_arrive(b_full(stage));
-#endif
           if (++stage == b_stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -711,54 +561,8 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
     __syncwarp();
   } else if (warp == 6) {
     // ================================ MMA issuer ==================================================
-#if B200SEP_KA_PAIR
-    // CTA pair: ONLY the leader (cluster rank 0) issues; one tcgen05.mma.cta_group::2 covers both CTAs' m-tiles
-    // (M = 256: 128 A rows from each CTA's A stage) against the k-block's weights (N/2 rows from each CTA's B stage)
-    // and accumulates into both CTAs' tensor memory.  Commits are multicast: both CTAs' producers / weight loaders /
-    // epilogues wait on their LOCAL a_empty / b_empty / tfull barriers.
-    if (lane == 0 && crank == 0) {
-      constexpr uint32_t idesc = make_idesc_pair(BN);
-      int bs = 0;
-      uint32_t bphase = 0;
-      for (int it = 0; it < n_visits; ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait_cluster_b(tb.flags, tempty_bar(as), aphase ^ 1u);  // both CTAs' epilogues have drained this accumulator
-        tcgen05_fence_after();
-        tl_stamp(it, 64);
-        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < 8; ++kb) {
-          const int nseq = it * 4 + (kb >> 1);               // k-blocks this group has produced before this one
-          const int g = (kb & 1) * Cfg::A_PG + (nseq & (Cfg::A_PG - 1));
-          const uint32_t gphase = (uint32_t)(nseq / Cfg::A_PG) & 1u;
-          mbar_wait_cluster_b(tb.flags, a_full(g), gphase);          // both CTAs' producer groups have written their A stage
-          mbar_wait_b(tb.flags, b_full(bs), bphase);                 // both halves of the weight k-block have landed
-          tcgen05_fence_after();
-          tl_stamp(it, 65 + kb);
-          const uint32_t sa = stage_a(g), sb = stage_b(bs);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t da = make_smem_desc(sa + j * 2048u, 8192u, 1024u);
-            const uint64_t db = make_smem_desc(sb + j * 32u, 16u, 1024u);
-            umma_f16_pair(tmem_d, da, db, idesc, (uint32_t)((kb | j) != 0));
-          }
-          umma_commit_pair(a_empty(g), (uint16_t)0x3);
-          umma_commit_pair(b_empty(bs), (uint16_t)0x3);
-          if (kb == 7) umma_commit_pair(tfull_bar(as), (uint16_t)0x3);
-          if (++bs == b_stages) { bs = 0; bphase ^= 1u; }
-        }
-      }
-      umma_commit_pair(done_bar, (uint16_t)0x1);  // every asynchronous arrive has landed before the pair tears down
-      mbar_wait_b(tb.flags, done_bar, 0);
-    }
-    __syncwarp();
-#else
     if (lane == 0) {
-#ifndef B200SEP_EXP_KA_HALF_N
       constexpr uint32_t idesc = make_idesc(BN);
-#else  // timing experiment: half the B operand reads
-      constexpr uint32_t idesc = make_idesc(BN / 2);
-#endif
       int bs = 0;
       uint32_t bphase = 0;
       for (int it = 0; it < n_visits; ++it) {
@@ -784,11 +588,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
             umma_f16(tmem_d, da, db, idesc, (uint32_t)((kb | j) != 0));
           }
           umma_commit(a_empty(g));
-#if B200SEP_KA_CLUSTER
-          umma_commit_mc(b_empty(bs), (uint16_t)0x3);  // releases the stage in both CTAs
-#else
           umma_commit(b_empty(bs));
-#endif
           if (kb == 7) umma_commit(tfull_bar(as));
           if (++bs == b_stages) { bs = 0; bphase ^= 1u; }
         }
@@ -798,7 +598,6 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       mbar_wait_b(tb.flags, done_bar, 0);
     }
     __syncwarp();
-#endif
   } else {
     // ================================ depthwise producers =========================================
     // Two groups of 8 warps; group g produces the k-blocks kb = g, g+2, ... (and owns A/B stage g), so
@@ -871,11 +670,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         const int a_idx = grp * Cfg::A_PG + (nseq & (Cfg::A_PG - 1));
         const uint32_t aphase = (uint32_t)(nseq / Cfg::A_PG) & 1u;
         const uint32_t sa = stage_a(a_idx) + a_off0;
-#if B200SEP_KA_PAIR
-        const uint32_t my_ab_full = mapa_rank(a_full(a_idx), 0);  // the LEADER's barrier (cluster address)
-#else
         const uint32_t my_ab_full = a_full(a_idx);
-#endif
         const uint32_t my_ab_empty = a_empty(a_idx);
         const int rs_ = grp + 2 * (nseq & (rpg - 1));             // raw stage of this k-block (= kb % raw_stages)
         const uint32_t rphase = (uint32_t)(nseq / rpg) & 1u;
@@ -889,43 +684,18 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
             // both steps' vectors and table entries first (independent shared-memory loads in flight) ...
             const uint4 vc0 = ld_shared_v4(raw + c_base + jj * c_step);
             const uint4 vc1 = ld_shared_v4(raw + c_base + (jj + 1) * c_step);
-            uint4 va0, vb0, va1, vb1;
-            if (D > 0 && B200SEP_KA_SHFL_TAPS) {
-              // d < 8: the taps reach D frames into the NEIGHBOURING 8-frame vectors, which the adjacent lanes have just
-              // loaded as their centre vectors: one or two words per side come over the warp shuffle network instead
-              // of two more 16-byte shared-memory reads per output vector (K_A is shared-memory-bandwidth bound); only the
-              // first / last lane of a 16-lane channel row reads its neighbour from the halo
-              va0.z = __shfl_up_sync(0xffffffffu, vc0.z, 1);   va0.w = __shfl_up_sync(0xffffffffu, vc0.w, 1);
-              vb0.x = __shfl_down_sync(0xffffffffu, vc0.x, 1); vb0.y = __shfl_down_sync(0xffffffffu, vc0.y, 1);
-              va1.z = __shfl_up_sync(0xffffffffu, vc1.z, 1);   va1.w = __shfl_up_sync(0xffffffffu, vc1.w, 1);
-              vb1.x = __shfl_down_sync(0xffffffffu, vc1.x, 1); vb1.y = __shfl_down_sync(0xffffffffu, vc1.y, 1);
-              va0.x = va0.y = vb0.z = vb0.w = va1.x = va1.y = vb1.z = vb1.w = 0u;
-              if (lane16 == 0) {
-                va0 = ld_shared_v4(raw + l_base + jj * l_step);
-                va1 = ld_shared_v4(raw + l_base + (jj + 1) * l_step);
-              }
-              if (lane16 == 15) {
-                vb0 = ld_shared_v4(raw + r_base + jj * r_step);
-                vb1 = ld_shared_v4(raw + r_base + (jj + 1) * r_step);
-              }
-            } else {
-              va0 = ld_shared_v4(raw + l_base + jj * l_step);
-              vb0 = ld_shared_v4(raw + r_base + jj * r_step);
-              va1 = ld_shared_v4(raw + l_base + (jj + 1) * l_step);
-              vb1 = ld_shared_v4(raw + r_base + (jj + 1) * r_step);
-            }
+            const uint4 va0 = ld_shared_v4(raw + l_base + jj * l_step);
+            const uint4 vb0 = ld_shared_v4(raw + r_base + jj * r_step);
+            const uint4 va1 = ld_shared_v4(raw + l_base + (jj + 1) * l_step);
+            const uint4 vb1 = ld_shared_v4(raw + r_base + (jj + 1) * r_step);
             const float4 ta = s_t0[ch0 + jj * 16], tb_ = s_t0[ch0 + jj * 16 + 16];
             const float cba = s_cb[ch0 + jj * 16], cbb = s_cb[ch0 + jj * 16 + 16];
             // ... then the arithmetic; the (single) A stage of this group is only needed for the stores, so the
             // tensor core drains the previous k-block of the group while the first two steps are computed
-#ifdef B200SEP_EXP_KA_NO_COMPUTE  // timing experiment: producers only move data
-            const uint4 o0 = make_uint4(vc0.x ^ va0.x, vc0.y ^ vb0.y, vc0.z, vc0.w);
-            const uint4 o1 = make_uint4(vc1.x ^ va1.x, vc1.y ^ vb1.y, vc1.z, vc1.w);
-            s2.x += ta.x + tb_.x + cba + cbb;
-#else
-            const uint4 o0 = dw_step_h2<D, A01>(vc0, va0, vb0, ta, cba, rstd, rm, alpha_h2, s2, q2);
-            const uint4 o1 = dw_step_h2<D, A01>(vc1, va1, vb1, tb_, cbb, rstd, rm, alpha_h2, s2, q2);
-#endif
+            __half2 sh = __float2half2_rn(0.f), qh = __float2half2_rn(0.f);
+            const uint4 o0 = dw_step_h2<D, A01>(vc0, va0, vb0, ta, cba, rstd, rm, alpha_h2, sh, qh);
+            const uint4 o1 = dw_step_h2<D, A01>(vc1, va1, vb1, tb_, cbb, rstd, rm, alpha_h2, sh, qh);
+            dw_stats_flush(sh, qh, s2, q2);
             if (jj == 0) {
               mbar_wait_b(tb.flags, my_ab_empty, aphase ^ 1u);
               if (tl_on) tl_stamp(it, tl_base + 3 * (kb >> 1) + 1);
@@ -965,12 +735,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
           }
         }
         fence_proxy_async();
-#if B200SEP_KA_PAIR
-        __syncwarp();  // every lane has fenced its A-stage writes; lane 0 arrives (release.cluster is cumulative)
-        if (lane == 0) mbar_arrive_cluster(my_ab_full);
-#else
         mbar_arrive(my_ab_full);
-#endif
         mbar_arrive(raw_empty(rs_));
         if (tl_on) tl_stamp(it, tl_base + 3 * (kb >> 1) + 2);
         ++nseq;
@@ -988,48 +753,24 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
 
   tcgen05_fence_before();
   __syncthreads();
-  if (B200SEP_KA_CL) cluster_sync_all();  // the peer may multicast into / arrive on this CTA's shared memory until it is done too
-  tl_stamp_ns(125);
   if (warp == 6) {
     tcgen05_fence_after();
-#if B200SEP_KA_PAIR
-    tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
-#else
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
-#endif
   }
 }
 
 // =================================================================================================
 // K_B: apply previous block's G_res (x += res) + in-conv GEMM -> h1
 // =================================================================================================
-#ifndef B200SEP_KB_TMA_STORE
-#define B200SEP_KB_TMA_STORE 0  // (lane = frame orientation only) 1: h1 via 2-byte st.shared staging + TMA stores: slower
-#endif
-#ifndef B200SEP_KB_TRANSPOSED
-#define B200SEP_KB_TRANSPOSED 1  // in-conv GEMM as D[channel][frame]: epilogue thread = channel, 16-byte staging stores
-#endif
 struct KbCfg {
   static constexpr int W_BYTES = C_HID * C_BN * 2;      // 128 KiB: [2 k-blocks][512 rows][64 k]
   static constexpr int XN_BYTES = TILE_M * C_BN * 2;    // 32 KiB: [2 k-blocks][64 k][128 m]
-#ifndef B200SEP_KB_PRO_WARPS
-#define B200SEP_KB_PRO_WARPS 8
-#endif
-#ifndef B200SEP_KB_PRO_RND
-#define B200SEP_KB_PRO_RND 4
-#endif
-#ifndef B200SEP_KB_DIRECT_MASK
-#define B200SEP_KB_DIRECT_MASK 0  // bit q set: chunk q of the transposed epilogue writes h1 with 16-byte global stores (LSU)
-                                  // instead of staging + TMA (shared memory); 0xF = all direct (89 us), 0 = all staged (60 us)
-#endif
-#ifndef B200SEP_KB_EPI16
-#define B200SEP_KB_EPI16 0  // 1: transposed epilogue on 16 warps (4 per TMEM lane quadrant, 32 frames each) instead of 8
-#endif
-  static constexpr int EPI_WARPS = (B200SEP_KB_TRANSPOSED && B200SEP_KB_EPI16) ? 16 : 8;  // EPI_WARPS / 4 per TMEM lane quadrant
-  static constexpr int PRO_WARPS = B200SEP_KB_PRO_WARPS;
+  static constexpr int EPI_WARPS = 8;   // two per TMEM lane quadrant
+  static constexpr int PRO_WARPS = 8;
+  static constexpr int PRO_RND = 4;     // prologue passes per round (global loads in flight per thread: 2 x PRO_RND vectors)
   static constexpr int THREADS = (EPI_WARPS + 1 + PRO_WARPS) * 32;  // 544
   static constexpr int TMEM_COLS = 512;                 // 4 chunks of 128 output channels
-  static constexpr int ST_BYTES = (B200SEP_KB_TMA_STORE || B200SEP_KB_TRANSPOSED) ? TILE_M * 128 * 2 : 0;  // h1 staging
+  static constexpr int ST_BYTES = TILE_M * 128 * 2;  // h1 staging
   static constexpr int OFF_XN = W_BYTES;
   static constexpr int OFF_ST = OFF_XN + 2 * XN_BYTES;
   static constexpr int OFF_TI = OFF_ST + ST_BYTES;
@@ -1040,17 +781,13 @@ struct KbCfg {
   static_assert(SMEM_BYTES <= 232448, "K_B shared memory over the 227 KiB limit");
 };
 
-#ifndef B200SEP_X16
-#define B200SEP_X16 1  // residual stream x stored in fp16 between blocks (the update itself is fp32 in registers): K_B moves
-                       // 1792 instead of 2304 B/frame; isolated cost 75 -> 69 dB on the oracle, measured on the whole path
-#endif
 struct ApplyParams {
   const __half* g;      // [nt][128][128] raw residual-conv output of the previous block (nullptr: block 0)
   const float2* part2;  // [nt] gLN2 partials of the previous block
   const float* rs;      // [>=128] rowsum(W_res . gamma2) of the previous block
   const float* cb;      // [>=128] W_res * beta2 + b_res
-  float* x;             // [nt][128][128] fp32 residual stream (updated in place)            (B200SEP_X16 == 0)
-  __half* x16;          // [nt][128][128] fp16 residual stream (updated in place)            (B200SEP_X16 == 1)
+  float* x;             // (unused by the fused pipeline: the unfused scaffold keeps an fp32 stream)
+  __half* x16;          // [nt][128][128] fp16 residual stream (updated in place; every update is computed in fp32)
   float eps2;           // eps of the previous block's gLN2 (shared_block.5)
 };
 
@@ -1077,7 +814,6 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
   const uint32_t done_bar = bar0 + 8u * 14;  // final tcgen05.commit: no async mbarrier arrive may outlive the CTA
 
   pdl_launch_dependents();  // PDL: the prologue below (barriers, TMEM, resident W_in, layout tables) reads constants only
-  tl_stamp_ns(120);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n_tiles = tb.n_tiles;
@@ -1116,81 +852,6 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
-#if B200SEP_KB_TRANSPOSED && B200SEP_KB_EPI16
-  if (warp < MMA_WARP) {
-    // ================================ epilogue: bias + PReLU -> h1, gLN1 partials ==================
-    // D[channel][frame]: TMEM lane = output channel of the 128-channel chunk, column = frame.  16 warps: warp =
-    // (lane quadrant, 32-frame quarter of the m-tile); per chunk a thread owns 32 consecutive frames of one channel (one
-    // tcgen05.ld): the bias is a per-lane constant, eight frames pack into one 16-byte st.shared (swizzled like a TMA
-    // box, conflict-free), and h1 leaves the SM as 64 x 64 TMA tile stores.  Four warps per scheduler hide the
-    // TMEM-load / shared-memory latencies that two could not (the traffic-free skeleton of the 8-warp version took
-    // 43 of the kernel's 60 us).
-    static_assert(Cfg::EPI_WARPS == 16, "epilogue mapping: four warps per TMEM lane quadrant");
-    const int ew = warp, quad = ew & 3, part = ew >> 2;   // part = 32-frame quarter of the m-tile
-    const int half = part >> 1, hh = part & 1;
-    const int cl = quad * 32 + lane;                       // channel inside the chunk
-    const int kb64 = cl >> 6, row = cl & 63;
-    const int grp = kb64 * 2 + half;                       // staging box = (64-channel block, frame half): 4 warps
-    const uint32_t st_box = smem_base + (uint32_t)(Cfg::OFF_ST + kb64 * 16384 + half * 8192);
-    const uint32_t st_row = st_box + (uint32_t)(row * 128);
-    const bool issuer = ((quad & 1) == 0 && hh == 0 && lane == 0);  // one thread per box issues its TMA store
-    const float alpha = epi.alpha;
-    const int f0 = part * 32;                              // first frame of this warp's piece inside the m-tile
-    int it = 0;
-    for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
-      const TileInfo ti = ti_get(s_ti, tb, it, w);
-      const int nvalid = ti.F - ti.t0;                     // frames >= nvalid lie beyond the segment end
-      const bool full = nvalid >= TILE_M;
-      float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
-      const uint32_t ph = (uint32_t)it & 1u;
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        float v[32];
-        mbar_wait_b(tb.flags, tfull_bar(q), ph);
-        tcgen05_fence_after();
-        if (threadIdx.x == 0) tl_stamp(it, 16 + q);
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(q * 128 + part * 32), v);
-        const float bch = __ldg(epi.bias + q * 128 + cl);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        mbar_arrive(tempty_bar(q));  // the warp's part of chunk q is in registers: the MMA may overwrite it
-        const float2 b2 = make_float2(bch, bch);
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float2 u = add2(make_float2(v[j], v[j + 1]), b2);
-          u = prelu2<A01>(u, alpha);
-          pk[j >> 1] = h2_as_u32(__floats2half2_rn(u.x, u.y));
-          if (!full) {  // statistics exclude frames beyond the segment end
-            if (f0 + j >= nvalid) u.x = 0.f;
-            if (f0 + j + 1 >= nvalid) u.y = 0.f;
-          }
-          s2 = add2(s2, u);
-          q2 = fma2(u, u, q2);
-        }
-        // the previous chunk's TMA store must have finished READING this staging box before it is rewritten
-        if (issuer) bulk_wait_read0();
-        named_bar_sync(1 + grp, 128);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          st_shared_v4(st_row + (uint32_t)((((hh * 4 + k) ^ (row & 7))) << 4),
-                       make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
-        fence_proxy_async();
-        named_bar_sync(1 + grp, 128);
-#ifndef B200SEP_EXP_KB_NO_H1_STORE
-        if (issuer) {
-          tma_store_2d(&tm_h1, st_box, half * 64, w * C_HID + q * 128 + kb64 * 64);
-          bulk_commit();
-        }
-#endif
-        if (threadIdx.x == 0) tl_stamp(it, 20 + q);
-      }
-      const float s = warp_sum(s2.x + s2.y), qq = warp_sum(q2.x + q2.y);
-      tile_partial_reduce(s_red + (it & 1) * Cfg::EPI_WARPS, s_cnt + (it & 1), Cfg::EPI_WARPS, ew, s, qq,
-                          epi.part_out + w);
-    }
-    if (issuer) bulk_wait0();  // all h1 tile stores complete before the CTA exits
-#elif B200SEP_KB_TRANSPOSED
   if (warp < MMA_WARP) {
     // ================================ epilogue: bias + PReLU -> h1, gLN1 partials ==================
     // D[channel][frame]: TMEM lane = output channel of the 128-channel chunk, column = frame.  A thread owns 32
@@ -1239,8 +900,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qn * 128 + half * 64 + ((pi + 1) & 1) * 32),
                     v[(pi + 1) & 1]);
         }
-        const bool direct = ((B200SEP_KB_DIRECT_MASK >> q) & 1) != 0;  // compile-time per unrolled piece
-        if (hh == 0 && !direct) {
+        if (hh == 0) {
           // the previous staged chunk's TMA store must have finished READING this staging box before it is rewritten
           if (issuer) bulk_wait_read0();
           named_bar_sync(1 + grp, 64);
@@ -1248,11 +908,6 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
         const float2 b2 = make_float2(bch, bch);
         const int f0 = half * 64 + hh * 32;  // first frame of the piece inside the m-tile
         uint32_t pk[16];
-#ifdef B200SEP_EXP_KB_NO_MATH  // timing experiment: no epilogue arithmetic
-#pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = __float_as_uint(v[pi & 1][j]) ^ __float_as_uint(v[pi & 1][j + 16]);
-        s2.x += b2.x;
-#else
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float2 u = add2(make_float2(v[pi & 1][j], v[pi & 1][j + 1]), b2);
@@ -1265,30 +920,17 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
           s2 = add2(s2, u);
           q2 = fma2(u, u, q2);
         }
-#endif
-#ifdef B200SEP_EXP_KB_NO_STS  // timing experiment: no staging stores
-        if (pk[0] == 0x12345678u && pk[7] == 0x9abcdef0u && pk[15] == 1u) st_shared_v4(st_row, make_uint4(pk[1], pk[2], pk[3], pk[4]));
-#else
-        if (direct) {  // 32 consecutive frames of this thread's channel = 64 contiguous bytes of h1: four 16-byte global stores
-          uint4* __restrict__ gp = reinterpret_cast<uint4*>(epi.h1 + tt_index(w, C_HID, q * 128 + cl, f0));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) gp[k] = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            st_shared_v4(st_row + (uint32_t)((((hh * 4 + k) ^ (row & 7))) << 4),
-                         make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
-        }
-#endif
-        if (hh == 1 && !direct) {
+        for (int k = 0; k < 4; ++k)
+          st_shared_v4(st_row + (uint32_t)((((hh * 4 + k) ^ (row & 7))) << 4),
+                       make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
+        if (hh == 1) {
           fence_proxy_async();
           named_bar_sync(1 + grp, 64);
-#ifndef B200SEP_EXP_KB_NO_H1_STORE  // (timing experiment when defined: h1 never leaves the SM)
           if (issuer) {
             tma_store_2d(&tm_h1, st_box, half * 64, w * C_HID + q * 128 + kb64 * 64);
             bulk_commit();
           }
-#endif
           if (threadIdx.x == 0) tl_stamp(it, 20 + q);
         }
         bch = bnext;
@@ -1298,126 +940,11 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
                           epi.part_out + w);
     }
     if (issuer) bulk_wait0();  // all h1 tile stores complete before the CTA exits
-#else
-  if (warp < MMA_WARP) {
-    // ================================ epilogue: bias + PReLU -> h1, gLN1 partials ==================
-    // warp = (TMEM lane quadrant, 64-channel half of the 128-channel chunk).  h1 goes through a swizzled
-    // shared-memory staging tile (2-byte st.shared, 32 lanes = 64 contiguous bytes: conflict-free) and is
-    // written to HBM by TMA tile stores -- not by 65 k two-byte global stores per m-tile through the LSU.
-    static_assert(Cfg::EPI_WARPS == 8, "epilogue mapping assumes two warps per TMEM lane quadrant");
-    const int ew = warp, quad = ew & 3, half = ew >> 2;
-    const int r = quad * 32 + lane;
-    // staging offsets of this thread's frame: [k64-block = half][frame half][row = channel][128 B], chunk ^ (row & 7)
-    const uint32_t st_base = smem_base + (uint32_t)(Cfg::OFF_ST + half * 16384 + (r >> 6) * 8192 + (r & 7) * 2);
-    uint32_t st_x[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) st_x[k] = st_base + (uint32_t)(((((r & 63) >> 3) ^ k)) << 4);
-    const bool issuer = (quad == 0 && lane == 0);  // one thread per half issues that half's TMA stores
-    const float alpha = epi.alpha;
-    int it = 0;
-    for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
-      const TileInfo ti = ti_get(s_ti, tb, it, w);
-      const float vm = ((ti.t0 + r) < ti.F) ? 1.f : 0.f;  // statistics exclude frames beyond the segment end
-      const float2 vm2 = make_float2(vm, vm);
-      float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
-      const uint32_t ph = (uint32_t)it & 1u;
-      __half* __restrict__ gdst = epi.h1 + tt_index(w, C_HID, half * 64, r);
-      // 8 pieces of 32 columns per m-tile (4 chunks x 2); the tcgen05.ld of piece i+1 is in flight while piece i
-      // is processed (TMEM drains at ~64 B/cycle/SM: loads and arithmetic must overlap inside a warp)
-      float v[2][32];
-      mbar_wait_b(tb.flags, tfull_bar(0), ph);
-      tcgen05_fence_after();
-      if (threadIdx.x == 0) tl_stamp(it, 16);
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 64), v[0]);
-#pragma unroll
-      for (int pi = 0; pi < 8; ++pi) {
-        const int q = pi >> 1, hh = pi & 1;
-        tmem_ld_wait();  // piece pi is in v[pi & 1]
-        if (hh == 1) {
-          tcgen05_fence_before();
-          mbar_arrive(tempty_bar(q));  // the warp's part of chunk q is in registers: the MMA may overwrite it
-        }
-        if (pi + 1 < 8) {
-          const int qn = (pi + 1) >> 1;
-          if (((pi + 1) & 1) == 0) {
-            mbar_wait_b(tb.flags, tfull_bar(qn), ph);
-            tcgen05_fence_after();
-            if (threadIdx.x == 0) tl_stamp(it, 16 + qn);
-          }
-          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qn * 128 + half * 64 + ((pi + 1) & 1) * 32),
-                    v[(pi + 1) & 1]);
-        }
-        const int n_base = q * 128 + half * 64 + hh * 32;
-#if B200SEP_KB_TMA_STORE
-        if (hh == 0) {
-          // the previous chunk's TMA stores must have finished READING the staging half before it is rewritten
-          if (issuer) bulk_wait_read0();
-          named_bar_sync(1 + half, 128);
-        }
-#endif
-#ifdef B200SEP_EXP_KB_TMEM_ONLY  // timing experiment: drain TMEM only
-        s2.x += v[pi & 1][0] + v[pi & 1][31];
-        if (s2.x == 123.456f) gdst[0] = __float2half(q2.x);
-#else
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = ldg4(epi.bias + n_base + j);
-          float2 v0 = add2(make_float2(v[pi & 1][j], v[pi & 1][j + 1]), make_float2(b4.x, b4.y));
-          float2 v1 = add2(make_float2(v[pi & 1][j + 2], v[pi & 1][j + 3]), make_float2(b4.z, b4.w));
-          v0 = prelu2<A01>(v0, alpha);
-          v1 = prelu2<A01>(v1, alpha);
-          const __half2 h0 = __floats2half2_rn(v0.x, v0.y), h1v = __floats2half2_rn(v1.x, v1.y);
-#if B200SEP_KB_TMA_STORE
-          const uint32_t u0 = h2_as_u32(h0), u1 = h2_as_u32(h1v);
-          const int cc = hh * 32 + j;  // channel inside the 64-channel half (row of the staging block)
-          st_shared_u16(st_x[(cc + 0) & 7] + (uint32_t)((cc + 0) * 128), (uint16_t)(u0 & 0xffffu));
-          st_shared_u16(st_x[(cc + 1) & 7] + (uint32_t)((cc + 1) * 128), (uint16_t)(u0 >> 16));
-          st_shared_u16(st_x[(cc + 2) & 7] + (uint32_t)((cc + 2) * 128), (uint16_t)(u1 & 0xffffu));
-          st_shared_u16(st_x[(cc + 3) & 7] + (uint32_t)((cc + 3) * 128), (uint16_t)(u1 >> 16));
-#else
-          __half* __restrict__ d = gdst + (size_t)(q * 128 + hh * 32 + j) * TILE_M;
-          d[0] = __low2half(h0);
-          d[TILE_M] = __high2half(h0);
-          d[2 * TILE_M] = __low2half(h1v);
-          d[3 * TILE_M] = __high2half(h1v);
-#endif
-          const float2 m0 = mul2(v0, vm2), m1 = mul2(v1, vm2);
-          s2 = add2(s2, add2(m0, m1));
-          q2 = fma2(m0, v0, fma2(m1, v1, q2));
-        }
-#endif
-#if B200SEP_KB_TMA_STORE
-        if (hh == 1) {
-          fence_proxy_async();
-          named_bar_sync(1 + half, 128);
-          if (issuer) {
-            const uint32_t src = smem_base + (uint32_t)(Cfg::OFF_ST + half * 16384);
-            const int row = w * C_HID + q * 128 + half * 64;
-            tma_store_2d(&tm_h1, src, 0, row);
-            tma_store_2d(&tm_h1, src + 8192u, 64, row);
-            bulk_commit();
-          }
-        }
-#endif
-        if (hh == 1 && threadIdx.x == 0) tl_stamp(it, 20 + q);
-      }
-      const float s = warp_sum(s2.x + s2.y), qq = warp_sum(q2.x + q2.y);
-      tile_partial_reduce(s_red + (it & 1) * Cfg::EPI_WARPS, s_cnt + (it & 1), Cfg::EPI_WARPS, ew, s, qq,
-                          epi.part_out + w);
-    }
-#if B200SEP_KB_TMA_STORE
-    if (issuer) bulk_wait0();  // all h1 tile stores complete before the CTA exits
-#endif
-#endif  // B200SEP_KB_TRANSPOSED
   } else if (warp == MMA_WARP) {
     // ================================ MMA issuer ==================================================
     if (lane == 0) {
-#if B200SEP_KB_TRANSPOSED
       // A = W_in chunk (K-major), B = x operand (MN-major): bit 15 (A major) = 0, bit 16 (B major) = 1
       constexpr uint32_t idesc = (1u << 4) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-#else
-      constexpr uint32_t idesc = make_idesc(128);
-#endif
       mbar_wait_b(tb.flags, w_bar, 0);
       int it = 0;
       for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
@@ -1437,11 +964,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
             for (int j = 0; j < 4; ++j) {
               const uint64_t dx = make_smem_desc(sa + (uint32_t)(kb * 16384 + j * 2048), 8192u, 1024u);  // MN-major
               const uint64_t dw = make_smem_desc(smem_w + (uint32_t)(kb * 65536 + q * 16384 + j * 32), 16u, 1024u);  // K-major
-#if B200SEP_KB_TRANSPOSED
               umma_f16(tmem_d, dw, dx, idesc, (uint32_t)((kb | j) != 0));  // D[channel][frame] = W . x^T
-#else
-              umma_f16(tmem_d, dx, dw, idesc, (uint32_t)((kb | j) != 0));  // D[frame][channel] = x . W^T
-#endif
             }
           }
           umma_commit(tfull_bar(q));
@@ -1480,51 +1003,27 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
       const uint16_t rstd_h = __half_as_ushort(rstd_hh);
       const float nmr = -mean * __half2float(rstd_hh);
       if (pt == 0) tl_stamp(it, 0);
-#ifndef B200SEP_EXP_KB_NO_L2PF
       if (pt == 0 && w + (int)gridDim.x < n_tiles) {  // next tile's x / G_res -> L2 while this tile is processed
         const size_t nidx = tt_index(w + gridDim.x, C_BN, 0, 0);
-#if B200SEP_X16
         l2_prefetch_bulk(ap.x16 + nidx, TILE_M * C_BN * 2);
-#else
-        l2_prefetch_bulk(ap.x + nidx, TILE_M * C_BN * 4);
-#endif
         if (has_g) l2_prefetch_bulk(ap.g + nidx, TILE_M * C_BN * 2);
       }
-#endif
-#if B200SEP_X16
       __half* __restrict__ xt = ap.x16 + tt_index(w, C_BN, 0, f0);
-#else
-      float* __restrict__ xt = ap.x + tt_index(w, C_BN, 0, f0);
-#endif
       const __half* __restrict__ gt = has_g ? ap.g + tt_index(w, C_BN, 0, f0) : nullptr;
       // all global loads of the tile are issued before the (possibly blocking) operand-buffer wait
       constexpr int PASSES = C_BN / ROWS;
       uint32_t xn = 0;
-      constexpr int RND = B200SEP_KB_PRO_RND;  // passes per round (global loads in flight per thread: 3 x RND vectors)
+      constexpr int RND = Cfg::PRO_RND;
       static_assert(PASSES % RND == 0, "prologue rounds");
 #pragma unroll 1
       for (int p0 = 0; p0 < PASSES; p0 += RND) {
-#if B200SEP_X16
         uint4 xh[RND];
-#else
-        float4 xa[RND], xb[RND];
-#endif
         uint4 gr[RND];
 #pragma unroll
         for (int j = 0; j < RND; ++j) {
           const size_t off = (size_t)((p0 + j) * ROWS + crow) * TILE_M;
-#if B200SEP_X16 && defined(B200SEP_EXP_NO_PRO_IO)  // timing experiment: no prologue global traffic
-          xh[j] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, (uint32_t)off); gr[j] = xh[j];
-#elif B200SEP_X16
           xh[j] = *reinterpret_cast<const uint4*>(xt + off);
           if (has_g) gr[j] = ldg_v4(gt + off);
-#elif !defined(B200SEP_EXP_NO_PRO_IO)
-          xa[j] = *reinterpret_cast<const float4*>(xt + off);
-          xb[j] = *reinterpret_cast<const float4*>(xt + off + 4);
-          if (has_g) gr[j] = ldg_v4(gt + off);
-#else
-          xa[j] = make_float4(0.1f, 0.2f, 0.3f, (float)off); xb[j] = xa[j]; gr[j] = make_uint4(0, 0, 0, 0);
-#endif
         }
         if (p0 == 0) {
           mbar_wait_b(tb.flags, xn_empty(b), ((uint32_t)(it >> 1) & 1u) ^ 1u);
@@ -1535,7 +1034,6 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
         for (int j = 0; j < RND; ++j) {
           const int c = (p0 + j) * ROWS + crow;
           const size_t off = (size_t)c * TILE_M;
-#if B200SEP_X16
           float xv[8];
           {
             const uint32_t xw[4] = {xh[j].x, xh[j].y, xh[j].z, xh[j].w};
@@ -1545,9 +1043,6 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
               xv[2 * i] = f.x; xv[2 * i + 1] = f.y;
             }
           }
-#else
-          float xv[8] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w, xb[j].x, xb[j].y, xb[j].z, xb[j].w};
-#endif
           if (has_g) {
             const float kr = fmaf(nmr, __ldg(ap.rs + c), __ldg(ap.cb + c));
             const uint32_t gw[4] = {gr[j].x, gr[j].y, gr[j].z, gr[j].w};
@@ -1558,23 +1053,12 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
               const float2 nx = fma2(dr, vm[i >> 1], make_float2(xv[i], xv[i + 1]));
               xv[i] = nx.x; xv[i + 1] = nx.y;
             }
-#if B200SEP_X16
             const uint4 pk = pack8(xv);  // the rounded stream IS the GEMM operand: one rounding, stored twice
-#ifndef B200SEP_EXP_NO_PRO_IO
             *reinterpret_cast<uint4*>(xt + off) = pk;
-#endif
             st_shared_v4(xn + (uint32_t)((c >> 6) * 16384) + a_chunk_off(c & 63, f0), pk);
             continue;
-#elif !defined(B200SEP_EXP_NO_PRO_IO)
-            *reinterpret_cast<float4*>(xt + off) = make_float4(xv[0], xv[1], xv[2], xv[3]);
-            *reinterpret_cast<float4*>(xt + off + 4) = make_float4(xv[4], xv[5], xv[6], xv[7]);
-#endif
           }
-#if B200SEP_X16
           st_shared_v4(xn + (uint32_t)((c >> 6) * 16384) + a_chunk_off(c & 63, f0), xh[j]);  // block 0: x as stored
-#else
-          st_shared_v4(xn + (uint32_t)((c >> 6) * 16384) + a_chunk_off(c & 63, f0), pack8(xv));
-#endif
         }
       }
       fence_proxy_async();
@@ -1585,7 +1069,6 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
 
   tcgen05_fence_before();
   __syncthreads();
-  tl_stamp_ns(121);
   if (warp == MMA_WARP) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

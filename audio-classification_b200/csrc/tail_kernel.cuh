@@ -24,9 +24,6 @@ using namespace tc;
 using fb::mbar_wait_b;
 using fb::st_shared_v4;
 
-#ifndef B200SEP_TAIL_EPI16
-#define B200SEP_TAIL_EPI16 1  // 16 epilogue warps (4 per TMEM lane quadrant, 32 filters each) instead of 8 (64 filters each)
-#endif
 // 16 fp32 columns of 32 lanes
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t* u = reinterpret_cast<uint32_t*>(v);
@@ -53,7 +50,7 @@ struct TailCfg {
   static constexpr int OFF_OLA = OFF_ST + ST_STAGES * ST_BYTES;
   static constexpr int OFF_BAR = (OFF_OLA + OLA_BYTES + 15) / 16 * 16;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-  static constexpr int EPI_WARPS = B200SEP_TAIL_EPI16 ? 16 : 8;
+  static constexpr int EPI_WARPS = 16;  // 4 per TMEM lane quadrant, 32 filters each
   static constexpr int THREADS = (4 + EPI_WARPS) * 32;
   static constexpr int TMEM_COLS = 512;
   static constexpr int DEC_COL0 = 256;                    // decoder accumulators start here
@@ -224,7 +221,6 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       mbar_wait_b(tb.flags, done_bar, 0);
     }
     __syncwarp();
-#if B200SEP_TAIL_EPI16
   } else if (warp >= 4) {
     // ================================ epilogue (16 warps) =========================================
     // warp = (TMEM lane quadrant, 32-filter quarter of the 128-filter chunk); a thread owns one frame x 32 filters,
@@ -340,132 +336,6 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       }
     }
   }
-#else
-  } else if (warp >= 4) {
-    // ================================ epilogue ====================================================
-    const int ew = warp - 4, quad = ew & 3, half = ew >> 2;
-    const int r = quad * 32 + lane;  // frame within the m-tile == TMEM lane
-    int n_acc = 0, n_st = 0, n_dec = 0;
-    for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
-      const TileInfo ti = load_tile_info(tb.tile_info + w);
-      const int seg = ti.seg, t0 = ti.t0, F = ti.F;
-      const int T_len = tb.seg_len[seg];
-      const bool fvalid = (t0 + r) < F;
-      for (int c = 0; c < n_chunks; ++c) {
-        const int src = c >> 2, cc = c & 3;
-        const int as = n_acc & 1, ss = n_st & 1;
-        const int ch0 = cc * 128 + half * 64;           // first filter of this warp's 64 columns
-        const __half* __restrict__ ep = p.enc + tt_index(w, C_ENC, ch0, r);
-        const float* __restrict__ bp = p.bias + src * C_ENC + ch0;
-        mbar_wait_b(tb.flags, acc_full(as), ((uint32_t)n_acc >> 1) & 1u);
-        tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 128 + half * 64);
-        float v[2][32];
-        tmem_ld32(taddr, v[0]);
-        tmem_ld32(taddr + 32u, v[1]);
-        uint32_t pk[32];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {  // two halves of 32 filters: keeps the live register set small
-          float e[32];
-#pragma unroll
-#ifdef B200SEP_EXP_TAIL_NO_ENC  // timing experiment: no encoder-output loads
-          for (int j = 0; j < 32; ++j) e[j] = 0.5f + (float)j;
-#else
-          for (int j = 0; j < 32; ++j) e[j] = __half2float(ep[(size_t)(h * 32 + j) * TILE_M]);
-#endif
-          if (h == 0) {
-            tmem_ld_wait();
-            tcgen05_fence_before();
-            mbar_arrive(acc_empty(as));  // both halves are in registers: the next mask MMA may overwrite the buffer
-            ++n_acc;
-          }
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const float2 b2 = __ldg(reinterpret_cast<const float2*>(bp + h * 32 + j));
-            const float a0 = v[h][j] + b2.x, a1 = v[h][j + 1] + b2.y;
-            float m0, m1;
-            if (p.act == 0) {
-              // sigmoid(v) = 0.5 * tanh(0.5 v) + 0.5 (one MUFU op per element)
-              float t0_, t1_;
-#ifdef B200SEP_EXP_TAIL_NO_TANH  // timing experiment: no MUFU
-              t0_ = 0.5f * a0; t1_ = 0.5f * a1;
-#else
-              asm("tanh.approx.f32 %0, %1;" : "=f"(t0_) : "f"(0.5f * a0));
-              asm("tanh.approx.f32 %0, %1;" : "=f"(t1_) : "f"(0.5f * a1));
-#endif
-              m0 = fmaf(t0_, 0.5f, 0.5f) * e[j];
-              m1 = fmaf(t1_, 0.5f, 0.5f) * e[j + 1];
-            } else {
-              m0 = fmaxf(a0, 0.f) * e[j];
-              m1 = fmaxf(a1, 0.f) * e[j + 1];
-            }
-            if (!fvalid) { m0 = 0.f; m1 = 0.f; }  // frames beyond the segment end contribute nothing
-            const __half2 hh2 = __floats2half2_rn(m0, m1);
-            pk[h * 16 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&hh2);
-          }
-        }
-        // masked chunk -> K-major SWIZZLE_128B operand: k-block = half, row = frame, 8 filters per 16-byte chunk
-        mbar_wait_b(tb.flags, st_empty(ss), (((uint32_t)n_st >> 1) & 1u) ^ 1u);
-        const uint32_t row_base = smem_st(ss) + (uint32_t)(half * 16384 + r * 128);
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          st_shared_v4(row_base + (uint32_t)((q ^ (r & 7)) << 4), make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]));
-        fence_proxy_async();
-        mbar_arrive(st_full(ss));
-        ++n_st;
-
-        if (cc == 3) {
-          // ---- decoder output of source `src`: taps -> overlap-add -> global (4 warps, one per lane quadrant)
-          if (half == 0) {
-            mbar_wait_b(tb.flags, dec_full, (uint32_t)n_dec & 1u);
-            tcgen05_fence_after();
-            float taps[32];
-            const uint32_t daddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::DEC_COL0 + (src & 1) * L);
-            if (L == 16) {
-              uint32_t* u = reinterpret_cast<uint32_t*>(taps);
-              asm volatile(
-                  "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                  : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
-                    "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
-                  : "r"(daddr)
-                  : "memory");
-            } else {
-              tmem_ld32(daddr, taps);
-            }
-            tmem_ld_wait();
-            tcgen05_fence_before();
-            mbar_arrive(dec_empty);
-#pragma unroll
-            for (int l = 0; l < L; ++l) s_ola[r][l] = taps[l];
-            fb::named_bar_sync(2, 128);
-            float* o = p.out + tb.seg_out_off[seg] + (size_t)src * T_len;
-            const int tid = quad * 32 + lane;
-            // hops hh = 0..128 of this tile: sample (t0 + hh) * S + l gets frame hh's first half and frame
-            // hh-1's second half
-            for (int i = tid; i < (TILE_M + 1) * S; i += 128) {
-              const int hh = i / S, l = i % S;
-              const int f_hi = t0 + hh, f_lo = t0 + hh - 1;
-              float val = 0.f;
-              bool any = false;
-              if (hh < TILE_M && f_hi < F) { val += s_ola[hh][l]; any = true; }
-              if (hh >= 1 && f_lo < F) { val += s_ola[hh - 1][S + l]; any = true; }
-              if (!any) continue;
-              // inf / NaN samples (fp16 overflow of an activation, or non-finite input): flagged for the host, which
-              // warns and points at precision="fp32"; the values are still written, as the reference would
-              if (!(fabsf(val) <= 3.0e38f)) atomicOr(tb.flags, 2);
-              const size_t idx = (size_t)(t0 + hh) * S + l;
-              if (hh == 0 || hh == TILE_M) atomicAdd(o + idx, val);
-              else o[idx] = val;
-            }
-            fb::named_bar_sync(2, 128);  // s_ola is reused by the next source
-          }
-          ++n_dec;
-        }
-      }
-    }
-  }
-
-#endif
 
   tcgen05_fence_before();
   __syncthreads();

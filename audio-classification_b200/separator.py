@@ -130,6 +130,8 @@ class SeparationEngine:
         self.max_batch_samples = int(os.environ.get("B200SEP_MAX_BATCH_SAMPLES", str(4 << 20)))
         self._pool = _PinnedPool(torch)  # page-locked output buffers
         self._pinned_in = None           # page-locked input staging of separate_and_score (grown on demand)
+        self._slots: List[Dict[str, Any]] = []  # per in-flight batch of separate_stream: stream + device scratch
+        self._stream_lock = threading.Lock()
         self.small_result_bytes = int(os.environ.get("B200SEP_SMALL_RESULT_BYTES", str(1 << 20)))
         self._flags = _FlagSlots(torch)
         self._tls = threading.local()  # flag slots of separate_device calls this thread has not checked yet
@@ -309,12 +311,13 @@ class SeparationEngine:
         records (and, if wanted, the waveforms) come back.  Every reference must have its mixture's length (the call
         site cuts both with the same indices, ``scripts/osd/overlap3_core.py:606-607, 716-722``); ragged cases go
         through ``pit_sisdr_batch``.  Returns ``(PitResult, waveforms or None)``."""
-        from .pit import PitResult, pit_sisdr_device
+        for out in self.score_stream([(chunks, refs)], variant, return_waveforms, depth=1):
+            return out
+
+    def _score_submit(self, chunks, refs, variant: str, return_waveforms: bool, slot: Dict[str, Any]):
+        from .pit import pit_sisdr_device
         torch = self._torch
         n = len(chunks)
-        if n == 0:
-            z = np.zeros(0)
-            return PitResult(z, z, np.zeros((0, 0), np.int32), np.zeros(0, bool), np.zeros((0, 3, 4))), []
         S = self.n_src
         K = len(refs[0])
         segs = [np.ascontiguousarray(np.asarray(c).reshape(-1), dtype=np.float32) for c in chunks]
@@ -324,10 +327,12 @@ class SeparationEngine:
             raise ValueError("separate_and_score needs K in {2, 3} references per segment, each of its mixture's length")
         total = int(sum(lens))
         dev = torch.device("cuda", self.device)
-        with self._lock, torch.cuda.device(dev):
-            if self._pinned_in is None or self._pinned_in.numel() < total * (1 + K):
-                self._pinned_in = torch.empty(max(2 * total * (1 + K), 1 << 16), dtype=torch.float32, pin_memory=True)
-            h_in = self._pinned_in[:total * (1 + K)]  # reusable: every call ends with a stream synchronise under the lock
+        st = slot["stream"]
+        with torch.cuda.device(dev):
+            if slot.get("pin_in") is None or slot["pin_in"].numel() < total * (1 + K):
+                st.synchronize()
+                slot["pin_in"] = torch.empty(max(2 * total * (1 + K), 1 << 16), dtype=torch.float32, pin_memory=True)
+            h_in = slot["pin_in"][:total * (1 + K)]  # reusable: the slot's previous batch was collected (stream synchronised)
             hv = h_in.numpy()
             o = 0
             for a in segs:
@@ -337,24 +342,75 @@ class SeparationEngine:
                 for a in r:
                     hv[o:o + ln] = np.asarray(a, dtype=np.float32).reshape(-1)
                     o += ln
-            d_in = h_in.to(dev, non_blocking=True)
-            d_mix, d_refs = d_in[:total], d_in[total:]
-            d_out = self.separate_device(d_mix, lens)
-            pair, sisdr, sisdri, perm, gap = pit_sisdr_device(d_refs, d_out, d_mix, lens, K, S, variant)
-            hout = None
-            if return_waveforms:
-                pinned_out, hout = self._acquire_pinned_out(total * S)
-                pinned_out[:total * S].copy_(d_out[:total * S], non_blocking=True)
-            pair, sisdr, sisdri, perm, gap = (pair.cpu().numpy(), sisdr.cpu().numpy(), sisdri.cpu().numpy(),
-                                              perm.cpu().numpy(), gap.cpu().numpy())
-            torch.cuda.current_stream(dev).synchronize()
-            rerun = self._needs_rerun(self.check())
-        if rerun:
-            return self._fallback_engine().separate_and_score(chunks, refs, variant, return_waveforms)
-        res = PitResult(sisdr, sisdri, perm[:, :K].astype(np.int32), perm[:, 3].astype(bool), pair, gap)
-        if not return_waveforms:
+            with torch.cuda.stream(st):
+                d_in = h_in.to(dev, non_blocking=True)
+                d_mix, d_refs = d_in[:total], d_in[total:]
+                d_out = self.separate_device(d_mix, lens)
+                pair, sisdr, sisdri, perm, gap = pit_sisdr_device(d_refs, d_out, d_mix, lens, K, S, variant)
+                hout = None
+                if return_waveforms:
+                    pinned_out, hout = self._acquire_pinned_out(total * S)
+                    pinned_out[:total * S].copy_(d_out[:total * S], non_blocking=True)
+                # one packed record block per batch: pair (12) | sisdr | sisdri | gap | perm (4)  -> a single D2H copy
+                rec = torch.cat([pair.reshape(n, 12), sisdr[:, None], sisdri[:, None], gap[:, None], perm.to(torch.float64)], 1)
+                if slot.get("pin_rec") is None or slot["pin_rec"].numel() < rec.numel():
+                    slot["pin_rec"] = torch.empty(max(2 * rec.numel(), 1 << 12), dtype=torch.float64, pin_memory=True)
+                h_rec = slot["pin_rec"][:rec.numel()].view(n, 19)
+                h_rec.copy_(rec, non_blocking=True)
+                for t in (d_in, d_out, rec):
+                    t.record_stream(st)
+            pend = getattr(self._tls, "pending", [])
+            self._tls.pending = []
+        return dict(stream=st, h_rec=h_rec, hout=hout, lens=lens, K=K, flag_slots=pend, chunks=chunks, refs=refs,
+                    variant=variant, wav=return_waveforms)
+
+    def _score_collect(self, t: Dict[str, Any]):
+        from .pit import PitResult
+        t["stream"].synchronize()
+        v = 0
+        for i in t["flag_slots"]:
+            v |= self._flags.read(i)
+        if self._needs_rerun(v):
+            return self._fallback_engine().separate_and_score(t["chunks"], t["refs"], t["variant"], t["wav"])
+        r = t["h_rec"].numpy().copy()
+        K = t["K"]
+        res = PitResult(r[:, 12], r[:, 13], r[:, 15:15 + K].astype(np.int32), r[:, 18].astype(bool),
+                        r[:, :12].reshape(-1, 3, 4), r[:, 14])
+        if not t["wav"]:
             return res, None
-        return res, self._results(hout, lens)
+        return res, self._results(t["hout"], t["lens"])
+
+    def score_stream(self, items, variant: str = "overlap3", return_waveforms: bool = False, depth: int = 2):
+        """Generator over ``separate_and_score(chunks, refs)`` for every ``(chunks, refs)`` of ``items`` with ``depth`` batches
+        in flight (each on its own stream with its own pinned staging): the host packing and H2D copy of batch k + 1 overlap
+        the forward + PIT kernels of batch k.  Results are identical to the one-at-a-time calls and come back in order."""
+        from collections import deque
+        from .pit import PitResult
+        torch = self._torch
+        if self._handle is None:
+            raise RuntimeError("Separator model is not initialized.")
+        depth = max(1, int(depth))
+        dev = torch.device("cuda", self.device)
+        with self._stream_lock:
+            while len(self._slots) < depth:
+                with torch.cuda.device(dev):
+                    self._slots.append(dict(stream=torch.cuda.Stream(device=dev), ws=None))
+            pending = deque()
+            k = 0
+            for chunks, refs in items:
+                if len(chunks) == 0:
+                    while pending:
+                        yield self._score_collect(pending.popleft())
+                    z = np.zeros(0)
+                    yield PitResult(z, z, np.zeros((0, 0), np.int32), np.zeros(0, bool), np.zeros((0, 3, 4)), z), \
+                        ([] if return_waveforms else None)
+                    continue
+                if len(pending) >= depth:
+                    yield self._score_collect(pending.popleft())
+                pending.append(self._score_submit(chunks, refs, variant, return_waveforms, self._slots[k % depth]))
+                k += 1
+            while pending:
+                yield self._score_collect(pending.popleft())
 
     def _acquire_pinned_out(self, n_floats: int):
         """``(pinned tensor, float32 ndarray over it)`` leased from the engine's pool (``_PinnedPool``)."""
@@ -377,6 +433,76 @@ class SeparationEngine:
             o += n
         return res
 
+    # ------------------------------------------------------------------ pipelined host boundary
+    def _as_segments(self, chunks: Sequence[np.ndarray]) -> List[np.ndarray]:
+        # (float32, 1-D, contiguous chunks -- what the pipeline passes -- are used in place; anything else is converted)
+        return [c if (type(c) is np.ndarray and c.dtype == np.float32 and c.ndim == 1 and c.flags.c_contiguous)
+                else np.ascontiguousarray(np.asarray(c).reshape(-1), dtype=np.float32) for c in chunks]
+
+    def _submit(self, segs: List[np.ndarray], slot: Dict[str, Any]) -> Dict[str, Any]:
+        """Queues gather -> H2D -> forward -> D2H of one batch on the slot's stream and returns a ticket."""
+        torch = self._torch
+        dev = torch.device("cuda", self.device)
+        lens = [a.shape[0] for a in segs]
+        total = int(sum(lens))
+        arr = nat.i32_array(lens)
+        ptrs = (C.c_void_p * len(segs))(*[_data_ptr(a) for a in segs])
+        need = int(nat.lib().b200sep_host_workspace_bytes(self._handle, arr, len(lens)))
+        if need == 0:
+            raise RuntimeError(f"b200sep_host_workspace_bytes: {nat.last_error()}")
+        pinned_out, hout = self._acquire_pinned_out(total * self.n_src)
+        with torch.cuda.device(dev):
+            if slot.get("ws") is None or slot["ws"].numel() < need + 256:
+                slot["stream"].synchronize()
+                slot["ws"] = None
+                slot["ws"] = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+            ws_ptr = (slot["ws"].data_ptr() + 255) // 256 * 256
+            ws_bytes = slot["ws"].numel() - (ws_ptr - slot["ws"].data_ptr())
+            fslot = self._flags.take()
+            nat.check(nat.lib().b200sep_separate_batch_host(
+                self._handle, ptrs, arr, len(lens), C.c_void_p(pinned_out.data_ptr()), C.c_void_p(ws_ptr),
+                C.c_size_t(ws_bytes), C.c_void_p(slot["stream"].cuda_stream), C.c_void_p(self._flags.ptr(fslot))),
+                "b200sep_separate_batch_host")
+        return dict(stream=slot["stream"], hout=hout, pinned=pinned_out, lens=lens, fslot=fslot, segs=segs)
+
+    def _collect(self, t: Dict[str, Any]) -> List[List[np.ndarray]]:
+        t["stream"].synchronize()
+        if self._needs_rerun(self._flags.read(t["fslot"])):
+            return self._fallback_engine().separate_batch(t["segs"])
+        return self._results(t["hout"], t["lens"])
+
+    def separate_stream(self, batches, depth: int = 2):
+        """Generator over ``separate_batch(b) for b in batches`` with ``depth`` batches in flight: every batch has its own
+        stream, device scratch and page-locked output, so the host gather / H2D copy of batch k + 1 and the D2H copy of
+        batch k - 1 overlap the kernels of batch k.  Results come back in order and are identical to ``separate_batch``
+        (a segment's arithmetic never depends on what else is in flight).  This is the throughput form of the host
+        boundary: an evaluation sweep or a multi-mixture pipeline that has more than one batch to separate."""
+        from collections import deque
+        torch = self._torch
+        if self._handle is None:
+            raise RuntimeError("Separator model is not initialized.")
+        depth = max(1, int(depth))
+        dev = torch.device("cuda", self.device)
+        with self._stream_lock:  # one streaming user at a time per engine (the slots are engine state)
+            while len(self._slots) < depth:
+                with torch.cuda.device(dev):
+                    self._slots.append(dict(stream=torch.cuda.Stream(device=dev), ws=None))
+            pending = deque()
+            k = 0
+            for chunks in batches:
+                segs = self._as_segments(chunks)
+                if not segs:
+                    while pending:
+                        yield self._collect(pending.popleft())
+                    yield []
+                    continue
+                if len(pending) >= depth:
+                    yield self._collect(pending.popleft())
+                pending.append(self._submit(segs, self._slots[k % depth]))
+                k += 1
+            while pending:
+                yield self._collect(pending.popleft())
+
     def separate_batch(self, chunks: Sequence[np.ndarray]) -> List[List[np.ndarray]]:
         """numpy in -> numpy out through pinned staging: one H2D copy, one forward, one D2H copy."""
         torch = self._torch
@@ -391,9 +517,7 @@ class SeparationEngine:
         # the kernels of the other).  The OUTPUT pinned buffer is allocated per call (torch's caching host allocator
         # makes that cheap) and handed to the caller as numpy views, so the 4 * S * T bytes of results are never
         # copied a second time on the host.
-        # (float32, 1-D, contiguous chunks -- what the pipeline passes -- are used in place; anything else is converted)
-        segs = [c if (type(c) is np.ndarray and c.dtype == np.float32 and c.ndim == 1 and c.flags.c_contiguous)
-                else np.ascontiguousarray(np.asarray(c).reshape(-1), dtype=np.float32) for c in chunks]
+        segs = self._as_segments(chunks)
         lens = [a.shape[0] for a in segs]
         total = int(sum(lens))
         if total > self.max_batch_samples and len(segs) > 1:
@@ -513,6 +637,13 @@ class Separator:
                 isinstance(c, np.ndarray) and c.dtype == np.float32 and c.ndim == 1 for c in chunks):
             return self._model.separate_batch_resampled(chunks, int(sr), int(self.sample_rate))
         return self._model.separate_batch([self._ensure_sr(c, sr) for c in chunks])
+
+    def separate_stream(self, batches, sr: int, depth: int = 2):
+        """``separate_batch(b, sr) for b in batches`` with ``depth`` batches in flight (copies of one batch overlap the
+        kernels of the next; see ``SeparationEngine.separate_stream``).  Results are identical and in order."""
+        if self._model is None:
+            raise RuntimeError("Separator model is not initialized.")
+        return self._model.separate_stream(([self._ensure_sr(c, sr) for c in b] for b in batches), depth)
 
     @property
     def engine(self) -> SeparationEngine:

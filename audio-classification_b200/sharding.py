@@ -95,13 +95,16 @@ def gather_records(local_ids: Sequence[int], local_records: np.ndarray, n_total:
 def evaluate_sharded(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.ndarray]], sr: int,
                      separate_batch: Callable, pit_batch: Callable, max_samples: int = 4 << 20,
                      kernel_size: int = 16, stride: int = 8, variant: str = "overlap3", device=None,
-                     separate_and_score: Callable = None, lens: Sequence[int] = None, n_refs: int = None):
+                     separate_and_score: Callable = None, lens: Sequence[int] = None, n_refs: int = None,
+                     score_stream: Callable = None):
     """Separation + PIT SI-SDR / SI-SDRi of a list of independent segments across the ranks of the initialised
     ``torch.distributed`` group (or this process alone): LPT partition on frame counts, length-bucketed batches per
     rank, ``separate_batch(chunks, sr)`` and ``pit_batch(mixes, refs, preds, variant)`` per batch, then ONE
     ``all_gather`` of the per-segment records ``(sisdr, sisdri, perm...)``.  With ``separate_and_score`` (the engine's
     device-resident ``separate_and_score(chunks, refs, variant, return_waveforms=False)``) the estimates never leave the
-    GPU between the forward and the PIT kernel.  Every rank returns the full table:
+    GPU between the forward and the PIT kernel; with ``score_stream`` (the engine's ``score_stream(items, variant)``
+    generator) consecutive batches are additionally pipelined, two in flight, so host packing and copies overlap the
+    kernels.  Every rank returns the full table:
     ``(sisdr[n], sisdri[n], perm[n, K], seconds_spent_separating_on_this_rank)``.  No waveform leaves its rank.
 
     ``mixes`` / ``refs`` may be sequences over ALL segments, or -- so that a rank only ever materialises its own shard --
@@ -123,7 +126,17 @@ def evaluate_sharded(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.nda
     rec = np.full((len(mine), 2 + K), np.nan)
     pos = {seg: k for k, seg in enumerate(mine)}
     t_sep = 0.0
-    for batch in bucket_by_length(mine, lens, max_samples):
+    batches = bucket_by_length(mine, lens, max_samples)
+    if score_stream is not None:
+        t0 = time.time()
+        items = (([mixes[i] for i in batch], [refs[i] for i in batch]) for batch in batches)
+        for batch, (res, _) in zip(batches, score_stream(items, variant)):
+            for k, i in enumerate(batch):
+                rec[pos[i], 0], rec[pos[i], 1] = res.sisdr[k], res.sisdri[k]
+                rec[pos[i], 2:] = np.asarray(res.perm[k][:K], dtype=np.float64)
+        t_sep = time.time() - t0
+        batches = []
+    for batch in batches:
         t0 = time.time()
         if separate_and_score is not None:
             res, _ = separate_and_score([mixes[i] for i in batch], [refs[i] for i in batch], variant, False)

@@ -375,7 +375,7 @@ def split_device_out(d_out, lens, n_src):
 
 
 # ------------------------------------------------------------------------------------------------ sweep (configs 2-4)
-def run_sweep(eng, pool, world, rank, dev, steps, variant, check_parity, model_cpu=None):
+def run_sweep(eng, pool, world, rank, dev, steps, variant, check_parity, model_cpu=None, sweep_batch_samples=2 << 20):
     """Separation + PIT of every segment of `pool` through sharding.evaluate_sharded (LPT shards, length buckets,
     device-resident separate_and_score, one all_gather).  Wall-clock per step bracketed by barriers, max over ranks."""
     import numpy as np
@@ -396,7 +396,8 @@ def run_sweep(eng, pool, world, rank, dev, steps, variant, check_parity, model_c
 
     def one():
         return sharding.evaluate_sharded(mixes, refs, SR, None, None, variant=variant, device=dev,
-                                         separate_and_score=eng.separate_and_score, lens=lens, n_refs=K)
+                                         score_stream=eng.score_stream, lens=lens, n_refs=K,
+                                         max_samples=sweep_batch_samples)
     one()  # warm-up (workspaces, pinned staging, NCCL)
     times = []
     out = None
@@ -416,7 +417,8 @@ def run_sweep(eng, pool, world, rank, dev, steps, variant, check_parity, model_c
            "scaling": "strong", "ranks": world, "segments_this_rank": len(mine),
            "sep_sisdr_mean": float(np.nanmean(sisdr)), "sep_sisdri_mean": float(np.nanmean(sisdri)),
            "records_gathered": int(np.sum(~np.isnan(sisdr))),
-           "api": "sharding.evaluate_sharded(separate_and_score=engine.separate_and_score): host arrays in, gathered records out"}
+           "api": "sharding.evaluate_sharded(score_stream=engine.score_stream): host arrays in, gathered records out, "
+                  f"batches of <= {sweep_batch_samples} samples, two in flight"}
     if check_parity and rank == 0 and model_cpu is not None:
         # oracle flow on a bounded sample of THIS rank's shard: oracle forward + the reference's PIT restatement
         from oracle import pit_restated as pr
@@ -589,18 +591,34 @@ def main():
             outs = sep.separate_batch(mixes, SR)  # referenced while the next call runs: two pinned output buffers)
         barrier()
         n_e2e = max(args.steps, int(SUSTAIN_S / (ms_per_step * 1.3e-3)))
+        # (a) one call at a time: Separator.separate_batch, every call synchronises before it returns
         t0 = time.perf_counter()
         for _ in range(n_e2e):
             outs = sep.separate_batch(mixes, SR)
         torch.cuda.synchronize(dev)
+        dt_sync = (time.perf_counter() - t0) / n_e2e
+        assert len(outs) == len(mixes) and outs[0][0].shape[0] == lens[0]
+        # (b) the streaming form of the same API: Separator.separate_stream keeps two batches in flight (own stream,
+        # scratch and pinned buffers each), so the H2D / D2H copies of one step overlap the kernels of the next; every
+        # step still gathers from the caller's NumPy arrays, copies 4 T bytes in and 4 S T bytes out
+        import itertools
+        for _o in sep.separate_stream(itertools.repeat(mixes, 4), SR):
+            pass
+        barrier()
+        t0 = time.perf_counter()
+        for _o in sep.separate_stream(itertools.repeat(mixes, n_e2e), SR):
+            outs = _o
+        torch.cuda.synchronize(dev)
         dt = (time.perf_counter() - t0) / n_e2e
         assert len(outs) == len(mixes) and outs[0][0].shape[0] == lens[0]
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        t = torch.tensor([dt, dt_sync], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": audio_all / float(t[0]), "unit": UNIT, "h2d_bytes_per_step": 4 * total,
                "d2h_bytes_per_step": 4 * total * n_src, "steps": n_e2e, "ms_per_step": 1e3 * float(t[0]),
-               "api": "Separator.separate_batch(chunks, sr) numpy in -> numpy out"}
+               "api": "Separator.separate_stream(batches, sr): numpy in -> numpy out, two batches in flight",
+               "one_call_at_a_time": {"value": audio_all / float(t[1]), "ms_per_step": 1e3 * float(t[1]),
+                                      "api": "Separator.separate_batch(chunks, sr)"}}
 
     # ---------------- parity of what was timed (rank 0): >= 40 dB vs the oracle's fp32 forward -------
     parity_db = None

@@ -178,3 +178,31 @@ def test_separate_and_score_on_device_equals_the_two_step_path(b200):
     t0 = time.perf_counter(); sep.engine.separate_and_score(mixes, srcs, "overlap3", return_waveforms=False); t1 = time.perf_counter()
     outs = sep.separate_batch(mixes, 8000); b200.pit_sisdr_batch(mixes, srcs, outs, "overlap3"); t2_ = time.perf_counter()
     print(f"separate_and_score {1e3 * (t1 - t0):.2f} ms vs two-step {1e3 * (t2_ - t1):.2f} ms for 40 segments")
+
+
+def test_stream_apis_match_the_one_at_a_time_calls(b200):
+    """separate_stream / score_stream keep two batches in flight (own stream, scratch and pinned staging each): results
+    must be bit-identical to the synchronous calls and come back in order, whatever the batch sizes."""
+    from b200sep import synth, weights
+    sd, args = weights.random_state_dict(3, 0)
+    sep = b200.Separator(backend="b200", device="cuda:0", sample_rate=8000, n_src=3, state_dict=sd, model_args=args)
+    batches, refs = [], []
+    for bi, n_seg in enumerate((5, 1, 9, 3, 7)):
+        lens = synth.segment_lengths(n_seg, 70 + bi, 0.2, 2.0)
+        ms = [synth.make_mixture(800 + 10 * bi + i, n, 3) for i, n in enumerate(lens)]
+        batches.append([m for m, _ in ms])
+        refs.append([s for _, s in ms])
+    want = [sep.separate_batch(b, 8000) for b in batches]
+    got = list(sep.separate_stream(batches, 8000))
+    assert len(got) == len(want)
+    for w, g in zip(want, got):
+        assert len(w) == len(g)
+        for ws, gs in zip(w, g):
+            for a, b_ in zip(ws, gs):
+                assert np.array_equal(a, b_)
+    one = [sep.engine.separate_and_score(b, r, "overlap3", return_waveforms=False)[0] for b, r in zip(batches, refs)]
+    two = [r for r, _ in sep.engine.score_stream(zip(batches, refs), "overlap3")]
+    for a, b_ in zip(one, two):
+        assert np.array_equal(a.sisdr, b_.sisdr) and np.array_equal(a.sisdri, b_.sisdri)
+        assert np.array_equal(a.perm, b_.perm) and np.array_equal(a.gap, b_.gap)
+    sep.engine.close()

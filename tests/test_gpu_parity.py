@@ -368,6 +368,30 @@ def test_fused_pipeline_many_tiles_per_cta_and_batch_independence(b200, model3):
     eng.close()
 
 
+def test_cta_pair_block_kernel_matches_the_single_cta_kernel(b200, model3, monkeypatch):
+    """K_A as a CTA pair (tcgen05 cta_group::2, [res | skip] weights resident in tensor memory as the MMA's A operand,
+    fused_pair.cuh; selected with B200SEP_KA=pair at model creation) against the default one-CTA kernel: same arithmetic
+    per element (fp16 operands, fp32 accumulation over the same k order), so the outputs must agree to >= 80 dB and
+    both must hold the gate against the oracle -- on a batch with an odd tile count, single-tile segments and more
+    tile pairs than SM pairs."""
+    from b200sep import synth
+    sd, args, model = model3
+    lens = [32000, 1600, 31999, 12345, 16, 24000, 8191, 30000] * 5 + [28000] * 3 + [900]
+    mixes = [synth.make_mixture(500 + i, n, 3)[0] for i, n in enumerate(lens)]
+    outs = {}
+    for mode in ("single", "pair"):
+        monkeypatch.setenv("B200SEP_KA", mode)
+        eng = b200.SeparationEngine(sd, args, 0, "fp16")
+        outs[mode] = eng.separate_batch(mixes)
+        assert eng.fallback_reruns == 0
+        eng.close()
+    for i in (0, 1, 4, 7, 20, 43):
+        assert min_sisdr(np.stack(outs["single"][i]), np.stack(outs["pair"][i])) >= 80.0, i
+    for i in (0, 3, 21):
+        ref = oracle_separate(model, mixes[i])
+        assert min_sisdr(ref, np.stack(outs["pair"][i])) >= GATE_FP16_DB
+
+
 def test_fused_and_unfused_pipelines_agree(b200, model3, monkeypatch):
     """The fused kernels (fused_block.cuh / tail_kernel.cuh) against the unfused three-kernels-per-block
     pipeline of the same precision mode: both within the gate of the oracle, and within 50 dB of each other."""

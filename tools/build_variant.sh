@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: scripts_gpu/build_variant.sh NAME [-DFLAG ...]  -> audio-classification_b200/variants/lib_NAME.so
+# usage: tools/build_variant.sh NAME [-DFLAG ...]  -> audio-classification_b200/variants/lib_NAME.so
 set -e
 cd "$(dirname "$0")/.."
 name=$1; shift

@@ -1,0 +1,26 @@
+"""Profiling / timing target of the PIT kernel at BASELINE.json configs[3] size: 3000 segments U[0.4, 4] s, K = N = 3."""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import b200sep
+from b200sep import synth
+from b200sep.pit import pit_sisdr_device
+lens = synth.segment_lengths(3000, 4, 0.4, 4.0)
+total = sum(lens)
+g = torch.Generator(device="cuda").manual_seed(0)
+d_mix = torch.randn(total, device="cuda", generator=g) * 0.05
+d_ref = torch.randn(3 * total, device="cuda", generator=g) * 0.05
+d_est = d_ref + 0.01 * torch.randn(3 * total, device="cuda", generator=g)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for _ in range(3):
+    pit_sisdr_device(d_ref, d_est, d_mix, lens, 3, 3, "overlap3")
+torch.cuda.synchronize()
+ts = []
+for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 5):
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record(); pit_sisdr_device(d_ref, d_est, d_mix, lens, 3, 3, "overlap3"); e1.record()
+    torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+ms = min(ts)
+print(f"pit 3000 segments, {total} samples: {ms:.3f} ms = {28 * total / ms / 1e6:.1f} GB/s (28 B/sample algorithmic), "
+      f"{total / 8000 / ms * 1e3:.0f} audio-s/s", flush=True)

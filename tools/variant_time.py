@@ -29,5 +29,12 @@ for _ in range(3):
     eng.separate_device(d_mix, lens, out=out, workspace=ws)
     for k, v in classify_launches(eng.profile_read(), 24, pipeline).items():
         acc[k].extend(v)
-print(os.path.basename(os.environ.get("B200SEP_LIB", "default")), f"{min(ts):.3f} ms",
+print(os.path.basename(os.environ.get("B200SEP_LIB", "default")), os.environ.get("B200SEP_KA", "pair"), f"{min(ts):.3f} ms",
       " ".join(f"{k}={1e3*sum(v)/len(v):.1f}" for k, v in acc.items() if v), flush=True)
+ka = acc["dw_rs_gemm"]
+if ka:  # per dilation (block i has d = 2^(i % 8)): mean over the 3 repeats x 3 stack repeats
+    n = len(ka) // 24
+    print("   K_A us by dilation:", " ".join(f"d{1 << k}={1e3 * np.mean([ka[r * 24 + b] for r in range(n) for b in range(24) if b % 8 == k]):.1f}" for k in range(8)), flush=True)
+kb = acc["apply_in_gemm"]
+if kb:
+    print(f"   K_B us: block0={1e3 * np.mean(kb[0::24]):.1f} others={1e3 * np.mean([v for i, v in enumerate(kb) if i % 24]):.1f}", flush=True)
