@@ -457,6 +457,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the configs[4] sweep object of a config-1 run")
     ap.add_argument("--no-eager", action="store_true", help="skip the torch-eager-on-B200 baseline")
     ap.add_argument("--sweep-segments", type=int, default=10000)
+    ap.add_argument("--sustain-s", type=float, default=SUSTAIN_S, help="seconds of identical load in front of the timed steps (0: none, for ncu launch lists)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -560,14 +561,14 @@ def main():
     # sustained lead-in: the same step, back to back, for >= SUSTAIN_S seconds (every step event-timed), then EXACTLY
     # `steps` timed steps with no gap in between: the headline is measured at the clocks the GPU holds under this load
     lead, t_lead0 = [], time.perf_counter()
-    while time.perf_counter() - t_lead0 < SUSTAIN_S:
+    while time.perf_counter() - t_lead0 < args.sustain_s:
         lead.extend(timed_steps(10))
         torch.cuda.synchronize(dev)
     evs = timed_steps(args.steps)
     barrier()
     clocks = sampler.stop()
     eng.check()
-    lead_ms = [e0.elapsed_time(e1) for e0, e1 in lead]
+    lead_ms = [e0.elapsed_time(e1) for e0, e1 in lead] or [float('nan')]
     step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
     ms_per_step = sum(step_ms) / len(step_ms)
     t = torch.tensor([ms_per_step, audio_s, sum(lead_ms) / len(lead_ms), min(lead_ms[:10])], dtype=torch.float64, device=dev)
@@ -578,7 +579,7 @@ def main():
     else:
         ms_max, audio_all, lead_mean, burst_ms = ms_per_step, audio_s, float(t[2]), float(t[3])
     value = audio_all / (ms_max * 1e-3)
-    sustained = {"lead_in_steps": len(lead_ms), "lead_in_seconds": SUSTAIN_S, "lead_in_ms_per_step": lead_mean,
+    sustained = {"lead_in_steps": len(lead), "lead_in_seconds": args.sustain_s, "lead_in_ms_per_step": lead_mean,
                  "first_steps_ms": burst_ms, "value_lead_in": audio_all / (lead_mean * 1e-3),
                  "note": "the K timed steps follow the lead-in without a gap; first_steps_ms = fastest of the first 10 "
                          "lead-in steps (burst clocks)"}
@@ -590,7 +591,7 @@ def main():
         for _ in range(max(args.warmup, 3)):  # same call pattern as the timed loop (the previous result is still
             outs = sep.separate_batch(mixes, SR)  # referenced while the next call runs: two pinned output buffers)
         barrier()
-        n_e2e = max(args.steps, int(SUSTAIN_S / (ms_per_step * 1.3e-3)))
+        n_e2e = max(args.steps, int(args.sustain_s / (ms_per_step * 1.3e-3)))
         # (a) one call at a time: Separator.separate_batch, every call synchronises before it returns
         t0 = time.perf_counter()
         for _ in range(n_e2e):
@@ -766,7 +767,7 @@ def main():
         whole_flops = FLOP_PER_FRAME[n_src] * frames * world  # LPT shards: every rank holds ~ the same frame count
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3) + len(lead_ms),
+            "warmup": max(args.warmup, 3) + len(lead),
             "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16" if args.precision != "fp32" else "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS[1], "segments_per_gpu": len(lens), "audio_s_per_gpu": audio_s, "sample_rate": SR,

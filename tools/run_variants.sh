@@ -1,3 +1,4 @@
 for ka in pair single; do
     B200SEP_KA=$ka timeout 120 python tools/variant_time.py 2>&1 | tail -3
 done
+B200SEP_KA=pair python tools/timeline.py 6 2>&1 | grep -A 9 "K_A" | cut -c1-900 | head -24
