@@ -713,8 +713,9 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
       // G_res / skip-stash store boxes.  Default: the one-CTA kernel (86 vs 92 us per launch on the configs[1] batch)
       const bool ka_pair = m->ka_pair;
       CUtensorMap tm_gres, tm_stash;
-      if (make_tmap_act(&tm_gres, gbuf, nt, C_BN)) return 1;
-      if (make_tmap_2d(&tm_stash, stash, TILE_M, (uint64_t)nt * m->n_layers * C_SKIP, TILE_M * 2, 64, 64)) return 1;
+      // (boxes of 32 channels x 64 frames: one per epilogue warp of the pair kernel)
+      if (make_tmap_2d(&tm_gres, gbuf, TILE_M, (uint64_t)nt * C_BN, TILE_M * 2, 64, 32)) return 1;
+      if (make_tmap_2d(&tm_stash, stash, TILE_M, (uint64_t)nt * m->n_layers * C_SKIP, TILE_M * 2, 64, 32)) return 1;
       if (make_tmap_act_raw(&tm_hc, h1, nt, C_HID, TILE_M)) return 1;
       for (int k = 0; k < 5; ++k)
         if (make_tmap_act_raw(&tm_hh[k], h1, nt, C_HID, 8 << k)) return 1;

@@ -281,30 +281,6 @@ struct KaCfg {
   static constexpr int SMEM_USABLE = SMEM_BYTES - 1024 /*alignment slack*/;
 };
 
-struct DwEdge { float2 ml[4], mc[4], mr[4]; };
-
-// left / right tap values of the thread's 8 frames from the three 8-frame vectors (centre, the vector
-// `shift` frames to the left, the one to the right): D == 0 -> the vectors ARE the taps (d % 8 == 0);
-// D in {1,2,4} -> vectors are the neighbouring 8 frames and the taps are picked across the seam.
-template <int D>
-__device__ __forceinline__ void dw_taps(const uint4 vc, const uint4 va, const uint4 vb, float (&ctr)[8],
-                                        float (&lft)[8], float (&rgt)[8]) {
-  unpack8(vc, ctr);
-  if (D == 0) {
-    unpack8(va, lft);
-    unpack8(vb, rgt);
-  } else {
-    float pv[8], nv[8];
-    unpack8(va, pv);
-    unpack8(vb, nv);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      lft[i] = (i - D >= 0) ? ctr[(i - D) & 7] : pv[(8 + i - D) & 7];
-      rgt[i] = (i + D < 8) ? ctr[(i + D) & 7] : nv[(i + D - 8) & 7];
-    }
-  }
-}
-
 // Interior-tile producer step in packed half arithmetic: 8 outputs of one channel from the three 8-frame
 // vectors.  Taps, PReLU and the operand rounding happen in fp16 (HFMA2 / HMUL2 / HMNMX2: no fp16 -> fp32
 // conversions on the tap path); only the gLN2 statistics are accumulated in fp32.
@@ -316,14 +292,14 @@ __device__ __forceinline__ float fma_f32_f16(uint16_t a, uint16_t b, float c) {
 }
 __device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 __device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
-template <int D, bool A01>
-__device__ __forceinline__ uint4 dw_step_h2(const uint4 vc, const uint4 va, const uint4 vb, const float4 t0,
-                                            const float cb, const float rstd, const float rm, const __half2 alpha2,
-                                            __half2& sh, __half2& qh) {
-  const uint32_t c[4] = {vc.x, vc.y, vc.z, vc.w};
+// left / right neighbour pairs of the thread's four fp16 pairs (8 frames) from the centre vector and the two neighbouring
+// vectors: D == 0 -> the neighbour vectors ARE the taps (d % 8 == 0); D in {1, 2, 4} -> picked across the seams.
+template <int D>
+__device__ __forceinline__ void dw_lr(const uint4 vc, const uint4 va, const uint4 vb, uint32_t (&c)[4], uint32_t (&l)[4],
+                                      uint32_t (&r)[4]) {
+  c[0] = vc.x; c[1] = vc.y; c[2] = vc.z; c[3] = vc.w;
   const uint32_t pv[4] = {va.x, va.y, va.z, va.w};
   const uint32_t nv[4] = {vb.x, vb.y, vb.z, vb.w};
-  uint32_t l[4], r[4];
   if (D == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { l[i] = pv[i]; r[i] = nv[i]; }
@@ -341,14 +317,25 @@ __device__ __forceinline__ uint4 dw_step_h2(const uint4 vc, const uint4 va, cons
     l[0] = pv[2]; l[1] = pv[3]; l[2] = c[0]; l[3] = c[1];
     r[0] = c[2]; r[1] = c[3]; r[2] = nv[0]; r[3] = nv[1];
   }
+}
+template <bool A01>
+__device__ __forceinline__ __half2 prelu_h2(__half2 u, const __half2 alpha2) {
+  if (A01) return __hmax2(u, __hmul2(u, alpha2));
+  return __hadd2(__hmax2(u, __float2half2_rn(0.f)), __hmul2(alpha2, __hmin2(u, __float2half2_rn(0.f))));
+}
+template <int D, bool A01>
+__device__ __forceinline__ uint4 dw_step_h2(const uint4 vc, const uint4 va, const uint4 vb, const float4 t0,
+                                            const float cb, const float rstd, const float rm, const __half2 alpha2,
+                                            __half2& sh, __half2& qh) {
+  uint32_t c[4], l[4], r[4];
+  dw_lr<D>(vc, va, vb, c, l, r);
   const __half2 w0 = __float2half2_rn(t0.x * rstd), w1 = __float2half2_rn(t0.y * rstd);
   const __half2 w2 = __float2half2_rn(t0.z * rstd), cw = __float2half2_rn(fmaf(-t0.w, rm, cb));
   uint32_t o[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     __half2 u = __hfma2(u32_as_h2(l[i]), w0, __hfma2(u32_as_h2(c[i]), w1, __hfma2(u32_as_h2(r[i]), w2, cw)));
-    if (A01) u = __hmax2(u, __hmul2(u, alpha2));
-    else u = __hadd2(__hmax2(u, __float2half2_rn(0.f)), __hmul2(alpha2, __hmin2(u, __float2half2_rn(0.f))));
+    u = prelu_h2<A01>(u, alpha2);
     o[i] = h2_as_u32(u);
     // gLN2 statistics of the ROUNDED outputs: first level in packed halves (two instructions per pair instead of four
     // scalar mixed-precision FMAs -- the producers are bound by the FMA pipe); the caller folds (sh, qh) into its fp32
@@ -357,6 +344,46 @@ __device__ __forceinline__ uint4 dw_step_h2(const uint4 vc, const uint4 va, cons
     qh = __hfma2(u, u, qh);
   }
   return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// Edge-tile producer step (a tap or a frame of the tile falls outside the segment), still in packed halves.  Zero
+// padding applies to the NORMALISED signal at the true segment ends, so every tap carries its own constant term
+// (a_k h + b_k) and is switched off as a whole by a bit mask (0xffff / 0 per fp16 lane: exact zero whatever the
+// masked-out raw value was -- the neighbouring segment's data or the TMA zero fill); frames >= F produce zeros.
+//   t0 = {w0 g, w1 g, w2 g, .}, t1 = {w0 beta, w1 beta, w2 beta, bias}:  a_k = t0_k rstd,  b_k = t1_k - t0_k rstd mean
+struct DwEdgeH { uint32_t ml[4], mc[4], mr[4]; };
+template <int D, bool A01>
+__device__ __forceinline__ uint4 dw_step_h2_edge(const uint4 vc, const uint4 va, const uint4 vb, const float4 t0,
+                                                 const float4 t1, const float rstd, const float rm, const __half2 alpha2,
+                                                 const DwEdgeH& mk, __half2& sh, __half2& qh) {
+  uint32_t c[4], l[4], r[4];
+  dw_lr<D>(vc, va, vb, c, l, r);
+  const __half2 w0 = __float2half2_rn(t0.x * rstd), w1 = __float2half2_rn(t0.y * rstd), w2 = __float2half2_rn(t0.z * rstd);
+  const __half2 b0 = __float2half2_rn(fmaf(-t0.x, rm, t1.x)), b1 = __float2half2_rn(fmaf(-t0.y, rm, t1.y));
+  const __half2 b2 = __float2half2_rn(fmaf(-t0.z, rm, t1.z)), bias = __float2half2_rn(t1.w);
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t ta = h2_as_u32(__hfma2(u32_as_h2(l[i]), w0, b0)) & mk.ml[i];
+    const uint32_t tc = h2_as_u32(__hfma2(u32_as_h2(c[i]), w1, b1)) & mk.mc[i];
+    const uint32_t tr = h2_as_u32(__hfma2(u32_as_h2(r[i]), w2, b2)) & mk.mr[i];
+    __half2 u = __hadd2(__hadd2(u32_as_h2(ta), u32_as_h2(tc)), __hadd2(u32_as_h2(tr), bias));
+    u = u32_as_h2(h2_as_u32(prelu_h2<A01>(u, alpha2)) & mk.mc[i]);
+    o[i] = h2_as_u32(u);
+    sh = __hadd2(sh, u);
+    qh = __hfma2(u, u, qh);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+// bit masks of the thread's 8 frames (segment-relative t_base .. t_base + 7) for dilation d in a segment of F frames
+__device__ __forceinline__ void dw_edge_masks(DwEdgeH& mk, int t_base, int d, int F) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int ta = t_base + 2 * k, tb2 = ta + 1;
+    mk.ml[k] = ((ta - d >= 0 && ta - d < F) ? 0xffffu : 0u) | ((tb2 - d >= 0 && tb2 - d < F) ? 0xffff0000u : 0u);
+    mk.mc[k] = (ta < F ? 0xffffu : 0u) | (tb2 < F ? 0xffff0000u : 0u);
+    mk.mr[k] = (ta + d < F ? 0xffffu : 0u) | (tb2 + d < F ? 0xffff0000u : 0u);
+  }
 }
 
 // fp16 partial statistics of (at most) two producer steps -> the thread's fp32 accumulators
@@ -607,7 +634,6 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
     const int grp = pw >> 3, gw = pw & 7;
     const int sub = lane >> 4, lane16 = lane & 15;
     const int row0 = gw * 2 + sub;        // k-row of step 0 inside a k-block; step j = row0 + 16 j
-    const float alpha = p.alpha2;
     // shared-memory offsets (inside a raw stage) of this thread's centre / left / right vectors
     const int sv = (D > 0) ? 1 : (d >> 3);  // tap distance in 8-frame vectors
     const int hv = hw >> 3;                 // halo width in vectors
@@ -623,7 +649,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
     const uint32_t c_step = 16u * c_pitch, l_step = 16u * l_pitch, r_step = 16u * r_pitch;
     const uint32_t a_off0 = a_chunk_off(row0, lane16 * 8);  // (row & 7) is the same for every step; step j = + 2048 j
     int nseq = 0;  // k-blocks produced by this group so far -> A stage / phase
-    const __half2 alpha_h2 = __float2half2_rn(alpha);
+    const __half2 alpha_h2 = __float2half2_rn(p.alpha2);
     const bool tl_on = (gw == 0 && lane == 0);
     const int tl_base = grp ? 100 : 40;  // timeline slots: group 0 40.., group 1 100..
 
@@ -653,18 +679,8 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       const int t_base = tile_t0 + lane16 * 8;
       const bool interior = (tile_t0 - d >= 0) && (tile_t0 + TILE_M - 1 + d < F);
       float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
-      DwEdge mk;
-      if (!interior) {
-        // taps and frames masked by segment-relative frame index (zero padding applies to the normalised
-        // signal at the TRUE segment ends); masked-out taps read finite values, so 0 * h is exactly 0
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int ta = t_base + 2 * k, tb2 = ta + 1;
-          mk.ml[k] = make_float2((ta - d >= 0 && ta - d < F) ? 1.f : 0.f, (tb2 - d >= 0 && tb2 - d < F) ? 1.f : 0.f);
-          mk.mc[k] = make_float2(ta < F ? 1.f : 0.f, tb2 < F ? 1.f : 0.f);
-          mk.mr[k] = make_float2(ta + d < F ? 1.f : 0.f, tb2 + d < F ? 1.f : 0.f);
-        }
-      }
+      DwEdgeH mk;
+      if (!interior) dw_edge_masks(mk, t_base, d, F);  // taps / frames switched off by segment-relative frame index
 #pragma unroll 1
       for (int kb = grp; kb < 8; kb += 2) {
         const int a_idx = grp * Cfg::A_PG + (nseq & (Cfg::A_PG - 1));
@@ -704,34 +720,23 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
             st_shared_v4(sa + (jj + 1) * 2048u, o1);
           }
         } else {
-#pragma unroll 1
-          for (int j = 0; j < 4; ++j) {
-            const int c = ch0 + j * 16;
-            const uint4 vc = ld_shared_v4(raw + c_base + j * c_step);
-            const uint4 va = ld_shared_v4(raw + l_base + j * l_step);
-            const uint4 vb = ld_shared_v4(raw + r_base + j * r_step);
-            const float4 t0 = s_t0[c], t1 = s_t1[c];
-            float ctr[8], lft[8], rgt[8];
-            dw_taps<D>(vc, va, vb, ctr, lft, rgt);
-            const float wa0 = t0.x * rstd, wa1 = t0.y * rstd, wa2 = t0.z * rstd;
-            const float wb0 = fmaf(-t0.x, rm, t1.x), wb1 = fmaf(-t0.y, rm, t1.y), wb2 = fmaf(-t0.z, rm, t1.z);
-            const float2 a0 = make_float2(wa0, wa0), a1 = make_float2(wa1, wa1), a2 = make_float2(wa2, wa2);
-            const float2 b0 = make_float2(wb0, wb0), b1 = make_float2(wb1, wb1), b2 = make_float2(wb2, wb2);
-            const float2 bias = make_float2(t1.w, t1.w);
-            float o[8];
 #pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-              const int k = i >> 1;
-              float2 u = fma2(fma2(make_float2(lft[i], lft[i + 1]), a0, b0), mk.ml[k], bias);
-              u = fma2(fma2(make_float2(ctr[i], ctr[i + 1]), a1, b1), mk.mc[k], u);
-              u = fma2(fma2(make_float2(rgt[i], rgt[i + 1]), a2, b2), mk.mr[k], u);
-              u = mul2(prelu2<A01>(u, alpha), mk.mc[k]);
-              o[i] = u.x; o[i + 1] = u.y;
-              s2 = add2(s2, u);
-              q2 = fma2(u, u, q2);
-            }
-            if (j == 0) mbar_wait_b(tb.flags, my_ab_empty, aphase ^ 1u);
-            st_shared_v4(sa + j * 2048u, pack8(o));
+          for (int jj = 0; jj < 4; jj += 2) {
+            const uint4 vc0 = ld_shared_v4(raw + c_base + jj * c_step);
+            const uint4 vc1 = ld_shared_v4(raw + c_base + (jj + 1) * c_step);
+            const uint4 va0 = ld_shared_v4(raw + l_base + jj * l_step);
+            const uint4 vb0 = ld_shared_v4(raw + r_base + jj * r_step);
+            const uint4 va1 = ld_shared_v4(raw + l_base + (jj + 1) * l_step);
+            const uint4 vb1 = ld_shared_v4(raw + r_base + (jj + 1) * r_step);
+            const float4 ta = s_t0[ch0 + jj * 16], tb_ = s_t0[ch0 + jj * 16 + 16];
+            const float4 ua = s_t1[ch0 + jj * 16], ub = s_t1[ch0 + jj * 16 + 16];
+            __half2 sh = __float2half2_rn(0.f), qh = __float2half2_rn(0.f);
+            const uint4 o0 = dw_step_h2_edge<D, A01>(vc0, va0, vb0, ta, ua, rstd, rm, alpha_h2, mk, sh, qh);
+            const uint4 o1 = dw_step_h2_edge<D, A01>(vc1, va1, vb1, tb_, ub, rstd, rm, alpha_h2, mk, sh, qh);
+            dw_stats_flush(sh, qh, s2, q2);
+            if (jj == 0) mbar_wait_b(tb.flags, my_ab_empty, aphase ^ 1u);
+            st_shared_v4(sa + jj * 2048u, o0);
+            st_shared_v4(sa + (jj + 1) * 2048u, o1);
           }
         }
         fence_proxy_async();

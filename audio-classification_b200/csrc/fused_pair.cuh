@@ -13,8 +13,12 @@
 //   * D[channel][frame]: rank 0 ends up with the residual-conv rows of BOTH tiles, rank 1 with the skip-conv rows; the
 //     epilogue (lane = channel) packs 8 frames per 16-byte st.shared into swizzled 64 x 64 boxes that leave as TMA tile
 //     stores (the pattern of K_B's epilogue).
-// Tensor memory: 256 columns of weights + one 256-column accumulator (no double buffering: the epilogue drains while the
-// producers already fill the next tile's first stages).
+// Tensor memory: 256 columns of weights + one 256-column accumulator.  The accumulator is single-buffered, so the MMAs
+// of a visit cannot start before the previous visit's accumulator has been read out; the kernel is built so that this
+// costs little: every epilogue warp owns its 32 channels end to end (private 32 x 64 staging boxes and its own TMA tile
+// stores -- no cross-warp barrier in the drain), the accumulator is released right after the last tcgen05.ld, and the
+// producers keep filling the four-stage h2 ring meanwhile (the tensor core is twice as fast as the producers and
+// catches up).
 #pragma once
 #include "pair_common.cuh"
 
@@ -25,26 +29,25 @@ struct KpCfg {
   static constexpr int S_STAGE = TILE_M * 64 * 2;   // 16 KiB: one h2 k-block of this CTA's m-tile (B operand)
   static constexpr int S_PG = 2;                    // stages per producer group
   static constexpr int N_STAGES = 2 * S_PG;
-  static constexpr int ST_BOX = 64 * 128;           // 8 KiB: 64 channels x 64 frames store box (SWIZZLE_128B image)
-  static constexpr int ST_BOXES = 4;                // two per 64-channel block
-  static constexpr int TAB_BYTES = C_HID * (16 + 16 + 4);
+  static constexpr int ST_BOX = 32 * 128;           // 4 KiB: 32 channels x 64 frames store box (SWIZZLE_128B image)
+  static constexpr int TAB_BYTES = C_HID * (16 + 4);  // t0 + cb (t1 is only read on edge tiles: from global / L1)
   static constexpr int EPI_WARPS = 4, PROD_WARPS = 16;
   static constexpr int THREADS = (EPI_WARPS + 3 + PROD_WARPS) * 32;  // 736
   static constexpr int TMEM_COLS = 512;
   static constexpr uint32_t D_COL0 = 0, A_COL0 = 256;
-  static constexpr int OFF_S = 0;
-  static constexpr int OFF_ST = OFF_S + N_STAGES * S_STAGE;
-  static constexpr int OFF_TAB = OFF_ST + ST_BOXES * ST_BOX;
+  static constexpr int OFF_TAB = 0;
   static constexpr int OFF_TI = OFF_TAB + TAB_BYTES;
   static constexpr int OFF_RED = OFF_TI + TI_CACHE * 32;
   static constexpr int OFF_CNT = OFF_RED + 2 * PROD_WARPS * 8;
   static constexpr int OFF_BAR = OFF_CNT + 16;
-  static constexpr int OFF_RAW = (OFF_BAR + 512 + 1023) / 1024 * 1024;
+  static constexpr int OFF_S = (OFF_BAR + 512 + 1023) / 1024 * 1024;   // h2 ring, then the store staging, then the raw ring
+  static constexpr int OFF_ST = OFF_S + N_STAGES * S_STAGE;
   static constexpr int SMEM_BYTES = 232448;
   static constexpr int SMEM_USABLE = SMEM_BYTES - 1024;
 };
 
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read3() { asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); }
 
 template <int D, bool A01>
 __global__ void __launch_bounds__(KpCfg::THREADS, 1)
@@ -58,8 +61,7 @@ dw_rs_pair_kernel(const __grid_constant__ CUtensorMap tm_hc, const __grid_consta
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   auto stage_s = [&](int s) { return smem_base + (uint32_t)(Cfg::OFF_S + s * Cfg::S_STAGE); };
   float4* s_t0 = reinterpret_cast<float4*>(smem_gen + Cfg::OFF_TAB);
-  float4* s_t1 = s_t0 + C_HID;
-  float* s_cb = reinterpret_cast<float*>(s_t1 + C_HID);
+  float* s_cb = reinterpret_cast<float*>(s_t0 + C_HID);
   TileInfo* s_ti = reinterpret_cast<TileInfo*>(smem_gen + Cfg::OFF_TI);
   float2* s_red = reinterpret_cast<float2*>(smem_gen + Cfg::OFF_RED);  // [2][16]
   int* s_cnt = reinterpret_cast<int*>(smem_gen + Cfg::OFF_CNT);          // [2]
@@ -94,12 +96,17 @@ dw_rs_pair_kernel(const __grid_constant__ CUtensorMap tm_hc, const __grid_consta
   const int hw = (D > 0) ? 8 : d;  // halo width in frames (multiple of 8, <= 128)
   const uint32_t halo_bytes = (uint32_t)(64 * hw * 2);
   const uint32_t raw_stage_bytes = (16384u + 2u * halo_bytes + 1023u) & ~1023u;
-  const int raw_stages = ((uint32_t)Cfg::OFF_RAW + 4u * raw_stage_bytes <= (uint32_t)Cfg::SMEM_USABLE) ? 4 : 2;
-  auto raw_st = [&](int s) { return smem_base + (uint32_t)Cfg::OFF_RAW + (uint32_t)s * raw_stage_bytes; };
+  // what is left after the h2 ring goes to the raw ring (4 stages = two k-blocks in flight per producer group, when they
+  // fit next to the small staging: the L2 -> shared-memory latency of a stage is about two k-block times) and to the
+  // store staging (4 boxes per epilogue warp = a whole visit, so the drain never waits for a TMA store; else 2)
+  const uint32_t dyn = (uint32_t)(Cfg::SMEM_USABLE - Cfg::OFF_ST);
+  const int raw_stages = (4u * raw_stage_bytes + 8u * (uint32_t)Cfg::ST_BOX <= dyn) ? 4 : 2;
+  const int st_pw = ((uint32_t)raw_stages * raw_stage_bytes + 16u * (uint32_t)Cfg::ST_BOX <= dyn) ? 4 : 2;
+  const uint32_t off_raw = (uint32_t)Cfg::OFF_ST + (uint32_t)(4 * st_pw) * (uint32_t)Cfg::ST_BOX;
+  auto raw_st = [&](int s) { return smem_base + off_raw + (uint32_t)s * raw_stage_bytes; };
 
   for (int i = threadIdx.x; i < C_HID; i += Cfg::THREADS) {
     s_t0[i] = __ldg(p.t0 + i);
-    s_t1[i] = __ldg(p.t1 + i);
     s_cb[i] = __ldg(p.cb + i);
   }
   if ((int)threadIdx.x < TI_CACHE && (int)threadIdx.x < n_visits) {
@@ -114,7 +121,7 @@ dw_rs_pair_kernel(const __grid_constant__ CUtensorMap tm_hc, const __grid_consta
     if (lane == 0) {
       for (int s = 0; s < 4; ++s) {
         mbar_init(raw_full(s), 1);
-        mbar_init(raw_empty(s), Cfg::PROD_WARPS * 16);   // the 256 threads of the owning producer group
+        mbar_init(raw_empty(s), Cfg::PROD_WARPS / 2);    // the 8 warps of the owning producer group, one arrival each
         mbar_init(s_full(s), Cfg::PROD_WARPS);            // 8 warps of the owning group x 2 CTAs, one arrival per warp
         mbar_init(s_empty(s), 1);
       }
@@ -147,14 +154,18 @@ dw_rs_pair_kernel(const __grid_constant__ CUtensorMap tm_hc, const __grid_consta
 
   if (warp < 4) {
     // ================================ epilogue: TMEM -> fp16 raw G (TMA tile stores) ===============
+    // Warp q owns this CTA's output channels [32 q, 32 q + 32) (its tensor-memory lanes): per visit four boxes of
+    // 32 channels x 64 frames (tile of the pair, frame half), each staged in a private swizzled buffer and stored by the
+    // warp's own lane 0 -- no barrier with the other epilogue warps.
     const int quad = warp;
-    const int cl = quad * 32 + lane;          // this CTA's output channel
-    const int kb64 = cl >> 6, row = cl & 63;
-    const bool issuer = ((quad & 1) == 0 && lane == 0);   // one thread per 64-channel block issues its boxes
     const CUtensorMap* tm_out = (crank == 0) ? &tm_res : &tm_skip;
     const bool store_on = !(crank == 0 && res_dead != 0);
     const uint32_t my_tempty = mapa_rank(tempty_bar, 0);
-    int nbox = 0;
+    const uint32_t st_warp = smem_base + (uint32_t)Cfg::OFF_ST + (uint32_t)(quad * st_pw) * (uint32_t)Cfg::ST_BOX;
+    const uint32_t st_row = (uint32_t)(lane * 128);
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::D_COL0;
+    int buf = 0;
     for (int it = 0; it < n_visits; ++it) {
       const int pt = pair_tile_at(it);
       mbar_wait_b(tb.flags, tfull_bar, (uint32_t)it & 1u);
@@ -164,44 +175,44 @@ dw_rs_pair_kernel(const __grid_constant__ CUtensorMap tm_hc, const __grid_consta
       for (int bx = 0; bx < 4; ++bx) {          // (tile of the pair, frame half)
         const int t = bx >> 1, h = bx & 1;
         const int wt = pt * 2 + t;
-        const uint32_t st_box = smem_base + (uint32_t)(Cfg::OFF_ST + (kb64 * 2 + (nbox & 1)) * Cfg::ST_BOX);
-        const uint32_t st_row = st_box + (uint32_t)(row * 128);
-        // the store issued from this staging buffer two boxes ago must have finished READING it
-        if (issuer) bulk_wait_read1();
-        named_bar_sync(1 + kb64, 64);
+        const uint32_t st_box = st_warp + (uint32_t)buf * (uint32_t)Cfg::ST_BOX;
+        // the store issued from this staging buffer st_pw boxes ago must have finished READING it
+        if (lane == 0) { if (st_pw == 4) bulk_wait_read3(); else bulk_wait_read1(); }
+        __syncwarp();
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + Cfg::D_COL0 + (uint32_t)(t * 128 + h * 64 + hh * 32), v);
+          tmem_ld32(t_lane + (uint32_t)(t * 128 + h * 64 + hh * 32), v);
           tmem_ld_wait();
           if (bx == 3 && hh == 1) {
-            // the accumulator is in registers / shared memory: the next visit's MMAs may overwrite it
+            // the accumulator is in registers: the next visit's MMAs may overwrite it
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(my_tempty);
+            if (threadIdx.x == 0) tl_stamp(it, 82);
           }
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) pk[j] = h2_as_u32(__floats2half2_rn(v[2 * j], v[2 * j + 1]));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            st_shared_v4(st_row + (uint32_t)((((hh * 4 + k) ^ (row & 7))) << 4),
+            st_shared_v4(st_box + st_row + ((((uint32_t)(hh * 4 + k)) ^ sw) << 4),
                          make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
         }
         fence_proxy_async();
-        named_bar_sync(1 + kb64, 64);
-        if (issuer) {
+        __syncwarp();
+        if (lane == 0) {
           if (store_on && wt < n_tiles) {
             const int r0 = (crank == 0) ? wt * C_BN : wt * skip_tile_rows + skip_row0;
-            tma_store_2d(tm_out, st_box, h * 64, r0 + kb64 * 64);
+            tma_store_2d(tm_out, st_box, h * 64, r0 + quad * 32);
           }
           bulk_commit();  // (an empty group when nothing was stored: keeps the wait_group arithmetic uniform)
         }
-        ++nbox;
+        if (++buf == st_pw) buf = 0;
       }
       if (threadIdx.x == 0) tl_stamp(it, 81);
     }
-    if (issuer) bulk_wait0();  // every tile store has completed before the CTA exits
+    if (lane == 0) bulk_wait0();  // every tile store has completed before the CTA exits
   } else if (warp == 4) {
     // ================================ TMA producer: raw h1 k-blocks + halos =======================
     if (lane == 0) {
@@ -272,7 +283,6 @@ dw_rs_pair_kernel(const __grid_constant__ CUtensorMap tm_hc, const __grid_consta
     const int grp = pw >> 3, gw = pw & 7;
     const int sub = lane >> 4, lane16 = lane & 15;
     const int row0 = gw * 2 + sub;        // k-row of step 0 inside a k-block; step j = row0 + 16 j
-    const float alpha = p.alpha2;
     const int sv = (D > 0) ? 1 : (d >> 3);  // tap distance in 8-frame vectors
     const int hv = hw >> 3;                 // halo width in vectors
     const uint32_t c_pitch = 256u;
@@ -286,7 +296,7 @@ dw_rs_pair_kernel(const __grid_constant__ CUtensorMap tm_hc, const __grid_consta
     const uint32_t c_step = 16u * c_pitch, l_step = 16u * l_pitch, r_step = 16u * r_pitch;
     const uint32_t a_off0 = a_chunk_off(row0, lane16 * 8);  // (row & 7) is the same for every step; step j = + 2048 j
     int nseq = 0;  // k-blocks produced by this group so far -> stage / phase
-    const __half2 alpha_h2 = __float2half2_rn(alpha);
+    const __half2 alpha_h2 = __float2half2_rn(p.alpha2);
     const bool tl_on = (gw == 0 && lane == 0);
     const int tl_base = grp ? 100 : 40;
 
@@ -316,18 +326,8 @@ dw_rs_pair_kernel(const __grid_constant__ CUtensorMap tm_hc, const __grid_consta
       const int t_base = tile_t0 + lane16 * 8;
       const bool interior = (tile_t0 - d >= 0) && (tile_t0 + TILE_M - 1 + d < F);
       float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
-      DwEdge mk;
-      if (!interior) {
-        // taps and frames masked by segment-relative frame index (zero padding applies to the normalised
-        // signal at the TRUE segment ends); masked-out taps read finite values, so 0 * h is exactly 0
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int ta = t_base + 2 * k, tb2 = ta + 1;
-          mk.ml[k] = make_float2((ta - d >= 0 && ta - d < F) ? 1.f : 0.f, (tb2 - d >= 0 && tb2 - d < F) ? 1.f : 0.f);
-          mk.mc[k] = make_float2(ta < F ? 1.f : 0.f, tb2 < F ? 1.f : 0.f);
-          mk.mr[k] = make_float2(ta + d < F ? 1.f : 0.f, tb2 + d < F ? 1.f : 0.f);
-        }
-      }
+      DwEdgeH mk;
+      if (!interior) dw_edge_masks(mk, t_base, d, F);  // taps / frames switched off by segment-relative frame index
 #pragma unroll 1
       for (int kb = grp; kb < 8; kb += 2) {
         const int s_idx = grp * Cfg::S_PG + (nseq & (Cfg::S_PG - 1));
@@ -366,40 +366,31 @@ dw_rs_pair_kernel(const __grid_constant__ CUtensorMap tm_hc, const __grid_consta
             st_shared_v4(sa + (jj + 1) * 2048u, o1);
           }
         } else {
-#pragma unroll 1
-          for (int j = 0; j < 4; ++j) {
-            const int c = ch0 + j * 16;
-            const uint4 vc = ld_shared_v4(raw + c_base + j * c_step);
-            const uint4 va = ld_shared_v4(raw + l_base + j * l_step);
-            const uint4 vb = ld_shared_v4(raw + r_base + j * r_step);
-            const float4 t0 = s_t0[c], t1 = s_t1[c];
-            float ctr[8], lft[8], rgt[8];
-            dw_taps<D>(vc, va, vb, ctr, lft, rgt);
-            const float wa0 = t0.x * rstd, wa1 = t0.y * rstd, wa2 = t0.z * rstd;
-            const float wb0 = fmaf(-t0.x, rm, t1.x), wb1 = fmaf(-t0.y, rm, t1.y), wb2 = fmaf(-t0.z, rm, t1.z);
-            const float2 a0 = make_float2(wa0, wa0), a1 = make_float2(wa1, wa1), a2 = make_float2(wa2, wa2);
-            const float2 b0 = make_float2(wb0, wb0), b1 = make_float2(wb1, wb1), b2 = make_float2(wb2, wb2);
-            const float2 bias = make_float2(t1.w, t1.w);
-            float o[8];
 #pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-              const int k = i >> 1;
-              float2 u = fma2(fma2(make_float2(lft[i], lft[i + 1]), a0, b0), mk.ml[k], bias);
-              u = fma2(fma2(make_float2(ctr[i], ctr[i + 1]), a1, b1), mk.mc[k], u);
-              u = fma2(fma2(make_float2(rgt[i], rgt[i + 1]), a2, b2), mk.mr[k], u);
-              u = mul2(prelu2<A01>(u, alpha), mk.mc[k]);
-              o[i] = u.x; o[i + 1] = u.y;
-              s2 = add2(s2, u);
-              q2 = fma2(u, u, q2);
-            }
-            if (j == 0) mbar_wait_b(tb.flags, my_s_empty, sphase ^ 1u);
-            st_shared_v4(sa + j * 2048u, pack8(o));
+          for (int jj = 0; jj < 4; jj += 2) {
+            const uint4 vc0 = ld_shared_v4(raw + c_base + jj * c_step);
+            const uint4 vc1 = ld_shared_v4(raw + c_base + (jj + 1) * c_step);
+            const uint4 va0 = ld_shared_v4(raw + l_base + jj * l_step);
+            const uint4 vb0 = ld_shared_v4(raw + r_base + jj * r_step);
+            const uint4 va1 = ld_shared_v4(raw + l_base + (jj + 1) * l_step);
+            const uint4 vb1 = ld_shared_v4(raw + r_base + (jj + 1) * r_step);
+            const float4 ta = s_t0[ch0 + jj * 16], tb_ = s_t0[ch0 + jj * 16 + 16];
+            const float4 ua = __ldg(p.t1 + ch0 + jj * 16), ub = __ldg(p.t1 + ch0 + jj * 16 + 16);
+            __half2 sh = __float2half2_rn(0.f), qh = __float2half2_rn(0.f);
+            const uint4 o0 = dw_step_h2_edge<D, A01>(vc0, va0, vb0, ta, ua, rstd, rm, alpha_h2, mk, sh, qh);
+            const uint4 o1 = dw_step_h2_edge<D, A01>(vc1, va1, vb1, tb_, ub, rstd, rm, alpha_h2, mk, sh, qh);
+            dw_stats_flush(sh, qh, s2, q2);
+            if (jj == 0) mbar_wait_b(tb.flags, my_s_empty, sphase ^ 1u);
+            st_shared_v4(sa + jj * 2048u, o0);
+            st_shared_v4(sa + (jj + 1) * 2048u, o1);
           }
         }
         fence_proxy_async();
         __syncwarp();  // every lane has fenced its stage writes; lane 0 arrives (release.cluster is cumulative)
-        if (lane == 0) mbar_arrive_cluster(my_s_full);
-        mbar_arrive(raw_empty(rs_));
+        if (lane == 0) {
+          mbar_arrive_cluster(my_s_full);
+          mbar_arrive(raw_empty(rs_));  // (the __syncwarp above also orders every lane's reads of the raw stage)
+        }
         if (tl_on) tl_stamp(it, tl_base + 3 * (kb >> 1) + 2);
         ++nseq;
         // statistics of the next tile's segment, off the tile-boundary critical path
