@@ -573,10 +573,10 @@ struct KpArgs {
   float2* p2;
   fb::DwTab tab;
 };
-template <int D, bool A01>
+template <int D, bool A01, int NG>
 static int launch_dw_rs_pair(const b200sep_model* m, const KpArgs& a, const Tables& tb, cudaStream_t st) {
   using Cfg = pr2::KpCfg;
-  auto kern = pr2::dw_rs_pair_kernel<D, A01>;
+  auto kern = pr2::dw_rs_pair_kernel<D, A01, NG>;
   { static DevOnce once; if (once.need(m->device)) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); once.done(m->device); } }
   const int n_pairs = std::max(1, std::min((tb.n_tiles + 1) / 2, m->n_sm / 2));
   cudaLaunchConfig_t cfg{};
@@ -597,11 +597,14 @@ static int launch_dw_rs_pair(const b200sep_model* m, const KpArgs& a, const Tabl
 }
 template <bool A01>
 static int launch_dw_rs_pair_d(const b200sep_model* m, const KpArgs& a, const Tables& tb, cudaStream_t st) {
+  // two producer groups (NG = 2).  Four groups of four warps (the kernel supports NG = 4 where four raw stages fit) were
+  // measured equal: 76.9 vs 76.4 us per launch -- the tensor core's own k-block time grows from ~550 to ~890 cycles when
+  // all producers stream at once (shared-memory bandwidth), see DESIGN.md.
   switch (a.tab.dilation) {
-    case 1: return launch_dw_rs_pair<1, A01>(m, a, tb, st);
-    case 2: return launch_dw_rs_pair<2, A01>(m, a, tb, st);
-    case 4: return launch_dw_rs_pair<4, A01>(m, a, tb, st);
-    default: return launch_dw_rs_pair<0, A01>(m, a, tb, st);
+    case 1: return launch_dw_rs_pair<1, A01, 2>(m, a, tb, st);
+    case 2: return launch_dw_rs_pair<2, A01, 2>(m, a, tb, st);
+    case 4: return launch_dw_rs_pair<4, A01, 2>(m, a, tb, st);
+    default: return launch_dw_rs_pair<0, A01, 2>(m, a, tb, st);
   }
 }
 template <bool A01>

@@ -350,17 +350,67 @@ __device__ __forceinline__ uint4 dw_step_h2(const uint4 vc, const uint4 va, cons
 // padding applies to the NORMALISED signal at the true segment ends, so every tap carries its own constant term
 // (a_k h + b_k) and is switched off as a whole by a bit mask (0xffff / 0 per fp16 lane: exact zero whatever the
 // masked-out raw value was -- the neighbouring segment's data or the TMA zero fill); frames >= F produce zeros.
-//   t0 = {w0 g, w1 g, w2 g, .}, t1 = {w0 beta, w1 beta, w2 beta, bias}:  a_k = t0_k rstd,  b_k = t1_k - t0_k rstd mean
+//   t0 = {w0 g, w1 g, w2 g, .}, t1 = {w0 beta, w1 beta, w2 beta, bias}:  a_k = fp16(t0_k rstd),  b_k = t1_k - a_k mean
+// (b_k from the ROUNDED a_k: the pair kernel only has the rounded taps in its per-visit table, and both kernels must
+// produce the same bits)
 struct DwEdgeH { uint32_t ml[4], mc[4], mr[4]; };
 template <int D, bool A01>
 __device__ __forceinline__ uint4 dw_step_h2_edge(const uint4 vc, const uint4 va, const uint4 vb, const float4 t0,
-                                                 const float4 t1, const float rstd, const float rm, const __half2 alpha2,
+                                                 const float4 t1, const float rstd, const float mean, const __half2 alpha2,
                                                  const DwEdgeH& mk, __half2& sh, __half2& qh) {
   uint32_t c[4], l[4], r[4];
   dw_lr<D>(vc, va, vb, c, l, r);
   const __half2 w0 = __float2half2_rn(t0.x * rstd), w1 = __float2half2_rn(t0.y * rstd), w2 = __float2half2_rn(t0.z * rstd);
-  const __half2 b0 = __float2half2_rn(fmaf(-t0.x, rm, t1.x)), b1 = __float2half2_rn(fmaf(-t0.y, rm, t1.y));
-  const __half2 b2 = __float2half2_rn(fmaf(-t0.z, rm, t1.z)), bias = __float2half2_rn(t1.w);
+  const __half2 b0 = __float2half2_rn(fmaf(-__low2float(w0), mean, t1.x));
+  const __half2 b1 = __float2half2_rn(fmaf(-__low2float(w1), mean, t1.y));
+  const __half2 b2 = __float2half2_rn(fmaf(-__low2float(w2), mean, t1.z)), bias = __float2half2_rn(t1.w);
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t ta = h2_as_u32(__hfma2(u32_as_h2(l[i]), w0, b0)) & mk.ml[i];
+    const uint32_t tc = h2_as_u32(__hfma2(u32_as_h2(c[i]), w1, b1)) & mk.mc[i];
+    const uint32_t tr = h2_as_u32(__hfma2(u32_as_h2(r[i]), w2, b2)) & mk.mr[i];
+    __half2 u = __hadd2(__hadd2(u32_as_h2(ta), u32_as_h2(tc)), __hadd2(u32_as_h2(tr), bias));
+    u = u32_as_h2(h2_as_u32(prelu_h2<A01>(u, alpha2)) & mk.mc[i]);
+    o[i] = h2_as_u32(u);
+    sh = __hadd2(sh, u);
+    qh = __hfma2(u, u, qh);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+// The same two steps with the per-visit tap table of the pair kernel (fused_pair.cuh): tap = {a0, a1, a2, cw} as
+// four halves, prepared once per visit and channel by the statistics warp; broadcast to half2 pairs here (PRMT).
+__device__ __forceinline__ __half2 bcast_lo(uint32_t u) { return u32_as_h2(__byte_perm(u, u, 0x1010)); }
+__device__ __forceinline__ __half2 bcast_hi(uint32_t u) { return u32_as_h2(__byte_perm(u, u, 0x3232)); }
+template <int D, bool A01>
+__device__ __forceinline__ uint4 dw_step_h2p(const uint4 vc, const uint4 va, const uint4 vb, const uint2 tap,
+                                             const __half2 alpha2, __half2& sh, __half2& qh) {
+  uint32_t c[4], l[4], r[4];
+  dw_lr<D>(vc, va, vb, c, l, r);
+  const __half2 w0 = bcast_lo(tap.x), w1 = bcast_hi(tap.x), w2 = bcast_lo(tap.y), cw = bcast_hi(tap.y);
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __half2 u = __hfma2(u32_as_h2(l[i]), w0, __hfma2(u32_as_h2(c[i]), w1, __hfma2(u32_as_h2(r[i]), w2, cw)));
+    u = prelu_h2<A01>(u, alpha2);
+    o[i] = h2_as_u32(u);
+    sh = __hadd2(sh, u);
+    qh = __hfma2(u, u, qh);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+// edge tiles: b_k = t1_k - a_k mean with the table's (rounded) a_k = fp16(t0_k rstd)
+template <int D, bool A01>
+__device__ __forceinline__ uint4 dw_step_h2p_edge(const uint4 vc, const uint4 va, const uint4 vb, const uint2 tap,
+                                                  const float4 t1, const float mean, const __half2 alpha2,
+                                                  const DwEdgeH& mk, __half2& sh, __half2& qh) {
+  uint32_t c[4], l[4], r[4];
+  dw_lr<D>(vc, va, vb, c, l, r);
+  const __half2 w0 = bcast_lo(tap.x), w1 = bcast_hi(tap.x), w2 = bcast_lo(tap.y);
+  const __half2 b0 = __float2half2_rn(fmaf(-__low2float(w0), mean, t1.x));
+  const __half2 b1 = __float2half2_rn(fmaf(-__low2float(w1), mean, t1.y));
+  const __half2 b2 = __float2half2_rn(fmaf(-__low2float(w2), mean, t1.z));
+  const __half2 bias = __float2half2_rn(t1.w);
   uint32_t o[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -731,8 +781,8 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
             const float4 ta = s_t0[ch0 + jj * 16], tb_ = s_t0[ch0 + jj * 16 + 16];
             const float4 ua = s_t1[ch0 + jj * 16], ub = s_t1[ch0 + jj * 16 + 16];
             __half2 sh = __float2half2_rn(0.f), qh = __float2half2_rn(0.f);
-            const uint4 o0 = dw_step_h2_edge<D, A01>(vc0, va0, vb0, ta, ua, rstd, rm, alpha_h2, mk, sh, qh);
-            const uint4 o1 = dw_step_h2_edge<D, A01>(vc1, va1, vb1, tb_, ub, rstd, rm, alpha_h2, mk, sh, qh);
+            const uint4 o0 = dw_step_h2_edge<D, A01>(vc0, va0, vb0, ta, ua, rstd, mean, alpha_h2, mk, sh, qh);
+            const uint4 o1 = dw_step_h2_edge<D, A01>(vc1, va1, vb1, tb_, ub, rstd, mean, alpha_h2, mk, sh, qh);
             dw_stats_flush(sh, qh, s2, q2);
             if (jj == 0) mbar_wait_b(tb.flags, my_ab_empty, aphase ^ 1u);
             st_shared_v4(sa + jj * 2048u, o0);

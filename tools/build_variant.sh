@@ -1,9 +1,8 @@
 #!/bin/bash
-# usage: tools/build_variant.sh NAME [-DFLAG ...]  -> audio-classification_b200/variants/lib_NAME.so
+# usage: tools/build_variant.sh <name> [-D...]   ->  audio-classification_b200/variants/lib_<name>.so  (kernel A/B experiments)
 set -e
-cd "$(dirname "$0")/.."
 name=$1; shift
-mkdir -p audio-classification_b200/variants
-nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -shared -Xcompiler -fPIC "$@" \
-  -o audio-classification_b200/variants/lib_$name.so audio-classification_b200/csrc/b200sep.cu
-echo built $name
+cd "$(dirname "$0")/../audio-classification_b200"
+mkdir -p variants
+nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -shared -Xcompiler -fPIC "$@" -o variants/lib_$name.so csrc/b200sep.cu
+echo built variants/lib_$name.so

@@ -1,0 +1,5 @@
+set -x
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -25
+B200SEP_KA=pair timeout 120 python tools/variant_time.py 2>&1 | tail -3 | head -2
+B200SEP_KA_NG=2 B200SEP_KA=pair timeout 120 python tools/variant_time.py 2>&1 | tail -3 | head -2
+B200SEP_KA=pair timeout 120 python tools/timeline.py 6 2>&1 | grep -A 9 "K_A" | cut -c1-1200 | head -8
