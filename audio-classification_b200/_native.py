@@ -26,7 +26,7 @@ EXPORTS = [
     "b200sep_workspace_bytes", "b200sep_separate_batch", "b200sep_pit_workspace_bytes",
     "b200sep_pit_sisdr_batch", "b200sep_debug_gemm", "b200sep_debug_set_stop",
     "b200sep_debug_layout", "b200sep_profile_enable", "b200sep_profile_read",
-    "b200sep_pipeline", "b200sep_debug_timeline",
+    "b200sep_pipeline", "b200sep_debug_timeline", "b200sep_pit_profile_enable", "b200sep_pit_profile_read",
     "b200sep_host_workspace_bytes", "b200sep_separate_batch_host", "b200sep_split_count",
     "b200sep_resample_out_lens", "b200sep_resample_batch", "b200sep_frame_rms_out_lens",
     "b200sep_frame_rms_batch", "b200sep_gt_overlap_mask_batch", "b200sep_debug_ts_probe",
@@ -144,10 +144,13 @@ FLAG_EPS_DOMINATED = 4  # B200SEP_FLAG_EPS_DOMINATED
 
 
 def i32_array(vals):
-    arr = (C.c_int32 * len(vals))(*[int(v) for v in vals])
-    return arr
+    """ctypes int32 array of `vals` (through NumPy: a sweep passes tens of thousands of lengths per call)."""
+    import numpy as np
+    a = np.array(vals, dtype=np.int32).reshape(-1)  # (always a fresh, writable copy: from_buffer shares it)
+    return (C.c_int32 * a.size).from_buffer(a)
 
 
 def i64_array(vals):
-    arr = (C.c_int64 * len(vals))(*[int(v) for v in vals])
-    return arr
+    import numpy as np
+    a = np.array(vals, dtype=np.int64).reshape(-1)
+    return (C.c_int64 * a.size).from_buffer(a)

@@ -239,6 +239,10 @@ struct b200sep_model {
 
 static Staging g_pit_staging[kMaxDev];  // per device (events and pinned slots belong to a device context)
 static std::mutex g_pit_mu;
+// optional per-launch timing of the PIT kernels (b200sep_pit_profile_enable / _read): three events per device
+struct PitProf { cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; bool valid = false; };
+static PitProf g_pit_prof[kMaxDev];
+static std::atomic<int> g_pit_prof_on{0};
 
 template <typename T> static T host_cvt(float v);
 template <> float host_cvt<float>(float v) { return v; }
@@ -1544,13 +1548,41 @@ int b200sep_pit_sisdr_batch(const float* d_refs, const float* d_ests, const floa
   PitArgs a{d_refs, d_ests, d_mix, reinterpret_cast<const int64_t*>(ws), reinterpret_cast<const int32_t*>(ws + off_bytes),
             K, N, chunk, max_chunks};
   dim3 grid(max_chunks, n_seg);
+  PitProf* prof = nullptr;
+  if (g_pit_prof_on.load() != 0) {
+    prof = &g_pit_prof[current_device_index()];
+    for (auto& e : prof->ev)
+      if (e == nullptr) CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(prof->ev[0], st));
+  }
   if (K == 2 && N == 2) pit_moments_kernel<2, 2><<<grid, 256, 0, st>>>(a, partial);
   else if (K == 2 && N == 3) pit_moments_kernel<2, 3><<<grid, 256, 0, st>>>(a, partial);
   else pit_moments_kernel<3, 3><<<grid, 256, 0, st>>>(a, partial);
   CK(cudaGetLastError());
+  if (prof) CK(cudaEventRecord(prof->ev[1], st));
   pit_finalize_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(partial, a.len, n_seg, max_chunks, K, N, variant, d_pair,
                                                          d_sisdr, d_sisdri, d_perm, d_gap);
   CK(cudaGetLastError());
+  if (prof) {
+    CK(cudaEventRecord(prof->ev[2], st));
+    prof->valid = true;
+  }
+  return 0;
+}
+
+int b200sep_pit_profile_enable(int on) {
+  g_pit_prof_on.store(on ? 1 : 0);
+  return 0;
+}
+
+int b200sep_pit_profile_read(float* ms_out) {
+  if (!ms_out) return fail("null argument");
+  std::lock_guard<std::mutex> lock(g_pit_mu);
+  PitProf& p = g_pit_prof[current_device_index()];
+  if (!p.valid) return fail("no profiled b200sep_pit_sisdr_batch call on this device");
+  CK(cudaEventSynchronize(p.ev[2]));
+  CK(cudaEventElapsedTime(&ms_out[0], p.ev[0], p.ev[1]));
+  CK(cudaEventElapsedTime(&ms_out[1], p.ev[1], p.ev[2]));
   return 0;
 }
 

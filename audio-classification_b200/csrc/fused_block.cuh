@@ -262,9 +262,10 @@ struct KaCfg {
   static constexpr int A_STAGE = TILE_M * 64 * 2;    // 16 KiB
   static constexpr int B_STAGE = BN * 64 * 2;  // 32 KiB
   static constexpr int B_MAX_STAGES = 4;
-  static constexpr int TAB_BYTES = C_HID * (16 + 16 + 4);  // 18 KiB
+  static constexpr int TAB_BYTES = C_HID * (2 * 8 + 16);  // per-visit folded tap table (two buffers) + static t1: 16 KiB
   static constexpr int EPI_WARPS = 4, PROD_WARPS = 16;
-  static constexpr int THREADS = (EPI_WARPS + 3 + PROD_WARPS) * 32;  // 736
+  static constexpr int W_STAT = EPI_WARPS + 3 + PROD_WARPS;          // statistics warp (the 24th warp costs no registers:
+  static constexpr int THREADS = (W_STAT + 1) * 32;                  // 768     23 and 24 warps get the same 80 per thread)
   static constexpr int TMEM_COLS = 2 * BN;
   // A stages per producer group: with 2 the producers of a group write k-block n + 1 while the MMA of k-block n (and, in
   // pair mode, the cross-SM arrive / commit round trip) is still in flight
@@ -275,7 +276,8 @@ struct KaCfg {
   static constexpr int OFF_TI = OFF_TAB + TAB_BYTES;
   static constexpr int OFF_RED = OFF_TI + TI_CACHE * 32;
   static constexpr int OFF_CNT = OFF_RED + 2 * PROD_WARPS * 8;
-  static constexpr int OFF_BAR = OFF_CNT + 16;
+  static constexpr int OFF_STAT = OFF_CNT + 16;  // [2] (mean, rstd) of the visit's segment
+  static constexpr int OFF_BAR = OFF_STAT + 16;
   static constexpr int OFF_RAW = (OFF_BAR + 512 + 1023) / 1024 * 1024;  // raw ring, then B ring
   static constexpr int SMEM_BYTES = 232448;          // everything an SM offers to one CTA
   static constexpr int SMEM_USABLE = SMEM_BYTES - 1024 /*alignment slack*/;
@@ -323,63 +325,15 @@ __device__ __forceinline__ __half2 prelu_h2(__half2 u, const __half2 alpha2) {
   if (A01) return __hmax2(u, __hmul2(u, alpha2));
   return __hadd2(__hmax2(u, __float2half2_rn(0.f)), __hmul2(alpha2, __hmin2(u, __float2half2_rn(0.f))));
 }
-template <int D, bool A01>
-__device__ __forceinline__ uint4 dw_step_h2(const uint4 vc, const uint4 va, const uint4 vb, const float4 t0,
-                                            const float cb, const float rstd, const float rm, const __half2 alpha2,
-                                            __half2& sh, __half2& qh) {
-  uint32_t c[4], l[4], r[4];
-  dw_lr<D>(vc, va, vb, c, l, r);
-  const __half2 w0 = __float2half2_rn(t0.x * rstd), w1 = __float2half2_rn(t0.y * rstd);
-  const __half2 w2 = __float2half2_rn(t0.z * rstd), cw = __float2half2_rn(fmaf(-t0.w, rm, cb));
-  uint32_t o[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __half2 u = __hfma2(u32_as_h2(l[i]), w0, __hfma2(u32_as_h2(c[i]), w1, __hfma2(u32_as_h2(r[i]), w2, cw)));
-    u = prelu_h2<A01>(u, alpha2);
-    o[i] = h2_as_u32(u);
-    // gLN2 statistics of the ROUNDED outputs: first level in packed halves (two instructions per pair instead of four
-    // scalar mixed-precision FMAs -- the producers are bound by the FMA pipe); the caller folds (sh, qh) into its fp32
-    // accumulators after at most 8 values per half lane (dw_stats_flush), so the fp16 partial sums stay short
-    sh = __hadd2(sh, u);
-    qh = __hfma2(u, u, qh);
-  }
-  return make_uint4(o[0], o[1], o[2], o[3]);
-}
-
 // Edge-tile producer step (a tap or a frame of the tile falls outside the segment), still in packed halves.  Zero
 // padding applies to the NORMALISED signal at the true segment ends, so every tap carries its own constant term
 // (a_k h + b_k) and is switched off as a whole by a bit mask (0xffff / 0 per fp16 lane: exact zero whatever the
 // masked-out raw value was -- the neighbouring segment's data or the TMA zero fill); frames >= F produce zeros.
 //   t0 = {w0 g, w1 g, w2 g, .}, t1 = {w0 beta, w1 beta, w2 beta, bias}:  a_k = fp16(t0_k rstd),  b_k = t1_k - a_k mean
-// (b_k from the ROUNDED a_k: the pair kernel only has the rounded taps in its per-visit table, and both kernels must
-// produce the same bits)
+// (b_k from the ROUNDED a_k: the per-visit table only holds the rounded taps)
 struct DwEdgeH { uint32_t ml[4], mc[4], mr[4]; };
-template <int D, bool A01>
-__device__ __forceinline__ uint4 dw_step_h2_edge(const uint4 vc, const uint4 va, const uint4 vb, const float4 t0,
-                                                 const float4 t1, const float rstd, const float mean, const __half2 alpha2,
-                                                 const DwEdgeH& mk, __half2& sh, __half2& qh) {
-  uint32_t c[4], l[4], r[4];
-  dw_lr<D>(vc, va, vb, c, l, r);
-  const __half2 w0 = __float2half2_rn(t0.x * rstd), w1 = __float2half2_rn(t0.y * rstd), w2 = __float2half2_rn(t0.z * rstd);
-  const __half2 b0 = __float2half2_rn(fmaf(-__low2float(w0), mean, t1.x));
-  const __half2 b1 = __float2half2_rn(fmaf(-__low2float(w1), mean, t1.y));
-  const __half2 b2 = __float2half2_rn(fmaf(-__low2float(w2), mean, t1.z)), bias = __float2half2_rn(t1.w);
-  uint32_t o[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t ta = h2_as_u32(__hfma2(u32_as_h2(l[i]), w0, b0)) & mk.ml[i];
-    const uint32_t tc = h2_as_u32(__hfma2(u32_as_h2(c[i]), w1, b1)) & mk.mc[i];
-    const uint32_t tr = h2_as_u32(__hfma2(u32_as_h2(r[i]), w2, b2)) & mk.mr[i];
-    __half2 u = __hadd2(__hadd2(u32_as_h2(ta), u32_as_h2(tc)), __hadd2(u32_as_h2(tr), bias));
-    u = u32_as_h2(h2_as_u32(prelu_h2<A01>(u, alpha2)) & mk.mc[i]);
-    o[i] = h2_as_u32(u);
-    sh = __hadd2(sh, u);
-    qh = __hfma2(u, u, qh);
-  }
-  return make_uint4(o[0], o[1], o[2], o[3]);
-}
-// The same two steps with the per-visit tap table of the pair kernel (fused_pair.cuh): tap = {a0, a1, a2, cw} as
-// four halves, prepared once per visit and channel by the statistics warp; broadcast to half2 pairs here (PRMT).
+// The producer steps read the per-visit tap table: tap = {a0, a1, a2, cw} as four halves, prepared once per visit and
+// channel by the statistics warp; broadcast to half2 pairs here (PRMT, on the otherwise idle ALU pipe).
 __device__ __forceinline__ __half2 bcast_lo(uint32_t u) { return u32_as_h2(__byte_perm(u, u, 0x1010)); }
 __device__ __forceinline__ __half2 bcast_hi(uint32_t u) { return u32_as_h2(__byte_perm(u, u, 0x3232)); }
 template <int D, bool A01>
@@ -448,7 +402,7 @@ __device__ __forceinline__ void dw_stats_flush(__half2& sh, __half2& qh, float2&
 }
 
 template <int BN, int D, bool A01>
-__global__ void __launch_bounds__(736, 1)
+__global__ void __launch_bounds__(KaCfg<256>::THREADS, 1)
 dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_hc,
              const __grid_constant__ CUtensorMap tm_hh, __half* __restrict__ g_res, __half* __restrict__ g_skip,
              size_t skip_tile_stride, const float2* __restrict__ part1, float2* __restrict__ part2, DwTab p,
@@ -458,9 +412,13 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   auto stage_a = [&](int s) { return smem_base + (uint32_t)(Cfg::OFF_A + s * Cfg::A_STAGE); };
-  float4* s_t0 = reinterpret_cast<float4*>(smem_gen + Cfg::OFF_TAB);
-  float4* s_t1 = s_t0 + C_HID;
-  float* s_cb = reinterpret_cast<float*>(s_t1 + C_HID);
+  // s_tap[b][c]: the channel's folded taps for the segment of visit it (b = it & 1) as four halves
+  //   { w0 g rstd, w1 g rstd, w2 g rstd, cb - (w0 + w1 + w2) g rstd mean }
+  // written by the statistics warp one visit ahead (the producers used to redo these 8 instructions per 8 outputs and
+  // the segment statistics in the middle of every tile)
+  uint2* s_tap = reinterpret_cast<uint2*>(smem_gen + Cfg::OFF_TAB);
+  float4* s_t1 = reinterpret_cast<float4*>(s_tap + 2 * C_HID);
+  float2* s_stat = reinterpret_cast<float2*>(smem_gen + Cfg::OFF_STAT);   // [2]
   TileInfo* s_ti = reinterpret_cast<TileInfo*>(smem_gen + Cfg::OFF_TI);
   float2* s_red = reinterpret_cast<float2*>(smem_gen + Cfg::OFF_RED);  // [2][16]
   int* s_cnt = reinterpret_cast<int*>(smem_gen + Cfg::OFF_CNT);          // [2]
@@ -475,6 +433,9 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   auto tempty_bar = [&](int s) { return bar0 + 8u * (18 + s); };
   const uint32_t tmem_ptr_smem = bar0 + 8u * 20;
   const uint32_t done_bar = bar0 + 8u * 21;  // final tcgen05.commit: no async mbarrier arrive may outlive the CTA
+  auto stat_full = [&](int s) { return bar0 + 8u * (38 + s); };  // [2] statistics warp -> producers
+  auto stat_empty = [&](int s) { return bar0 + 8u * (40 + s); }; // [2] producers (one arrival per warp) -> statistics warp
+  auto red_full = [&](int s) { return bar0 + 8u * (42 + s); };   // [2] producers' per-warp gLN2 partials -> statistics warp
 
   // PDL: everything up to the prologue barrier touches only constants (weights, tap tables, per-call layout
   // tables), so it may overlap the previous kernel's tail; activations are read after pdl_wait().
@@ -511,11 +472,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   auto raw_st = [&](int s) { return smem_base + (uint32_t)Cfg::OFF_RAW + (uint32_t)s * raw_stage_bytes; };
 
   // static tables -> shared memory
-  for (int i = threadIdx.x; i < C_HID; i += Cfg::THREADS) {
-    s_t0[i] = __ldg(p.t0 + i);
-    s_t1[i] = __ldg(p.t1 + i);
-    s_cb[i] = __ldg(p.cb + i);
-  }
+  for (int i = threadIdx.x; i < C_HID; i += Cfg::THREADS) s_t1[i] = __ldg(p.t1 + i);
   if ((int)threadIdx.x < TI_CACHE && (int)threadIdx.x < n_visits) {
     bool v_;
     s_ti[threadIdx.x] = load_tile_info(tb.tile_info + tile_at(threadIdx.x, v_));
@@ -543,6 +500,11 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         mbar_init(b_empty(s), 1);
       }
       mbar_init(done_bar, 1);
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(stat_full(s), 1);
+        mbar_init(stat_empty(s), Cfg::PROD_WARPS);
+        mbar_init(red_full(s), Cfg::PROD_WARPS);
+      }
       fence_barrier_init();
     }
     __syncwarp();
@@ -675,6 +637,53 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       mbar_wait_b(tb.flags, done_bar, 0);
     }
     __syncwarp();
+  } else if (warp == Cfg::W_STAT) {
+    // ================================ statistics warp ==============================================
+    // gLN1 (mean, rstd) of every visit's segment (fp64 reduction of the per-tile partials K_B left behind) folded into
+    // the visit's per-channel tap table, one visit ahead of the producers; and the gLN2 partial of the previous visit
+    // (the 16 producer warps' (sum, sumsq) pairs added in warp order: a fixed order, no producer warp stays behind).
+    auto reduce_visit = [&](int it) {
+      bool valid;
+      const int w = tile_at(it, valid);
+      mbar_wait_b(tb.flags, red_full(it & 1), ((uint32_t)it >> 1) & 1u);
+      const float2 v = (lane < Cfg::PROD_WARPS) ? s_red[(it & 1) * Cfg::PROD_WARPS + lane] : make_float2(0.f, 0.f);
+      float ts = 0.f, tq = 0.f;
+#pragma unroll
+      for (int k = 0; k < Cfg::PROD_WARPS; ++k) {
+        ts += __shfl_sync(0xffffffffu, v.x, k);
+        tq += __shfl_sync(0xffffffffu, v.y, k);
+      }
+      if (lane == 0 && valid) part2[w] = make_float2(ts, tq);
+    };
+    for (int it = 0; it < n_visits; ++it) {
+      bool v_;
+      const TileInfo ti = ti_get(s_ti, tb, it, tile_at(it, v_));
+      const float2 pre = part_prefetch(part1, ti);
+      float mean, rstd;
+      seg_stats_pre(part1, ti, pre, p.eps1, mean, rstd, tb.flags);
+      const float rm = rstd * mean;
+      mbar_wait_b(tb.flags, stat_empty(it & 1), (((uint32_t)it >> 1) & 1u) ^ 1u);
+      uint2* tap = s_tap + (it & 1) * C_HID;
+#pragma unroll 1
+      for (int c0 = 0; c0 < C_HID; c0 += 128) {
+        float4 t0[4];
+        float cb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          t0[j] = __ldg(p.t0 + c0 + j * 32 + lane);
+          cb[j] = __ldg(p.cb + c0 + j * 32 + lane);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          tap[c0 + j * 32 + lane] = make_uint2(h2_as_u32(__floats2half2_rn(t0[j].x * rstd, t0[j].y * rstd)),
+                                               h2_as_u32(__floats2half2_rn(t0[j].z * rstd, fmaf(-t0[j].w, rm, cb[j]))));
+      }
+      if (lane == 0) s_stat[it & 1] = make_float2(mean, rstd);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(stat_full(it & 1));  // (release at CTA scope orders the warp's stores before the arrival)
+      if (it > 0) reduce_visit(it - 1);
+    }
+    if (n_visits > 0) reduce_visit(n_visits - 1);
   } else {
     // ================================ depthwise producers =========================================
     // Two groups of 8 warps; group g produces the k-blocks kb = g, g+2, ... (and owns A/B stage g), so
@@ -704,27 +713,14 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
     const int tl_base = grp ? 100 : 40;  // timeline slots: group 0 40.., group 1 100..
 
     const int rpg = raw_stages >> 1;  // raw stages per group
-    float nmean = 0.f, nrstd = 0.f;  // statistics of the NEXT tile's segment (computed mid-tile)
-    if (n_visits > 0) {
-      bool v_;
-      const TileInfo t0i = ti_get(s_ti, tb, 0, tile_at(0, v_));
-      seg_stats_pre(part1, t0i, part_prefetch(part1, t0i), p.eps1, nmean, nrstd, tb.flags);
-    }
     for (int it = 0; it < n_visits; ++it) {
       bool valid;
       const int w = tile_at(it, valid);
       const TileInfo ti = ti_get(s_ti, tb, it, w);
       const int F = ti.F, tile_t0 = ti.t0;
-      const float mean = nmean, rstd = nrstd;
-      const bool has_next = it + 1 < n_visits;
-      TileInfo tn = ti;
-      float2 pre = make_float2(0.f, 0.f);
-      if (has_next) {
-        bool v_;
-        tn = ti_get(s_ti, tb, it + 1, tile_at(it + 1, v_));
-        pre = part_prefetch(part1, tn);
-      }
-      const float rm = rstd * mean;
+      mbar_wait_b(tb.flags, stat_full(it & 1), ((uint32_t)it >> 1) & 1u);
+      const float mean = s_stat[it & 1].x;   // (the tap table of the visit carries rstd)
+      const uint2* tap = s_tap + (it & 1) * C_HID;
       if (tl_on) tl_stamp(it, 32 + grp);
       const int t_base = tile_t0 + lane16 * 8;
       const bool interior = (tile_t0 - d >= 0) && (tile_t0 + TILE_M - 1 + d < F);
@@ -754,13 +750,12 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
             const uint4 vb0 = ld_shared_v4(raw + r_base + jj * r_step);
             const uint4 va1 = ld_shared_v4(raw + l_base + (jj + 1) * l_step);
             const uint4 vb1 = ld_shared_v4(raw + r_base + (jj + 1) * r_step);
-            const float4 ta = s_t0[ch0 + jj * 16], tb_ = s_t0[ch0 + jj * 16 + 16];
-            const float cba = s_cb[ch0 + jj * 16], cbb = s_cb[ch0 + jj * 16 + 16];
+            const uint2 ta = tap[ch0 + jj * 16], tb_ = tap[ch0 + jj * 16 + 16];
             // ... then the arithmetic; the (single) A stage of this group is only needed for the stores, so the
             // tensor core drains the previous k-block of the group while the first two steps are computed
             __half2 sh = __float2half2_rn(0.f), qh = __float2half2_rn(0.f);
-            const uint4 o0 = dw_step_h2<D, A01>(vc0, va0, vb0, ta, cba, rstd, rm, alpha_h2, sh, qh);
-            const uint4 o1 = dw_step_h2<D, A01>(vc1, va1, vb1, tb_, cbb, rstd, rm, alpha_h2, sh, qh);
+            const uint4 o0 = dw_step_h2p<D, A01>(vc0, va0, vb0, ta, alpha_h2, sh, qh);
+            const uint4 o1 = dw_step_h2p<D, A01>(vc1, va1, vb1, tb_, alpha_h2, sh, qh);
             dw_stats_flush(sh, qh, s2, q2);
             if (jj == 0) {
               mbar_wait_b(tb.flags, my_ab_empty, aphase ^ 1u);
@@ -778,11 +773,11 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
             const uint4 vb0 = ld_shared_v4(raw + r_base + jj * r_step);
             const uint4 va1 = ld_shared_v4(raw + l_base + (jj + 1) * l_step);
             const uint4 vb1 = ld_shared_v4(raw + r_base + (jj + 1) * r_step);
-            const float4 ta = s_t0[ch0 + jj * 16], tb_ = s_t0[ch0 + jj * 16 + 16];
+            const uint2 ta = tap[ch0 + jj * 16], tb_ = tap[ch0 + jj * 16 + 16];
             const float4 ua = s_t1[ch0 + jj * 16], ub = s_t1[ch0 + jj * 16 + 16];
             __half2 sh = __float2half2_rn(0.f), qh = __float2half2_rn(0.f);
-            const uint4 o0 = dw_step_h2_edge<D, A01>(vc0, va0, vb0, ta, ua, rstd, mean, alpha_h2, mk, sh, qh);
-            const uint4 o1 = dw_step_h2_edge<D, A01>(vc1, va1, vb1, tb_, ub, rstd, mean, alpha_h2, mk, sh, qh);
+            const uint4 o0 = dw_step_h2p_edge<D, A01>(vc0, va0, vb0, ta, ua, mean, alpha_h2, mk, sh, qh);
+            const uint4 o1 = dw_step_h2p_edge<D, A01>(vc1, va1, vb1, tb_, ub, mean, alpha_h2, mk, sh, qh);
             dw_stats_flush(sh, qh, s2, q2);
             if (jj == 0) mbar_wait_b(tb.flags, my_ab_empty, aphase ^ 1u);
             st_shared_v4(sa + jj * 2048u, o0);
@@ -794,14 +789,16 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         mbar_arrive(raw_empty(rs_));
         if (tl_on) tl_stamp(it, tl_base + 3 * (kb >> 1) + 2);
         ++nseq;
-        // statistics of the next tile's segment, off the tile-boundary critical path
-        if (kb == 4 + grp && has_next) seg_stats_pre(part1, tn, pre, p.eps1, nmean, nrstd, tb.flags);
       }
-      // gLN2 partial of this m-tile: fixed-order block reduction -> one slot per tile
+      // gLN2 partial of this m-tile: every warp publishes its (sum, sumsq); the statistics warp adds the 16 pairs in
+      // warp order and writes the tile's single partial.  The visit's tap table / statistics are free again.
       const float s_acc = warp_sum(s2.x + s2.y);
       const float q_acc = warp_sum(q2.x + q2.y);
-      tile_partial_reduce(s_red + (it & 1) * Cfg::PROD_WARPS, s_cnt + (it & 1), Cfg::PROD_WARPS, pw, s_acc, q_acc,
-                          valid ? part2 + w : nullptr);
+      if (lane == 0) {
+        s_red[(it & 1) * Cfg::PROD_WARPS + pw] = make_float2(s_acc, q_acc);
+        mbar_arrive(red_full(it & 1));
+        mbar_arrive(stat_empty(it & 1));
+      }
       if (tl_on) tl_stamp(it, 34 + grp);
     }
   }

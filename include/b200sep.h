@@ -259,6 +259,15 @@ int b200sep_debug_ts_probe(const float* d_w, const float* d_h, float* d_out, int
 int b200sep_profile_enable(b200sep_model* m, int on);
 int b200sep_profile_read(b200sep_model* m, float* ms_out, int32_t cap, int32_t* n_out);
 
+/*
+ * Per-launch timing of the PIT entry point (bench.py, tools/pit_target.py): after b200sep_pit_profile_enable(1) every
+ * b200sep_pit_sisdr_batch call brackets its two kernels with CUDA events on the caller's stream;
+ * b200sep_pit_profile_read waits for the last call on the current device and returns ms_out[0] = moments kernel,
+ * ms_out[1] = finalize kernel.
+ */
+int b200sep_pit_profile_enable(int on);
+int b200sep_pit_profile_read(float* ms_out);
+
 /* Test hooks: stop the forward after the k-th kernel launch (0 = run everything), and report the
  * byte offsets of the intermediate activations inside the workspace:
  * out[0..10] = enc, x, xa, skip, skipa, h1, h2, masked, n_tiles, total, g. */

@@ -22,5 +22,19 @@ for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 5):
     e0.record(); pit_sisdr_device(d_ref, d_est, d_mix, lens, 3, 3, "overlap3"); e1.record()
     torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 ms = min(ts)
-print(f"pit 3000 segments, {total} samples: {ms:.3f} ms = {28 * total / ms / 1e6:.1f} GB/s (28 B/sample algorithmic), "
-      f"{total / 8000 / ms * 1e3:.0f} audio-s/s", flush=True)
+print(f"pit 3000 segments, {total} samples: {ms:.3f} ms per call (host marshalling + two launches, GPU idle in between) = "
+      f"{28 * total / ms / 1e6:.1f} GB/s (28 B/sample algorithmic), {total / 8000 / ms * 1e3:.0f} audio-s/s", flush=True)
+# kernel-level: CUDA events around the two launches inside the C entry point
+import ctypes as C
+from b200sep import _native as nat
+nat.lib().b200sep_pit_profile_enable(1)
+km = []
+for _ in range(5):
+    flush.zero_()
+    pit_sisdr_device(d_ref, d_est, d_mix, lens, 3, 3, "overlap3")
+    out = (C.c_float * 2)()
+    nat.check(nat.lib().b200sep_pit_profile_read(out), "pit_profile_read")
+    km.append((out[0], out[1]))
+nat.lib().b200sep_pit_profile_enable(0)
+m0 = min(k[0] for k in km); f0 = min(k[1] for k in km)
+print(f"   kernels: moments {m0 * 1e3:.1f} us = {28 * total / m0 / 1e6:.1f} GB/s, finalize {f0 * 1e3:.1f} us", flush=True)
