@@ -484,15 +484,15 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
     if (lane == 0) {
       for (int s = 0; s < 4; ++s) {
         mbar_init(raw_full(s), 1);
-        mbar_init(raw_empty(s), Cfg::PROD_WARPS * 16);
+        mbar_init(raw_empty(s), Cfg::PROD_WARPS / 2);   // one arrival per warp of the owning group
       }
       for (int s = 0; s < 2; ++s) {
         // pair mode: the producers / epilogue threads of BOTH CTAs arrive on the leader's a_full / tempty
         mbar_init(tfull_bar(s), 1);
-        mbar_init(tempty_bar(s), 32 * Cfg::EPI_WARPS);
+        mbar_init(tempty_bar(s), Cfg::EPI_WARPS);
       }
       for (int s = 0; s < 2 * Cfg::A_PG; ++s) {
-        mbar_init(a_full(s), Cfg::PROD_WARPS * 16);
+        mbar_init(a_full(s), Cfg::PROD_WARPS / 2);
         mbar_init(a_empty(s), 1);
       }
       for (int s = 0; s < Cfg::B_MAX_STAGES; ++s) {
@@ -551,7 +551,8 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
         }
       }
       tcgen05_fence_before();
-      mbar_arrive(tempty_bar(as));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
       if (threadIdx.x == 0) tl_stamp(it, 81);
     }
   } else if (warp == 4) {
@@ -785,8 +786,11 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
           }
         }
         fence_proxy_async();
-        mbar_arrive(my_ab_full);
-        mbar_arrive(raw_empty(rs_));
+        __syncwarp();  // every lane has fenced its stage writes and finished its reads of the raw stage
+        if (lane == 0) {
+          mbar_arrive(my_ab_full);
+          mbar_arrive(raw_empty(rs_));
+        }
         if (tl_on) tl_stamp(it, tl_base + 3 * (kb >> 1) + 2);
         ++nseq;
       }
@@ -879,12 +883,12 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
       tma_prefetch_desc(&tm_h1);
       mbar_init(w_bar, 1);
       for (int b = 0; b < 2; ++b) {
-        mbar_init(xn_full(b), Cfg::PRO_WARPS * 32);
+        mbar_init(xn_full(b), Cfg::PRO_WARPS);           // one arrival per warp
         mbar_init(xn_empty(b), 1);
       }
       for (int q = 0; q < 4; ++q) {
         mbar_init(tfull_bar(q), 1);
-        mbar_init(tempty_bar(q), Cfg::EPI_WARPS * 32);
+        mbar_init(tempty_bar(q), Cfg::EPI_WARPS);
       }
       mbar_init(done_bar, 1);
       fence_barrier_init();
@@ -938,7 +942,8 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
         tmem_ld_wait();  // piece pi (32 frames) is in v[pi & 1]
         if (hh == 1) {
           tcgen05_fence_before();
-          mbar_arrive(tempty_bar(q));  // the warp's part of chunk q is in registers: the MMA may overwrite it
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(q));  // the warp's part of chunk q is in registers: the MMA may overwrite it
         }
         float bnext = bch;
         if (pi + 1 < 8) {
@@ -1114,7 +1119,8 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
         }
       }
       fence_proxy_async();
-      mbar_arrive(xn_full(b));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(xn_full(b));
       if (pt == 0) tl_stamp(it, 2);
     }
   }

@@ -2,15 +2,22 @@
 // (n_src x 512 x F, the largest activation of the forward) never leaves the SM.
 //
 //   per m-tile (128 frames), for every source s and every 128-filter chunk c of its 512 filters:
-//     MMA 1 : score[frame][n] = sum_k PReLU(skip_sum)[frame][k] * W_mask[s*512 + c*128 + n][k]   (K = 128)
-//     epi 1 : masked = act(score + b) * tf_rep[c*128 + n][frame]  -> fp16 -> swizzled K-major smem operand
+//     MMA 1 : score[n][frame] = sum_k W_mask[s*512 + c*128 + n][k] * PReLU(skip_sum)[frame][k]   (K = 128; TRANSPOSED:
+//             TMEM lane = filter, column = frame, as in K_B)
+//     epi 1 : masked = act(score + b) * tf_rep[c*128 + n][frame]  -> fp16 -> swizzled MN-major smem operand.  A thread
+//             owns one filter x 32 consecutive frames: the bias is a per-lane constant and the encoder output comes in
+//             as 16-byte vectors along the frames of its row (the lane = frame mapping needed one 2-byte load per value
+//             and re-read the bias row per thread)
 //     MMA 2 : dec[frame][l] += sum_n masked[frame][n] * W_dec[c*128 + n][l]      (N = L taps, K = 128 / chunk)
-//   after the 4 chunks of a source:
+//   Chunk order: filter chunk outermost, source innermost -- the encoder-output rows of a chunk are loaded ONCE and
+//   multiply all n_src masks (source-outermost re-read them per source: 3 x 128 KiB per m-tile from L2, and this kernel
+//   is bound by what an SM can pull from L2: 384 KiB of mask weights + the encoder output per m-tile).
+//   After the last chunk of a source:
 //     epi 2 : overlap-add of the L taps of the 128 frames (stride L/2) + zero tail (pad_x_to_y) -> d_out
 //
 // (asteroid: mask_net + output_act, `est_masks * tf_rep.unsqueeze(1)`, Decoder(FreeFB) = conv_transpose1d;
 //  SURVEY.md A.2.)  Warp roles as in gemm_tc.cuh: warp 0 TMA, warp 1 MMA issuer (both MMAs), warp 2 TMEM
-// allocator, warps 4-11 epilogue (lane = frame).  TMEM: 2 x 128 score columns (double-buffered) + n_src x L
+// allocator, warps 4-19 epilogue (lane = filter; the overlap-add runs with lane = frame).  TMEM: 2 x 128 score columns (double-buffered) + n_src x L
 // decoder columns.  d_out must be zero-filled by the caller (the two hops shared with the neighbouring
 // m-tiles are accumulated with atomicAdd: two addends onto zero, order-independent).
 #pragma once
@@ -39,10 +46,14 @@ template <int L>
 struct TailCfg {
   static constexpr int A_BYTES = TILE_M * C_SKIP * 2;     // 32 KiB: PReLU(skip_sum) tile, 2 k-blocks
   static constexpr int B_STAGE = 128 * C_SKIP * 2;        // 32 KiB: 128 mask-conv rows x 128 k
-  static constexpr int B_STAGES = 2;
+  // weight ring: a 32 KiB W_mask chunk takes ~5 k cycles from L2 to shared memory here (every CTA pulls the same chunk at
+  // the same time) while a chunk's epilogue takes ~2 k: with two stages the kernel ran at the latency of the weight stream
+  // (tools/timeline_tail.py).  As many stages as fit; the masked-chunk staging needs only one (the decoder MMAs that
+  // read it are issued the moment it is complete and take a few hundred cycles).
+  static constexpr int B_STAGES = (L == 16) ? 4 : 3;
   static constexpr int WD_BYTES = L * C_ENC * 2;          // decoder filterbank [L][512] fp16, 8 k-blocks
   static constexpr int ST_BYTES = TILE_M * 128 * 2;       // 32 KiB: masked chunk [128 frames][128 filters]
-  static constexpr int ST_STAGES = 2;
+  static constexpr int ST_STAGES = 1;
   static constexpr int OLA_BYTES = TILE_M * (L + 1) * 4;
   static constexpr int OFF_B = A_BYTES;
   static constexpr int OFF_WD = OFF_B + B_STAGES * B_STAGE;
@@ -56,12 +67,6 @@ struct TailCfg {
   static constexpr int DEC_COL0 = 256;                    // decoder accumulators start here
   static_assert(SMEM_BYTES <= 232448, "tail kernel shared memory over the 227 KiB limit");
 };
-
-// kind::f16 instruction descriptor, D = fp32, A = B = fp16, both K-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t make_idesc_kk(int n) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(TILE_M >> 4) << 24);
-}
 
 struct TailParams {
   const float* bias;   // [S*512] mask conv bias
@@ -88,8 +93,8 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const uint32_t bar0 = smem_base + Cfg::OFF_BAR;
   const uint32_t wd_bar = bar0;                                  // decoder filterbank landed (once)
   const uint32_t a_full = bar0 + 8u, a_empty = bar0 + 16u;       // skip operand of the m-tile
-  auto b_full = [&](int s) { return bar0 + 8u * (3 + s); };
-  auto b_empty = [&](int s) { return bar0 + 8u * (5 + s); };
+  auto b_full = [&](int s) { return bar0 + 8u * (20 + s); };     // [B_STAGES <= 4]
+  auto b_empty = [&](int s) { return bar0 + 8u * (24 + s); };
   auto acc_full = [&](int s) { return bar0 + 8u * (7 + s); };
   auto acc_empty = [&](int s) { return bar0 + 8u * (9 + s); };
   auto st_full = [&](int s) { return bar0 + 8u * (11 + s); };
@@ -114,16 +119,18 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     mbar_init(wd_bar, 1);
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < Cfg::B_STAGES; ++s) {
       mbar_init(b_full(s), 1);
       mbar_init(b_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full(s), 1);
-      mbar_init(acc_empty(s), Cfg::EPI_WARPS * 32);
-      mbar_init(st_full(s), Cfg::EPI_WARPS * 32);
+      mbar_init(acc_empty(s), Cfg::EPI_WARPS);   // one arrival per warp
+      mbar_init(st_full(s), Cfg::EPI_WARPS);
       mbar_init(st_empty(s), 1);
     }
     mbar_init(dec_full, 1);
-    mbar_init(dec_empty, 128);
+    mbar_init(dec_empty, 4);
     mbar_init(done_bar, 1);
     fence_barrier_init();
   }
@@ -144,6 +151,7 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       uint32_t bphase = 0;
       int it = 0;
       for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
+        const int rot = (load_tile_info(tb.tile_info + w).t0 >> 7) & 3;
         mbar_wait_b(tb.flags, a_empty, ((uint32_t)it & 1u) ^ 1u);
         mbar_expect_tx(a_full, Cfg::A_BYTES);
         for (int kb = 0; kb < 2; ++kb) {
@@ -152,9 +160,13 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         for (int c = 0; c < n_chunks; ++c) {
           mbar_wait_b(tb.flags, b_empty(bs), bphase ^ 1u);
+          tl_stamp(it, 80 + c);
           mbar_expect_tx(b_full(bs), Cfg::B_STAGE);
-          tma_load_2d(smem_b(bs), &tm_b, b_full(bs), 0, c * 128);
-          tma_load_2d(smem_b(bs) + 16384u, &tm_b, b_full(bs), 64, c * 128);
+          // chunk c = (filter chunk (c / n_src + rot) % 4, source c % n_src); rot staggers the filter-chunk order by the
+          // tile's position in its segment, so that the CTAs do not all pull the same 32 KiB of W_mask at the same time
+          const int row0 = ((c % p.n_src) * 4 + ((c / p.n_src + rot) & 3)) * 128;
+          tma_load_2d(smem_b(bs), &tm_b, b_full(bs), 0, row0);
+          tma_load_2d(smem_b(bs) + 16384u, &tm_b, b_full(bs), 64, row0);
           if (++bs == Cfg::B_STAGES) { bs = 0; bphase ^= 1u; }
         }
       }
@@ -163,26 +175,28 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   } else if (warp == 1) {
     // ================================ MMA issuer (mask GEMM + decoder GEMM) =======================
     if (lane == 0) {
-      constexpr uint32_t idesc_mask = make_idesc(128);     // A MN-major (tile-transposed skip operand)
-      constexpr uint32_t idesc_dec = make_idesc_kk(L);     // A K-major (masked chunk written by the epilogue)
+      // mask GEMM: A = W_mask chunk (K-major), B = skip operand (MN-major, frames contiguous): D[filter][frame]
+      constexpr uint32_t idesc_mask = (1u << 4) | (1u << 16) | ((uint32_t)(TILE_M >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      constexpr uint32_t idesc_dec = make_idesc(L);        // A MN-major (masked chunk written by the epilogue), B K-major
       mbar_wait_b(tb.flags, wd_bar, 0);
       int bs = 0;
       uint32_t bphase = 0;
       int n_acc = 0, n_st = 0, n_dec = 0;  // running counters -> stage / phase
+      int tl_it = 0;
       auto issue_mask = [&](int c) {
-        (void)c;
         const int as = n_acc & 1;
         mbar_wait_b(tb.flags, acc_empty(as), (((uint32_t)n_acc >> 1) & 1u) ^ 1u);
         mbar_wait_b(tb.flags, b_full(bs), bphase);
         tcgen05_fence_after();
+        tl_stamp(tl_it, c);
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * 128);
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint64_t da = make_smem_desc(smem_a + (uint32_t)(kb * 16384 + j * 2048), 8192u, 1024u);
-            const uint64_t db = make_smem_desc(smem_b(bs) + (uint32_t)(kb * 16384 + j * 32), 16u, 1024u);
-            umma_f16(tmem_d, da, db, idesc_mask, (uint32_t)((kb | j) != 0));
+            const uint64_t dx = make_smem_desc(smem_a + (uint32_t)(kb * 16384 + j * 2048), 8192u, 1024u);     // skip, MN-major
+            const uint64_t dw = make_smem_desc(smem_b(bs) + (uint32_t)(kb * 16384 + j * 32), 16u, 1024u);     // W_mask, K-major
+            umma_f16(tmem_d, dw, dx, idesc_mask, (uint32_t)((kb | j) != 0));
           }
         }
         umma_commit(b_empty(bs));
@@ -192,23 +206,27 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       };
       int it = 0;
       for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
+        const int rot = (load_tile_info(tb.tile_info + w).t0 >> 7) & 3;
         mbar_wait_b(tb.flags, a_full, (uint32_t)it & 1u);
+        tl_it = it;
         issue_mask(0);
         for (int c = 0; c < n_chunks; ++c) {
           if (c + 1 < n_chunks) issue_mask(c + 1);  // keeps the tensor core busy while chunk c is in its epilogue
           else umma_commit(a_empty);                // all mask MMAs of this m-tile issued: operand reusable when done
-          const int src = c >> 2, cc = c & 3;
-          const int ss = n_st & 1;
-          if (cc == 0) mbar_wait_b(tb.flags, dec_empty, ((uint32_t)n_dec & 1u) ^ 1u);  // overlap-add drained the accumulator
-          mbar_wait_b(tb.flags, st_full(ss), ((uint32_t)n_st >> 1) & 1u);
+          const int src = c % p.n_src, cc = c / p.n_src;
+          const int ss = 0;
+          // (cc == 0: the previous m-tile's overlap-adds -- all of them, they finish in order -- drained the accumulators)
+          if (cc == 0) mbar_wait_b(tb.flags, dec_empty, ((uint32_t)n_dec & 1u) ^ 1u);
+          mbar_wait_b(tb.flags, st_full(ss), (uint32_t)n_st & 1u);
           tcgen05_fence_after();
-          const uint32_t tmem_dec = tmem_base + (uint32_t)(Cfg::DEC_COL0 + (src & 1) * L);
+          tl_stamp(it, 16 + c);
+          const uint32_t tmem_dec = tmem_base + (uint32_t)(Cfg::DEC_COL0 + src * L);
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint64_t da = make_smem_desc(smem_st(ss) + (uint32_t)(kb * 16384 + j * 32), 16u, 1024u);
-              const uint64_t db = make_smem_desc(smem_wd + (uint32_t)((cc * 2 + kb) * L * 128 + j * 32), 16u, 1024u);
+              const uint64_t da = make_smem_desc(smem_st(ss) + (uint32_t)(kb * 16384 + j * 2048), 8192u, 1024u);  // MN-major
+              const uint64_t db = make_smem_desc(smem_wd + (uint32_t)((((cc + rot) & 3) * 2 + kb) * L * 128 + j * 32), 16u, 1024u);
               umma_f16(tmem_dec, da, db, idesc_dec, (uint32_t)((cc | kb | j) != 0));
             }
           }
@@ -223,30 +241,59 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     __syncwarp();
   } else if (warp >= 4) {
     // ================================ epilogue (16 warps) =========================================
-    // warp = (TMEM lane quadrant, 32-filter quarter of the 128-filter chunk); a thread owns one frame x 32 filters,
-    // processed as two 16-column pieces (small live register set: 640 threads share the register file).  Four warps
-    // per scheduler hide the encoder-output loads and the tcgen05.ld / MUFU latencies two could not.
+    // warp = (TMEM lane quadrant = 32 filters of the chunk, 32-frame quarter of the m-tile); a thread owns one filter x
+    // 32 frames, processed as two 16-column pieces (small live register set: 640 threads share the register file).
     const int ew = warp - 4, quad = ew & 3, part = ew >> 2;
-    const int half = part >> 1;                  // 64-filter k-block of the staged operand
-    const int r = quad * 32 + lane;              // frame within the m-tile == TMEM lane
+    const int fl = quad * 32 + lane;             // filter within the 128-filter chunk == TMEM lane
+    const int r = fl;                            // (the overlap-add below runs with lane = frame)
     int n_acc = 0, n_st = 0, n_dec = 0;
+    const bool tl_on = (ew == 0 && lane == 0);
+    int tl_it = -1;
     for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
+      ++tl_it;
       const TileInfo ti = load_tile_info(tb.tile_info + w);
       const int seg = ti.seg, t0 = ti.t0, F = ti.F;
       const int T_len = tb.seg_len[seg];
-      const bool fvalid = (t0 + r) < F;
-      for (int c = 0; c < n_chunks; ++c) {
-        const int src = c >> 2, cc = c & 3;
-        const int as = n_acc & 1, ss = n_st & 1;
-        const int ch0 = cc * 128 + part * 32;          // first filter of this warp's 32 columns
-        const __half* __restrict__ ep = p.enc + tt_index(w, C_ENC, ch0, r);
-        const float* __restrict__ bp = p.bias + src * C_ENC + ch0;
-        // encoder output of this frame for the 32 filters: issued before the (possibly blocking) accumulator wait
-        __half eh[32];
+      const int nvalid = F - t0 - part * 32;       // frames of this thread's 32 that lie inside the segment
+      const int rot = (t0 >> 7) & 3;               // filter-chunk order of this tile (see the TMA producer)
+      // encoder output of this thread's filter x 32 frames in fp32, pre-scaled by 0.5 for the sigmoid form below; loaded
+      // and converted once per filter chunk, used by every source
+      float2 ef[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) eh[j] = ep[(size_t)j * TILE_M];
+      for (int j = 0; j < 16; ++j) ef[j] = make_float2(0.f, 0.f);
+      const float esc = (p.act == 0) ? 0.5f : 1.0f;
+      // raw rows of the NEXT filter chunk: requested a whole chunk before they are converted (L2 latency off the path)
+      uint4 eh[4];
+      {
+        const __half* __restrict__ ep = p.enc + tt_index(w, C_ENC, rot * 128 + fl, part * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) eh[j] = __ldg(reinterpret_cast<const uint4*>(ep) + j);
+      }
+      for (int c = 0; c < n_chunks; ++c) {
+        const int src = c % p.n_src, cc = c / p.n_src;
+        const int as = n_acc & 1, ss = 0;
+        const int ch = ((cc + rot) & 3) * 128 + fl;    // this thread's filter
+        const float bias = __ldg(p.bias + src * C_ENC + ch) * esc;   // (0.5 b for the sigmoid form)
+        // encoder output of this filter for the 32 frames, once per filter chunk (it serves all sources): issued before
+        // the (possibly blocking) accumulator wait
+        if (src == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t ew4[4] = {eh[j].x, eh[j].y, eh[j].z, eh[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ef[j * 4 + k] = mul2(__half22float2(*reinterpret_cast<const __half2*>(&ew4[k])), make_float2(esc, esc));
+          }
+        }
+        if (src == p.n_src - 1 && cc < 3) {
+          const __half* __restrict__ ep = p.enc + tt_index(w, C_ENC, ((cc + 1 + rot) & 3) * 128 + fl, part * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) eh[j] = __ldg(reinterpret_cast<const uint4*>(ep) + j);
+        }
+        if (tl_on) tl_stamp(tl_it, 32 + c);
         mbar_wait_b(tb.flags, acc_full(as), ((uint32_t)n_acc >> 1) & 1u);
         tcgen05_fence_after();
+        if (tl_on) tl_stamp(tl_it, 48 + c);
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 128 + part * 32);
         uint32_t pk[16];
 #pragma unroll
@@ -256,48 +303,59 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           tmem_ld_wait();
           if (h == 1) {
             tcgen05_fence_before();
-            mbar_arrive(acc_empty(as));  // this thread's 32 columns are in registers: the next mask MMA may overwrite them
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty(as));  // the warp's columns are in registers: the next mask MMA may overwrite them
             ++n_acc;
           }
+          // sigmoid(a) e = (0.5 tanh(0.5 a) + 0.5) e = t e' + e'  with  t = tanh(0.5 v + 0.5 b),  e' = 0.5 e:
+          // one packed FMA, one MUFU per element, one packed FMA per pair (was ~10 scalar instructions per element)
+          const float2 b2 = make_float2(bias, bias);
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
-            const float2 b2 = __ldg(reinterpret_cast<const float2*>(bp + h * 16 + j));
-            const float a0 = v[j] + b2.x, a1 = v[j + 1] + b2.y;
-            const float e0 = __half2float(eh[h * 16 + j]), e1 = __half2float(eh[h * 16 + j + 1]);
-            float m0, m1;
+            const float2 e2 = ef[h * 8 + (j >> 1)];
+            float2 m2;
             if (p.act == 0) {
-              float t0_, t1_;  // sigmoid(v) = 0.5 * tanh(0.5 v) + 0.5 (one MUFU op per element)
-              asm("tanh.approx.f32 %0, %1;" : "=f"(t0_) : "f"(0.5f * a0));
-              asm("tanh.approx.f32 %0, %1;" : "=f"(t1_) : "f"(0.5f * a1));
-              m0 = fmaf(t0_, 0.5f, 0.5f) * e0;
-              m1 = fmaf(t1_, 0.5f, 0.5f) * e1;
+              const float2 a2 = fma2(make_float2(v[j], v[j + 1]), make_float2(0.5f, 0.5f), b2);
+              float2 t2;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t2.x) : "f"(a2.x));
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t2.y) : "f"(a2.y));
+              m2 = fma2(t2, e2, e2);
             } else {
-              m0 = fmaxf(a0, 0.f) * e0;
-              m1 = fmaxf(a1, 0.f) * e1;
+              const float2 a2 = add2(make_float2(v[j], v[j + 1]), b2);
+              m2 = mul2(make_float2(fmaxf(a2.x, 0.f), fmaxf(a2.y, 0.f)), e2);
             }
-            if (!fvalid) { m0 = 0.f; m1 = 0.f; }  // frames beyond the segment end contribute nothing
-            const __half2 hh2 = __floats2half2_rn(m0, m1);
+            const __half2 hh2 = __floats2half2_rn(m2.x, m2.y);
             pk[h * 8 + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&hh2);
           }
         }
-        // masked quarter -> K-major SWIZZLE_128B operand: k-block = half, row = frame, 8 filters per 16-byte chunk
-        mbar_wait_b(tb.flags, st_empty(ss), (((uint32_t)n_st >> 1) & 1u) ^ 1u);
-        const uint32_t row_base = smem_st(ss) + (uint32_t)(half * 16384 + r * 128);
+        if (nvalid < 32) {   // (warp-uniform, last tile of a segment only) frames beyond the segment end contribute nothing
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (2 * j >= nvalid) pk[j] = 0u;
+            else if (2 * j + 1 >= nvalid) pk[j] &= 0xffffu;
+          }
+        }
+        // masked row -> MN-major SWIZZLE_128B operand (the image of K_A's h2 stage): k-block = filter / 64, row =
+        // filter % 64, 8 frames per 16-byte chunk
+        mbar_wait_b(tb.flags, st_empty(ss), ((uint32_t)n_st & 1u) ^ 1u);
+        const uint32_t row_base = smem_st(ss) + (uint32_t)((fl >> 6) * 16384);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          st_shared_v4(row_base + (uint32_t)((((part & 1) * 4 + q) ^ (r & 7)) << 4),
+          st_shared_v4(row_base + fb::a_chunk_off(fl & 63, part * 32 + q * 8),
                        make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]));
         fence_proxy_async();
-        mbar_arrive(st_full(ss));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(st_full(ss));
+        if (tl_on) tl_stamp(tl_it, 64 + c);
         ++n_st;
 
-        if (cc == 3) {
+        if (cc == 3) {   // (the last filter chunk: the sources complete one after the other)
           // ---- decoder output of source `src`: taps -> overlap-add -> global (4 warps, one per lane quadrant)
           if (part == 0) {
             mbar_wait_b(tb.flags, dec_full, (uint32_t)n_dec & 1u);
             tcgen05_fence_after();
             float taps[32];
-            const uint32_t daddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::DEC_COL0 + (src & 1) * L);
+            const uint32_t daddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::DEC_COL0 + src * L);
             if (L == 16) {
               float t16[16];
               tmem_ld16(daddr, t16);
@@ -308,7 +366,8 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             }
             tmem_ld_wait();
             tcgen05_fence_before();
-            mbar_arrive(dec_empty);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dec_empty);
 #pragma unroll
             for (int l = 0; l < L; ++l) s_ola[r][l] = taps[l];
             fb::named_bar_sync(2, 128);

@@ -7,19 +7,24 @@ reference's separation stage runs (reference call sites:
 ``load_state_dict``, ``:83`` forward; pin ``asteroid==0.7.0`` in
 ``/root/reference/requirements.txt:1``).
 
-PARITY UNPINNED for the model forward: ``asteroid`` is a third-party
-dependency that is NOT vendored under ``/root/reference`` and is not installable
-here (no wheel, no network), and the reference holds no golden vectors for this
-path.  This file restates the published algorithm of
+PARITY PIN of the model forward: ``asteroid`` itself is a third-party dependency that is NOT vendored under
+``/root/reference`` and is not installable here (no wheel, no network), and the reference holds no golden vectors for
+this path -- so the restatement cannot be run against asteroid 0.7.0 ("parity unpinned" with respect to that package).
+It IS pinned to the strongest evidence available in the container: ``torchaudio.models.ConvTasNet`` (torchaudio 2.11,
+an independent implementation of the same network by other authors) run on this module's weights reproduces the
+restatement's WHOLE forward to 120-125 dB on four cases (3-src sigmoid, 2-src relu, (32, 16) filterbank, 0.3-1 s
+inputs): ``oracle/make_golden_torchaudio.py`` -> ``tests/golden/torchaudio_convtasnet_golden.npz``, checked by
+``tests/test_oracle_model.py::test_whole_model_matches_torchaudio_convtasnet_golden`` (CPU) and by
+``tests/test_gpu_parity.py::test_cuda_path_matches_torchaudio_convtasnet_golden`` (the CUDA path against torchaudio's
+outputs).  What torchaudio cannot vouch for is asteroid-specific packaging: state-dict key names, ``pad_x_to_y``, the
+dead residual conv of the last block, ``from_pretrained`` -- restated from the published source as summarised in
+SURVEY.md Appendix A:
   asteroid/models/conv_tasnet.py, asteroid/models/base_models.py
   (BaseEncoderMaskerDecoder.forward), asteroid/masknn/convolutional.py
   (TDConvNet, Conv1DBlock), asteroid/masknn/norms.py (GlobLN),
   asteroid/utils/torch_utils.py (pad_x_to_y), asteroid_filterbanks/enc_dec.py +
   free_fb.py (Encoder / Decoder / FreeFB)
-as summarised in SURVEY.md Appendix A, and keeps the state-dict key names of
-Appendix A.5 so real Asteroid checkpoints load unchanged.  Independent
-in-container evidence: the TCN block arithmetic is cross-checked against
-``torchaudio.models.conv_tasnet.ConvBlock`` in ``tests/test_oracle_model.py``.
+with the state-dict key names of Appendix A.5, so real Asteroid checkpoints load unchanged.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 ``--impl reference`` legs may import this module.

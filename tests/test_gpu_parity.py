@@ -368,6 +368,27 @@ def test_fused_pipeline_many_tiles_per_cta_and_batch_independence(b200, model3):
     eng.close()
 
 
+def test_cuda_path_matches_torchaudio_convtasnet_golden(b200, golden_dir):
+    """The CUDA path against outputs of torchaudio.models.ConvTasNet (an independent installed implementation of the
+    network; oracle/make_golden_torchaudio.py) on the same weights and inputs: >= 40 dB in the fp16 tensor-core mode,
+    >= 100 dB in fp32.  torchaudio(x) == asteroid(pad(x, stride, stride))[stride:-stride]."""
+    g = np.load(os.path.join(golden_dir, "torchaudio_convtasnet_golden.npz"))
+    n_cases = sum(1 for k in g.files if k.endswith("_meta"))
+    for ci in range(n_cases):
+        n_src, seed, n, kernel, stride, relu = [int(v) for v in g[f"case{ci}_meta"]]
+        m = ar.make_model(n_src, seed=seed, mask_act="relu" if relu else "sigmoid", kernel_size=kernel, stride=stride)
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        args = m.get_model_args()
+        x = np.pad(g[f"case{ci}_x"], (stride, stride)).astype(np.float32)
+        ref = g[f"case{ci}_y"]
+        for prec, gate in (("fp16", GATE_FP16_DB), ("fp32", GATE_FP32_DB)):
+            eng = b200.SeparationEngine(sd, args, 0, prec)
+            out = np.stack(eng.separate_batch([x])[0])[:, stride:-stride]
+            eng.close()
+            assert out.shape == ref.shape
+            assert min_sisdr(ref, out) >= gate, (ci, prec, min_sisdr(ref, out))
+
+
 def test_cta_pair_block_kernel_matches_the_single_cta_kernel(b200, model3, monkeypatch):
     """K_A as a CTA pair (tcgen05 cta_group::2, [res | skip] weights resident in tensor memory as the MMA's A operand,
     fused_pair.cuh; selected with B200SEP_KA=pair at model creation) against the default one-CTA kernel: same arithmetic

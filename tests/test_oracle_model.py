@@ -90,6 +90,40 @@ def test_block_matches_torchaudio_convblock():
     assert torch.allclose(s1, s2, atol=2e-5, rtol=1e-4)
 
 
+def test_whole_model_matches_torchaudio_convtasnet_golden(golden_dir):
+    """PIN of the forward oracle: torchaudio.models.ConvTasNet -- an independent, installed implementation of the same
+    network -- run on the oracle's weights (oracle/make_golden_torchaudio.py, outputs committed under tests/golden/).
+    torchaudio(x) == asteroid(pad(x, stride, stride))[stride:-stride] (its encoder / decoder carry padding = stride)."""
+    g = np.load(os.path.join(golden_dir, "torchaudio_convtasnet_golden.npz"))
+    n_cases = sum(1 for k in g.files if k.endswith("_meta"))
+    assert n_cases >= 4
+    for ci in range(n_cases):
+        n_src, seed, n, kernel, stride, relu = [int(v) for v in g[f"case{ci}_meta"]]
+        m = ar.make_model(n_src, seed=seed, mask_act="relu" if relu else "sigmoid", kernel_size=kernel, stride=stride)
+        x = torch.from_numpy(g[f"case{ci}_x"])
+        with torch.no_grad():
+            y = m(torch.nn.functional.pad(x, (stride, stride))[None])[0].numpy()[:, stride:-stride]
+        ref = g[f"case{ci}_y"]
+        assert y.shape == ref.shape == (n_src, n)
+        worst = min(pr.si_sdr_f64(ref[s], y[s]) for s in range(n_src))
+        assert worst >= 100.0, (ci, worst)
+
+
+def test_torchaudio_golden_is_reproducible():
+    """The committed golden equals what the generating script produces from the installed torchaudio (skipped where
+    torchaudio is absent, e.g. a trimmed GPU box)."""
+    pytest.importorskip("torchaudio.models")
+    from oracle import make_golden_torchaudio as mg
+    n_src, seed, n, act, kernel, stride = mg.CASES[1]
+    m = ar.make_model(n_src, seed=seed, mask_act=act, kernel_size=kernel, stride=stride)
+    t = mg.to_torchaudio(m, n_src, act, kernel, stride)
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "torchaudio_convtasnet_golden.npz"))
+    x = torch.from_numpy(gold["case1_x"])
+    with torch.no_grad():
+        y = t(x[None, None])[0].numpy()
+    assert min(pr.si_sdr_f64(gold["case1_y"][s], y[s]) for s in range(n_src)) >= 100.0
+
+
 def test_checkpoint_roundtrip_from_pretrained(tmp_path):
     m = ar.make_model(2, seed=5, n_blocks=2, n_repeats=1, mask_act="relu", kernel_size=32, stride=16)
     path = str(tmp_path / "pytorch_model.bin")
