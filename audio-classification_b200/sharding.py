@@ -23,13 +23,16 @@ def lpt_partition(costs: Sequence[int], world_size: int) -> List[List[int]]:
     Returns, per rank, the (ascending) list of segment indices it owns."""
     if world_size < 1:
         raise ValueError("world_size must be >= 1")
-    order = sorted(range(len(costs)), key=lambda i: (-int(costs[i]), i))
-    load = [0] * world_size
+    import heapq
+    c = np.asarray(costs, dtype=np.int64).reshape(-1)
+    order = np.lexsort((np.arange(c.size), -c))          # descending cost, ties by ascending index
+    heap = [(0, k) for k in range(world_size)]            # (load, rank): the least loaded rank, ties by lowest rank
     shards: List[List[int]] = [[] for _ in range(world_size)]
-    for i in order:
-        r = min(range(world_size), key=lambda k: (load[k], k))
+    cl = c.tolist()
+    for i in order.tolist():
+        load, r = heapq.heappop(heap)
         shards[r].append(i)
-        load[r] += int(costs[i])
+        heapq.heappush(heap, (load + cl[i], r))
     return [sorted(s) for s in shards]
 
 
