@@ -29,6 +29,7 @@
 #include "fused_block.cuh"
 #include "pair_common.cuh"
 #include "fused_pair.cuh"
+#include "encoder_tc.cuh"
 #include "tail_kernel.cuh"
 #include "pit.cuh"
 #include "aux_kernels.cuh"
@@ -684,7 +685,22 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
   const int slots1 = (kHalf && m->use_tc) ? C_HID / 256 : C_HID / 128;  // partial slots the in-conv GEMM writes
 
   // 1. encoder (+ bottleneck-gLN partials)
-  if constexpr (L == 16) {
+  static const bool enc_tc = [] { const char* e = getenv("B200SEP_ENCODER"); return !(e && strcmp(e, "simt") == 0); }();
+  bool enc_done = false;
+  if constexpr (kHalf) {
+    if (m->use_tc && enc_tc) {
+      // tensor-core encoder (encoder_tc.cuh): taps as the K dimension of one MMA per 128-filter chunk, the waveform
+      // split into hi + lo halves; B200SEP_ENCODER=simt selects the CUDA-core kernel
+      using Cfg = enc::EncCfg<L>;
+      auto kern = enc::encoder_tc_kernel<L>;
+      { static DevOnce once; if (once.need(m->device)) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); once.done(m->device); } }
+      CK(launch_k(kern, dim3(std::min(nt, m->n_sm)), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tm_enc, d_mix,
+                  (const float*)m->enc_w, p0, tb));
+      enc_done = true;
+    }
+  }
+  if (enc_done) {
+  } else if constexpr (L == 16) {
     // B200SEP_ENCODER_V2=1: four frames per thread with packed FFMA2 (bandwidth_kernels.cuh) -- half the instructions and a
     // quarter of the shared-memory wavefronts per output, but measured SLOWER (102 vs 94 us: 88 registers, 37 KB of
     // shared memory per CTA, and FFMA2 issues at half rate), so the one-frame-per-thread kernel stays the default
