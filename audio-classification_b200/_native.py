@@ -23,7 +23,7 @@ PIT_VARIANTS = {"overlap3": 0, "evalsrc": 1}
 # every symbol include/b200sep.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "b200sep_version", "b200sep_last_error", "b200sep_model_create", "b200sep_model_destroy",
-    "b200sep_workspace_bytes", "b200sep_separate_batch", "b200sep_pit_workspace_bytes",
+    "b200sep_workspace_bytes", "b200sep_separate_batch", "b200sep_pit_workspace_bytes", "b200sep_pit_workspace_bytes_n",
     "b200sep_pit_sisdr_batch", "b200sep_debug_gemm", "b200sep_debug_set_stop",
     "b200sep_debug_layout", "b200sep_profile_enable", "b200sep_profile_read",
     "b200sep_pipeline", "b200sep_debug_timeline", "b200sep_pit_profile_enable", "b200sep_pit_profile_read",
@@ -105,6 +105,8 @@ def lib() -> C.CDLL:
         L.b200sep_separate_batch_host.argtypes = [vp, C.POINTER(vp), i32p, i32, vp, vp, C.c_size_t, vp, vp]
         L.b200sep_pit_workspace_bytes.restype = C.c_size_t
         L.b200sep_pit_workspace_bytes.argtypes = [i32p, i32]
+        L.b200sep_pit_workspace_bytes_n.restype = C.c_size_t
+        L.b200sep_pit_workspace_bytes_n.argtypes = [i32p, i32, i32]
         L.b200sep_pit_sisdr_batch.restype = C.c_int
         L.b200sep_pit_sisdr_batch.argtypes = [vp, vp, vp, i64p, i32p, i32, i32, i32, i32, vp, vp,
                                               vp, vp, vp, vp, C.c_size_t, vp]

@@ -1521,11 +1521,16 @@ static int pit_geometry(const int32_t* lens, int n_seg, int* chunk, int* max_chu
   return 0;
 }
 
-size_t b200sep_pit_workspace_bytes(const int32_t* lens, int32_t n_seg) {
+size_t b200sep_pit_workspace_bytes_n(const int32_t* lens, int32_t n_seg, int32_t N) {
   int chunk, max_chunks;
   if (pit_geometry(lens, n_seg, &chunk, &max_chunks)) return 0;
+  if (N < 1 || N > PIT_MAX_N) { fail("PIT supports at most %d estimates per segment (got %d)", PIT_MAX_N, N); return 0; }
   const size_t tables = align_up((size_t)n_seg * 8, 256) + align_up((size_t)n_seg * 4, 256);
-  return tables + (size_t)n_seg * max_chunks * PIT_NACC * sizeof(double);
+  const size_t groups = (size_t)((N + PIT_GROUP - 1) / PIT_GROUP);
+  return tables + groups * (size_t)n_seg * max_chunks * PIT_NACC * sizeof(double);
+}
+size_t b200sep_pit_workspace_bytes(const int32_t* lens, int32_t n_seg) {
+  return b200sep_pit_workspace_bytes_n(lens, n_seg, 3);
 }
 
 int b200sep_pit_sisdr_batch(const float* d_refs, const float* d_ests, const float* d_mix, const int64_t* offsets,
@@ -1534,12 +1539,13 @@ int b200sep_pit_sisdr_batch(const float* d_refs, const float* d_ests, const floa
                             size_t ws_bytes, void* stream) {
   if (!d_refs || !d_ests || !d_mix || !lens || !d_pair || !d_sisdr || !d_sisdri || !d_perm || !d_ws)
     return fail("null argument");
-  if (!(K == 2 || K == 3) || N < K || N > 3) return fail("PIT supports K in {2,3}, K <= N <= 3 (got K=%d N=%d)", K, N);
+  if (!(K == 2 || K == 3) || N < K || N > PIT_MAX_N)
+    return fail("PIT supports K in {2,3}, K <= N <= %d (got K=%d N=%d)", PIT_MAX_N, K, N);
   if (variant != B200SEP_PIT_OVERLAP3 && variant != B200SEP_PIT_EVALSRC) return fail("bad PIT variant");
   if ((reinterpret_cast<uintptr_t>(d_ws) & 255u) != 0) return fail("d_ws must be 256-byte aligned");
   int chunk, max_chunks;
   if (pit_geometry(lens, n_seg, &chunk, &max_chunks)) return 1;
-  const size_t need = b200sep_pit_workspace_bytes(lens, n_seg);
+  const size_t need = b200sep_pit_workspace_bytes_n(lens, n_seg, N);
   if (ws_bytes < need) return fail("PIT workspace too small: %zu < %zu", ws_bytes, need);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   std::lock_guard<std::mutex> lock(g_pit_mu);
@@ -1562,7 +1568,7 @@ int b200sep_pit_sisdr_batch(const float* d_refs, const float* d_ests, const floa
   double* partial = reinterpret_cast<double*>(ws + off_bytes + len_bytes);
 
   PitArgs a{d_refs, d_ests, d_mix, reinterpret_cast<const int64_t*>(ws), reinterpret_cast<const int32_t*>(ws + off_bytes),
-            K, N, chunk, max_chunks};
+            K, N, chunk, max_chunks, N, 0};
   dim3 grid(max_chunks, n_seg);
   PitProf* prof = nullptr;
   if (g_pit_prof_on.load() != 0) {
@@ -1571,10 +1577,24 @@ int b200sep_pit_sisdr_batch(const float* d_refs, const float* d_ests, const floa
       if (e == nullptr) CK(cudaEventCreate(&e));
     CK(cudaEventRecord(prof->ev[0], st));
   }
-  if (K == 2 && N == 2) pit_moments_kernel<2, 2><<<grid, 256, 0, st>>>(a, partial);
-  else if (K == 2 && N == 3) pit_moments_kernel<2, 3><<<grid, 256, 0, st>>>(a, partial);
-  else pit_moments_kernel<3, 3><<<grid, 256, 0, st>>>(a, partial);
-  CK(cudaGetLastError());
+  // one pass per group of <= 3 estimates (N <= 3, every reference call site: a single pass, each sample read once)
+  const size_t group_stride = (size_t)n_seg * max_chunks * PIT_NACC;
+  for (int g = 0; g * PIT_GROUP < N; ++g) {
+    PitArgs ag = a;
+    ag.j0 = g * PIT_GROUP;
+    ag.N = std::min(PIT_GROUP, N - ag.j0);
+    double* pg = partial + (size_t)g * group_stride;
+    const int key = K * 10 + ag.N;
+    switch (key) {
+      case 21: pit_moments_kernel<2, 1><<<grid, 256, 0, st>>>(ag, pg); break;
+      case 22: pit_moments_kernel<2, 2><<<grid, 256, 0, st>>>(ag, pg); break;
+      case 23: pit_moments_kernel<2, 3><<<grid, 256, 0, st>>>(ag, pg); break;
+      case 31: pit_moments_kernel<3, 1><<<grid, 256, 0, st>>>(ag, pg); break;
+      case 32: pit_moments_kernel<3, 2><<<grid, 256, 0, st>>>(ag, pg); break;
+      default: pit_moments_kernel<3, 3><<<grid, 256, 0, st>>>(ag, pg); break;
+    }
+    CK(cudaGetLastError());
+  }
   if (prof) CK(cudaEventRecord(prof->ev[1], st));
   pit_finalize_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(partial, a.len, n_seg, max_chunks, K, N, variant, d_pair,
                                                          d_sisdr, d_sisdri, d_perm, d_gap);

@@ -23,11 +23,15 @@ constexpr int PA_MM = 13;
 constexpr int PA_RE = 14;  // [3][3]
 constexpr int PA_RM = 23;  // [3]
 
+constexpr int PIT_MAX_N = 8;       // estimates per segment (the reference's combinations(range(N), K) takes any N >= K)
+constexpr int PIT_GROUP = 3;       // estimates per moments pass: N > 3 runs ceil(N / 3) passes over groups of <= 3
 struct PitArgs {
   const float* refs; const float* ests; const float* mix;
   const int64_t* off;  // [n_seg] device
   const int32_t* len;  // [n_seg] device
   int K, N, chunk, max_chunks;
+  int n_total;         // estimates per segment in the ragged layout (N = the estimates of THIS pass, first one j0)
+  int j0;
 };
 
 template <int K, int N>
@@ -44,7 +48,7 @@ __global__ void __launch_bounds__(256) pit_moments_kernel(PitArgs a, double* __r
   const int end = min(T, beg + a.chunk);
   const int64_t off = a.off[seg];
   const float* r = a.refs + (size_t)K * off;
-  const float* e = a.ests + (size_t)N * off;
+  const float* e = a.ests + (size_t)a.n_total * off + (size_t)a.j0 * T;
   const float* m = a.mix + off;
   double acc[PIT_NACC];
 #pragma unroll
@@ -118,6 +122,9 @@ __device__ __forceinline__ double si_sdr_from_moments(double Srr, double See, do
   return 10.0 * log10(num / den);
 }
 
+// `partial` holds one [n_seg][max_chunks][PIT_NACC] block per estimate group (group g = estimates 3g .. 3g+2); the
+// reference / mixture moments are the same in every block (group 0's are used).  pair is [n_seg][3][W], W =
+// max(N, 3) + 1, column W - 1 = SI-SDR against the mixture (N <= 3: the [3][4] layout).
 __global__ void pit_finalize_kernel(const double* __restrict__ partial, const int32_t* __restrict__ len,
                                     int n_seg, int max_chunks, int K, int N, int variant,
                                     double* __restrict__ pair, double* __restrict__ sisdr,
@@ -125,82 +132,64 @@ __global__ void pit_finalize_kernel(const double* __restrict__ partial, const in
                                     double* __restrict__ gap_out) {
   const int seg = blockIdx.x * blockDim.x + threadIdx.x;
   if (seg >= n_seg) return;
-  double a[PIT_NACC];
-  for (int i = 0; i < PIT_NACC; ++i) a[i] = 0.0;
-  const double* p = partial + (size_t)seg * max_chunks * PIT_NACC;
-  for (int c = 0; c < max_chunks; ++c)
-    for (int i = 0; i < PIT_NACC; ++i) a[i] += p[(size_t)c * PIT_NACC + i];
   const double n = (double)len[seg];
   const double inv_n = (n > 0.0) ? 1.0 / n : 0.0;
+  const int W = (N > 3 ? N : 3) + 1, MIXC = W - 1;
+  const int n_groups = (N + PIT_GROUP - 1) / PIT_GROUP;
+  const size_t group_stride = (size_t)n_seg * max_chunks * PIT_NACC;
 
-  double M[3][4];
+  double M[3][PIT_MAX_N + 1];
   for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 4; ++j) M[i][j] = nan("");
-  for (int i = 0; i < K; ++i) {
-    const double Srr = a[PA_RR + i] - a[PA_R + i] * a[PA_R + i] * inv_n;
-    for (int j = 0; j < N; ++j) {
-      const double See = a[PA_EE + j] - a[PA_E + j] * a[PA_E + j] * inv_n;
-      const double Sre = a[PA_RE + i * 3 + j] - a[PA_R + i] * a[PA_E + j] * inv_n;
-      M[i][j] = si_sdr_from_moments(Srr, See, Sre);
+    for (int j = 0; j <= PIT_MAX_N; ++j) M[i][j] = nan("");
+  for (int g = 0; g < n_groups; ++g) {
+    double a[PIT_NACC];
+    for (int i = 0; i < PIT_NACC; ++i) a[i] = 0.0;
+    const double* p = partial + g * group_stride + (size_t)seg * max_chunks * PIT_NACC;
+    for (int c = 0; c < max_chunks; ++c)
+      for (int i = 0; i < PIT_NACC; ++i) a[i] += p[(size_t)c * PIT_NACC + i];
+    const int nb = min(PIT_GROUP, N - g * PIT_GROUP);
+    for (int i = 0; i < K; ++i) {
+      const double Srr = a[PA_RR + i] - a[PA_R + i] * a[PA_R + i] * inv_n;
+      for (int j = 0; j < nb; ++j) {
+        const double See = a[PA_EE + j] - a[PA_E + j] * a[PA_E + j] * inv_n;
+        const double Sre = a[PA_RE + i * 3 + j] - a[PA_R + i] * a[PA_E + j] * inv_n;
+        M[i][g * PIT_GROUP + j] = si_sdr_from_moments(Srr, See, Sre);
+      }
+      if (g == 0) {
+        const double Smm = a[PA_MM] - a[PA_M] * a[PA_M] * inv_n;
+        const double Srm = a[PA_RM + i] - a[PA_R + i] * a[PA_M] * inv_n;
+        M[i][MIXC] = si_sdr_from_moments(Srr, Smm, Srm);
+      }
     }
-    const double Smm = a[PA_MM] - a[PA_M] * a[PA_M] * inv_n;
-    const double Srm = a[PA_RM + i] - a[PA_R + i] * a[PA_M] * inv_n;
-    M[i][3] = si_sdr_from_moments(Srr, Smm, Srm);
   }
   for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 4; ++j) pair[(size_t)seg * 12 + i * 4 + j] = M[i][j];
+    for (int j = 0; j < W; ++j) pair[((size_t)seg * 3 + i) * W + j] = M[i][j];
 
   // baseline: mean_i SI-SDR(ref_i, mix)
   double base;
   if (variant == 1 && K == 2) {
-    base = 0.5 * (M[0][3] + M[1][3]);  // evaluate_with_sources.py:389
+    base = 0.5 * (M[0][MIXC] + M[1][MIXC]);  // evaluate_with_sources.py:389
   } else {
     double s = 0.0;  // np.mean over a K-list == pairwise sum (K <= 3: left to right) / K
-    for (int i = 0; i < K; ++i) s += M[i][3];
+    for (int i = 0; i < K; ++i) s += M[i][MIXC];
     base = s / (double)K;
   }
 
   double best = -1e9;
   // top-2 gap: best minus the second-best mean over the DISTINCT assignments (how far the choice is from flipping)
-  double cand[6];
+  double b1 = -INFINITY, b2 = -INFINITY;
   int n_cand = 0;
+  auto candidate = [&](double v) {
+    ++n_cand;
+    if (v > b1) { b2 = b1; b1 = v; }
+    else if (v > b2) b2 = v;
+  };
   int bi[3] = {-1, -1, -1};
   int swapped = 0;
   bool found = false;
   const int perms3[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
   const int perms2[2][2] = {{0, 1}, {1, 0}};
-  if (variant == 0) {
-    // overlap3_core.py:78-97 -- cols in combinations(range(N), K), perm in permutations(range(K)):
-    // s = sum_r M[perm[r]][cols[r]], mean = s / K, strict >, assigned[i] = cols[perm.index(i)]
-    const int combos2of3[3][2] = {{0, 1}, {0, 2}, {1, 2}};
-    const int n_combo = (N == K) ? 1 : 3;  // (K,N) in {(2,2),(3,3),(2,3)}
-    for (int ci = 0; ci < n_combo; ++ci) {
-      int cols[3] = {0, 1, 2};
-      if (N != K) { cols[0] = combos2of3[ci][0]; cols[1] = combos2of3[ci][1]; }
-      const int n_perm = (K == 3) ? 6 : 2;
-      for (int pi = 0; pi < n_perm; ++pi) {
-        int pm[3];
-        for (int q = 0; q < K; ++q) pm[q] = (K == 3) ? perms3[pi][q] : perms2[pi][q];
-        double s = 0.0;
-        bool valid = true;
-        for (int q = 0; q < K; ++q) {
-          const double v = M[pm[q]][cols[q]];
-          if (isnan(v)) { valid = false; break; }
-          s += v;
-        }
-        if (!valid) continue;
-        const double mean_sdr = s / (double)K;
-        if (n_cand < 6) cand[n_cand++] = mean_sdr;
-        if (mean_sdr > best) {
-          best = mean_sdr;
-          found = true;
-          for (int i = 0; i < K; ++i)
-            for (int q = 0; q < K; ++q)
-              if (pm[q] == i) bi[i] = cols[q];
-        }
-      }
-    }
-  } else if (K == 2) {
+  if (variant == 1 && K == 2) {
     // evaluate_with_sources.py:352-373 -- ordered pairs j != k, unswapped preferred on >=
     for (int j = 0; j < N; ++j)
       for (int k = 0; k < N; ++k) {
@@ -209,26 +198,51 @@ __global__ void pit_finalize_kernel(const double* __restrict__ partial, const in
         const double s21 = 0.5 * (M[0][k] + M[1][j]);
         double cur;
         int sw;
-        if (!isnan(s12) && n_cand < 6) cand[n_cand++] = s12;  // (j, k) unswapped; its swap is pair (k, j)'s unswapped
+        if (!isnan(s12)) candidate(s12);  // (j, k) unswapped; its swap is pair (k, j)'s unswapped
         if (s12 >= s21) { cur = s12; sw = 0; } else { cur = s21; sw = 1; }
         if (cur > best) { best = cur; bi[0] = j; bi[1] = k; swapped = sw; found = true; }
       }
   } else {
-    // evaluate_with_sources.py:418-427 -- permutations(cols, 3), perm[i] = estimate for ref i
-    for (int pi = 0; pi < 6; ++pi) {
-      const double cur = (M[0][perms3[pi][0]] + M[1][perms3[pi][1]] + M[2][perms3[pi][2]]) / 3.0;
-      if (!isnan(cur) && n_cand < 6) cand[n_cand++] = cur;
-      if (cur > best) { best = cur; found = true; for (int i = 0; i < 3; ++i) bi[i] = perms3[pi][i]; }
-    }
+    // cols in itertools.combinations(range(N), K), lexicographic (c0 < c1 < c2)
+    for (int c0 = 0; c0 < N; ++c0)
+      for (int c1 = c0 + 1; c1 < N; ++c1)
+        for (int c2 = (K == 3) ? c1 + 1 : N; c2 < ((K == 3) ? N : N + 1); ++c2) {
+          const int cols[3] = {c0, c1, c2};
+          const int n_perm = (K == 3) ? 6 : 2;
+          for (int pi = 0; pi < n_perm; ++pi) {
+            int pm[3];
+            for (int q = 0; q < K; ++q) pm[q] = (K == 3) ? perms3[pi][q] : perms2[pi][q];
+            if (variant == 0) {
+              // overlap3_core.py:78-97 -- perm in permutations(range(K)): s = sum_r M[perm[r]][cols[r]], mean = s / K,
+              // NaN assignments skipped, strict >, assigned[i] = cols[perm.index(i)]
+              double s = 0.0;
+              bool valid = true;
+              for (int q = 0; q < K; ++q) {
+                const double v = M[pm[q]][cols[q]];
+                if (isnan(v)) { valid = false; break; }
+                s += v;
+              }
+              if (!valid) continue;
+              const double mean_sdr = s / (double)K;
+              candidate(mean_sdr);
+              if (mean_sdr > best) {
+                best = mean_sdr;
+                found = true;
+                for (int i = 0; i < K; ++i)
+                  for (int q = 0; q < K; ++q)
+                    if (pm[q] == i) bi[i] = cols[q];
+              }
+            } else {
+              // evaluate_with_sources.py:418-427 (K == 3) -- perm in permutations(cols, 3), perm[i] = estimate for ref i
+              const double cur = (M[0][cols[pm[0]]] + M[1][cols[pm[1]]] + M[2][cols[pm[2]]]) / 3.0;
+              if (!isnan(cur)) candidate(cur);
+              if (cur > best) { best = cur; found = true; for (int i = 0; i < 3; ++i) bi[i] = cols[pm[i]]; }
+            }
+          }
+        }
   }
-  if (gap_out != nullptr) {
-    double b1 = -INFINITY, b2 = -INFINITY;
-    for (int c = 0; c < n_cand; ++c) {
-      if (cand[c] > b1) { b2 = b1; b1 = cand[c]; }
-      else if (cand[c] > b2) b2 = cand[c];
-    }
+  if (gap_out != nullptr)
     gap_out[seg] = (found && n_cand > 1) ? b1 - b2 : ((found && n_cand == 1) ? INFINITY : nan(""));
-  }
   if (!found || isnan(base)) {
     sisdr[seg] = nan("");
     sisdri[seg] = nan("");

@@ -27,7 +27,7 @@ class PitResult:
     sisdri: np.ndarray   # [n_seg] float64 best - mean_i SI-SDR(ref_i, mix)
     perm: np.ndarray     # [n_seg, K] int32: estimate index assigned to reference i (-1 when undefined)
     swapped: np.ndarray  # [n_seg] bool, K=2 "evalsrc" variant only
-    pair: np.ndarray     # [n_seg, 3, 4] float64: pair[i][j] = SI-SDR(ref_i, est_j); [:, :, 3] = vs mixture
+    pair: np.ndarray     # [n_seg, 3, W] float64, W = max(N, 3) + 1: pair[i][j] = SI-SDR(ref_i, est_j); [:, :, -1] = vs mixture
     gap: np.ndarray = None  # [n_seg] float64: best - second-best mean SI-SDR over the distinct assignments (dB)
 
 
@@ -35,7 +35,8 @@ def pit_sisdr_device(d_refs, d_ests, d_mix, lens: Sequence[int], K: int, N: int,
                      variant: str = "overlap3"):
     """Device-resident entry: all tensors 1-D float32 CUDA, ragged layout of include/b200sep.h
     (segment i, source k at ``K*off_i + k*len_i``).  Returns CUDA tensors
-    ``(pair [n,3,4] f64, sisdr [n] f64, sisdri [n] f64, perm [n,4] i32, gap [n] f64)``; asynchronous."""
+    ``(pair [n,3,W] f64, sisdr [n] f64, sisdri [n] f64, perm [n,4] i32, gap [n] f64)``, W = max(N, 3) + 1 (N <= 8;
+    the last column is the SI-SDR against the mixture); asynchronous."""
     import torch
     if variant not in nat.PIT_VARIANTS:
         raise ValueError(f"unknown PIT variant {variant!r}")
@@ -48,12 +49,12 @@ def pit_sisdr_device(d_refs, d_ests, d_mix, lens: Sequence[int], K: int, N: int,
     if d_refs.numel() < K * total or d_ests.numel() < N * total or d_mix.numel() < total:
         raise RuntimeError("PIT input tensors are shorter than the ragged layout requires")
     arr = nat.i32_array(lens)
-    need = int(nat.lib().b200sep_pit_workspace_bytes(arr, n))
+    need = int(nat.lib().b200sep_pit_workspace_bytes_n(arr, n, int(N)))
     if need == 0:
-        raise RuntimeError(f"b200sep_pit_workspace_bytes: {nat.last_error()}")
+        raise RuntimeError(f"b200sep_pit_workspace_bytes_n: {nat.last_error()}")
     ws = torch.empty(need + 256, dtype=torch.uint8, device=dev)
     ws_ptr = (ws.data_ptr() + 255) // 256 * 256
-    pair = torch.empty((n, 3, 4), dtype=torch.float64, device=dev)
+    pair = torch.empty((n, 3, max(int(N), 3) + 1), dtype=torch.float64, device=dev)
     sisdr = torch.empty(n, dtype=torch.float64, device=dev)
     sisdri = torch.empty(n, dtype=torch.float64, device=dev)
     perm = torch.empty((n, 4), dtype=torch.int32, device=dev)
@@ -136,6 +137,7 @@ def pit_sisdr_batch(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.ndar
         z = np.zeros(0)
         return PitResult(z, z, np.zeros((0, 0), np.int32), np.zeros(0, bool), np.zeros((0, 3, 4)))
     K, N = len(refs[0]), len(preds[0])
+    W = max(N, 3) + 1
     if any(len(r) != K for r in refs) or any(len(p) != N for p in preds):
         raise ValueError("all segments of a batch must have the same K and N")
     # pseudo-segments: (segment index, truncation length)
@@ -169,7 +171,7 @@ def pit_sisdr_batch(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.ndar
         pair, sisdr, sisdri, perm, gap = pit_sisdr_device(d_ref, d_est, d_mix, lens, K, N, variant)
         pair, sisdr, sisdri, perm, gap = (pair.cpu().numpy(), sisdr.cpu().numpy(), sisdri.cpu().numpy(), perm.cpu().numpy(),
                                           gap.cpu().numpy())
-    o_pair = np.full((n, 3, 4), np.nan)
+    o_pair = np.full((n, 3, W), np.nan)
     o_sisdr, o_sisdri = np.full(n, np.nan), np.full(n, np.nan)
     o_perm, o_sw = np.full((n, K), -1, np.int32), np.zeros(n, bool)
     o_gap = np.full(n, np.nan)
@@ -179,12 +181,12 @@ def pit_sisdr_batch(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.ndar
             o_perm[i], o_sw[i] = perm[j, :K], bool(perm[j, 3])
             o_gap[i] = gap[j]
     for i, info in ragged.items():
-        M = np.full((3, 4), np.nan)
+        M = np.full((3, W), np.nan)
         for a in range(K):
             for b in range(N):
                 M[a, b] = pair[info["jobs"][min(info["lr"][a], info["lp"][b])], a, b]
-            M[a, 3] = pair[info["jobs"][min(info["lr"][a], info["lm"])], a, 3]
-        best, sdri, idx, sw = _select_host(M[:, :3], M[:, 3], K, N, variant)
+            M[a, W - 1] = pair[info["jobs"][min(info["lr"][a], info["lm"])], a, W - 1]
+        best, sdri, idx, sw = _select_host(M[:, :W - 1], M[:, W - 1], K, N, variant)
         o_pair[i], o_sisdr[i], o_sisdri[i], o_perm[i], o_sw[i] = M, best, sdri, idx, sw
     return PitResult(o_sisdr, o_sisdri, o_perm, o_sw, o_pair, o_gap)
 

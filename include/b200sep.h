@@ -171,8 +171,9 @@ int b200sep_separate_batch_host(b200sep_model* m, const float* const* h_segs, co
                                 int32_t n_seg, float* h_out, void* d_ws, size_t ws_bytes, void* stream,
                                 int32_t* h_flags);
 
-/* doubles of device scratch needed by b200sep_pit_sisdr_batch */
+/* bytes of device scratch needed by b200sep_pit_sisdr_batch for N <= 3 estimates per segment / for N <= 8 */
 size_t b200sep_pit_workspace_bytes(const int32_t* lens, int32_t n_seg);
+size_t b200sep_pit_workspace_bytes_n(const int32_t* lens, int32_t n_seg, int32_t N);
 
 /*
  * Replaces _compute_sdr_improvement_pit_k / _pit_best_si_sdr_k / _si_sdr
@@ -183,9 +184,12 @@ size_t b200sep_pit_workspace_bytes(const int32_t* lens, int32_t n_seg);
  *   d_refs : K  reference sources per segment, segment i source k at d_refs + K*offsets[i] + k*lens[i]
  *   d_ests : N  estimates per segment (same layout with N; the layout b200sep_separate_batch writes)
  *   d_mix  : mixture, segment i at d_mix + offsets[i]
- *   K in {2,3}, K <= N <= 3.
+ *   K in {2,3}, K <= N <= 8 (the reference enumerates itertools.combinations(range(N), K) for any N >= K,
+ *   overlap3_core.py:81, evaluate_with_sources.py:352-355 / :421; N > 3 costs one extra pass over the samples per
+ *   further group of three estimates and needs b200sep_pit_workspace_bytes_n(lens, n_seg, N) of scratch).
  * Outputs (device):
- *   d_pair  [n_seg][3][4] fp64 : pair[i][j] = SI-SDR(ref_i, est_j) dB for j<N, pair[i][3] = SI-SDR(ref_i, mix)
+ *   d_pair  [n_seg][3][W] fp64 : W = max(N, 3) + 1 (N <= 3: [3][4]); pair[i][j] = SI-SDR(ref_i, est_j) dB for j<N,
+ *                                pair[i][W-1] = SI-SDR(ref_i, mix); unused entries NaN
  *   d_sisdr [n_seg] fp64       : best mean SI-SDR over permutations
  *   d_sisdri[n_seg] fp64       : best - mean_i SI-SDR(ref_i, mix)
  *   d_perm  [n_seg][4] int32   : perm[i] = estimate index assigned to reference i (i<K);

@@ -4,6 +4,8 @@
   pit_golden.npz        -- outputs of the REFERENCE's own PIT functions (imported unmodified from
                            /root/reference/scripts/osd/{overlap3_core,evaluate_with_sources}.py)
                            on seeded inputs: pins oracle/pit_restated.py and the CUDA PIT kernel.
+  pit_golden_many.npz   -- the same functions with more estimates than references (N = 4 .. 8, K = 2 / 3), same keys as
+                           pit_golden_ties.npz.
   pit_golden_ties.npz   -- the same functions on exact ties and near-ties (duplicated estimates / references, all
                            scores equal, 1e-7-relative differences) + the top-2 gap of the reference's pair matrix.
   separator_golden.npz  -- output of the REFERENCE's own Separator wrapper
@@ -148,10 +150,33 @@ def _top2_gap(pair, K, N):
     return v[0] - v[1] if len(v) > 1 else float("inf")
 
 
-def make_pit_tie_golden():
+def pit_many_cases():
+    """More estimates than references (N = 4 .. 8; the reference enumerates combinations(range(N), K) for any N >= K,
+    overlap3_core.py:81, evaluate_with_sources.py:352-355 / :421): clean and noisy permutations, duplicated
+    estimates (ties between combinations), a silent estimate."""
+    rng = np.random.default_rng(20261019)
+    cases = []
+    for ci, (K, N) in enumerate(((3, 4), (2, 4), (3, 5), (2, 5), (3, 6), (2, 7), (3, 8), (2, 8), (3, 4), (3, 7))):
+        n = int(rng.integers(300, 4000))
+        refs = [(rng.standard_normal(n) * 10 ** rng.uniform(-2.5, -1)).astype(np.float32) for _ in range(K)]
+        extra = [(rng.standard_normal(n) * 0.03).astype(np.float32) for _ in range(N - K)]
+        order = rng.permutation(N)
+        noise = 10 ** rng.uniform(-2.0, -0.3)
+        base = refs + extra
+        preds = [(base[j] + noise * rng.standard_normal(n).astype(np.float32) * float(np.std(base[j]) + 1e-3)).astype(np.float32)
+                 for j in order]
+        if ci == 8:
+            preds[3] = preds[0].copy()                   # duplicated estimate: two combinations tie exactly
+        if ci == 9:
+            preds[5] = np.zeros(n, np.float32)           # a silent estimate
+        cases.append((K, N, np.sum(refs, axis=0).astype(np.float32), refs, preds))
+    return cases
+
+
+def make_pit_tie_golden(cases=None, fname="pit_golden_ties.npz"):
     o3, ews = shim.import_reference_pit()
     out = {}
-    cases = pit_tie_cases()
+    cases = pit_tie_cases() if cases is None else cases
     out["n_cases"] = np.int64(len(cases))
     for ci, (K, N, mix, refs, preds) in enumerate(cases):
         out[f"c{ci}_KN"] = np.array([K, N], np.int64)
@@ -173,8 +198,8 @@ def make_pit_tie_golden():
             best, sdri, idx = ews.compute_sdr_improvement_pit_k(mix, refs, preds)
         out[f"c{ci}_ews_res"] = np.array([best, sdri], np.float64)
         out[f"c{ci}_ews_idx"] = np.array(idx, np.int64)
-    np.savez_compressed(os.path.join(OUT, "pit_golden_ties.npz"), **out)
-    print("wrote pit_golden_ties.npz with", len(cases), "cases")
+    np.savez_compressed(os.path.join(OUT, fname), **out)
+    print("wrote", fname, "with", len(cases), "cases")
 
 
 def make_separator_golden():
@@ -213,7 +238,11 @@ if __name__ == "__main__":
     if not shim.reference_available():
         raise SystemExit("/root/reference not present: golden vectors can only be generated in the build container")
     os.makedirs(OUT, exist_ok=True)
+    if "--many-only" in sys.argv:
+        make_pit_tie_golden(pit_many_cases(), "pit_golden_many.npz")
+        raise SystemExit(0)
     if "--ties-only" not in sys.argv:   # (the round-1 fixtures stay byte-identical unless regenerated on purpose)
         make_pit_golden()
         make_separator_golden()
     make_pit_tie_golden()
+    make_pit_tie_golden(pit_many_cases(), "pit_golden_many.npz")

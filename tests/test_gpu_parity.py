@@ -212,12 +212,14 @@ def test_pit_kernel_against_reference_golden(b200, golden_dir):
         assert m > 0
 
 
-def test_pit_kernel_ties_and_near_ties_against_reference_golden(b200, golden_dir):
-    """Exact ties (duplicated estimates / references, all scores equal) must resolve to the SAME permutation as the
+@pytest.mark.parametrize("fixture", ["pit_golden_ties.npz", "pit_golden_many.npz"])
+def test_pit_kernel_ties_and_near_ties_against_reference_golden(b200, golden_dir, fixture):
+    """pit_golden_many.npz: more estimates than references (N = 4 .. 8: one moments pass per group of three estimates,
+    generic combinations x permutations enumeration).  pit_golden_ties.npz: exact ties (duplicated estimates / references, all scores equal) must resolve to the SAME permutation as the
     reference's enumeration + strict `>`; near-ties (reference gap ~1e-5 .. 1e-7 dB, below the ~2e-3 dB difference
     between the kernel's fp64 moments and the reference's fp32 reductions) may legitimately flip, and the kernel must
     then REPORT a gap of that size (PitResult.gap) so that callers can tell."""
-    g = np.load(os.path.join(golden_dir, "pit_golden_ties.npz"))
+    g = np.load(os.path.join(golden_dir, fixture))
     for ci in range(int(g["n_cases"])):
         K, N = [int(v) for v in g[f"c{ci}_KN"]]
         mix = g[f"c{ci}_mix"]
@@ -226,6 +228,8 @@ def test_pit_kernel_ties_and_near_ties_against_reference_golden(b200, golden_dir
         ref_gap = float(g[f"c{ci}_o3_gap"])
         for variant, tag in (("overlap3", "o3"), ("evalsrc", "ews")):
             res = b200.pit_sisdr_batch([mix], [refs], [preds], variant)
+            assert res.pair.shape == (1, 3, max(N, 3) + 1)
+            assert np.allclose(res.pair[0, :K, :N], g[f"c{ci}_o3_pair"], rtol=2e-5, atol=2e-3), (ci, tag)
             best, sdri = g[f"c{ci}_{tag}_res"]
             assert abs(res.sisdr[0] - best) < 2e-3, (ci, tag)
             if abs(sdri) < 100.0:   # (t3: mix == 3 * ref exactly -> the baseline SI-SDR is rounding noise at ~135 dB)

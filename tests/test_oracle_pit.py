@@ -40,11 +40,12 @@ def test_restatement_matches_reference_golden_bit_exact(golden_dir):
     assert n == 18
 
 
-def test_restatement_matches_reference_on_ties_bit_exact(golden_dir):
-    """Tie-breaking (enumeration order, strict `>`, the K=2 `>=` swap rule) pinned on the reference's own outputs for
+@pytest.mark.parametrize("fixture,n_cases", [("pit_golden_ties.npz", 8), ("pit_golden_many.npz", 10)])
+def test_restatement_matches_reference_on_ties_bit_exact(golden_dir, fixture, n_cases):
+    """pit_golden_many.npz: N = 4 .. 8 estimates for K = 2 / 3 references.  pit_golden_ties.npz: tie-breaking (enumeration order, strict `>`, the K=2 `>=` swap rule) pinned on the reference's own outputs for
     duplicated estimates / references, all-equal scores and 1e-7-relative near-ties (oracle/make_golden.py)."""
-    g = np.load(os.path.join(golden_dir, "pit_golden_ties.npz"))
-    assert int(g["n_cases"]) == 8
+    g = np.load(os.path.join(golden_dir, fixture))
+    assert int(g["n_cases"]) == n_cases
     for ci in range(int(g["n_cases"])):
         K, N = [int(v) for v in g[f"c{ci}_KN"]]
         mix = g[f"c{ci}_mix"]
