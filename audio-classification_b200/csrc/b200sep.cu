@@ -845,7 +845,7 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
           { static DevOnce once; if (once.need(m->device)) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); once.done(m->device); } }
       tail::TailParams tp{m->mask_b, enc, d_out, c.n_src, c.mask_act};
       CK(launch_k(kern, dim3(std::min(nt, m->n_sm)), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tm_skipa, m->tm_mask128,
-                  m->tm_wd, tp, tb));
+                  m->tm_wd, tm_enc, tp, tb));
       stop();
       return sync_failed ? 1 : 0;
     }

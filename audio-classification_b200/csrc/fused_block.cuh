@@ -41,7 +41,18 @@ __device__ __forceinline__ void tl_stamp(int it, int slot) {
   long long* tl = c_timeline;
   if (tl != nullptr && it < TL_TILES) tl[((size_t)blockIdx.x * TL_TILES + it) * TL_SLOTS + slot] = clock64();
 }
-
+// kernel-level stamps (entry / dependency wait returned / exit) in globaltimer nanoseconds AND clock64, in the row of the
+// last visit slot (single-visit launches -- the one-call latency path -- leave it free): tools/single_call_timeline.py
+__device__ __forceinline__ void tl_stamp_ns(int slot) {
+  long long* tl = c_timeline;
+  if (tl != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    long long* row = tl + ((size_t)blockIdx.x * TL_TILES + (TL_TILES - 1)) * TL_SLOTS;
+    row[slot] = (long long)t;
+    row[slot + 4] = clock64();
+  }
+}
 
 namespace fb {
 using namespace tc;
@@ -440,6 +451,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   // PDL: everything up to the prologue barrier touches only constants (weights, tap tables, per-call layout
   // tables), so it may overlap the previous kernel's tail; activations are read after pdl_wait().
   pdl_launch_dependents();
+  if (threadIdx.x == 0) tl_stamp_ns(112);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n_tiles = tb.n_tiles;
@@ -514,6 +526,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
   __syncthreads();
   tcgen05_fence_after();
   pdl_wait();
+  if (threadIdx.x == 0) tl_stamp_ns(113);
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
@@ -809,6 +822,7 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
 
   tcgen05_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) tl_stamp_ns(114);
   if (warp == 6) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -870,6 +884,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
   const uint32_t done_bar = bar0 + 8u * 14;  // final tcgen05.commit: no async mbarrier arrive may outlive the CTA
 
   pdl_launch_dependents();  // PDL: the prologue below (barriers, TMEM, resident W_in, layout tables) reads constants only
+  if (threadIdx.x == 0) tl_stamp_ns(24);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int n_tiles = tb.n_tiles;
@@ -905,6 +920,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   pdl_wait();
+  if (threadIdx.x == 0) tl_stamp_ns(25);
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
 
@@ -1127,6 +1143,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
 
   tcgen05_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) tl_stamp_ns(26);
   if (warp == MMA_WARP) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);

@@ -42,6 +42,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
       : "memory");
 }
 
+// 4 / 8 fp32 columns of 32 lanes
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t* u = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr)
+               : "memory");
+}
+
 template <int L>
 struct TailCfg {
   static constexpr int A_BYTES = TILE_M * C_SKIP * 2;     // 32 KiB: PReLU(skip_sum) tile, 2 k-blocks
@@ -50,15 +66,22 @@ struct TailCfg {
   // the same time) while a chunk's epilogue takes ~2 k: with two stages the kernel ran at the latency of the weight stream
   // (tools/timeline_tail.py).  As many stages as fit; the masked-chunk staging needs only one (the decoder MMAs that
   // read it are issued the moment it is complete and take a few hundred cycles).
-  static constexpr int B_STAGES = (L == 16) ? 4 : 3;
+  static constexpr int B_STAGES = (L == 16) ? 3 : 2;
   static constexpr int WD_BYTES = L * C_ENC * 2;          // decoder filterbank [L][512] fp16, 8 k-blocks
   static constexpr int ST_BYTES = TILE_M * 128 * 2;       // 32 KiB: masked chunk [128 frames][128 filters]
   static constexpr int ST_STAGES = 1;
-  static constexpr int OLA_BYTES = TILE_M * (L + 1) * 4;
+  static constexpr int OLA_BYTES = 2 * TILE_M * (L + 1) * 4;   // two buffers (sources alternate)
   static constexpr int OFF_B = A_BYTES;
   static constexpr int OFF_WD = OFF_B + B_STAGES * B_STAGE;
   static constexpr int OFF_ST = OFF_WD + WD_BYTES;
-  static constexpr int OFF_OLA = OFF_ST + ST_STAGES * ST_BYTES;
+  // encoder-output rows of the current filter chunk (128 filters x 128 frames fp16 as four swizzled 64 x 64 TMA boxes):
+  // each epilogue thread needs 64 contiguous bytes of ITS filter row, i.e. a warp-level global load touches 32 different
+  // lines -- 64 such loads per filter chunk issued by all 16 warps at once kept the load/store unit busy for ~2.5 k
+  // cycles on the chunk-to-chunk critical path (tools/timeline_tail.py); the TMA unit fetches whole rows instead and
+  // the threads read their pieces from shared memory (4 conflict-free ld.shared.v4 each)
+  static constexpr int ENC_BYTES = 128 * TILE_M * 2;      // 32 KiB
+  static constexpr int OFF_ENC = OFF_ST + ST_STAGES * ST_BYTES;
+  static constexpr int OFF_OLA = OFF_ENC + ENC_BYTES;
   static constexpr int OFF_BAR = (OFF_OLA + OLA_BYTES + 15) / 16 * 16;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static constexpr int EPI_WARPS = 16;  // 4 per TMEM lane quadrant, 32 filters each
@@ -66,6 +89,7 @@ struct TailCfg {
   static constexpr int TMEM_COLS = 512;
   static constexpr int DEC_COL0 = 256;                    // decoder accumulators start here
   static_assert(SMEM_BYTES <= 232448, "tail kernel shared memory over the 227 KiB limit");
+  static_assert(L == 16 || L == 32, "overlap-add mapping: L / 4 taps per warp");
 };
 
 struct TailParams {
@@ -79,7 +103,8 @@ struct TailParams {
 template <int L>
 __global__ void __launch_bounds__(TailCfg<L>::THREADS, 1)
 mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                const __grid_constant__ CUtensorMap tm_wd, TailParams p, Tables tb) {
+                const __grid_constant__ CUtensorMap tm_wd, const __grid_constant__ CUtensorMap tm_enc, TailParams p,
+                Tables tb) {
   using Cfg = TailCfg<L>;
   constexpr int S = L / 2;
   extern __shared__ uint8_t smem_raw[];
@@ -88,8 +113,9 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const uint32_t smem_a = smem_base;
   auto smem_b = [&](int s) { return smem_base + (uint32_t)(Cfg::OFF_B + s * Cfg::B_STAGE); };
   const uint32_t smem_wd = smem_base + Cfg::OFF_WD;
+  const uint32_t smem_enc = smem_base + Cfg::OFF_ENC;
   auto smem_st = [&](int s) { return smem_base + (uint32_t)(Cfg::OFF_ST + s * Cfg::ST_BYTES); };
-  float (*s_ola)[L + 1] = reinterpret_cast<float (*)[L + 1]>(smem_gen + Cfg::OFF_OLA);
+  float (*s_ola)[TILE_M][L + 1] = reinterpret_cast<float (*)[TILE_M][L + 1]>(smem_gen + Cfg::OFF_OLA);   // [2]
   const uint32_t bar0 = smem_base + Cfg::OFF_BAR;
   const uint32_t wd_bar = bar0;                                  // decoder filterbank landed (once)
   const uint32_t a_full = bar0 + 8u, a_empty = bar0 + 16u;       // skip operand of the m-tile
@@ -99,9 +125,12 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   auto acc_empty = [&](int s) { return bar0 + 8u * (9 + s); };
   auto st_full = [&](int s) { return bar0 + 8u * (11 + s); };
   auto st_empty = [&](int s) { return bar0 + 8u * (13 + s); };
-  const uint32_t dec_full = bar0 + 8u * 15;                      // decoder accumulator of a source complete
+  // decoder accumulator of a source complete: two barriers, sources alternate (the overlap-add of source s runs one
+  // chunk late, so a single barrier could run two phases ahead of a waiter and alias its parity)
+  auto dec_full = [&](int s) { return bar0 + 8u * (28 + s); };
   const uint32_t dec_empty = bar0 + 8u * 16;                     // ... drained by the overlap-add
   const uint32_t tmem_ptr_smem = bar0 + 8u * 17;
+  const uint32_t enc_full = bar0 + 8u * 19, enc_empty = bar0 + 8u * 30;   // encoder rows of a filter chunk
   const uint32_t done_bar = bar0 + 8u * 18;  // final tcgen05.commit: no async mbarrier arrive may outlive the CTA
 
   pdl_launch_dependents();  // PDL: the prologue reads constants only (see fused_block.cuh)
@@ -114,6 +143,7 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     tma_prefetch_desc(&tm_wd);
+    tma_prefetch_desc(&tm_enc);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(wd_bar, 1);
@@ -129,9 +159,12 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       mbar_init(st_full(s), Cfg::EPI_WARPS);
       mbar_init(st_empty(s), 1);
     }
-    mbar_init(dec_full, 1);
-    mbar_init(dec_empty, 4);
+    mbar_init(dec_full(0), 1);
+    mbar_init(dec_full(1), 1);
+    mbar_init(dec_empty, Cfg::EPI_WARPS);
     mbar_init(done_bar, 1);
+    mbar_init(enc_full, 1);
+    mbar_init(enc_empty, Cfg::EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
@@ -231,12 +264,29 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             }
           }
           umma_commit(st_empty(ss));
-          if (cc == 3) { umma_commit(dec_full); ++n_dec; }
+          if (cc == 3) { umma_commit(dec_full(n_dec & 1)); ++n_dec; }
           ++n_st;
         }
       }
       umma_commit(done_bar);  // the last b_empty / st_empty / a_empty arrivals have no waiter
       mbar_wait_b(tb.flags, done_bar, 0);
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ================================ TMA producer: encoder rows of the filter chunks =============
+    if (lane == 0) {
+      int n_enc = 0;
+      for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
+        const int rot = (load_tile_info(tb.tile_info + w).t0 >> 7) & 3;
+        for (int cc = 0; cc < 4; ++cc, ++n_enc) {
+          mbar_wait_b(tb.flags, enc_empty, ((uint32_t)n_enc & 1u) ^ 1u);  // every epilogue warp has converted the last chunk
+          mbar_expect_tx(enc_full, Cfg::ENC_BYTES);
+          const int row0 = w * C_ENC + ((cc + rot) & 3) * 128;
+          for (int rb = 0; rb < 2; ++rb)
+            for (int fbx = 0; fbx < 2; ++fbx)
+              tma_load_2d(smem_enc + (uint32_t)((rb * 2 + fbx) * 8192), &tm_enc, enc_full, fbx * 64, row0 + rb * 64);
+        }
+      }
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -246,8 +296,11 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const int ew = warp - 4, quad = ew & 3, part = ew >> 2;
     const int fl = quad * 32 + lane;             // filter within the 128-filter chunk == TMEM lane
     const int r = fl;                            // (the overlap-add below runs with lane = frame)
-    int n_acc = 0, n_st = 0, n_dec = 0;
+    int n_acc = 0, n_st = 0, n_dec = 0, n_enc = 0;
     const bool tl_on = (ew == 0 && lane == 0);
+    // this thread's 64 bytes (32 frames) of its filter row inside the staged chunk: box (filter / 64, frame half), row
+    // filter % 64, four 16-byte pieces at the swizzled positions
+    const uint32_t enc_row = smem_enc + (uint32_t)(((fl >> 6) * 2 + (part >> 1)) * 8192 + (fl & 63) * 128);
     int tl_it = -1;
     for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
       ++tl_it;
@@ -262,33 +315,62 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 16; ++j) ef[j] = make_float2(0.f, 0.f);
       const float esc = (p.act == 0) ? 0.5f : 1.0f;
-      // raw rows of the NEXT filter chunk: requested a whole chunk before they are converted (L2 latency off the path)
-      uint4 eh[4];
-      {
-        const __half* __restrict__ ep = p.enc + tt_index(w, C_ENC, rot * 128 + fl, part * 32);
+      auto ola = [&](int src) {
+        constexpr int LP = L / 4;                  // taps per warp of a quadrant
+        float (*buf)[L + 1] = s_ola[n_dec & 1];
+        mbar_wait_b(tb.flags, dec_full(n_dec & 1), ((uint32_t)n_dec >> 1) & 1u);
+        tcgen05_fence_after();
+        float taps[LP];
+        const uint32_t daddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::DEC_COL0 + src * L + part * LP);
+        if (LP == 4) tmem_ld4(daddr, reinterpret_cast<float (&)[4]>(taps));
+        else tmem_ld8(daddr, reinterpret_cast<float (&)[8]>(taps));
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dec_empty);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) eh[j] = __ldg(reinterpret_cast<const uint4*>(ep) + j);
-      }
+        for (int l = 0; l < LP; ++l) buf[r][part * LP + l] = taps[l];
+        // (one barrier per source: the buffer written here was last read two sources ago, and every thread has passed
+        // the barrier of the source in between since)
+        fb::named_bar_sync(2, Cfg::EPI_WARPS * 32);
+        float* o = p.out + tb.seg_out_off[seg] + (size_t)src * T_len;
+        const int tid = ew * 32 + lane;
+        // hops hh = 0..128 of this tile: sample (t0 + hh) * S + l gets frame hh's first half and frame
+        // hh-1's second half
+        for (int i = tid; i < (TILE_M + 1) * S; i += Cfg::EPI_WARPS * 32) {
+          const int hh = i / S, l = i % S;
+          const int f_hi = t0 + hh, f_lo = t0 + hh - 1;
+          float val = 0.f;
+          bool any = false;
+          if (hh < TILE_M && f_hi < F) { val += buf[hh][l]; any = true; }
+          if (hh >= 1 && f_lo < F) { val += buf[hh - 1][S + l]; any = true; }
+          if (!any) continue;
+          if (!(fabsf(val) <= 3.0e38f)) atomicOr(tb.flags, 2);  // inf / NaN samples: flagged for the host
+          const size_t idx = (size_t)(t0 + hh) * S + l;
+          if (hh == 0 || hh == TILE_M) atomicAdd(o + idx, val);
+          else o[idx] = val;
+        }
+        ++n_dec;
+      };
       for (int c = 0; c < n_chunks; ++c) {
         const int src = c % p.n_src, cc = c / p.n_src;
         const int as = n_acc & 1, ss = 0;
         const int ch = ((cc + rot) & 3) * 128 + fl;    // this thread's filter
         const float bias = __ldg(p.bias + src * C_ENC + ch) * esc;   // (0.5 b for the sigmoid form)
-        // encoder output of this filter for the 32 frames, once per filter chunk (it serves all sources): issued before
-        // the (possibly blocking) accumulator wait
+        // encoder output of this filter for the 32 frames, once per filter chunk (it serves all sources)
         if (src == 0) {
+          mbar_wait_b(tb.flags, enc_full, (uint32_t)n_enc & 1u);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint32_t ew4[4] = {eh[j].x, eh[j].y, eh[j].z, eh[j].w};
+            const uint4 e4 = fb::ld_shared_v4(enc_row + (uint32_t)(((((part & 1) * 4 + j) ^ (fl & 7))) << 4));
+            const uint32_t ew4[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               ef[j * 4 + k] = mul2(__half22float2(*reinterpret_cast<const __half2*>(&ew4[k])), make_float2(esc, esc));
           }
-        }
-        if (src == p.n_src - 1 && cc < 3) {
-          const __half* __restrict__ ep = p.enc + tt_index(w, C_ENC, ((cc + 1 + rot) & 3) * 128 + fl, part * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) eh[j] = __ldg(reinterpret_cast<const uint4*>(ep) + j);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(enc_empty);   // the next filter chunk's rows may land
+          ++n_enc;
         }
         if (tl_on) tl_stamp(tl_it, 32 + c);
         mbar_wait_b(tb.flags, acc_full(as), ((uint32_t)n_acc >> 1) & 1u);
@@ -350,47 +432,13 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         ++n_st;
 
         if (cc == 3) {   // (the last filter chunk: the sources complete one after the other)
-          // ---- decoder output of source `src`: taps -> overlap-add -> global (4 warps, one per lane quadrant)
-          if (part == 0) {
-            mbar_wait_b(tb.flags, dec_full, (uint32_t)n_dec & 1u);
-            tcgen05_fence_after();
-            float taps[32];
-            const uint32_t daddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::DEC_COL0 + src * L);
-            if (L == 16) {
-              float t16[16];
-              tmem_ld16(daddr, t16);
-#pragma unroll
-              for (int l = 0; l < 16; ++l) taps[l] = t16[l];
-            } else {
-              tmem_ld32(daddr, taps);
-            }
-            tmem_ld_wait();
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dec_empty);
-#pragma unroll
-            for (int l = 0; l < L; ++l) s_ola[r][l] = taps[l];
-            fb::named_bar_sync(2, 128);
-            float* o = p.out + tb.seg_out_off[seg] + (size_t)src * T_len;
-            const int tid = quad * 32 + lane;
-            // hops hh = 0..128 of this tile: sample (t0 + hh) * S + l gets frame hh's first half and frame
-            // hh-1's second half
-            for (int i = tid; i < (TILE_M + 1) * S; i += 128) {
-              const int hh = i / S, l = i % S;
-              const int f_hi = t0 + hh, f_lo = t0 + hh - 1;
-              float val = 0.f;
-              bool any = false;
-              if (hh < TILE_M && f_hi < F) { val += s_ola[hh][l]; any = true; }
-              if (hh >= 1 && f_lo < F) { val += s_ola[hh - 1][S + l]; any = true; }
-              if (!any) continue;
-              if (!(fabsf(val) <= 3.0e38f)) atomicOr(tb.flags, 2);  // inf / NaN samples: flagged for the host
-              const size_t idx = (size_t)(t0 + hh) * S + l;
-              if (hh == 0 || hh == TILE_M) atomicAdd(o + idx, val);
-              else o[idx] = val;
-            }
-            fb::named_bar_sync(2, 128);  // s_ola is reused by the next source
-          }
-          ++n_dec;
+          // decoder output of a source: taps -> overlap-add -> global, by ALL 16 epilogue warps (warp (quad, part) drains
+          // taps [part L/4, +L/4) of its quadrant's 32 frames; the 129 x S output samples are dealt over the 512 threads).
+          // Source s is drained after chunk s + 1 has been staged (its decoder MMAs have long completed by then); only the
+          // last source waits for its own MMAs.  The 4 warps of part 0 used to do all of this while the other 12 waited
+          // for them at the next staging barrier (~3.5 k cycles per source on the chunk-to-chunk critical path).
+          if (src > 0) ola(src - 1);
+          if (src == p.n_src - 1) ola(src);
         }
       }
     }
