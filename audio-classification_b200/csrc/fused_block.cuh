@@ -22,6 +22,7 @@
 // Every mbarrier wait is bounded (Tables::flags): a protocol bug degrades into wrong numbers plus an error
 // flag the host reads, never into a hung GPU.
 #pragma once
+#include <type_traits>
 #include "bandwidth_kernels.cuh"
 #include "common.cuh"
 #include "epilogues.cuh"
@@ -981,18 +982,24 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
         const float2 b2 = make_float2(bch, bch);
         const int f0 = half * 64 + hh * 32;  // first frame of the piece inside the m-tile
         uint32_t pk[16];
+        // two copies of the piece arithmetic behind one uniform branch: the per-element frame masks of a segment's last
+        // tile cost ~60 of the ~270 instructions of a piece when they are if-converted into the common path
+        auto piece_math = [&](auto full_c) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float2 u = add2(make_float2(v[pi & 1][j], v[pi & 1][j + 1]), b2);
-          u = prelu2<A01>(u, alpha);
-          pk[j >> 1] = h2_as_u32(__floats2half2_rn(u.x, u.y));
-          if (!full) {  // statistics exclude frames beyond the segment end
-            if (f0 + j >= nvalid) u.x = 0.f;
-            if (f0 + j + 1 >= nvalid) u.y = 0.f;
+          for (int j = 0; j < 32; j += 2) {
+            float2 u = add2(make_float2(v[pi & 1][j], v[pi & 1][j + 1]), b2);
+            u = prelu2<A01>(u, alpha);
+            pk[j >> 1] = h2_as_u32(__floats2half2_rn(u.x, u.y));
+            if constexpr (!decltype(full_c)::value) {  // statistics exclude frames beyond the segment end
+              if (f0 + j >= nvalid) u.x = 0.f;
+              if (f0 + j + 1 >= nvalid) u.y = 0.f;
+            }
+            s2 = add2(s2, u);
+            q2 = fma2(u, u, q2);
           }
-          s2 = add2(s2, u);
-          q2 = fma2(u, u, q2);
-        }
+        };
+        if (full) piece_math(std::true_type{});
+        else piece_math(std::false_type{});
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           st_shared_v4(st_row + (uint32_t)((((hh * 4 + k) ^ (row & 7))) << 4),
