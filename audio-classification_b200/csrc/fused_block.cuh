@@ -1099,11 +1099,16 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
       for (int p0 = 0; p0 < PASSES; p0 += RND) {
         uint4 xh[RND];
         uint4 gr[RND];
+        float rsv[RND], cbv[RND];   // per-channel constants of the round: requested with the vectors, not at their first use
 #pragma unroll
         for (int j = 0; j < RND; ++j) {
           const size_t off = (size_t)((p0 + j) * ROWS + crow) * TILE_M;
           xh[j] = *reinterpret_cast<const uint4*>(xt + off);
-          if (has_g) gr[j] = ldg_v4(gt + off);
+          if (has_g) {
+            gr[j] = ldg_v4(gt + off);
+            rsv[j] = __ldg(ap.rs + (p0 + j) * ROWS + crow);
+            cbv[j] = __ldg(ap.cb + (p0 + j) * ROWS + crow);
+          }
         }
         if (p0 == 0) {
           mbar_wait_b(tb.flags, xn_empty(b), ((uint32_t)(it >> 1) & 1u) ^ 1u);
@@ -1124,7 +1129,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
             }
           }
           if (has_g) {
-            const float kr = fmaf(nmr, __ldg(ap.rs + c), __ldg(ap.cb + c));
+            const float kr = fmaf(nmr, rsv[j], cbv[j]);
             const uint32_t gw[4] = {gr[j].x, gr[j].y, gr[j].z, gr[j].w};
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
