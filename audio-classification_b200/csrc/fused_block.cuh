@@ -674,24 +674,37 @@ dw_rs_kernel(const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ C
       bool v_;
       const TileInfo ti = ti_get(s_ti, tb, it, tile_at(it, v_));
       const float2 pre = part_prefetch(part1, ti);
+      // (the constants of the first 128 channels are requested before the statistics, those of the next 128 before this
+      // group's table entries are computed: four back-to-back load latencies behind the fp64 reduction were ~2 k cycles
+      // in front of the FIRST k-block of a launch, where nothing hides them)
+      float4 t0[2][4];
+      float cb[2][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        t0[0][j] = __ldg(p.t0 + j * 32 + lane);
+        cb[0][j] = __ldg(p.cb + j * 32 + lane);
+      }
       float mean, rstd;
       seg_stats_pre(part1, ti, pre, p.eps1, mean, rstd, tb.flags);
       const float rm = rstd * mean;
       mbar_wait_b(tb.flags, stat_empty(it & 1), (((uint32_t)it >> 1) & 1u) ^ 1u);
       uint2* tap = s_tap + (it & 1) * C_HID;
-#pragma unroll 1
-      for (int c0 = 0; c0 < C_HID; c0 += 128) {
-        float4 t0[4];
-        float cb[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          t0[j] = __ldg(p.t0 + c0 + j * 32 + lane);
-          cb[j] = __ldg(p.cb + c0 + j * 32 + lane);
+      for (int g = 0; g < C_HID / 128; ++g) {
+        const int c0 = g * 128;
+        if (g + 1 < C_HID / 128) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            t0[(g + 1) & 1][j] = __ldg(p.t0 + c0 + 128 + j * 32 + lane);
+            cb[(g + 1) & 1][j] = __ldg(p.cb + c0 + 128 + j * 32 + lane);
+          }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          tap[c0 + j * 32 + lane] = make_uint2(h2_as_u32(__floats2half2_rn(t0[j].x * rstd, t0[j].y * rstd)),
-                                               h2_as_u32(__floats2half2_rn(t0[j].z * rstd, fmaf(-t0[j].w, rm, cb[j]))));
+        for (int j = 0; j < 4; ++j) {
+          const float4 t = t0[g & 1][j];
+          tap[c0 + j * 32 + lane] = make_uint2(h2_as_u32(__floats2half2_rn(t.x * rstd, t.y * rstd)),
+                                               h2_as_u32(__floats2half2_rn(t.z * rstd, fmaf(-t.w, rm, cb[g & 1][j]))));
+        }
       }
       if (lane == 0) s_stat[it & 1] = make_float2(mean, rstd);
       __syncwarp();
@@ -1068,6 +1081,29 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
     for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
       const int b = it & 1;
       const TileInfo ti = ti_get(s_ti, tb, it, w);
+      __half* __restrict__ xt = ap.x16 + tt_index(w, C_BN, 0, f0);
+      const __half* __restrict__ gt = has_g ? ap.g + tt_index(w, C_BN, 0, f0) : nullptr;
+      constexpr int PASSES = C_BN / ROWS;
+      constexpr int RND = Cfg::PRO_RND;
+      static_assert(PASSES % RND == 0, "prologue rounds");
+      uint4 xh[RND];
+      uint4 gr[RND];
+      float rsv[RND], cbv[RND];   // per-channel constants of the round: requested with the vectors, not at their first use
+      auto load_round = [&](int p0) {
+#pragma unroll
+        for (int j = 0; j < RND; ++j) {
+          const size_t off = (size_t)((p0 + j) * ROWS + crow) * TILE_M;
+          xh[j] = *reinterpret_cast<const uint4*>(xt + off);
+          if (has_g) {
+            gr[j] = ldg_v4(gt + off);
+            rsv[j] = __ldg(ap.rs + (p0 + j) * ROWS + crow);
+            cbv[j] = __ldg(ap.cb + (p0 + j) * ROWS + crow);
+          }
+        }
+      };
+      // the first round's global loads are in flight while the segment statistics are reduced (fp64, ~500 cycles), all
+      // of them are issued before the (possibly blocking) operand-buffer wait
+      load_round(0);
       float mean = 0.f, rstd = 0.f;
       if (has_g) {
         seg_stats_pre(ap.part2, ti, pre, ap.eps2, mean, rstd, tb.flags);
@@ -1088,47 +1124,20 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
         l2_prefetch_bulk(ap.x16 + nidx, TILE_M * C_BN * 2);
         if (has_g) l2_prefetch_bulk(ap.g + nidx, TILE_M * C_BN * 2);
       }
-      __half* __restrict__ xt = ap.x16 + tt_index(w, C_BN, 0, f0);
-      const __half* __restrict__ gt = has_g ? ap.g + tt_index(w, C_BN, 0, f0) : nullptr;
-      // all global loads of the tile are issued before the (possibly blocking) operand-buffer wait
-      constexpr int PASSES = C_BN / ROWS;
       uint32_t xn = 0;
-      constexpr int RND = Cfg::PRO_RND;
-      static_assert(PASSES % RND == 0, "prologue rounds");
-#pragma unroll 1
-      for (int p0 = 0; p0 < PASSES; p0 += RND) {
-        uint4 xh[RND];
-        uint4 gr[RND];
-        float rsv[RND], cbv[RND];   // per-channel constants of the round: requested with the vectors, not at their first use
-#pragma unroll
-        for (int j = 0; j < RND; ++j) {
-          const size_t off = (size_t)((p0 + j) * ROWS + crow) * TILE_M;
-          xh[j] = *reinterpret_cast<const uint4*>(xt + off);
-          if (has_g) {
-            gr[j] = ldg_v4(gt + off);
-            rsv[j] = __ldg(ap.rs + (p0 + j) * ROWS + crow);
-            cbv[j] = __ldg(ap.cb + (p0 + j) * ROWS + crow);
-          }
-        }
-        if (p0 == 0) {
-          mbar_wait_b(tb.flags, xn_empty(b), ((uint32_t)(it >> 1) & 1u) ^ 1u);
-          xn = smem_xn(b);
-          if (pt == 0) tl_stamp(it, 1);
-        }
+      auto compute_round = [&](int p0) {
 #pragma unroll
         for (int j = 0; j < RND; ++j) {
           const int c = (p0 + j) * ROWS + crow;
           const size_t off = (size_t)c * TILE_M;
-          float xv[8];
-          {
+          if (has_g) {
+            float xv[8];
             const uint32_t xw[4] = {xh[j].x, xh[j].y, xh[j].z, xh[j].w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float2 f = __half22float2(u32_as_h2(xw[i]));
               xv[2 * i] = f.x; xv[2 * i + 1] = f.y;
             }
-          }
-          if (has_g) {
             const float kr = fmaf(nmr, rsv[j], cbv[j]);
             const uint32_t gw[4] = {gr[j].x, gr[j].y, gr[j].z, gr[j].w};
 #pragma unroll
@@ -1141,10 +1150,19 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
             const uint4 pk = pack8(xv);  // the rounded stream IS the GEMM operand: one rounding, stored twice
             *reinterpret_cast<uint4*>(xt + off) = pk;
             st_shared_v4(xn + (uint32_t)((c >> 6) * 16384) + a_chunk_off(c & 63, f0), pk);
-            continue;
+          } else {
+            st_shared_v4(xn + (uint32_t)((c >> 6) * 16384) + a_chunk_off(c & 63, f0), xh[j]);  // block 0: x as stored
           }
-          st_shared_v4(xn + (uint32_t)((c >> 6) * 16384) + a_chunk_off(c & 63, f0), xh[j]);  // block 0: x as stored
         }
+      };
+      mbar_wait_b(tb.flags, xn_empty(b), ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      xn = smem_xn(b);
+      if (pt == 0) tl_stamp(it, 1);
+      compute_round(0);
+#pragma unroll 1
+      for (int p0 = RND; p0 < PASSES; p0 += RND) {
+        load_round(p0);
+        compute_round(p0);
       }
       fence_proxy_async();
       __syncwarp();
