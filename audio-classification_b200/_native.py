@@ -22,7 +22,7 @@ PIT_VARIANTS = {"overlap3": 0, "evalsrc": 1}
 
 # every symbol include/b200sep.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "b200sep_version", "b200sep_last_error", "b200sep_model_create", "b200sep_model_destroy",
+    "b200sep_version", "b200sep_lpt_partition", "b200sep_last_error", "b200sep_model_create", "b200sep_model_destroy",
     "b200sep_workspace_bytes", "b200sep_separate_batch", "b200sep_pit_workspace_bytes", "b200sep_pit_workspace_bytes_n",
     "b200sep_pit_sisdr_batch", "b200sep_debug_gemm", "b200sep_debug_set_stop",
     "b200sep_debug_layout", "b200sep_profile_enable", "b200sep_profile_read",
@@ -77,6 +77,8 @@ def lib() -> C.CDLL:
             raise RuntimeError(f"failed to load {LIB_PATH}: {e}") from e
         vp, i32, i64p, i32p = C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32)
         L.b200sep_version.restype = C.c_int
+        L.b200sep_lpt_partition.restype = C.c_int
+        L.b200sep_lpt_partition.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.b200sep_last_error.restype = C.c_char_p
         L.b200sep_model_create.restype = C.c_int
         L.b200sep_model_create.argtypes = [C.POINTER(Config), C.POINTER(Weights), C.c_int,

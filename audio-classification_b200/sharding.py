@@ -18,11 +18,8 @@ def frames_of(n_samples: int, kernel_size: int = 16, stride: int = 8) -> int:
     return (int(n_samples) - kernel_size) // stride + 1
 
 
-def lpt_partition(costs: Sequence[int], world_size: int) -> List[List[int]]:
-    """Deterministic longest-processing-time-first partition.  ``costs[i]`` ~ frames of segment i.
-    Returns, per rank, the (ascending) list of segment indices it owns."""
-    if world_size < 1:
-        raise ValueError("world_size must be >= 1")
+def _lpt_partition_py(costs: Sequence[int], world_size: int) -> List[List[int]]:
+    """Pure-Python statement of the partition rule (the test oracle of the native helper)."""
     import heapq
     c = np.asarray(costs, dtype=np.int64).reshape(-1)
     order = np.lexsort((np.arange(c.size), -c))          # descending cost, ties by ascending index
@@ -34,6 +31,22 @@ def lpt_partition(costs: Sequence[int], world_size: int) -> List[List[int]]:
         shards[r].append(i)
         heapq.heappush(heap, (load + cl[i], r))
     return [sorted(s) for s in shards]
+
+
+def lpt_partition(costs: Sequence[int], world_size: int) -> List[List[int]]:
+    """Deterministic longest-processing-time-first partition.  ``costs[i]`` ~ frames of segment i.
+    Returns, per rank, the (ascending) list of segment indices it owns.  Runs in the native library
+    (``b200sep_lpt_partition``: every rank of a sweep computes it for ALL segments, a fixed cost in front of its shard)."""
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    from . import _native as nat
+    c = np.ascontiguousarray(np.asarray(costs, dtype=np.int64).reshape(-1))
+    owner = np.empty(c.size, dtype=np.int32)
+    nat.check(nat.lib().b200sep_lpt_partition(c.ctypes.data, int(c.size), int(world_size), owner.ctypes.data),
+              "b200sep_lpt_partition")
+    idx = np.argsort(owner, kind="stable")               # ascending index inside every rank
+    bounds = np.searchsorted(owner[idx], np.arange(world_size + 1))
+    return [idx[bounds[r]:bounds[r + 1]].tolist() for r in range(world_size)]
 
 
 def bucket_by_length(indices: Sequence[int], lens: Sequence[int], max_samples: int) -> List[List[int]]:
@@ -125,7 +138,7 @@ def evaluate_sharded(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.nda
     lens = [int(v) for v in lens]
     n = len(lens)
     K = int(n_refs) if n_refs is not None else (len(refs[0]) if n else 0)
-    mine = lpt_partition([frames_of(v, kernel_size, stride) for v in lens], world)[rank] if n else []
+    mine = lpt_partition((np.asarray(lens, dtype=np.int64) - kernel_size) // stride + 1, world)[rank] if n else []
     rec = np.full((len(mine), 2 + K), np.nan)
     pos = {seg: k for k, seg in enumerate(mine)}
     t_sep = 0.0
@@ -134,9 +147,9 @@ def evaluate_sharded(mixes: Sequence[np.ndarray], refs: Sequence[Sequence[np.nda
         t0 = time.time()
         items = (([mixes[i] for i in batch], [refs[i] for i in batch]) for batch in batches)
         for batch, (res, _) in zip(batches, score_stream(items, variant)):
-            for k, i in enumerate(batch):
-                rec[pos[i], 0], rec[pos[i], 1] = res.sisdr[k], res.sisdri[k]
-                rec[pos[i], 2:] = np.asarray(res.perm[k][:K], dtype=np.float64)
+            rows = [pos[i] for i in batch]
+            rec[rows, 0], rec[rows, 1] = res.sisdr, res.sisdri
+            rec[rows, 2:] = np.asarray(res.perm, dtype=np.float64)[:, :K]
         t_sep = time.time() - t0
         batches = []
     for batch in batches:

@@ -107,6 +107,14 @@ typedef struct b200sep_model b200sep_model; /* opaque: device weights, TMA descr
 /* Library / ABI version (B200SEP_VERSION). */
 int b200sep_version(void);
 
+/*
+ * Host-only helper of the multi-GPU evaluation sweep (no reference counterpart: the reference runs its per-segment loop,
+ * scripts/osd/overlap3_core.py:604-744, in one process): deterministic longest-processing-time-first partition of n
+ * independent segments over `world` ranks.  Segments in descending `costs` (ties: ascending index) each go to the least
+ * loaded rank (ties: lowest rank); owner[i] = rank of segment i.  Every rank computes the same partition.
+ */
+int b200sep_lpt_partition(const int64_t* costs, int32_t n, int32_t world, int32_t* owner);
+
 /* Thread-local message of the last failing call on this thread ("" if none). */
 const char* b200sep_last_error(void);
 

@@ -155,6 +155,7 @@ def test_lpt_partition_and_buckets():
         loads = [sum(costs[i] for i in s) for s in shards]
         assert max(loads) - min(loads) <= max(costs)                # LPT balance bound
         assert shards == sharding.lpt_partition(costs, world)       # deterministic
+        assert shards == sharding._lpt_partition_py(costs, world)   # the native helper follows the stated rule exactly
     b = sharding.bucket_by_length(range(200), lens, 400000)
     assert sorted(i for x in b for i in x) == list(range(200))
     assert all(sum(lens[i] for i in x) <= 400000 or len(x) == 1 for x in b)
@@ -163,6 +164,8 @@ def test_lpt_partition_and_buckets():
     assert sharding.frames_of(32000) == 3999 and sharding.frames_of(1600) == 199
     with pytest.raises(ValueError):
         sharding.lpt_partition([1], 0)
+    assert sharding.lpt_partition([], 3) == [[], [], []]
+    assert sharding.lpt_partition([5, 5, 5, 5], 2) == sharding._lpt_partition_py([5, 5, 5, 5], 2) == [[0, 2], [1, 3]]   # ties
 
 
 def test_metrics_match_reference_aggregation():
