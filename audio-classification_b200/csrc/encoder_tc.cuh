@@ -144,11 +144,6 @@ encoder_tc_kernel(const __grid_constant__ CUtensorMap tm_enc, const float* __res
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qn * 128 + half * 64 + ((pi + 1) & 1) * 32),
                     v[(pi + 1) & 1]);
         }
-        if (hh == 0) {
-          // the previous staged chunk's TMA store must have finished READING this staging box before it is rewritten
-          if (issuer) bulk_wait_read0();
-          named_bar_sync(1 + grp, 64);
-        }
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
@@ -156,6 +151,12 @@ encoder_tc_kernel(const __grid_constant__ CUtensorMap tm_enc, const float* __res
           pk[j >> 1] = h2_as_u32(__floats2half2_rn(u.x, u.y));
           s2 = add2(s2, u);
           q2 = fma2(u, u, q2);
+        }
+        if (hh == 0) {
+          // the previous staged chunk's TMA store must have finished READING this staging box before it is rewritten (waited
+          // for after the piece's arithmetic: see K_B)
+          if (issuer) bulk_wait_read0();
+          named_bar_sync(1 + grp, 64);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k)

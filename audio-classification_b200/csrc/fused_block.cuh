@@ -952,7 +952,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
     const uint32_t st_box = smem_base + (uint32_t)(Cfg::OFF_ST + kb64 * 16384 + half * 8192);
     const uint32_t st_row = st_box + (uint32_t)(row * 128);
     const bool issuer = ((quad & 1) == 0 && lane == 0);    // one thread per box issues its TMA store
-    const float alpha = epi.alpha;
+    const __half2 alpha_h2 = __float2half2_rn(epi.alpha);
     int it = 0;
     for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
       const TileInfo ti = ti_get(s_ti, tb, it, w);
@@ -987,32 +987,42 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(qn * 128 + half * 64 + ((pi + 1) & 1) * 32),
                     v[(pi + 1) & 1]);
         }
-        if (hh == 0) {
-          // the previous staged chunk's TMA store must have finished READING this staging box before it is rewritten
-          if (issuer) bulk_wait_read0();
-          named_bar_sync(1 + grp, 64);
-        }
         const float2 b2 = make_float2(bch, bch);
         const int f0 = half * 64 + hh * 32;  // first frame of the piece inside the m-tile
         uint32_t pk[16];
         // two copies of the piece arithmetic behind one uniform branch: the per-element frame masks of a segment's last
         // tile cost ~60 of the ~270 instructions of a piece when they are if-converted into the common path
+        // bias in fp32, then packed halves as in K_A's producers: PReLU on the rounded pair (HMUL2 + HMNMX2: identical to
+        // the fp32 form for u >= 0, one extra fp16 rounding of alpha u below), and the gLN1 statistics of the values AS
+        // STORED -- first level in packed halves (8 pairs), then mixed-precision FMAs into the fp32 accumulators.  Per pair
+        // 6.75 single-issue instructions instead of 7 of which four were two-cycle packed-fp32 ones: the epilogue warps
+        // (two per scheduler) pace this kernel.
         auto piece_math = [&](auto full_c) {
+          __half2 sh = __float2half2_rn(0.f), qh = __float2half2_rn(0.f);
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
-            float2 u = add2(make_float2(v[pi & 1][j], v[pi & 1][j + 1]), b2);
-            u = prelu2<A01>(u, alpha);
-            pk[j >> 1] = h2_as_u32(__floats2half2_rn(u.x, u.y));
+            const float2 u = add2(make_float2(v[pi & 1][j], v[pi & 1][j + 1]), b2);
+            __half2 h = prelu_h2<A01>(__floats2half2_rn(u.x, u.y), alpha_h2);
+            pk[j >> 1] = h2_as_u32(h);
             if constexpr (!decltype(full_c)::value) {  // statistics exclude frames beyond the segment end
-              if (f0 + j >= nvalid) u.x = 0.f;
-              if (f0 + j + 1 >= nvalid) u.y = 0.f;
+              const uint32_t mk = ((f0 + j) < nvalid ? 0xffffu : 0u) | ((f0 + j + 1) < nvalid ? 0xffff0000u : 0u);
+              h = u32_as_h2(h2_as_u32(h) & mk);
             }
-            s2 = add2(s2, u);
-            q2 = fma2(u, u, q2);
+            sh = __hadd2(sh, h);
+            qh = __hfma2(h, h, qh);
+            if ((j & 14) == 14) dw_stats_flush(sh, qh, s2, q2);
           }
         };
         if (full) piece_math(std::true_type{});
         else piece_math(std::false_type{});
+        if (hh == 0) {
+          // the previous staged chunk's TMA store must have finished READING this staging box before it is rewritten: waited
+          // for AFTER this piece's arithmetic (the store was issued only a few hundred cycles ago, at the end of the
+          // previous piece; in front of the arithmetic the issuer -- and its partner warp at the barrier -- sat out the TMA
+          // unit's latency once per chunk)
+          if (issuer) bulk_wait_read0();
+          named_bar_sync(1 + grp, 64);
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           st_shared_v4(st_row + (uint32_t)((((hh * 4 + k) ^ (row & 7))) << 4),
