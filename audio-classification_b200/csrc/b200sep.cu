@@ -695,7 +695,9 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
       using Cfg = enc::EncCfg<L>;
       auto kern = enc::encoder_tc_kernel<L>;
       { static DevOnce once; if (once.need(m->device)) { CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); once.done(m->device); } }
-      CK(launch_k(kern, dim3(std::min(nt, m->n_sm)), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tm_enc, d_mix,
+      CUtensorMap tm_enc_st;   // store boxes of 64 frames x 32 filters: one per epilogue warp and chunk
+      if (make_tmap_2d(&tm_enc_st, enc, TILE_M, (uint64_t)nt * C_ENC, TILE_M * 2, 64, 32)) return 1;
+      CK(launch_k(kern, dim3(std::min(nt, m->n_sm)), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, tm_enc_st, d_mix,
                   (const float*)m->enc_w, p0, tb));
       enc_done = true;
     }
@@ -731,8 +733,9 @@ static int forward(b200sep_model* m, const Layout& lo, const Tables& tb, const f
       // GEMM -> raw G_res + skip stash slot); after the last block the stash is merged into the mask operand
       __half* stash = reinterpret_cast<__half*>(ws + lo.o_stash);
       CUtensorMap tm_hc, tm_hh[5];  // raw h1 views: centre box and halo boxes of 8..128 frames
-      CUtensorMap tm_h1s;  // swizzled 64 x 64 store boxes of h1 (K_B epilogue)
-      if (make_tmap_act(&tm_h1s, h1, nt, C_HID)) return 1;
+      CUtensorMap tm_h1s;  // swizzled store boxes of h1 (K_B epilogue)
+      // (64 frames x 32 channels per store: one box per epilogue warp and chunk)
+      if (make_tmap_2d(&tm_h1s, h1, TILE_M, (uint64_t)nt * C_HID, TILE_M * 2, 64, 32)) return 1;
       // K_A as a CTA pair with tensor-memory-resident weights (fused_pair.cuh; model created under B200SEP_KA=pair): raw
       // G_res / skip-stash store boxes.  Default: the one-CTA kernel (86 vs 92 us per launch on the configs[1] batch)
       const bool ka_pair = m->ka_pair;

@@ -113,11 +113,11 @@ encoder_tc_kernel(const __grid_constant__ CUtensorMap tm_enc, const float* __res
     // ================================ epilogue: fp16 tf_rep + bottleneck-gLN partials =============
     const int ew = warp, quad = ew & 3, half = ew >> 2;   // half = frame half of the m-tile
     const int cl = quad * 32 + lane;                       // filter inside the chunk
-    const int kb64 = cl >> 6, row = cl & 63;
-    const int grp = kb64 * 2 + half;                       // staging box = (64-filter block, frame half): 2 warps
-    const uint32_t st_box = smem_base + (uint32_t)(Cfg::OFF_ST + kb64 * 16384 + half * 8192);
+    // every epilogue warp stages and stores its own 32 filters x 64 frames (a 4 KiB box per chunk), as in K_B
+    const int row = lane;
+    const uint32_t st_box = smem_base + (uint32_t)(Cfg::OFF_ST + ew * 4096);
     const uint32_t st_row = st_box + (uint32_t)(row * 128);
-    const bool issuer = ((quad & 1) == 0 && lane == 0);    // one thread per box issues its TMA store
+    const bool issuer = (lane == 0);                       // one thread per box issues its TMA store
     int it = 0;
     for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
       float2 s2 = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
@@ -156,7 +156,7 @@ encoder_tc_kernel(const __grid_constant__ CUtensorMap tm_enc, const float* __res
           // the previous staged chunk's TMA store must have finished READING this staging box before it is rewritten (waited
           // for after the piece's arithmetic: see K_B)
           if (issuer) bulk_wait_read0();
-          named_bar_sync(1 + grp, 64);
+          __syncwarp();
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -164,9 +164,9 @@ encoder_tc_kernel(const __grid_constant__ CUtensorMap tm_enc, const float* __res
                        make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
         if (hh == 1) {
           fence_proxy_async();
-          named_bar_sync(1 + grp, 64);
+          __syncwarp();
           if (issuer) {
-            tma_store_2d(&tm_enc, st_box, half * 64, w * C_ENC + q * 128 + kb64 * 64);
+            tma_store_2d(&tm_enc, st_box, half * 64, w * C_ENC + q * 128 + quad * 32);
             bulk_commit();
           }
         }

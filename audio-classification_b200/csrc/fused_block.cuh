@@ -160,6 +160,7 @@ __device__ __forceinline__ void tma_store_2d(const void* desc, uint32_t smem_src
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
@@ -947,11 +948,12 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
     static_assert(Cfg::EPI_WARPS == 8, "epilogue mapping assumes two warps per TMEM lane quadrant");
     const int ew = warp, quad = ew & 3, half = ew >> 2;   // half = frame half of the m-tile
     const int cl = quad * 32 + lane;                       // channel inside the chunk
-    const int kb64 = cl >> 6, row = cl & 63;
-    const int grp = kb64 * 2 + half;                       // staging box = (64-channel block, frame half): 2 warps
-    const uint32_t st_box = smem_base + (uint32_t)(Cfg::OFF_ST + kb64 * 16384 + half * 8192);
-    const uint32_t st_row = st_box + (uint32_t)(row * 128);
-    const bool issuer = ((quad & 1) == 0 && lane == 0);    // one thread per box issues its TMA store
+    const int row = lane;                                  // row inside the warp's staging box
+    // every epilogue warp stages and stores its own 32 channels x 64 frames (a 4 KiB box per chunk): no barrier between
+    // warps, only __syncwarp (two warps sharing a 64 x 64 box met at two named barriers per chunk: 56.0 vs 55.4 us)
+    const uint32_t st_box = smem_base + (uint32_t)(Cfg::OFF_ST + ew * 4096);
+    const uint32_t st_row = st_box + (uint32_t)(lane * 128);
+    const bool issuer = (lane == 0);                       // one thread per box issues its TMA store
     const __half2 alpha_h2 = __float2half2_rn(epi.alpha);
     int it = 0;
     for (int w = blockIdx.x; w < n_tiles; w += gridDim.x, ++it) {
@@ -1021,7 +1023,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
           // previous piece; in front of the arithmetic the issuer -- and its partner warp at the barrier -- sat out the TMA
           // unit's latency once per chunk)
           if (issuer) bulk_wait_read0();
-          named_bar_sync(1 + grp, 64);
+          __syncwarp();
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -1029,9 +1031,9 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
                        make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]));
         if (hh == 1) {
           fence_proxy_async();
-          named_bar_sync(1 + grp, 64);
+          __syncwarp();
           if (issuer) {
-            tma_store_2d(&tm_h1, st_box, half * 64, w * C_HID + q * 128 + kb64 * 64);
+            tma_store_2d(&tm_h1, st_box, half * 64, w * C_HID + q * 128 + quad * 32);
             bulk_commit();
           }
           if (threadIdx.x == 0) tl_stamp(it, 20 + q);
