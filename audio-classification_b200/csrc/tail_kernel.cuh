@@ -315,6 +315,8 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 16; ++j) ef[j] = make_float2(0.f, 0.f);
       const float esc = (p.act == 0) ? 0.5f : 1.0f;
+      float bias_raw = __ldg(p.bias + (rot & 3) * 128 + fl);   // chunk 0: source 0, filter chunk rot
+      float* const o_seg = p.out + tb.seg_out_off[seg];        // (loaded per tile, not behind the overlap-add's barrier)
       auto ola = [&](int src) {
         constexpr int LP = L / 4;                  // taps per warp of a quadrant
         float (*buf)[L + 1] = s_ola[n_dec & 1];
@@ -333,7 +335,7 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         // (one barrier per source: the buffer written here was last read two sources ago, and every thread has passed
         // the barrier of the source in between since)
         fb::named_bar_sync(2, Cfg::EPI_WARPS * 32);
-        float* o = p.out + tb.seg_out_off[seg] + (size_t)src * T_len;
+        float* o = o_seg + (size_t)src * T_len;
         const int tid = ew * 32 + lane;
         // hops hh = 0..128 of this tile: sample (t0 + hh) * S + l gets frame hh's first half and frame
         // hh-1's second half
@@ -355,8 +357,10 @@ mask_dec_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       for (int c = 0; c < n_chunks; ++c) {
         const int src = c % p.n_src, cc = c / p.n_src;
         const int as = n_acc & 1, ss = 0;
-        const int ch = ((cc + rot) & 3) * 128 + fl;    // this thread's filter
-        const float bias = __ldg(p.bias + src * C_ENC + ch) * esc;   // (0.5 b for the sigmoid form)
+        // (this chunk's bias was requested one chunk ago: read at its first use it was a long-scoreboard stall per chunk)
+        const float bias = bias_raw * esc;             // (0.5 b for the sigmoid form)
+        if (c + 1 < n_chunks)
+          bias_raw = __ldg(p.bias + ((c + 1) % p.n_src) * C_ENC + (((c + 1) / p.n_src + rot) & 3) * 128 + fl);
         // encoder output of this filter for the 32 frames, once per filter chunk (it serves all sources)
         if (src == 0) {
           mbar_wait_b(tb.flags, enc_full, (uint32_t)n_enc & 1u);
