@@ -1,5 +1,7 @@
 # Final measurement set of a round (run on a B200 through gpurun): bench lines, launch list, ncu --set full captures.
 set -x
+python -m pytest tests -m gpu -x -q > gpurun_out/r_gpu_tests.log 2>&1
+python __graft_entry__.py smoke > gpurun_out/r_smoke.log 2>&1
 python bench.py > gpurun_out/r_bench_n1.json 2> gpurun_out/r_bench_n1.err
 python bench.py --impl reference > gpurun_out/r_bench_reference.json 2> gpurun_out/r_ref.err
 for c in 2 3 4; do python bench.py --config $c > gpurun_out/r_bench_config$c.json 2> gpurun_out/r_c$c.err; done
