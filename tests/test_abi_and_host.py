@@ -168,6 +168,25 @@ def test_lpt_partition_and_buckets():
     assert sharding.lpt_partition([5, 5, 5, 5], 2) == sharding._lpt_partition_py([5, 5, 5, 5], 2) == [[0, 2], [1, 3]]   # ties
 
 
+def test_pit_and_partition_argument_validation(built_lib):
+    """Error paths that return before any CUDA call (so they run without a GPU)."""
+    from b200sep import _native as nat
+    lens = nat.i32_array([1000, 2000])
+    assert built_lib.b200sep_pit_workspace_bytes_n(lens, 2, 9) == 0 and "at most 8" in nat.last_error()
+    assert built_lib.b200sep_pit_workspace_bytes_n(lens, 2, 8) > built_lib.b200sep_pit_workspace_bytes_n(lens, 2, 3) \
+        == built_lib.b200sep_pit_workspace_bytes(lens, 2)          # one block of partial moments per group of three
+    dummy = (C.c_double * 64)()
+    p = C.cast(dummy, C.c_void_p)
+    for K, N in ((1, 3), (4, 4), (3, 2), (2, 9)):
+        rc = built_lib.b200sep_pit_sisdr_batch(p, p, p, None, lens, 2, K, N, 0, p, p, p, p, None, p, C.c_size_t(1 << 20), None)
+        assert rc != 0 and "K in {2,3}" in nat.last_error(), (K, N, nat.last_error())
+    owner = (C.c_int32 * 4)()
+    costs = (C.c_int64 * 4)(5, 1, 5, 3)
+    assert built_lib.b200sep_lpt_partition(C.cast(costs, C.c_void_p), 4, 0, C.cast(owner, C.c_void_p)) != 0
+    assert built_lib.b200sep_lpt_partition(C.cast(costs, C.c_void_p), 4, 2, C.cast(owner, C.c_void_p)) == 0
+    assert list(owner) == [0, 1, 1, 0]    # 5 -> r0, 5 -> r1, 3 -> r0 (tie: lowest rank), 1 -> r1
+
+
 def test_metrics_match_reference_aggregation():
     from b200sep import metrics
     vals = [10.1234567, 12.5, float("nan"), 9.75]
