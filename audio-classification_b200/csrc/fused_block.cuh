@@ -3,8 +3,8 @@
 //
 //   K_B  apply_in_kernel :  x += gLN2-scaled residual output of the previous block (elementwise
 //                           prologue on the raw G_res), x -> fp16 operand in shared memory -> tcgen05
-//                           in-conv GEMM (128 -> 512, W_in resident in shared memory) -> bias + PReLU
-//                           -> h1 (fp16) + gLN1 partial sums.
+//                           in-conv GEMM (128 -> 512, W_in resident in shared memory) -> bias (fp32) -> fp16 ->
+//                           PReLU (packed halves) -> h1 + gLN1 partial sums of the stored values.
 //   K_A  dw_rs_kernel    :  raw h1 k-blocks (+ dilation halos) staged into shared memory by TMA; 16
 //                           producer warps fold gLN1 into the dilated depthwise taps, apply PReLU and
 //                           write the result straight into the swizzled shared-memory A-operand ring
@@ -943,7 +943,7 @@ apply_in_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
     // ================================ epilogue: bias + PReLU -> h1, gLN1 partials ==================
     // D[channel][frame]: TMEM lane = output channel of the 128-channel chunk, column = frame.  A thread owns 32
     // consecutive frames of one channel per tcgen05.ld: the bias is a per-lane constant, eight frames pack into one
-    // 16-byte st.shared (swizzled like a TMA box, conflict-free), and h1 leaves the SM as 64 x 64 TMA tile stores --
+    // 16-byte st.shared (swizzled like a TMA box, conflict-free), and h1 leaves the SM as 64-frame x 32-channel TMA tile stores --
     // 1/8 of the LSU instructions of the lane = frame mapping (which needs one 2-byte store per value).
     static_assert(Cfg::EPI_WARPS == 8, "epilogue mapping assumes two warps per TMEM lane quadrant");
     const int ew = warp, quad = ew & 3, half = ew >> 2;   // half = frame half of the m-tile

@@ -5,19 +5,20 @@
 //     MMA 1 : score[n][frame] = sum_k W_mask[s*512 + c*128 + n][k] * PReLU(skip_sum)[frame][k]   (K = 128; TRANSPOSED:
 //             TMEM lane = filter, column = frame, as in K_B)
 //     epi 1 : masked = act(score + b) * tf_rep[c*128 + n][frame]  -> fp16 -> swizzled MN-major smem operand.  A thread
-//             owns one filter x 32 consecutive frames: the bias is a per-lane constant and the encoder output comes in
-//             as 16-byte vectors along the frames of its row (the lane = frame mapping needed one 2-byte load per value
-//             and re-read the bias row per thread)
+//             owns one filter x 32 consecutive frames: the bias is a per-lane constant and the encoder output of the
+//             filter chunk is staged by TMA (four swizzled 64 x 64 boxes) and read as four 16-byte ld.shared per thread
+//             (the lane = frame mapping needed one 2-byte load per value and re-read the bias row per thread; direct
+//             16-byte global loads of a thread's row piece touch 32 lines per warp instruction and serialised in the LSU)
 //     MMA 2 : dec[frame][l] += sum_n masked[frame][n] * W_dec[c*128 + n][l]      (N = L taps, K = 128 / chunk)
 //   Chunk order: filter chunk outermost, source innermost -- the encoder-output rows of a chunk are loaded ONCE and
-//   multiply all n_src masks (source-outermost re-read them per source: 3 x 128 KiB per m-tile from L2, and this kernel
-//   is bound by what an SM can pull from L2: 384 KiB of mask weights + the encoder output per m-tile).
+//   multiply all n_src masks (source-outermost re-read them per source: 3 x 128 KiB per m-tile from L2).
 //   After the last chunk of a source:
 //     epi 2 : overlap-add of the L taps of the 128 frames (stride L/2) + zero tail (pad_x_to_y) -> d_out
 //
 // (asteroid: mask_net + output_act, `est_masks * tf_rep.unsqueeze(1)`, Decoder(FreeFB) = conv_transpose1d;
-//  SURVEY.md A.2.)  Warp roles as in gemm_tc.cuh: warp 0 TMA, warp 1 MMA issuer (both MMAs), warp 2 TMEM
-// allocator, warps 4-19 epilogue (lane = filter; the overlap-add runs with lane = frame).  TMEM: 2 x 128 score columns (double-buffered) + n_src x L
+//  SURVEY.md A.2.)  Warp roles: warp 0 TMA (skip operand, W_mask chunks, decoder filterbank), warp 1 MMA issuer (both
+// MMAs), warp 2 TMEM allocator, warp 3 TMA (encoder rows of the filter chunks), warps 4-19 epilogue (lane = filter; the
+// overlap-add runs on all 16 warps with lane = frame, L / 4 taps each, one chunk after the source's last MMA).  TMEM: 2 x 128 score columns (double-buffered) + n_src x L
 // decoder columns.  d_out must be zero-filled by the caller (the two hops shared with the neighbouring
 // m-tiles are accumulated with atomicAdd: two addends onto zero, order-independent).
 #pragma once
@@ -62,10 +63,9 @@ template <int L>
 struct TailCfg {
   static constexpr int A_BYTES = TILE_M * C_SKIP * 2;     // 32 KiB: PReLU(skip_sum) tile, 2 k-blocks
   static constexpr int B_STAGE = 128 * C_SKIP * 2;        // 32 KiB: 128 mask-conv rows x 128 k
-  // weight ring: a 32 KiB W_mask chunk takes ~5 k cycles from L2 to shared memory here (every CTA pulls the same chunk at
-  // the same time) while a chunk's epilogue takes ~2 k: with two stages the kernel ran at the latency of the weight stream
-  // (tools/timeline_tail.py).  As many stages as fit; the masked-chunk staging needs only one (the decoder MMAs that
-  // read it are issued the moment it is complete and take a few hundred cycles).
+  // weight ring: as many stages as fit next to the encoder-row buffer (three; two measured 5 us slower even with a second
+  // masked-chunk staging buffer in exchange); the masked-chunk staging needs only one (the decoder MMAs that read it are
+  // issued the moment it is complete and take a few hundred cycles).
   static constexpr int B_STAGES = (L == 16) ? 3 : 2;
   static constexpr int WD_BYTES = L * C_ENC * 2;          // decoder filterbank [L][512] fp16, 8 k-blocks
   static constexpr int ST_BYTES = TILE_M * 128 * 2;       // 32 KiB: masked chunk [128 frames][128 filters]
