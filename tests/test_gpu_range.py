@@ -74,6 +74,29 @@ def test_scaled_weights_stay_within_gate(s, mixes):
     eng.close()
 
 
+@pytest.mark.parametrize("s", [1e-2, 1e3])
+def test_scaled_residual_stream_stays_within_gate(s, mixes):
+    """The residual stream is never normalised: scaling the bottleneck conv and every residual conv by s scales x, and with
+    it the pre-gLN1 activations h1 = W_in x (stored in fp16, summed for the gLN1 statistics), by s.  The conditioning's
+    white model of x has to take that scale out again (no fp32 re-run, >= 40 dB)."""
+    import b200sep
+    from b200sep import weights
+    sd0, args = weights.random_state_dict(3, 0)
+    sd = {k: v.clone() for k, v in sd0.items()}
+    for k in sd:
+        if k.startswith("masker.bottleneck.1.") or ".res_conv." in k:
+            sd[k] = sd[k] * s
+    model = _oracle(sd, args)
+    eng = b200sep.SeparationEngine(sd, args, 0, "fp16")
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        worst = _worst_db(model, eng, mixes[:4])
+    assert eng.fallback_reruns == 0
+    print(f"[range] residual stream x {s:g}: worst SI-SDR vs oracle fp32 = {worst:.1f} dB; conditioning {eng.conditioning}")
+    assert worst >= GATE_DB, (s, worst)
+    eng.close()
+
+
 def test_eps_dominated_scale_is_detected_and_rerun_in_fp32(mixes):
     """s = 1e-4 on the encoder filters puts the encoder output's variance 1e4 below the bottleneck gLN's eps = 1e-8:
     the norm then divides by sqrt(eps), the signal reaches the TCN as a ripple ~250 x smaller than the biases, and fp16
