@@ -27,7 +27,7 @@ EXPORTS = [
     "b200sep_pit_sisdr_batch", "b200sep_debug_gemm", "b200sep_debug_set_stop",
     "b200sep_debug_layout", "b200sep_profile_enable", "b200sep_profile_read",
     "b200sep_pipeline", "b200sep_debug_timeline", "b200sep_pit_profile_enable", "b200sep_pit_profile_read",
-    "b200sep_host_workspace_bytes", "b200sep_separate_batch_host", "b200sep_split_count",
+    "b200sep_host_workspace_bytes", "b200sep_separate_batch_host", "b200sep_split_count", "b200sep_set_max_split",
     "b200sep_resample_out_lens", "b200sep_resample_batch", "b200sep_frame_rms_out_lens",
     "b200sep_frame_rms_batch", "b200sep_gt_overlap_mask_batch", "b200sep_debug_ts_probe",
 ]
@@ -101,6 +101,8 @@ def lib() -> C.CDLL:
         L.b200sep_gt_overlap_mask_batch.argtypes = [vp, vp, i32p, i32, C.c_float, vp, vp]
         L.b200sep_split_count.restype = C.c_int
         L.b200sep_split_count.argtypes = [vp, i32p, i32]
+        L.b200sep_set_max_split.restype = C.c_int
+        L.b200sep_set_max_split.argtypes = [vp, i32]
         L.b200sep_host_workspace_bytes.restype = C.c_size_t
         L.b200sep_host_workspace_bytes.argtypes = [vp, i32p, i32]
         L.b200sep_separate_batch_host.restype = C.c_int

@@ -397,20 +397,29 @@ class SeparationEngine:
                     self._slots.append(dict(stream=torch.cuda.Stream(device=dev), ws=None))
             pending = deque()
             k = 0
-            for chunks, refs in items:
-                if len(chunks) == 0:
-                    while pending:
+            self._set_max_split(1 if depth >= 2 else 0)   # batches in flight fill each other's launch tails
+            try:
+                for chunks, refs in items:
+                    if len(chunks) == 0:
+                        while pending:
+                            yield self._score_collect(pending.popleft())
+                        z = np.zeros(0)
+                        yield PitResult(z, z, np.zeros((0, 0), np.int32), np.zeros(0, bool), np.zeros((0, 3, 4)), z), \
+                            ([] if return_waveforms else None)
+                        continue
+                    if len(pending) >= depth:
                         yield self._score_collect(pending.popleft())
-                    z = np.zeros(0)
-                    yield PitResult(z, z, np.zeros((0, 0), np.int32), np.zeros(0, bool), np.zeros((0, 3, 4)), z), \
-                        ([] if return_waveforms else None)
-                    continue
-                if len(pending) >= depth:
+                    pending.append(self._score_submit(chunks, refs, variant, return_waveforms, self._slots[k % depth]))
+                    k += 1
+                while pending:
                     yield self._score_collect(pending.popleft())
-                pending.append(self._score_submit(chunks, refs, variant, return_waveforms, self._slots[k % depth]))
-                k += 1
-            while pending:
-                yield self._score_collect(pending.popleft())
+            finally:
+                self._set_max_split(0)
+
+    def _set_max_split(self, n: int) -> None:
+        """Cap on the concurrent sub-batches of a call (``b200sep_set_max_split``; 0 = automatic)."""
+        if self._handle is not None:
+            nat.check(nat.lib().b200sep_set_max_split(self._handle, int(n)), "b200sep_set_max_split")
 
     def _acquire_pinned_out(self, n_floats: int):
         """``(pinned tensor, float32 ndarray over it)`` leased from the engine's pool (``_PinnedPool``)."""
@@ -489,19 +498,23 @@ class SeparationEngine:
                     self._slots.append(dict(stream=torch.cuda.Stream(device=dev), ws=None))
             pending = deque()
             k = 0
-            for chunks in batches:
-                segs = self._as_segments(chunks)
-                if not segs:
-                    while pending:
+            self._set_max_split(1 if depth >= 2 else 0)   # batches in flight fill each other's launch tails
+            try:
+                for chunks in batches:
+                    segs = self._as_segments(chunks)
+                    if not segs:
+                        while pending:
+                            yield self._collect(pending.popleft())
+                        yield []
+                        continue
+                    if len(pending) >= depth:
                         yield self._collect(pending.popleft())
-                    yield []
-                    continue
-                if len(pending) >= depth:
+                    pending.append(self._submit(segs, self._slots[k % depth]))
+                    k += 1
+                while pending:
                     yield self._collect(pending.popleft())
-                pending.append(self._submit(segs, self._slots[k % depth]))
-                k += 1
-            while pending:
-                yield self._collect(pending.popleft())
+            finally:
+                self._set_max_split(0)
 
     def separate_batch(self, chunks: Sequence[np.ndarray]) -> List[List[np.ndarray]]:
         """numpy in -> numpy out through pinned staging: one H2D copy, one forward, one D2H copy."""

@@ -164,6 +164,13 @@ int b200sep_separate_batch(b200sep_model* m, const float* d_mix, const int64_t* 
  * SMs the other has drained; 1 while profiling / debugging hooks are on; B200SEP_SPLIT=<n> overrides).  -1 on error.
  */
 int b200sep_split_count(const b200sep_model* m, const int32_t* lens, int32_t n_seg);
+/*
+ * Cap on the number of concurrent sub-batches the two forward entry points cut a call into (0: automatic, the default).
+ * For callers that already overlap several batches on their own streams -- the pipelined forms of Separator.separate
+ * (src/osd/separation.py:66-89) in audio-classification_b200/separator.py -- where a second level of splitting costs
+ * more than it fills.  Results never depend on it.
+ */
+int b200sep_set_max_split(b200sep_model* m, int32_t n);
 
 /*
  * Host boundary of the same forward: replaces Separator.separate (src/osd/separation.py:66-89: numpy in ->
