@@ -617,7 +617,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": audio_all / float(t[0]), "unit": UNIT, "h2d_bytes_per_step": 4 * total,
                "d2h_bytes_per_step": 4 * total * n_src, "steps": n_e2e, "ms_per_step": 1e3 * float(t[0]),
-               "api": "Separator.separate_stream(batches, sr): numpy in -> numpy out, two batches in flight",
+               "api": "Separator.separate_stream(batches, sr): numpy in -> numpy out, two batches in flight "
+                      "(each as ONE sub-batch: the batches in flight fill each other's launch tails)",
                "one_call_at_a_time": {"value": audio_all / float(t[1]), "ms_per_step": 1e3 * float(t[1]),
                                       "api": "Separator.separate_batch(chunks, sr)"}}
 
